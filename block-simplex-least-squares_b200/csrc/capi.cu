@@ -1,0 +1,311 @@
+// capi.cu -- the C ABI of libbsls_b200.so (see include/bsls_b200.h).
+//
+// Host-buffer entry points keep the reference's native signatures
+// (python/c_extensions/c_extensions.pyx:15-19,52-61) and do H2D -> kernels -> D2H.
+// Device entry points are asynchronous on the caller's stream.  There is no CPU
+// fallback anywhere: without an sm_100 device every call fails with BSLS_ERR_NO_DEVICE.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "kernels.h"
+
+namespace bsls {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static int device_ok() {
+    static thread_local int cached = -1;
+    if (cached == BSLS_OK) return BSLS_OK;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error("no CUDA device (%s); libbsls_b200 has no CPU fallback", e == cudaSuccess ? "count=0" : cudaGetErrorString(e));
+        cudaGetLastError();
+        return BSLS_ERR_NO_DEVICE;
+    }
+    int dev = 0, major = 0;
+    BSLS_CUDA_TRY(cudaGetDevice(&dev));
+    BSLS_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major < 10) {
+        set_error("device %d has compute capability %d.x; this library is built for sm_100a only", dev, major);
+        return BSLS_ERR_NO_DEVICE;
+    }
+    cached = BSLS_OK;
+    return BSLS_OK;
+}
+
+}  // namespace bsls
+
+using namespace bsls;
+
+struct bsls_plan {
+    int nb = 0, n = 0, first = 0;
+    int uniform = 0, min_size = 0, max_size = 0;
+    int32_t *d_starts = nullptr;      // nb + 1 entries, last = n
+    // ragged layouts only
+    int tiles = 0, large = 0;
+    int32_t *d_tile_first = nullptr;  // tiles + 1 entries
+    int32_t *d_large_ids = nullptr;   // `large` block indices (size > kPlanTileMaxBlock)
+    bool ragged = false;
+};
+
+// ------------------------------------------------------------------------------------
+// device entry points: projections
+// ------------------------------------------------------------------------------------
+template <typename T> static int dev_project(const bsls_plan *plan, T *y, int mode, cudaStream_t stream) {
+    if (int rc = device_ok()) return rc;
+    if (!plan || !y) {
+        set_error("projection: null plan or buffer");
+        return BSLS_ERR_ARG;
+    }
+    if (plan->uniform > 0 && plan->uniform <= 512) {
+        if constexpr (sizeof(T) == 8)
+            return proj_uniform_f64((double *)y, plan->first, plan->nb, plan->uniform, mode, stream);
+        else
+            return proj_uniform_f32((float *)y, plan->first, plan->nb, plan->uniform, mode, stream);
+    }
+    if (plan->max_size > kPlanLargeMaxBlock) {
+        set_error("projection: a block of %d entries exceeds the %d-entry limit of this revision", plan->max_size, kPlanLargeMaxBlock);
+        return BSLS_ERR_ARG;
+    }
+    const int ntiles = plan->ragged ? plan->tiles : 0;
+    const int32_t *ids = plan->ragged ? plan->d_large_ids : nullptr;  // uniform large blocks: all of them
+    const int nlarge = plan->ragged ? plan->large : plan->nb;
+    if constexpr (sizeof(T) == 8)
+        return proj_ragged_f64((double *)y, plan->d_starts, plan->d_tile_first, ntiles, ids, nlarge, plan->max_size, mode, stream);
+    else
+        return proj_ragged_f32((float *)y, plan->d_starts, plan->d_tile_first, ntiles, ids, nlarge, plan->max_size, mode, stream);
+}
+
+
+namespace {
+
+struct HostWorkspace {  // grow-only device staging owned by the calling thread
+    double *d_y = nullptr;
+    size_t y_cap = 0;
+    int32_t *d_blocks = nullptr;
+    size_t b_cap = 0;
+    cudaStream_t stream = nullptr;
+    int reserve(size_t n, size_t nb) {
+        if (!stream) BSLS_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        if (n > y_cap) {
+            if (d_y) cudaFree(d_y);
+            d_y = nullptr;
+            y_cap = 0;
+            BSLS_CUDA_TRY(cudaMalloc(&d_y, n * sizeof(double)));
+            y_cap = n;
+        }
+        if (nb > b_cap) {
+            if (d_blocks) cudaFree(d_blocks);
+            d_blocks = nullptr;
+            b_cap = 0;
+            BSLS_CUDA_TRY(cudaMalloc(&d_blocks, nb * sizeof(int32_t)));
+            b_cap = nb;
+        }
+        return BSLS_OK;
+    }
+};
+thread_local HostWorkspace g_ws;
+
+// the reference's Python-side asserts (c_extensions.pyx:33-34), checked on the host copy
+int validate_blocks(const int *blocks, int numblocks, int n) {
+    if (!blocks || numblocks <= 0 || n <= 0) {
+        set_error("need numblocks > 0 and n > 0");
+        return BSLS_ERR_ARG;
+    }
+    if (blocks[0] < 0 || blocks[numblocks - 1] >= n) {
+        set_error("block starts out of range");
+        return BSLS_ERR_ARG;
+    }
+    for (int i = 1; i < numblocks; ++i)
+        if (blocks[i] <= blocks[i - 1]) {
+            set_error("block starts not strictly increasing at %d", i);
+            return BSLS_ERR_ARG;
+        }
+    return BSLS_OK;
+}
+
+int host_project(double *y, const int *blocks, int numblocks, int n, int mode) {
+    if (int rc = device_ok()) return rc;
+    if (!y) {
+        set_error("null buffer");
+        return BSLS_ERR_ARG;
+    }
+    if (int rc = validate_blocks(blocks, numblocks, n)) return rc;
+    const int first = blocks[0];
+    const size_t span = (size_t)n - first;  // entries before blocks[0] never leave the host
+    if (int rc = g_ws.reserve(span, (size_t)numblocks)) return rc;
+    cudaStream_t st = g_ws.stream;
+    BSLS_CUDA_TRY(cudaMemcpyAsync(g_ws.d_y, y + first, span * sizeof(double), cudaMemcpyHostToDevice, st));
+    // rebase the starts so that the staged span begins at 0
+    std::vector<int32_t> rebased((size_t)numblocks);
+    for (int i = 0; i < numblocks; ++i) rebased[i] = blocks[i] - first;
+    BSLS_CUDA_TRY(cudaMemcpyAsync(g_ws.d_blocks, rebased.data(), (size_t)numblocks * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    bsls_plan *plan = nullptr;
+    if (int rc = bsls_plan_create(g_ws.d_blocks, numblocks, (int)span, st, &plan)) return rc;
+    int rc = dev_project<double>(plan, g_ws.d_y, mode, st);
+    bsls_plan_destroy(plan);
+    if (rc) return rc;
+    BSLS_CUDA_TRY(cudaMemcpyAsync(y + first, g_ws.d_y, span * sizeof(double), cudaMemcpyDeviceToHost, st));
+    BSLS_CUDA_TRY(cudaStreamSynchronize(st));
+    return BSLS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *bsls_last_error(void) { return g_err; }
+const char *bsls_version(void) { return "bsls_b200 0.1 (sm_100a)"; }
+int bsls_device_ok(void) { return device_ok(); }
+
+// ------------------------------------------------------------------------------------
+// plans
+// ------------------------------------------------------------------------------------
+int bsls_plan_create(const int32_t *d_blocks, int numblocks, int n, bsls_stream_t stream_, bsls_plan **out) {
+    if (!out) return BSLS_ERR_ARG;
+    *out = nullptr;
+    if (int rc = device_ok()) return rc;
+    if (!d_blocks || numblocks <= 0 || n <= 0) {
+        set_error("plan_create: need numblocks > 0 and n > 0 (got %d, %d)", numblocks, n);
+        return BSLS_ERR_ARG;
+    }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    bsls_plan *p = new bsls_plan();
+    p->nb = numblocks;
+    p->n = n;
+    LayoutStats *d_stats = nullptr;
+    LayoutStats h_stats = {0x7fffffff, 0, 0};
+    int first = 0;
+    auto fail = [&](int rc) {
+        if (d_stats) cudaFree(d_stats);
+        if (p->d_starts) cudaFree(p->d_starts);
+        if (p->d_tile_first) cudaFree(p->d_tile_first);
+        if (p->d_large_ids) cudaFree(p->d_large_ids);
+        delete p;
+        return rc;
+    };
+#define TRY_OR_FAIL(expr)                                                                    \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return fail(BSLS_ERR_CUDA);                                                      \
+        }                                                                                    \
+    } while (0)
+    TRY_OR_FAIL(cudaMalloc(&p->d_starts, sizeof(int32_t) * ((size_t)numblocks + 1)));
+    TRY_OR_FAIL(cudaMalloc(&d_stats, sizeof(LayoutStats)));
+    TRY_OR_FAIL(cudaMemcpyAsync(p->d_starts, d_blocks, sizeof(int32_t) * (size_t)numblocks, cudaMemcpyDeviceToDevice, stream));
+    TRY_OR_FAIL(cudaMemcpyAsync(p->d_starts + numblocks, &n, sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+    TRY_OR_FAIL(cudaMemcpyAsync(d_stats, &h_stats, sizeof(LayoutStats), cudaMemcpyHostToDevice, stream));
+    if (int rc = plan_layout_stats(p->d_starts, numblocks, n, d_stats, stream)) return fail(rc);
+    TRY_OR_FAIL(cudaMemcpyAsync(&h_stats, d_stats, sizeof(LayoutStats), cudaMemcpyDeviceToHost, stream));
+    TRY_OR_FAIL(cudaMemcpyAsync(&first, p->d_starts, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    TRY_OR_FAIL(cudaStreamSynchronize(stream));
+    cudaFree(d_stats);
+    d_stats = nullptr;
+    if (h_stats.bad || first < 0 || first >= n) {
+        // the reference's asserts (c_extensions.pyx:33-34): strictly increasing, within [0, n)
+        set_error("plan_create: block starts must be strictly increasing with 0 <= blocks[0] and blocks[-1] < n");
+        return fail(BSLS_ERR_ARG);
+    }
+    p->first = first;
+    p->min_size = h_stats.min_size;
+    p->max_size = h_stats.max_size;
+    p->uniform = (h_stats.min_size == h_stats.max_size) ? h_stats.min_size : 0;
+    if (!p->uniform) {
+        // ragged: fixed tile grid over [first, n) + list of blocks too long for a tile
+        p->ragged = true;
+        p->tiles = (int)(((long long)n - first + kPlanTileElems - 1) / kPlanTileElems);
+        int *d_count = nullptr;
+        int h_count = 0;
+        TRY_OR_FAIL(cudaMalloc(&p->d_tile_first, sizeof(int32_t) * ((size_t)p->tiles + 1)));
+        TRY_OR_FAIL(cudaMalloc(&d_count, sizeof(int)));
+        TRY_OR_FAIL(cudaMemsetAsync(d_count, 0, sizeof(int), stream));
+        if (int rc = plan_tile_first(p->d_starts, numblocks, first, n, p->d_tile_first, p->tiles, stream)) return fail(rc);
+        if (p->max_size > kPlanTileMaxBlock) {
+            if (int rc = plan_large_list(p->d_starts, numblocks, kPlanTileMaxBlock, nullptr, d_count, stream)) return fail(rc);
+            TRY_OR_FAIL(cudaMemcpyAsync(&h_count, d_count, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            TRY_OR_FAIL(cudaStreamSynchronize(stream));
+            TRY_OR_FAIL(cudaMalloc(&p->d_large_ids, sizeof(int32_t) * (size_t)h_count));
+            TRY_OR_FAIL(cudaMemsetAsync(d_count, 0, sizeof(int), stream));
+            if (int rc = plan_large_list(p->d_starts, numblocks, kPlanTileMaxBlock, p->d_large_ids, d_count, stream)) return fail(rc);
+            p->large = h_count;
+        }
+        TRY_OR_FAIL(cudaStreamSynchronize(stream));
+        cudaFree(d_count);
+    }
+#undef TRY_OR_FAIL
+    *out = p;
+    return BSLS_OK;
+}
+
+int bsls_plan_destroy(bsls_plan *plan) {
+    if (!plan) return BSLS_OK;
+    if (plan->d_starts) cudaFree(plan->d_starts);
+    if (plan->d_tile_first) cudaFree(plan->d_tile_first);
+    if (plan->d_large_ids) cudaFree(plan->d_large_ids);
+    delete plan;
+    return BSLS_OK;
+}
+
+int bsls_plan_info(const bsls_plan *plan, int64_t info[8]) {
+    if (!plan || !info) return BSLS_ERR_ARG;
+    info[0] = plan->nb;
+    info[1] = plan->n;
+    info[2] = plan->first;
+    info[3] = plan->uniform;
+    info[4] = plan->min_size;
+    info[5] = plan->max_size;
+    info[6] = plan->tiles;
+    info[7] = plan->large;
+    return BSLS_OK;
+}
+
+// device entry points: projections
+int bsls_dev_proj_multi_simplex_f64(const bsls_plan *plan, double *y, bsls_stream_t s) { return dev_project<double>(plan, y, 0, (cudaStream_t)s); }
+int bsls_dev_proj_multi_ball_f64(const bsls_plan *plan, double *y, bsls_stream_t s) { return dev_project<double>(plan, y, 1, (cudaStream_t)s); }
+int bsls_dev_proj_multi_simplex_f32(const bsls_plan *plan, float *y, bsls_stream_t s) { return dev_project<float>(plan, y, 0, (cudaStream_t)s); }
+int bsls_dev_proj_multi_ball_f32(const bsls_plan *plan, float *y, bsls_stream_t s) { return dev_project<float>(plan, y, 1, (cudaStream_t)s); }
+
+// ------------------------------------------------------------------------------------
+// host entry points
+// ------------------------------------------------------------------------------------
+int bsls_proj_simplex(double *y, int start, int end) {
+    // single block [start, end): argument checks are the caller's (c_extensions.pyx:24-25);
+    // an empty range is a no-op exactly as there
+    if (start >= end) return BSLS_OK;
+    if (start < 0) {
+        set_error("proj_simplex: start < 0");
+        return BSLS_ERR_ARG;
+    }
+    const int one = start;
+    return host_project(y, &one, 1, end, 0);
+}
+
+int bsls_proj_multi_simplex(double *y, const int *blocks, int numblocks, int n) { return host_project(y, blocks, numblocks, n, 0); }
+int bsls_proj_multi_ball(double *y, const int *blocks, int numblocks, int n) { return host_project(y, blocks, numblocks, n, 1); }
+
+int bsls_host_alloc(void **ptr, int64_t bytes) {
+    if (!ptr || bytes <= 0) return BSLS_ERR_ARG;
+    if (int rc = device_ok()) return rc;
+    BSLS_CUDA_TRY(cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocDefault));
+    return BSLS_OK;
+}
+
+int bsls_host_free(void *ptr) {
+    if (!ptr) return BSLS_OK;
+    BSLS_CUDA_TRY(cudaFreeHost(ptr));
+    return BSLS_OK;
+}
+
+}  // extern "C"

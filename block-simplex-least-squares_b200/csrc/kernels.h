@@ -1,0 +1,29 @@
+// kernels.h -- internal launch interface between the translation units of libbsls_b200.
+#pragma once
+#include "common.cuh"
+
+namespace bsls {
+
+// proj_f64.cu / proj_f32.cu: all blocks have K entries, first block starts at `first`.
+int proj_uniform_f64(double *y, long long first, int nb, int K, int mode, cudaStream_t stream);
+int proj_uniform_f32(float *y, long long first, int nb, int K, int mode, cudaStream_t stream);
+
+
+// ragged layouts: tile kernel + one-CTA-per-large-block kernel (proj_ragged.cuh)
+int proj_ragged_f64(double *y, const int32_t *starts, const int32_t *tile_first, int ntiles, const int32_t *large_ids,
+                    int nlarge, int max_large, int mode, cudaStream_t stream);
+int proj_ragged_f32(float *y, const int32_t *starts, const int32_t *tile_first, int ntiles, const int32_t *large_ids,
+                    int nlarge, int max_large, int mode, cudaStream_t stream);
+
+// plan.cu: layout analysis on the device
+struct LayoutStats {
+    int min_size, max_size, bad;  // bad != 0: not strictly increasing / out of range
+};
+int plan_layout_stats(const int32_t *starts /* nb+1 */, int nb, int n, LayoutStats *d_out, cudaStream_t stream);
+int plan_tile_first(const int32_t *starts, int nb, int first, int n, int32_t *tile_first, int ntiles, cudaStream_t stream);
+int plan_large_list(const int32_t *starts, int nb, int threshold, int32_t *ids, int *d_count, cudaStream_t stream);
+constexpr int kPlanTileElems = 2048;      // == kTileElems (proj_ragged.cuh)
+constexpr int kPlanTileMaxBlock = 512;    // == kTileMaxBlock
+constexpr int kPlanLargeMaxBlock = 8192;  // == kLargeMaxBlock
+
+}  // namespace bsls

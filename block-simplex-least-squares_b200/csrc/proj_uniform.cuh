@@ -1,0 +1,275 @@
+// proj_uniform.cuh -- segmented simplex / l1-ball projection, all blocks of one size K.
+//
+// Replaces proj_multi_simplex / proj_multi_ball (python/c_extensions/proj_simplex.h:37-74)
+// for the layouts of BASELINE configs 1, 2, 4, 5 (K = 5, 4/16/64, 20, 16).
+//
+// HBM-bound streaming kernel, one pass over y (read 1x, write 1x):
+//   * persistent CTAs (grid = SMs x resident CTAs), each looping over tiles of TB blocks;
+//   * a tile is pulled into shared memory with ONE 1-D bulk copy (TMA, UBLKCP) signalled
+//     on an mbarrier; two stages, so the next tile is in flight while this one is sorted;
+//   * every block is sorted in the registers of G lanes (simplex_core.cuh); shared-memory
+//     reads are 128-bit and rotated by the lane so that equal strides do not bank-conflict;
+//   * the output pass re-reads the tile from shared memory and writes y with 128-bit
+//     streaming stores, fully coalesced.
+#pragma once
+#include "simplex_core.cuh"
+
+namespace bsls {
+
+enum ProjMode { kSimplex = 0, kBall = 1 };
+
+template <typename T> struct Vec16;  // one 16-byte granule
+template <> struct Vec16<double> {
+    static constexpr int N = 2;
+    using type = double2;
+};
+template <> struct Vec16<float> {
+    static constexpr int N = 4;
+    using type = float4;
+};
+
+template <typename T> __device__ __forceinline__ T clip_neg(T v) { return (v < T(0)) ? T(0) : v; }
+
+// Loads the K values of one block (at blkp, in shared memory) into the registers of its G
+// lanes.  Which lane/register receives which element is irrelevant to the sort, so the
+// lanes interleave: granule slot (e2*G + sub) reads granule (e2*G + lane) mod KV.  Inside a
+// block that is a rotation (a bijection); across the quarter-warp that serves one 128-bit
+// shared-memory wavefront the eight lanes hit eight different 16-byte bank groups even
+// when every block starts on the same bank (K*sizeof(T) a multiple of 128 bytes).
+template <typename T, int E, int G, int MODE>
+__device__ __forceinline__ void load_block_regs(T (&v)[E], const T *blkp, int K, int lane, bool live, bool vec_ok) {
+    constexpr int VN = Vec16<T>::N;
+    using VT = typename Vec16<T>::type;
+    const T ninf = Num<T>::neg_inf();
+    const int sub = lane & (G - 1);
+    if (vec_ok && (E % VN == 0)) {
+        const int KV = K / VN;  // granules per block (vec_ok: K % VN == 0)
+        int q = lane % KV;
+        const int step = G % KV;
+#pragma unroll
+        for (int e2 = 0; e2 < E / VN; ++e2) {
+            const int slot = e2 * G + sub;
+            T tmp[VN];
+#pragma unroll
+            for (int j = 0; j < VN; ++j) tmp[j] = ninf;
+            if (live && slot < KV) {
+                const VT g = *reinterpret_cast<const VT *>(blkp + q * VN);
+                if constexpr (VN == 2) {
+                    tmp[0] = g.x;
+                    tmp[1] = g.y;
+                } else {
+                    tmp[0] = g.x;
+                    tmp[1] = g.y;
+                    tmp[2] = g.z;
+                    tmp[3] = g.w;
+                }
+                if (MODE == kBall) {
+#pragma unroll
+                    for (int j = 0; j < VN; ++j) tmp[j] = clip_neg(tmp[j]);
+                }
+            }
+            q += step;
+            if (q >= KV) q -= KV;
+#pragma unroll
+            for (int j = 0; j < VN; ++j) v[e2 * VN + j] = tmp[j];
+        }
+    } else {
+        int q = lane % K;
+        const int step = G % K;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int slot = e * G + sub;
+            T x = ninf;
+            if (live && slot < K) {
+                x = blkp[q];
+                if (MODE == kBall) x = clip_neg(x);
+            }
+            q += step;
+            if (q >= K) q -= K;
+            v[e] = x;
+        }
+    }
+}
+
+template <typename T, int E, int G, int THREADS, int MODE>
+__global__ void __launch_bounds__(THREADS)
+proj_uniform_kernel(T *__restrict__ y, long long first, int nb, int K, FastDiv kdiv, int aligned) {
+    constexpr int TB = THREADS / G;  // blocks per tile
+    constexpr int VN = Vec16<T>::N;
+    using VT = typename Vec16<T>::type;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tile_elems = TB * K;
+    T *stage0 = reinterpret_cast<T *>(smem_raw);
+    T *stage1 = stage0 + tile_elems;
+    T *lam = stage1 + tile_elems;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(lam + TB + (TB & 1));  // 8-byte aligned for float too
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int blk = tid / G;
+    const int sub = tid & (G - 1);
+    const int ntiles = (nb + TB - 1) / TB;
+    T *ybase = y + first;
+    const bool vec_ok = (K % VN) == 0;  // block starts are 16-byte aligned inside the tile
+
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        mbar_init_fence();
+    }
+    __syncthreads();
+
+    auto issue = [&](int t, int s) {  // thread 0: start the bulk copy of a full tile
+        if (aligned && (nb - t * TB) >= TB) {
+            const uint32_t bytes = (uint32_t)(tile_elems * sizeof(T));
+            mbar_expect_tx(&bar[s], bytes);
+            bulk_g2s(s ? stage1 : stage0, ybase + (size_t)t * tile_elems, bytes, &bar[s]);
+        }
+    };
+
+    int tile = blockIdx.x;
+    if (tile < ntiles && tid == 0) issue(tile, 0);
+
+    for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+        const int s = it & 1;
+        const int nxt = tile + gridDim.x;
+        if (nxt < ntiles && tid == 0) issue(nxt, s ^ 1);
+
+        const int nblk = min(TB, nb - tile * TB);
+        const int nel = nblk * K;
+        T *buf = s ? stage1 : stage0;
+        T *gy = ybase + (size_t)tile * tile_elems;
+
+        if (aligned && nblk == TB) {
+            mbar_wait(&bar[s], (it >> 1) & 1);
+        } else {  // ragged last tile or unaligned base: plain coalesced loads
+            for (int i = tid; i < nel; i += THREADS) buf[i] = gy[i];
+            __syncthreads();
+        }
+
+        // ---- shift of every block -------------------------------------------------------
+        {
+            const bool live = blk < nblk;
+            const T *blkp = buf + blk * K;
+            bool project = true;
+            if (MODE == kBall) {
+                // clip negatives; project only when the clipped block sums to more than 1
+                // (sum left to right over the kept entries, proj_simplex.h:54-62)
+                T total = T(0);
+                if (live && sub == 0)
+                    for (int k = 0; k < K; ++k) {
+                        const T x = blkp[k];
+                        if (!(x < T(0))) total += x;
+                    }
+                if (G > 1) total = __shfl_sync(0xffffffffu, total, lane & ~(G - 1));
+                project = total > T(1);
+            }
+            T v[E];
+            load_block_regs<T, E, G, MODE>(v, blkp, K, lane, live, vec_ok);
+            sort_desc_group<T, E, G>(v, lane);
+            T shift = simplex_shift_sorted<T, E, G>(v, K, lane);
+            if (MODE == kBall && !project) shift = T(0);
+            if (live && sub == 0) lam[blk] = shift;
+        }
+        __syncthreads();
+
+        // ---- output pass: y <- max(y + shift, 0), coalesced 16-byte stores -------------------
+        if (aligned) {
+            const int nvec = nel / VN;
+            for (int i = tid; i < nvec; i += THREADS) {
+                const VT g = reinterpret_cast<const VT *>(buf)[i];
+                T x[VN];
+                if constexpr (VN == 2) {
+                    x[0] = g.x;
+                    x[1] = g.y;
+                } else {
+                    x[0] = g.x;
+                    x[1] = g.y;
+                    x[2] = g.z;
+                    x[3] = g.w;
+                }
+                const uint32_t e0 = (uint32_t)i * VN;
+                const uint32_t b0 = fdiv(e0, kdiv);
+#pragma unroll
+                for (int j = 0; j < VN; ++j) {
+                    const uint32_t b = vec_ok ? b0 : fdiv(e0 + j, kdiv);
+                    T t = x[j];
+                    if (MODE == kBall) t = clip_neg(t);
+                    t = lam[b] + t;
+                    x[j] = (t < T(0)) ? T(0) : t;
+                }
+                if constexpr (VN == 2)
+                    st_stream_v2(gy + e0, x[0], x[1]);
+                else
+                    st_stream_v4(gy + e0, x[0], x[1], x[2], x[3]);
+            }
+            for (int i = nvec * VN + tid; i < nel; i += THREADS) {
+                T t = buf[i];
+                if (MODE == kBall) t = clip_neg(t);
+                t = lam[fdiv((uint32_t)i, kdiv)] + t;
+                gy[i] = (t < T(0)) ? T(0) : t;
+            }
+        } else {
+            for (int i = tid; i < nel; i += THREADS) {
+                T t = buf[i];
+                if (MODE == kBall) t = clip_neg(t);
+                t = lam[fdiv((uint32_t)i, kdiv)] + t;
+                gy[i] = (t < T(0)) ? T(0) : t;
+            }
+        }
+        __syncthreads();  // stage s and lam[] are free again
+    }
+}
+
+// ---- host side: pick (E, G, THREADS) for K and launch ------------------------------------------
+template <typename T, int E, int G, int THREADS, int MODE>
+int launch_proj_uniform_cfg(T *y, long long first, int nb, int K, cudaStream_t stream) {
+    constexpr int TB = THREADS / G;
+    auto kern = proj_uniform_kernel<T, E, G, THREADS, MODE>;
+    const size_t smem = (size_t)2 * TB * K * sizeof(T) + (size_t)(TB + (TB & 1)) * sizeof(T) + 2 * sizeof(uint64_t);
+    static thread_local int cached_blocks_per_sm = -1;
+    static thread_local size_t cached_smem = 0;
+    static thread_local int num_sm = 0;
+    if (cached_blocks_per_sm < 0 || cached_smem != smem) {
+        BSLS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int dev = 0;
+        BSLS_CUDA_TRY(cudaGetDevice(&dev));
+        BSLS_CUDA_TRY(cudaDeviceGetAttribute(&num_sm, cudaDevAttrMultiProcessorCount, dev));
+        int per = 0;
+        BSLS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, THREADS, smem));
+        if (per < 1) {
+            set_error("proj_uniform: block size K=%d does not fit shared memory (%zu B)", K, smem);
+            return BSLS_ERR_ARG;
+        }
+        cached_blocks_per_sm = per;
+        cached_smem = smem;
+    }
+    const int ntiles = (nb + TB - 1) / TB;
+    const int grid = ntiles < num_sm * cached_blocks_per_sm ? ntiles : num_sm * cached_blocks_per_sm;
+    const int aligned = ((reinterpret_cast<uintptr_t>(y + first) % 16) == 0) ? 1 : 0;
+    kern<<<grid, THREADS, smem, stream>>>(y, first, nb, K, make_fastdiv((uint32_t)K), aligned);
+    BSLS_LAUNCH_CHECK();
+    return BSLS_OK;
+}
+
+constexpr int kUniformMaxK = 512;  // larger uniform blocks go through the ragged/large path
+
+template <typename T, int MODE> int launch_proj_uniform(T *y, long long first, int nb, int K, cudaStream_t stream) {
+    if (nb <= 0) return BSLS_OK;
+    if (K <= 4) return launch_proj_uniform_cfg<T, 4, 1, 256, MODE>(y, first, nb, K, stream);
+    if (K <= 8) return launch_proj_uniform_cfg<T, 8, 1, 256, MODE>(y, first, nb, K, stream);
+    if (K <= 12) return launch_proj_uniform_cfg<T, 12, 1, 256, MODE>(y, first, nb, K, stream);
+    if (K <= 16) return launch_proj_uniform_cfg<T, 16, 1, 256, MODE>(y, first, nb, K, stream);
+    if (K <= 20) return launch_proj_uniform_cfg<T, 20, 1, 128, MODE>(y, first, nb, K, stream);
+    if (K <= 24) return launch_proj_uniform_cfg<T, 24, 1, 128, MODE>(y, first, nb, K, stream);
+    if (K <= 32) return launch_proj_uniform_cfg<T, 32, 1, 128, MODE>(y, first, nb, K, stream);
+    if (K <= 64) return launch_proj_uniform_cfg<T, 16, 4, 256, MODE>(y, first, nb, K, stream);
+    if (K <= 128) return launch_proj_uniform_cfg<T, 16, 8, 256, MODE>(y, first, nb, K, stream);
+    if (K <= 256) return launch_proj_uniform_cfg<T, 16, 16, 256, MODE>(y, first, nb, K, stream);
+    if (K <= 512) return launch_proj_uniform_cfg<T, 16, 32, 256, MODE>(y, first, nb, K, stream);
+    set_error("launch_proj_uniform: K=%d above %d", K, kUniformMaxK);
+    return BSLS_ERR_ARG;
+}
+
+}  // namespace bsls

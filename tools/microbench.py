@@ -1,0 +1,61 @@
+"""Quick kernel timings on one GPU (development aid; bench.py is the contract)."""
+import json
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+import __graft_entry__ as g
+
+g.build()
+import bsls_b200
+
+
+def time_proj(K, nb, reps=10, dtype=torch.float64, ball=False):
+    n = nb * K
+    gen = torch.Generator(device="cuda").manual_seed(K)
+    starts = torch.arange(0, n, K, dtype=torch.int64, device="cuda")
+    plan = bsls_b200.BlockPlan(starts, n)
+    bufs = [torch.randn(n, dtype=dtype, device="cuda", generator=gen) for _ in range(reps + 3)]
+    fn = bsls_b200.proj_multi_ball_c if ball else bsls_b200.proj_multi_simplex_c
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for b in bufs[:3]:
+        fn(b, plan)
+    flush.zero_()
+    torch.cuda.synchronize()
+    evs = []
+    for b in bufs[3:]:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn(b, plan)
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    ms = np.array([a.elapsed_time(b) for a, b in evs])
+    es = bufs[0].element_size()
+    bytes_ = 2 * es * n + 4 * nb
+    return {"K": K, "nb": nb, "dtype": str(dtype), "ball": ball, "ms_med": float(np.median(ms)), "ms_min": float(ms.min()),
+            "gvar_s": n / np.median(ms) / 1e6, "GBs": bytes_ / np.median(ms) / 1e6}
+
+
+if __name__ == "__main__":
+    print(torch.cuda.get_device_name(0))
+    a = torch.empty(1 << 28, dtype=torch.float64, device="cuda")
+    b = torch.empty_like(a)
+    for _ in range(3):
+        b.copy_(a)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        b.copy_(a)
+    e1.record()
+    torch.cuda.synchronize()
+    print("copy GB/s", 5 * 2 * a.numel() * 8 / e0.elapsed_time(e1) / 1e6)
+    del a, b
+    for K, nb in [(4, 10 ** 6), (5, 10 ** 6), (16, 10 ** 6), (20, 10 ** 6), (32, 10 ** 6), (64, 10 ** 6), (128, 500000), (512, 100000),
+                  (16, 6250000), (4, 25 * 10 ** 6), (64, 1562500)]:
+        print(json.dumps(time_proj(K, nb)))
+    print(json.dumps(time_proj(16, 10 ** 6, dtype=torch.float32)))
+    print(json.dumps(time_proj(16, 10 ** 6, ball=True)))
