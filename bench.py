@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the block-simplex hot path (contract: see the task).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+Default workload = BASELINE.json configs[1]: the proj_simplex_c microbench, 10^6 uniform
+blocks of size 4, 16 and 64 in fp64.  One STEP = one pass of the segmented simplex
+projection over all three arrays (84e6 variables) on inputs that were never touched before
+(a fresh N(0,1) buffer set per step, far larger than L2 in aggregate).
+
+Prints ONE JSON line.  `value` = projected variables / s over all GPUs with inputs resident
+in HBM; `e2e` = the same metric through the reference-facing host C ABI
+(bsls_proj_multi_simplex on pinned HOST buffers, copies inside the timed region);
+`roofline` = the dominant kernel (K=64 array) against the measured HBM peak;
+`cpu_baseline` = the reference's own C++ (oracle/_ref) timed on this box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 237423433
+SIZES = (4, 16, 64)
+NB = 10 ** 6
+METRIC = "projected_variables_per_sec"
+UNIT = "var/s"
+WORKLOAD = ("C2 proj_simplex_c microbench: 10^6 uniform blocks x K in {4,16,64}, fp64, N(0,1); "
+            "one step projects all three arrays (84e6 variables)")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for (_, r) in self.rows]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm: the reference's own C++ on the host cores
+# --------------------------------------------------------------------------------------------
+def ref_checker():
+    from oracle import cpu
+    cpu.build()
+    r = cpu.ref()
+    return (r, "reference") if r is not None else (cpu.port(), "port")
+
+
+def cpu_project_parallel(chk, y, K, threads):
+    """Runs the checker's proj_multi_simplex over disjoint slices from `threads` host threads
+    (blocks are independent; ctypes releases the GIL)."""
+    nb = y.size // K
+    cuts = np.linspace(0, nb, threads + 1).astype(np.int64)
+
+    def work(i):
+        lo, hi = int(cuts[i]) * K, int(cuts[i + 1]) * K
+        if hi > lo:
+            chk.proj_multi_simplex(y[lo:hi], np.arange(0, hi - lo, K, dtype=np.int32))
+
+    if threads == 1:
+        work(0)
+        return
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+
+
+def cpu_baseline_sample(threads=1, reps=2):
+    """Reference CPU path on a bounded sample (the full 84e6-variable step, `reps` timed passes)."""
+    chk, kind = ref_checker()
+    rng = np.random.RandomState(SEED)
+    data = {K: rng.randn(NB * K) for K in SIZES}
+    best = float("inf")
+    for rep in range(reps + 1):
+        work = {K: data[K].copy() for K in SIZES}
+        t0 = time.perf_counter()
+        for K in SIZES:
+            cpu_project_parallel(chk, work[K], K, threads)
+        dt = time.perf_counter() - t0
+        if rep > 0:
+            best = min(best, dt)
+    nvar = NB * sum(SIZES)
+    return {"value": nvar / best, "unit": UNIT, "cores": threads, "kind": kind,
+            "sample": "one full step (10^6 blocks x K=4,16,64 = 84e6 variables), best of %d after 1 warm-up, "
+                      "%d host thread(s) over disjoint block ranges" % (reps, threads),
+            "seconds_per_step": best}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    chk, kind = ref_checker()
+    rng = np.random.RandomState(SEED)
+    data = {K: rng.randn(NB * K) for K in SIZES}
+    # bounded sample: keep the whole run within a few minutes
+    probe = {K: data[K][: (NB // 16) * K].copy() for K in SIZES}
+    t0 = time.perf_counter()
+    for K in SIZES:
+        cpu_project_parallel(chk, probe[K], K, threads)
+    est_full = (time.perf_counter() - t0) * 16
+    frac = min(1.0, 120.0 / max(1e-9, est_full * (args.steps + args.warmup)))
+    nb_s = max(1000, int(NB * frac))
+    times = []
+    for it in range(args.warmup + args.steps):
+        work = {K: data[K][: nb_s * K].copy() for K in SIZES}
+        t0 = time.perf_counter()
+        for K in SIZES:
+            cpu_project_parallel(chk, work[K], K, threads)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    total = float(np.sum(times))
+    nvar = nb_s * sum(SIZES)
+    value = nvar * args.steps / total
+    sample = "%d of 10^6 blocks per K (%.0f%% of the workload) per step, %d host threads" % (nb_s, 100.0 * nb_s / NB, threads)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if rank == 0:
+        g.build()
+    if world > 1:
+        dist.barrier()
+    import bsls_b200
+
+    steps, warmup = args.steps, args.warmup
+    gen = torch.Generator(device=dev).manual_seed(SEED + 1 + rank)
+    starts = {K: torch.arange(0, NB * K, K, dtype=torch.int64, device=dev) for K in SIZES}
+    plans = {K: bsls_b200.BlockPlan(starts[K], NB * K) for K in SIZES}
+    # a fresh, never-touched input set for every step (672 MB each; aggregate >> 126 MB L2)
+    bufs = [{K: torch.randn(NB * K, dtype=torch.float64, device=dev, generator=gen) for K in SIZES}
+            for _ in range(steps + warmup)]
+    keep = {K: bufs[-1][K][: 1024 * K].clone() for K in SIZES}  # for the post-run spot check
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+    def step(b, events=None):
+        for K in SIZES:
+            if events is not None:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+            bsls_b200.proj_multi_simplex_c(b[K], plans[K])
+            if events is not None:
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record()
+                events[K].append((e0, e1))
+
+    for i in range(warmup):
+        step(bufs[i])
+    flush.zero_()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    events = {K: [] for K in SIZES}
+    t_wall0 = time.time()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(steps):
+        step(bufs[warmup + i], events)
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1)
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+
+    # spot check against the oracle (outside the timed region): bit-exact
+    from oracle import cpu
+    for K in SIZES:
+        want = keep[K].cpu().numpy().copy()
+        cpu.port().proj_multi_simplex(want, np.arange(0, want.size, K))
+        got = bufs[-1][K][: 1024 * K].cpu().numpy()
+        assert np.array_equal(got, want), "bench output differs from the oracle (K=%d)" % K
+
+    nvar_step = NB * sum(SIZES)
+    value = world * nvar_step * steps / (ms * 1e-3)
+
+    if rank != 0:
+        return
+    peak, peak_src = peaks()
+    kern = {}
+    for K in SIZES:
+        d = np.array([a.elapsed_time(b) for a, b in events[K]])
+        bytes_ = 2 * 8 * NB * K + 4 * NB  # B_proj = 2*s*n + 4*nb
+        kern["K=%d" % K] = {"avg_ms": float(d.mean()), "algorithmic_bytes": bytes_, "GBs": bytes_ / d.mean() / 1e6,
+                            "frac": bytes_ / d.mean() / 1e6 / peak, "gvar_s": NB * K / d.mean() / 1e6}
+    dom = kern["K=64"]
+    roofline = {"bound": "hbm", "achieved": dom["GBs"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
+                "traffic": None, "kernel": "proj_uniform_kernel<double,E=16,G=4> on the K=64 array (76% of the step's bytes)",
+                "peak_source": peak_src, "per_kernel": kern}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        with open(prof) as fh:
+            roofline["traffic"] = json.load(fh).get("proj_uniform_K64_bytes_per_launch")
+
+    # ---- e2e: host C ABI, pinned host buffers, copies inside the timed region -----------------
+    e2e_steps = max(1, min(steps, args.e2e_steps))
+    rng = np.random.RandomState(SEED + 7)
+    host = {K: torch.empty(NB * K, dtype=torch.float64).pin_memory() for K in SIZES}
+    src = {K: rng.randn(NB * K) for K in SIZES}
+    hblocks = {K: np.arange(0, NB * K, K, dtype=np.int32) for K in SIZES}
+    times = []
+    for it in range(e2e_steps + 1):
+        for K in SIZES:
+            host[K].numpy()[:] = src[K]
+        t0 = time.perf_counter()
+        for K in SIZES:
+            bsls_b200.proj_multi_simplex_c(host[K].numpy(), hblocks[K])
+        dt = time.perf_counter() - t0
+        if it > 0:
+            times.append(dt)
+    e2e_t = float(np.mean(times))
+    for K in SIZES:
+        want = src[K][: 512 * K].copy()
+        cpu.port().proj_multi_simplex(want, np.arange(0, want.size, K))
+        assert np.array_equal(host[K].numpy()[: 512 * K], want)
+    h2d = sum(8 * NB * K + 4 * NB for K in SIZES)
+    d2h = sum(8 * NB * K for K in SIZES)
+    e2e = {"value": world * nvar_step / e2e_t, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "ms_per_step": 1e3 * e2e_t, "steps": e2e_steps,
+           "api": "bsls_proj_multi_simplex(double*, const int*, int, int) on pinned host buffers via ctypes"}
+
+    cpu_base = cpu_baseline_sample(threads=1, reps=2) if world == 1 else None
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "l2": "fresh input buffers every step (inputs larger than L2); L2 flushed before timing",
+                       "per_gpu_variables_per_step": nvar_step},
+            "roofline": roofline, "e2e": e2e, "gpu_launches": 3 * steps, "clocks": clocks}
+    if cpu_base is not None:
+        line["cpu_baseline"] = cpu_base
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

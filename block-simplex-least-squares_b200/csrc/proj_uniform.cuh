@@ -12,6 +12,8 @@
 //   * the output pass re-reads the tile from shared memory and writes y with 128-bit
 //     streaming stores, fully coalesced.
 #pragma once
+#include <cstdlib>
+
 #include "simplex_core.cuh"
 
 namespace bsls {
@@ -91,23 +93,32 @@ __device__ __forceinline__ void load_block_regs(T (&v)[E], const T *blkp, int K,
     }
 }
 
-template <typename T, int E, int G, int THREADS, int MODE>
-__global__ void __launch_bounds__(THREADS)
-proj_uniform_kernel(T *__restrict__ y, long long first, int nb, int K, FastDiv kdiv, int aligned) {
-    constexpr int TB = THREADS / G;  // blocks per tile
+// Kernel configuration (all compile time):
+//   E, G     registers per lane / lanes per block (E*G >= K)
+//   THREADS  CTA size;  BPT blocks per lane-group per tile  =>  tile = THREADS/G*BPT blocks
+//   STAGES   2: the next tile is in flight while this one is processed (fewer, fatter CTAs)
+//            1: one buffer, latency hidden by the other resident CTAs (more warps per SM)
+//   MINB     minimum resident CTAs per SM the register allocator must allow
+//   KC       block size when known at compile time (0: runtime K <= E*G, -inf padded)
+template <typename T, int E, int G, int THREADS, int MINB, int BPT, int STAGES, int KC, int MODE>
+__global__ void __launch_bounds__(THREADS, MINB)
+proj_uniform_kernel(T *__restrict__ y, long long first, int nb, int Krt, FastDiv kdiv, int aligned) {
+    constexpr int GROUPS = THREADS / G;
+    constexpr int TB = GROUPS * BPT;  // blocks per tile
     constexpr int VN = Vec16<T>::N;
     using VT = typename Vec16<T>::type;
+    const int K = KC ? KC : Krt;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tile_elems = TB * K;
     T *stage0 = reinterpret_cast<T *>(smem_raw);
-    T *stage1 = stage0 + tile_elems;
+    T *stage1 = stage0 + (STAGES == 2 ? tile_elems : 0);
     T *lam = stage1 + tile_elems;
     uint64_t *bar = reinterpret_cast<uint64_t *>(lam + TB + (TB & 1));  // 8-byte aligned for float too
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const int blk = tid / G;
+    const int grp = tid / G;
     const int sub = tid & (G - 1);
     const int ntiles = (nb + TB - 1) / TB;
     T *ybase = y + first;
@@ -115,7 +126,7 @@ proj_uniform_kernel(T *__restrict__ y, long long first, int nb, int K, FastDiv k
 
     if (tid == 0) {
         mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
+        if (STAGES == 2) mbar_init(&bar[1], 1);
         mbar_init_fence();
     }
     __syncthreads();
@@ -127,14 +138,19 @@ proj_uniform_kernel(T *__restrict__ y, long long first, int nb, int K, FastDiv k
             bulk_g2s(s ? stage1 : stage0, ybase + (size_t)t * tile_elems, bytes, &bar[s]);
         }
     };
+    auto kdivide = [&](uint32_t e) -> uint32_t { return KC ? e / (uint32_t)(KC ? KC : 1) : fdiv(e, kdiv); };
 
     int tile = blockIdx.x;
-    if (tile < ntiles && tid == 0) issue(tile, 0);
+    if (STAGES == 2 && tile < ntiles && tid == 0) issue(tile, 0);
 
     for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
-        const int s = it & 1;
-        const int nxt = tile + gridDim.x;
-        if (nxt < ntiles && tid == 0) issue(nxt, s ^ 1);
+        const int s = (STAGES == 2) ? (it & 1) : 0;
+        if (STAGES == 2) {
+            const int nxt = tile + gridDim.x;
+            if (nxt < ntiles && tid == 0) issue(nxt, s ^ 1);
+        } else if (tid == 0) {
+            issue(tile, 0);
+        }
 
         const int nblk = min(TB, nb - tile * TB);
         const int nel = nblk * K;
@@ -142,14 +158,16 @@ proj_uniform_kernel(T *__restrict__ y, long long first, int nb, int K, FastDiv k
         T *gy = ybase + (size_t)tile * tile_elems;
 
         if (aligned && nblk == TB) {
-            mbar_wait(&bar[s], (it >> 1) & 1);
+            mbar_wait(&bar[s], (STAGES == 2) ? ((it >> 1) & 1) : (it & 1));
         } else {  // ragged last tile or unaligned base: plain coalesced loads
             for (int i = tid; i < nel; i += THREADS) buf[i] = gy[i];
             __syncthreads();
         }
 
         // ---- shift of every block -------------------------------------------------------
-        {
+#pragma unroll 1
+        for (int j = 0; j < BPT; ++j) {
+            const int blk = j * GROUPS + grp;
             const bool live = blk < nblk;
             const T *blkp = buf + blk * K;
             bool project = true;
@@ -190,10 +208,10 @@ proj_uniform_kernel(T *__restrict__ y, long long first, int nb, int K, FastDiv k
                     x[3] = g.w;
                 }
                 const uint32_t e0 = (uint32_t)i * VN;
-                const uint32_t b0 = fdiv(e0, kdiv);
+                const uint32_t b0 = kdivide(e0);
 #pragma unroll
                 for (int j = 0; j < VN; ++j) {
-                    const uint32_t b = vec_ok ? b0 : fdiv(e0 + j, kdiv);
+                    const uint32_t b = vec_ok ? b0 : kdivide(e0 + j);
                     T t = x[j];
                     if (MODE == kBall) t = clip_neg(t);
                     t = lam[b] + t;
@@ -207,27 +225,27 @@ proj_uniform_kernel(T *__restrict__ y, long long first, int nb, int K, FastDiv k
             for (int i = nvec * VN + tid; i < nel; i += THREADS) {
                 T t = buf[i];
                 if (MODE == kBall) t = clip_neg(t);
-                t = lam[fdiv((uint32_t)i, kdiv)] + t;
+                t = lam[kdivide((uint32_t)i)] + t;
                 gy[i] = (t < T(0)) ? T(0) : t;
             }
         } else {
             for (int i = tid; i < nel; i += THREADS) {
                 T t = buf[i];
                 if (MODE == kBall) t = clip_neg(t);
-                t = lam[fdiv((uint32_t)i, kdiv)] + t;
+                t = lam[kdivide((uint32_t)i)] + t;
                 gy[i] = (t < T(0)) ? T(0) : t;
             }
         }
-        __syncthreads();  // stage s and lam[] are free again
+        __syncthreads();  // the stage and lam[] are free again
     }
 }
 
-// ---- host side: pick (E, G, THREADS) for K and launch ------------------------------------------
-template <typename T, int E, int G, int THREADS, int MODE>
+// ---- host side: pick a configuration for K and launch ------------------------------------------
+template <typename T, int E, int G, int THREADS, int MINB, int BPT, int STAGES, int KC, int MODE>
 int launch_proj_uniform_cfg(T *y, long long first, int nb, int K, cudaStream_t stream) {
-    constexpr int TB = THREADS / G;
-    auto kern = proj_uniform_kernel<T, E, G, THREADS, MODE>;
-    const size_t smem = (size_t)2 * TB * K * sizeof(T) + (size_t)(TB + (TB & 1)) * sizeof(T) + 2 * sizeof(uint64_t);
+    constexpr int TB = THREADS / G * BPT;
+    auto kern = proj_uniform_kernel<T, E, G, THREADS, MINB, BPT, STAGES, KC, MODE>;
+    const size_t smem = (size_t)STAGES * TB * K * sizeof(T) + (size_t)(TB + (TB & 1)) * sizeof(T) + 2 * sizeof(uint64_t);
     static thread_local int cached_blocks_per_sm = -1;
     static thread_local size_t cached_smem = 0;
     static thread_local int num_sm = 0;
@@ -253,21 +271,52 @@ int launch_proj_uniform_cfg(T *y, long long first, int nb, int K, cudaStream_t s
     return BSLS_OK;
 }
 
-constexpr int kUniformMaxK = 512;  // larger uniform blocks go through the ragged/large path
+constexpr int kUniformMaxK = 512;  // larger uniform blocks go through the large-block kernel
+
+// BSLS_TUNE=<n> (development aid) selects alternative configurations for the hot sizes.
+inline int tune_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("BSLS_TUNE");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
 
 template <typename T, int MODE> int launch_proj_uniform(T *y, long long first, int nb, int K, cudaStream_t stream) {
     if (nb <= 0) return BSLS_OK;
-    if (K <= 4) return launch_proj_uniform_cfg<T, 4, 1, 256, MODE>(y, first, nb, K, stream);
-    if (K <= 8) return launch_proj_uniform_cfg<T, 8, 1, 256, MODE>(y, first, nb, K, stream);
-    if (K <= 12) return launch_proj_uniform_cfg<T, 12, 1, 256, MODE>(y, first, nb, K, stream);
-    if (K <= 16) return launch_proj_uniform_cfg<T, 16, 1, 256, MODE>(y, first, nb, K, stream);
-    if (K <= 20) return launch_proj_uniform_cfg<T, 20, 1, 128, MODE>(y, first, nb, K, stream);
-    if (K <= 24) return launch_proj_uniform_cfg<T, 24, 1, 128, MODE>(y, first, nb, K, stream);
-    if (K <= 32) return launch_proj_uniform_cfg<T, 32, 1, 128, MODE>(y, first, nb, K, stream);
-    if (K <= 64) return launch_proj_uniform_cfg<T, 16, 4, 256, MODE>(y, first, nb, K, stream);
-    if (K <= 128) return launch_proj_uniform_cfg<T, 16, 8, 256, MODE>(y, first, nb, K, stream);
-    if (K <= 256) return launch_proj_uniform_cfg<T, 16, 16, 256, MODE>(y, first, nb, K, stream);
-    if (K <= 512) return launch_proj_uniform_cfg<T, 16, 32, 256, MODE>(y, first, nb, K, stream);
+    const int tv = tune_variant();
+    // sizes the BASELINE configs name, with K known at compile time
+#define CFG(E, G, TH, MINB, BPT, ST, KC) return launch_proj_uniform_cfg<T, E, G, TH, MINB, BPT, ST, KC, MODE>(y, first, nb, K, stream)
+    if (K == 4) CFG(4, 1, 256, 4, 4, 2, 4);
+    if (K == 16) {
+        if (tv == 1) CFG(16, 1, 128, 6, 1, 1, 16);
+        if (tv == 2) CFG(16, 1, 256, 3, 1, 1, 16);
+        if (tv == 3) CFG(16, 1, 128, 6, 1, 2, 16);
+        if (tv == 4) CFG(16, 1, 256, 3, 1, 2, 0);
+        if (tv == 5) CFG(16, 1, 128, 6, 1, 1, 0);
+        CFG(16, 1, 256, 3, 1, 2, 16);
+    }
+    if (K == 64) {
+        if (tv == 1) CFG(16, 4, 128, 4, 1, 1, 64);
+        if (tv == 2) CFG(16, 4, 256, 2, 1, 1, 64);
+        if (tv == 3) CFG(32, 2, 128, 2, 1, 1, 64);
+        if (tv == 4) CFG(16, 4, 256, 2, 1, 2, 0);
+        if (tv == 5) CFG(16, 4, 128, 4, 1, 1, 0);
+        CFG(16, 4, 256, 2, 1, 2, 64);
+    }
+    if (K <= 4) CFG(4, 1, 256, 4, 4, 2, 0);
+    if (K <= 8) CFG(8, 1, 256, 4, 2, 2, 0);
+    if (K <= 12) CFG(12, 1, 256, 3, 1, 2, 0);
+    if (K <= 16) CFG(16, 1, 256, 3, 1, 2, 0);
+    if (K <= 20) CFG(20, 1, 128, 5, 1, 2, 0);
+    if (K <= 24) CFG(24, 1, 128, 4, 1, 2, 0);
+    if (K <= 32) CFG(32, 1, 128, 4, 1, 2, 0);
+    if (K <= 64) CFG(16, 4, 256, 2, 1, 2, 0);
+    if (K <= 128) CFG(16, 8, 256, 2, 1, 2, 0);
+    if (K <= 256) CFG(16, 16, 256, 2, 1, 2, 0);
+    if (K <= 512) CFG(16, 32, 256, 2, 1, 2, 0);
+#undef CFG
     set_error("launch_proj_uniform: K=%d above %d", K, kUniformMaxK);
     return BSLS_ERR_ARG;
 }

@@ -17,12 +17,23 @@
 
 namespace bsls {
 
-template <typename T> __device__ __forceinline__ void cmpx_desc(T &hi, T &lo) {
-    const T a = hi, b = lo;
+// compare-exchange, larger value first.  fp64: one DSETP + four 32-bit SELs (sm_100a has no
+// native fp64 min/max: fmax() expands to DSETP + SEL + FSEL + NaN fix-up + moves, which is
+// slower).  fp32: FMNMX pairs.  Inputs are never NaN.
+__device__ __forceinline__ void cmpx_desc(double &hi, double &lo) {
+    const double a = hi, b = lo;
     const bool sw = a < b;
     hi = sw ? b : a;
     lo = sw ? a : b;
 }
+__device__ __forceinline__ void cmpx_desc(float &hi, float &lo) {
+    const float a = hi, b = lo;
+    hi = fmaxf(a, b);
+    lo = fminf(a, b);
+}
+// keep the larger (take_min == false) or the smaller (take_min == true) of a and b
+__device__ __forceinline__ double pick(double a, double b, bool take_min) { return ((a < b) != take_min) ? b : a; }
+__device__ __forceinline__ float pick(float a, float b, bool take_min) { return take_min ? fminf(a, b) : fmaxf(a, b); }
 
 #define CE(i, j) cmpx_desc(v[i], v[j]);
 #include "sortnet_gen.cuh"
@@ -55,14 +66,13 @@ template <typename T, int E, int G> __device__ __forceinline__ void sort_desc_gr
             // keeps the same direction and -inf padding stays at the tail.
             {
                 const bool upper = (lane & L) != 0;
-                T w[E];
 #pragma unroll
-                for (int e = 0; e < E; ++e) w[e] = __shfl_xor_sync(0xffffffffu, v[E - 1 - e], 2 * L - 1);
-#pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    const T a = v[e], b = w[e];
-                    const bool a_lt_b = a < b;
-                    v[e] = (a_lt_b != upper) ? b : a;  // lower lane keeps the max, upper the min
+                for (int e = 0; e < E / 2; ++e) {
+                    const T a = v[e], b = v[E - 1 - e];
+                    const T pa = __shfl_xor_sync(0xffffffffu, b, 2 * L - 1);  // partner's element E-1-e
+                    const T pb = __shfl_xor_sync(0xffffffffu, a, 2 * L - 1);  // partner's element e
+                    v[e] = pick(a, pa, upper);  // lower lane keeps the max, upper the min
+                    v[E - 1 - e] = pick(b, pb, upper);
                 }
             }
 #pragma unroll
@@ -72,13 +82,40 @@ template <typename T, int E, int G> __device__ __forceinline__ void sort_desc_gr
                 for (int e = 0; e < E; ++e) {
                     const T a = v[e];
                     const T b = __shfl_xor_sync(0xffffffffu, a, D);
-                    const bool a_lt_b = a < b;
-                    v[e] = (a_lt_b != upper) ? b : a;
+                    v[e] = pick(a, b, upper);
                 }
             }
             bitonic_merge_regs<T, E>(v);
         }
     }
+}
+
+// ---- the candidate test without a division ---------------------------------------------
+// The reference accepts position k (0-based, d = k + 1) when  u_k + fl(w / d) > 0  with
+// w = fl(1 - running_k)  (proj_simplex.h:29-31).  A sum of two doubles is positive iff it is
+// positive in exact arithmetic, and fl() is monotone, so with X = w + u_k * d (exact):
+//     X <  0                      =>  w/d <  -u_k        =>  fl(w/d) <= -u_k  =>  rejected
+//     X >= d * ulp_above(-u_k)    =>  w/d >= succ(-u_k)  =>  fl(w/d) >  -u_k  =>  accepted
+// X is evaluated with ONE fused multiply-add (its sign is exact) and the acceptance margin
+// is over-estimated by |u_k| * d * 2^-51 (+ a tiny floor that covers subnormal u_k).  Only
+// when X falls in the sliver between the two tests is the reference's own expression
+// evaluated, so the decision is always the reference's, at ~5 instructions instead of an
+// IEEE division per element.
+template <typename T> struct Margin;
+template <> struct Margin<double> {
+    __device__ __forceinline__ static double scale() { return 4.440892098500626e-16; }   // 2^-51
+    __device__ __forceinline__ static double floor_() { return 1.0e-290; }
+};
+template <> struct Margin<float> {
+    __device__ __forceinline__ static float scale() { return 2.384185791015625e-07f; }   // 2^-22
+    __device__ __forceinline__ static float floor_() { return 1.0e-30f; }
+};
+
+// classification of one candidate: +1 accepted, -1 rejected, 0 undecided (near-tie)
+template <typename T> __device__ __forceinline__ int candidate_class(T u, T w, T d) {
+    const T x = fma(u, d, w);
+    const T m = fma(fabs(u), d * Margin<T>::scale(), Margin<T>::floor_());
+    return (x > m) ? 1 : ((x < T(0)) ? -1 : 0);
 }
 
 // Shift (the reference's `lambda`) of one block whose K values sit, sorted descending, in
@@ -87,23 +124,46 @@ template <typename T, int E, int G> __device__ __forceinline__ void sort_desc_gr
 template <typename T, int E, int G>
 __device__ __forceinline__ T simplex_shift_sorted(const T (&v)[E], int K, int lane) {
     if constexpr (G == 1) {
-        // one lane owns the whole block: the reference loop, verbatim (proj_simplex.h:24-32)
+        // one lane owns the whole block: the reference loop (proj_simplex.h:24-32); the
+        // winning candidate is remembered as (numerator, position) and divided once.
         T run = v[0];
-        T shift = T(1) - run;
+        T num = T(1) - run;
+        int last = 0;
+        bool undecided = false;
 #pragma unroll
         for (int e = 1; e < E; ++e) {
             if (e < K) {
                 run += v[e];
-                const T cand = (T(1) - run) / (T(e) + T(1));
-                if (v[e] + cand > T(0)) shift = cand;
+                const T w = T(1) - run;
+                const int c = candidate_class<T>(v[e], w, T(e) + T(1));
+                undecided |= (c == 0);
+                if (c > 0) {
+                    num = w;
+                    last = e;
+                }
             }
         }
-        return shift;
-    }
-    const int sub = lane & (G - 1);
-    T run = T(0);
-    T pre[E];  // pre[e] = running sum up to and including this lane's element e
-    {
+        if (undecided) {  // some candidate was a near-tie: redo the block with the reference's division
+            run = v[0];
+            num = T(1) - run;
+            last = 0;
+#pragma unroll
+            for (int e = 1; e < E; ++e) {
+                if (e < K) {
+                    run += v[e];
+                    const T w = T(1) - run;
+                    if (v[e] + w / (T(e) + T(1)) > T(0)) {
+                        num = w;
+                        last = e;
+                    }
+                }
+            }
+        }
+        return num / (T(last) + T(1));  // /1 reproduces `lambda = 1 - sum` of position 0 exactly
+    } else {
+        const int sub = lane & (G - 1);
+        T run = T(0);
+        T pre[E];  // pre[e] = running sum up to and including this lane's element e
 #pragma unroll
         for (int r = 0; r < G; ++r) {
             if (sub == r) {
@@ -116,34 +176,49 @@ __device__ __forceinline__ T simplex_shift_sorted(const T (&v)[E], int K, int la
             }
             run = __shfl_sync(0xffffffffu, run, (lane & ~(G - 1)) + r);
         }
-    }
-    // candidates; position 0 is accepted unconditionally (proj_simplex.h:25), later ones
-    // when sorted[k] + (1 - running_k)/(k + 1) > 0 (proj_simplex.h:29-31).
-    T shift = T(0);
-    int last = -1;
+        // position 0 is accepted unconditionally (proj_simplex.h:25), later ones by the test
+        T num = T(0);
+        int last = -1;
+        bool undecided = false;
 #pragma unroll
-    for (int e = 0; e < E; ++e) {
-        const int pos = sub * E + e;
-        if (pos < K) {
-            const T cand = (pos == 0) ? (T(1) - pre[e]) : (T(1) - pre[e]) / (T(pos) + T(1));
-            if (pos == 0 || v[e] + cand > T(0)) {
-                shift = cand;
-                last = pos;
+        for (int e = 0; e < E; ++e) {
+            const int pos = sub * E + e;
+            if (pos < K) {
+                const T w = T(1) - pre[e];
+                const int c = (pos == 0) ? 1 : candidate_class<T>(v[e], w, T(pos) + T(1));
+                undecided |= (c == 0);
+                if (c > 0) {
+                    num = w;
+                    last = pos;
+                }
             }
         }
-    }
-    if constexpr (G > 1) {
+        if (undecided) {
+            num = T(0);
+            last = -1;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int pos = sub * E + e;
+                if (pos < K) {
+                    const T w = T(1) - pre[e];
+                    if (pos == 0 || v[e] + w / (T(pos) + T(1)) > T(0)) {
+                        num = w;
+                        last = pos;
+                    }
+                }
+            }
+        }
 #pragma unroll
         for (int D = 1; D < G; D <<= 1) {
             const int o_last = __shfl_xor_sync(0xffffffffu, last, D);
-            const T o_shift = __shfl_xor_sync(0xffffffffu, shift, D);
+            const T o_num = __shfl_xor_sync(0xffffffffu, num, D);
             if (o_last > last) {
                 last = o_last;
-                shift = o_shift;
+                num = o_num;
             }
         }
+        return num / (T(last) + T(1));
     }
-    return shift;
 }
 
 }  // namespace bsls

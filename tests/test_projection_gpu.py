@@ -259,3 +259,41 @@ def test_config3_power_law_full_size(api):
     assert np.array_equal(got, want)
     sums = np.add.reduceat(got, starts)
     assert np.abs(sums - 1).max() < 1e-12 and got.min() >= 0
+
+
+@pytest.mark.parametrize("K", [4, 16, 20, 64, 300])
+def test_adversarial_near_ties(api, K):
+    """Blocks built so that the reference's acceptance test u_k + (1 - S_k)/(k+1) > 0 lands
+    exactly on, or within a few ulps of, zero at some position k: this drives the kernel's
+    exact fall-back (the fast sign test cannot decide) and pins the active set bit for bit."""
+    rng = np.random.RandomState(SEED + 31 * K)
+    blocks = []
+    for trial in range(4000):
+        k = rng.randint(1, K)                      # position of the borderline element
+        head = np.sort(rng.rand(k) * rng.choice([0.3, 1.0, 3.0]))[::-1]
+        s = 0.0
+        for v in head:
+            s += v                                  # running sum, left to right
+        u = (s - 1.0) / k                           # makes u*(k+1) + 1 - (s + u) ~ 0
+        for _ in range(abs(int(rng.randint(-4, 5)))):
+            u = np.nextafter(u, np.inf if rng.rand() < 0.5 else -np.inf)
+        if u > head[-1]:
+            continue
+        tail = u - 1.0 - rng.rand(K - k - 1) * 5
+        blk = np.concatenate([head, [u], tail])
+        rng.shuffle(blk)
+        blocks.append(blk)
+    y = np.concatenate(blocks)
+    nb = len(blocks)
+    starts = np.arange(0, nb * K, K, dtype=np.int64)
+    want = y.copy()
+    cpu_port().proj_multi_simplex(want, starts)
+    got = gpu_project(api, y, starts)
+    assert np.array_equal(got > 0, want > 0)
+    assert np.array_equal(got, want)
+    # the same blocks behind two odd-sized blocks: a ragged layout, i.e. the tile kernel
+    starts2 = np.concatenate(([0, 1], 3 + starts))
+    y2 = np.concatenate((rng.randn(3), y))
+    want = y2.copy()
+    cpu_port().proj_multi_simplex(want, starts2)
+    assert np.array_equal(gpu_project(api, y2, starts2), want)

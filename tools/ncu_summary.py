@@ -1,0 +1,31 @@
+"""Print the handful of ncu metrics we track from a `--page raw --csv` dump."""
+import csv
+import sys
+
+WANT = ['Kernel Name', 'launch__grid_size', 'launch__block_size', 'launch__registers_per_thread',
+        'launch__shared_mem_per_block_dynamic', 'launch__waves_per_multiprocessor', 'launch__occupancy_limit_registers',
+        'launch__occupancy_limit_shared_mem', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+        'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
+        'smsp__issue_active.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_fp64.sum', 'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_alu.sum', 'sm__inst_executed_pipe_lsu.sum',
+        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
+        'lts__t_sector_hit_rate.pct',
+        'smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct', 'smsp__warp_issue_stalled_barrier_per_warp_active.pct',
+        'smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct',
+        'smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct', 'smsp__warp_issue_stalled_wait_per_warp_active.pct',
+        'smsp__warp_issue_stalled_not_selected_per_warp_active.pct', 'smsp__warp_issue_stalled_mio_throttle_per_warp_active.pct',
+        'smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct', 'smsp__warp_issue_stalled_membar_per_warp_active.pct',
+        'smsp__warp_issue_stalled_no_instruction_per_warp_active.pct', 'smsp__warp_issue_stalled_dispatch_stall_per_warp_active.pct',
+        'smsp__warp_issue_stalled_branch_resolving_per_warp_active.pct', 'smsp__warp_issue_stalled_sleeping_per_warp_active.pct',
+        'smsp__warp_issue_stalled_selected_per_warp_active.pct']
+
+rows = list(csv.reader(open(sys.argv[1])))
+hdr, units = rows[0], rows[1]
+for r in rows[2:]:
+    print('-----')
+    for w in WANT:
+        if w in hdr:
+            i = hdr.index(w)
+            print('%-75s %s %s' % (w, r[i][:110], units[i]))
