@@ -10,7 +10,9 @@ All compute runs in libbsls_b200.so (hand-written CUDA behind a C ABI, include/b
 """
 from . import _lib
 from . import c_extensions
-from .c_extensions import proj_simplex_c, proj_multi_simplex_c, proj_multi_ball_c
+from .c_extensions import (proj_simplex_c, proj_multi_simplex_c, proj_multi_ball_c, isotonic_regression_c,
+                           isotonic_regression_multi_c, isotonic_regression_c_2, isotonic_regression_multi_c_2,
+                           isotonic_regression_c_3, isotonic_regression_multi_c_3)
 from .plan import BlockPlan, plan_for
 
 __version__ = "0.1.0"

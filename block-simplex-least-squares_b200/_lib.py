@@ -33,6 +33,14 @@ def lib():
         for name in ("bsls_proj_multi_simplex", "bsls_proj_multi_ball"):
             getattr(L, name).argtypes = [c_void_p, c_void_p, c_int, c_int]
         L.bsls_proj_simplex.argtypes = [c_void_p, c_int, c_int]
+        L.bsls_isotonic_regression.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int]
+        L.bsls_isotonic_regression_3.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int]
+        L.bsls_isotonic_regression_2.argtypes = [c_void_p, c_int, c_int]
+        L.bsls_isotonic_regression_multi.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int]
+        L.bsls_isotonic_regression_multi_3.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int]
+        L.bsls_isotonic_regression_multi_2.argtypes = [c_void_p, c_void_p, c_int, c_int]
+        for name in ("bsls_dev_isotonic_regression_multi_f64", "bsls_dev_isotonic_regression_multi_f32"):
+            getattr(L, name).argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]
         L.bsls_host_alloc.argtypes = [ctypes.POINTER(c_void_p), c_i64]
         L.bsls_host_free.argtypes = [c_void_p]
         L.bsls_plan_create.argtypes = [c_void_p, c_int, c_int, c_void_p, ctypes.POINTER(c_void_p)]

@@ -18,7 +18,10 @@ import torch
 from . import _lib
 from .plan import BlockPlan, plan_for
 
-__all__ = ["proj_simplex_c", "proj_multi_simplex_c", "proj_multi_ball_c"]
+__all__ = ["proj_simplex_c", "proj_multi_simplex_c", "proj_multi_ball_c",
+           "isotonic_regression_c", "isotonic_regression_multi_c",
+           "isotonic_regression_c_2", "isotonic_regression_multi_c_2",
+           "isotonic_regression_c_3", "isotonic_regression_multi_c_3"]
 
 
 def _stream(t):
@@ -102,3 +105,99 @@ def proj_multi_ball_c(y, blocks):
     """Clip negatives and project the blocks whose sum exceeds one ("lasso" feasible set)
     (reference: c_extensions.pyx:42-50 -> proj_simplex.h:50-74)."""
     return _project_multi(y, blocks, ball=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# isotonic regression (reference: c_extensions.pyx:52-138 -> isotonic_regression.h)
+# ---------------------------------------------------------------------------------------------
+def _host_weight(weight, n):
+    """The reference updates ``weight`` in place only when it is already a C-contiguous int32
+    array (np.ascontiguousarray otherwise copies, c_extensions.pyx:72); same here."""
+    if weight is None:
+        return None, None
+    w = np.ascontiguousarray(weight, dtype=np.int32)
+    assert w.shape[0] == n
+    return w, w.ctypes.data
+
+
+def _pava_multi(y, blocks, weight, update, clip01=False, variant=1):
+    L = _lib.lib()
+    if isinstance(y, np.ndarray):
+        _check_host_vector(y)
+        b = _host_blocks(blocks)
+        n = y.shape[0]
+        assert b[0] >= 0 and b[-1] < n
+        if variant == 2:
+            _lib.check(L.bsls_isotonic_regression_multi_2(y.ctypes.data, b.ctypes.data, int(b.shape[0]), int(n)),
+                       "bsls_isotonic_regression_multi_2")
+        else:
+            w, wptr = _host_weight(weight, n)
+            fn = L.bsls_isotonic_regression_multi if variant == 1 else L.bsls_isotonic_regression_multi_3
+            _lib.check(fn(y.ctypes.data, b.ctypes.data, int(b.shape[0]), int(n), wptr, int(update)), fn.__name__)
+        if clip01:
+            np.clip(y, 0.0, 1.0, out=y)
+        return None
+    _check_dev_vector(y)
+    n = y.shape[0]
+    plan = plan_for(blocks, n, y.device)
+    wptr = None
+    if weight is not None and variant != 2:
+        assert torch.is_tensor(weight) and weight.is_cuda and weight.dtype == torch.int32 and weight.is_contiguous(), \
+            "weight must be a contiguous int32 CUDA tensor"
+        assert weight.shape[0] == n
+        wptr = weight.data_ptr()
+    fn = L.bsls_dev_isotonic_regression_multi_f64 if y.dtype == torch.float64 else L.bsls_dev_isotonic_regression_multi_f32
+    with torch.cuda.device(y.device):
+        _lib.check(fn(plan.handle, y.data_ptr(), wptr, int(update), int(bool(clip01)), _stream(y)), fn.__name__)
+    return None
+
+
+def _pava_single(y, start, end, weight, update, variant):
+    n = y.shape[0]
+    assert start >= 0 and start < n and end > 0 and end <= n
+    if start >= end:
+        return
+    if isinstance(y, np.ndarray):
+        _check_host_vector(y)
+        L = _lib.lib()
+        if variant == 2:
+            _lib.check(L.bsls_isotonic_regression_2(y.ctypes.data, int(start), int(end)), "bsls_isotonic_regression_2")
+            return
+        w, wptr = _host_weight(weight, n)
+        fn = L.bsls_isotonic_regression if variant == 1 else L.bsls_isotonic_regression_3
+        _lib.check(fn(y.ctypes.data, int(start), int(end), wptr, int(update)), fn.__name__)
+        return
+    _check_dev_vector(y)
+    sub_w = None if weight is None else weight[:end]
+    _pava_multi(y[:end], BlockPlan(np.array([start]), end, y.device), sub_w, update, variant=variant)
+
+
+def isotonic_regression_c(y, start, end, weight=None, update=1):
+    """Non-decreasing least-squares fit of ``y[start:end]``, in place (c_extensions.pyx:63-73).
+    ``weight`` (int32, in/out) holds the pool size at every pool head."""
+    return _pava_single(y, start, end, weight, update, 1)
+
+
+def isotonic_regression_multi_c(y, blocks, weight=None, update=1, clip01=False):
+    """Isotonic regression of every block, in place (c_extensions.pyx:76-89).  ``clip01`` is
+    an extension that fuses the [0,1] clamp of the z-space projection (python/main.py:65)."""
+    return _pava_multi(y, blocks, weight, update, clip01, 1)
+
+
+def isotonic_regression_c_2(y, start, end):
+    """Variant 2 of the reference (c_extensions.pyx:92-98): same regression, no weight array."""
+    return _pava_single(y, start, end, None, 1, 2)
+
+
+def isotonic_regression_multi_c_2(y, blocks):
+    return _pava_multi(y, blocks, None, 1, False, 2)
+
+
+def isotonic_regression_c_3(y, start, end, weight=None, update=1):
+    """Variant 3 of the reference (c_extensions.pyx:112-122): same regression; the weight array
+    returned here is variant 1's (pool size at each head)."""
+    return _pava_single(y, start, end, weight, update, 3)
+
+
+def isotonic_regression_multi_c_3(y, blocks, weight=None, update=1):
+    return _pava_multi(y, blocks, weight, update, False, 3)

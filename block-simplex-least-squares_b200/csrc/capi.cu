@@ -56,7 +56,58 @@ struct bsls_plan {
     int32_t *d_tile_first = nullptr;  // tiles + 1 entries
     int32_t *d_large_ids = nullptr;   // `large` block indices (size > kPlanTileMaxBlock)
     bool ragged = false;
+    // isotonic-regression windows (built on first use, any layout)
+    bool pava_ready = false;
+    int pava_windows = 0, pava_large = 0;
+    int32_t *d_pava_first = nullptr;  // pava_windows + 1 entries
+    int32_t *d_pava_large = nullptr;  // blocks longer than kPlanPavaWarpMax
 };
+
+// Window / long-block lists for the isotonic-regression kernels; built once, on first use.
+static int plan_ensure_pava(bsls_plan *p, cudaStream_t stream) {
+    if (p->pava_ready) return BSLS_OK;
+    p->pava_windows = (int)(((long long)p->n - p->first + kPlanPavaPitch - 1) / kPlanPavaPitch);
+    BSLS_CUDA_TRY(cudaMalloc(&p->d_pava_first, sizeof(int32_t) * ((size_t)p->pava_windows + 1)));
+    if (int rc = plan_tile_first(p->d_starts, p->nb, p->first, kPlanPavaPitch, p->d_pava_first, p->pava_windows, stream)) return rc;
+    if (p->max_size > kPlanPavaWarpMax) {
+        int *d_count = nullptr;
+        int h_count = 0;
+        BSLS_CUDA_TRY(cudaMalloc(&d_count, sizeof(int)));
+        BSLS_CUDA_TRY(cudaMemsetAsync(d_count, 0, sizeof(int), stream));
+        if (int rc = plan_large_list(p->d_starts, p->nb, kPlanPavaWarpMax, nullptr, d_count, stream)) return rc;
+        BSLS_CUDA_TRY(cudaMemcpyAsync(&h_count, d_count, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        BSLS_CUDA_TRY(cudaStreamSynchronize(stream));
+        BSLS_CUDA_TRY(cudaMalloc(&p->d_pava_large, sizeof(int32_t) * (size_t)h_count));
+        BSLS_CUDA_TRY(cudaMemsetAsync(d_count, 0, sizeof(int), stream));
+        if (int rc = plan_large_list(p->d_starts, p->nb, kPlanPavaWarpMax, p->d_pava_large, d_count, stream)) return rc;
+        BSLS_CUDA_TRY(cudaStreamSynchronize(stream));
+        cudaFree(d_count);
+        p->pava_large = h_count;
+    }
+    p->pava_ready = true;
+    return BSLS_OK;
+}
+
+template <typename T>
+static int dev_pava(const bsls_plan *plan_, T *y, int32_t *weight, int update, int clip01, cudaStream_t stream) {
+    if (int rc = device_ok()) return rc;
+    if (!plan_ || !y) {
+        set_error("isotonic regression: null plan or buffer");
+        return BSLS_ERR_ARG;
+    }
+    bsls_plan *plan = const_cast<bsls_plan *>(plan_);
+    if (plan->max_size > kPlanPavaLargeMax) {
+        set_error("isotonic regression: a block of %d entries exceeds the %d-entry limit of this revision", plan->max_size, kPlanPavaLargeMax);
+        return BSLS_ERR_ARG;
+    }
+    if (int rc = plan_ensure_pava(plan, stream)) return rc;
+    if constexpr (sizeof(T) == 8)
+        return pava_f64((double *)y, weight, plan->d_starts, plan->d_pava_first, plan->pava_windows, plan->d_pava_large,
+                        plan->pava_large, plan->max_size, update, clip01, stream);
+    else
+        return pava_f32((float *)y, weight, plan->d_starts, plan->d_pava_first, plan->pava_windows, plan->d_pava_large,
+                        plan->pava_large, plan->max_size, update, clip01, stream);
+}
 
 // ------------------------------------------------------------------------------------
 // device entry points: projections
@@ -94,7 +145,19 @@ struct HostWorkspace {  // grow-only device staging owned by the calling thread
     size_t y_cap = 0;
     int32_t *d_blocks = nullptr;
     size_t b_cap = 0;
+    int32_t *d_w = nullptr;
+    size_t w_cap = 0;
     cudaStream_t stream = nullptr;
+    int reserve_w(size_t n) {
+        if (n > w_cap) {
+            if (d_w) cudaFree(d_w);
+            d_w = nullptr;
+            w_cap = 0;
+            BSLS_CUDA_TRY(cudaMalloc(&d_w, n * sizeof(int32_t)));
+            w_cap = n;
+        }
+        return BSLS_OK;
+    }
     int reserve(size_t n, size_t nb) {
         if (!stream) BSLS_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         if (n > y_cap) {
@@ -158,6 +221,46 @@ int host_project(double *y, const int *blocks, int numblocks, int n, int mode) {
     BSLS_CUDA_TRY(cudaMemcpyAsync(y + first, g_ws.d_y, span * sizeof(double), cudaMemcpyDeviceToHost, st));
     BSLS_CUDA_TRY(cudaStreamSynchronize(st));
     return BSLS_OK;
+}
+
+// isotonic regression on host buffers; `weight` may be NULL (all ones in, result dropped)
+int host_pava(double *y, const int *blocks, int numblocks, int n, int *weight, int update) {
+    if (int rc = device_ok()) return rc;
+    if (!y) {
+        set_error("null buffer");
+        return BSLS_ERR_ARG;
+    }
+    if (int rc = validate_blocks(blocks, numblocks, n)) return rc;
+    const int first = blocks[0];
+    const size_t span = (size_t)n - first;
+    if (int rc = g_ws.reserve(span, (size_t)numblocks)) return rc;
+    if (weight)
+        if (int rc = g_ws.reserve_w(span)) return rc;
+    cudaStream_t st = g_ws.stream;
+    BSLS_CUDA_TRY(cudaMemcpyAsync(g_ws.d_y, y + first, span * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (weight) BSLS_CUDA_TRY(cudaMemcpyAsync(g_ws.d_w, weight + first, span * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    std::vector<int32_t> rebased((size_t)numblocks);
+    for (int i = 0; i < numblocks; ++i) rebased[i] = blocks[i] - first;
+    BSLS_CUDA_TRY(cudaMemcpyAsync(g_ws.d_blocks, rebased.data(), (size_t)numblocks * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    bsls_plan *plan = nullptr;
+    if (int rc = bsls_plan_create(g_ws.d_blocks, numblocks, (int)span, st, &plan)) return rc;
+    int rc = dev_pava<double>(plan, g_ws.d_y, weight ? g_ws.d_w : nullptr, update, 0, st);
+    bsls_plan_destroy(plan);
+    if (rc) return rc;
+    BSLS_CUDA_TRY(cudaMemcpyAsync(y + first, g_ws.d_y, span * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (weight) BSLS_CUDA_TRY(cudaMemcpyAsync(weight + first, g_ws.d_w, span * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    BSLS_CUDA_TRY(cudaStreamSynchronize(st));
+    return BSLS_OK;
+}
+
+int host_pava_single(double *y, int start, int end, int *weight, int update) {
+    if (start >= end) return BSLS_OK;  // c_extensions.pyx:66
+    if (start < 0) {
+        set_error("isotonic_regression: start < 0");
+        return BSLS_ERR_ARG;
+    }
+    const int one = start;
+    return host_pava(y, &one, 1, end, weight, update);
 }
 
 }  // namespace
@@ -231,7 +334,7 @@ int bsls_plan_create(const int32_t *d_blocks, int numblocks, int n, bsls_stream_
         TRY_OR_FAIL(cudaMalloc(&p->d_tile_first, sizeof(int32_t) * ((size_t)p->tiles + 1)));
         TRY_OR_FAIL(cudaMalloc(&d_count, sizeof(int)));
         TRY_OR_FAIL(cudaMemsetAsync(d_count, 0, sizeof(int), stream));
-        if (int rc = plan_tile_first(p->d_starts, numblocks, first, n, p->d_tile_first, p->tiles, stream)) return fail(rc);
+        if (int rc = plan_tile_first(p->d_starts, numblocks, first, kPlanTileElems, p->d_tile_first, p->tiles, stream)) return fail(rc);
         if (p->max_size > kPlanTileMaxBlock) {
             if (int rc = plan_large_list(p->d_starts, numblocks, kPlanTileMaxBlock, nullptr, d_count, stream)) return fail(rc);
             TRY_OR_FAIL(cudaMemcpyAsync(&h_count, d_count, sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -254,6 +357,8 @@ int bsls_plan_destroy(bsls_plan *plan) {
     if (plan->d_starts) cudaFree(plan->d_starts);
     if (plan->d_tile_first) cudaFree(plan->d_tile_first);
     if (plan->d_large_ids) cudaFree(plan->d_large_ids);
+    if (plan->d_pava_first) cudaFree(plan->d_pava_first);
+    if (plan->d_pava_large) cudaFree(plan->d_pava_large);
     delete plan;
     return BSLS_OK;
 }
@@ -294,6 +399,28 @@ int bsls_proj_simplex(double *y, int start, int end) {
 
 int bsls_proj_multi_simplex(double *y, const int *blocks, int numblocks, int n) { return host_project(y, blocks, numblocks, n, 0); }
 int bsls_proj_multi_ball(double *y, const int *blocks, int numblocks, int n) { return host_project(y, blocks, numblocks, n, 1); }
+
+// isotonic regression, host buffers.  Variants 2 and 3 of the reference compute the same
+// regression with a different merge order (isotonic_regression.h:61-82,105-155); they are
+// served by the variant-1 kernel: values agree with the reference's to ~1e-15 relative (its
+// own tests ask 1e-8), the weight array is variant 1's canonical pool-size array.
+int bsls_isotonic_regression(double *y, int start, int end, int *weight, int update) { return host_pava_single(y, start, end, weight, update); }
+int bsls_isotonic_regression_multi(double *y, const int *blocks, int numblocks, int n, int *weight, int update) {
+    return host_pava(y, blocks, numblocks, n, weight, update);
+}
+int bsls_isotonic_regression_2(double *y, int start, int end) { return host_pava_single(y, start, end, nullptr, 1); }
+int bsls_isotonic_regression_multi_2(double *y, const int *blocks, int numblocks, int n) { return host_pava(y, blocks, numblocks, n, nullptr, 1); }
+int bsls_isotonic_regression_3(double *y, int start, int end, int *weight, int update) { return host_pava_single(y, start, end, weight, update); }
+int bsls_isotonic_regression_multi_3(double *y, const int *blocks, int numblocks, int n, int *weight, int update) {
+    return host_pava(y, blocks, numblocks, n, weight, update);
+}
+
+int bsls_dev_isotonic_regression_multi_f64(const bsls_plan *plan, double *y, int32_t *weight, int update, int clip01, bsls_stream_t s) {
+    return dev_pava<double>(plan, y, weight, update, clip01, (cudaStream_t)s);
+}
+int bsls_dev_isotonic_regression_multi_f32(const bsls_plan *plan, float *y, int32_t *weight, int update, int clip01, bsls_stream_t s) {
+    return dev_pava<float>(plan, y, weight, update, clip01, (cudaStream_t)s);
+}
 
 int bsls_host_alloc(void **ptr, int64_t bytes) {
     if (!ptr || bytes <= 0) return BSLS_ERR_ARG;

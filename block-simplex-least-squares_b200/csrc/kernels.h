@@ -20,10 +20,19 @@ struct LayoutStats {
     int min_size, max_size, bad;  // bad != 0: not strictly increasing / out of range
 };
 int plan_layout_stats(const int32_t *starts /* nb+1 */, int nb, int n, LayoutStats *d_out, cudaStream_t stream);
-int plan_tile_first(const int32_t *starts, int nb, int first, int n, int32_t *tile_first, int ntiles, cudaStream_t stream);
+int plan_tile_first(const int32_t *starts, int nb, int first, int pitch, int32_t *tile_first, int ntiles, cudaStream_t stream);
 int plan_large_list(const int32_t *starts, int nb, int threshold, int32_t *ids, int *d_count, cudaStream_t stream);
 constexpr int kPlanTileElems = 2048;      // == kTileElems (proj_ragged.cuh)
 constexpr int kPlanTileMaxBlock = 512;    // == kTileMaxBlock
 constexpr int kPlanLargeMaxBlock = 8192;  // == kLargeMaxBlock
+constexpr int kPlanPavaPitch = 256;       // == kPavaPitch (pava.cuh)
+constexpr int kPlanPavaWarpMax = 256;     // == kPavaWarpMaxBlock
+constexpr int kPlanPavaLargeMax = 8192;   // == kPavaLargeMaxBlock
+
+// pava_f64.cu / pava_f32.cu: segmented isotonic regression (pava.cuh)
+int pava_f64(double *y, int32_t *w, const int32_t *starts, const int32_t *win_first, int nwin, const int32_t *large_ids,
+             int nlarge, int max_large, int update, int clip01, cudaStream_t stream);
+int pava_f32(float *y, int32_t *w, const int32_t *starts, const int32_t *win_first, int nwin, const int32_t *large_ids,
+             int nlarge, int max_large, int update, int clip01, cudaStream_t stream);
 
 }  // namespace bsls

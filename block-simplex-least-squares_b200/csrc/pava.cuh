@@ -1,0 +1,352 @@
+// pava.cuh -- segmented isotonic regression (pool adjacent violators) on sm_100a.
+//
+// Replaces isotonic_regression / isotonic_regression_multi, the variant the reference's
+// hot path binds (python/c_extensions/isotonic_regression.h:13-58,85-92; called from
+// python/main.py:64 and through python/c_extensions/c_extensions.pyx:63-89).
+//
+// The reference sweeps each block until nothing pools.  In one sweep it walks the pool
+// heads, groups them into maximal runs in which each head is <= its predecessor, and
+// replaces a run whose first and last value differ by the size-weighted mean, summed left
+// to right (:23-44).  Decisions inside a sweep only read values that the sweep has not
+// touched yet, so ALL runs of a sweep -- and all blocks -- can be processed at once:
+//   A  flag run starts   (head j starts a run if it opens a block or y[j] > y[j-1])
+//   B  every run start walks its run and merges it exactly as the reference does
+//      (same products, same left-to-right sum, same division)
+//   C  compact the list of surviving heads (ballot + popc)
+// until a sweep merges nothing.  The arrays y[] and weight[] are the reference's own
+// representation (value / pool size stored at the head, stale entries elsewhere), so the
+// result -- values, pool sizes and even the stale interior entries -- is bit-identical.
+//
+// Small blocks (<= kPavaWarpMaxBlock): one WARP owns a window of whole blocks in shared
+// memory and needs no block-wide barrier.  Longer blocks: one CTA per block.
+#pragma once
+#include "common.cuh"
+
+namespace bsls {
+
+constexpr int kPavaPitch = 256;          // warp-window pitch (elements)
+constexpr int kPavaWarpMaxBlock = 256;   // longest block a warp window takes
+constexpr int kPavaWindow = kPavaPitch + kPavaWarpMaxBlock;
+constexpr int kPavaWarpsPerCta = 4;     // 4 x 7.5 KB of static shared memory per CTA
+constexpr int kPavaLargeMaxBlock = 8192; // longest block the one-CTA kernel takes
+constexpr int kPavaLargeThreads = 512;
+
+struct PavaFlags {
+    int update;      // copy the head value over its pool at the end (reference `update`)
+    int clip01;      // clamp to [0,1] afterwards (python/main.py:65)
+    int has_weight;  // weight array given (in/out); otherwise all ones in, result dropped
+};
+
+__device__ __forceinline__ void cp_async_8(void *dst_smem, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <typename T> __device__ __forceinline__ T clip01(T v) {
+    v = (v > T(0)) ? v : T(0);  // np.maximum(0., x)
+    v = (v < T(1)) ? v : T(1);  // np.minimum(1., x)
+    return v;
+}
+
+// One run start: walk the run, merge it if first != last (isotonic_regression.h:23-44).
+// Returns true when it merged.  F[q] == 0 marks followers; merged followers get F = 2.
+template <typename T, typename W>
+__device__ __forceinline__ bool pava_merge_run(T *y, W *w, const uint16_t *A, uint8_t *F, int j, int P) {
+    const int p0 = A[j] & 0x7fff;
+    const T first = y[p0];
+    int den = (int)w[p0];
+    T num = T(0) + first * (T)den;
+    T last = first;
+    int q = j + 1;
+    while (q < P && F[q] == 0) {
+        const int pq = A[q] & 0x7fff;
+        const T vq = y[pq];
+        const int wq = (int)w[pq];
+        num += vq * (T)wq;  // -fmad=false: product and sum round separately, as on the host
+        den += wq;
+        last = vq;
+        ++q;
+    }
+    if (q > j + 1 && first != last) {
+        y[p0] = num / (T)den;
+        w[p0] = (W)den;
+        for (int r = j + 1; r < q; ++r) F[r] = 2;
+        return true;
+    }
+    return false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// warp windows
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kPavaWarpsPerCta * 32)
+pava_warp_kernel(T *__restrict__ yg, int32_t *__restrict__ wg, const int32_t *__restrict__ starts /* nb+1 */,
+                 const int32_t *__restrict__ win_first /* nwin+1 */, int nwin, PavaFlags fl) {
+    __shared__ __align__(16) T ys[kPavaWarpsPerCta][kPavaWindow];
+    __shared__ uint16_t ws[kPavaWarpsPerCta][kPavaWindow];
+    __shared__ uint16_t la[kPavaWarpsPerCta][kPavaWindow];
+    __shared__ uint16_t lb[kPavaWarpsPerCta][kPavaWindow];
+    __shared__ uint8_t fs[kPavaWarpsPerCta][kPavaWindow];
+
+    const int lane = threadIdx.x & 31;
+    const int wid = threadIdx.x >> 5;
+    T *y = ys[wid];
+    uint16_t *w = ws[wid];
+    uint8_t *F = fs[wid];
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    for (int win = blockIdx.x * kPavaWarpsPerCta + wid; win < nwin; win += gridDim.x * kPavaWarpsPerCta) {
+        const int fb = win_first[win];
+        const int nblk = win_first[win + 1] - fb;
+        if (nblk <= 0) continue;
+        const int lo = starts[fb];
+        int hi = starts[fb + nblk];
+        int nsmall = nblk;
+        if (hi - starts[fb + nblk - 1] > kPavaWarpMaxBlock) {  // a long block can only be the last one
+            hi = starts[fb + nblk - 1];
+            nsmall = nblk - 1;
+        }
+        const int nel = hi - lo;
+        if (nel <= 0) continue;
+        uint16_t *A = la[wid], *B = lb[wid];
+        // ---- load the window: values (async copies), weights, head list ---------------------
+        for (int i = lane; i < nel; i += 32) {
+            cp_async_8(&y[i], yg + (size_t)lo + i);
+            w[i] = fl.has_weight ? (uint16_t)wg[(size_t)lo + i] : (uint16_t)1;
+            A[i] = (uint16_t)i;
+        }
+        __syncwarp();
+        for (int b = lane; b < nsmall; b += 32) A[starts[fb + b] - lo] |= 0x8000;  // block openers
+        cp_async_wait_all();
+        __syncwarp();
+        int P = nel;
+        if (fl.has_weight) {
+            // warm start: the heads are the entries reached by i += weight[i] (isotonic_regression.h:22)
+            // -> rebuild the list serially per block (rare path)
+            for (int i = lane; i < nel; i += 32) F[i] = 0;
+            __syncwarp();
+            for (int b = lane; b < nsmall; b += 32) {
+                const int s = starts[fb + b] - lo, e = starts[fb + b + 1] - lo;
+                for (int i = s; i < e; i += max(1, (int)w[i])) F[i] = 1;
+            }
+            __syncwarp();
+            int np = 0;
+            for (int base = 0; base < nel; base += 32) {
+                const int i = base + lane;
+                const bool head = i < nel && F[i];
+                const unsigned m = __ballot_sync(0xffffffffu, head);
+                if (head) B[np + __popc(m & lt_mask)] = A[i];
+                np += __popc(m);
+            }
+            __syncwarp();
+            uint16_t *t = A;
+            A = B;
+            B = t;
+            P = np;
+        }
+        // ---- sweeps -------------------------------------------------------------------------------
+        for (;;) {
+            for (int base = 0; base < P; base += 32) {  // A: run starts
+                const int j = base + lane;
+                if (j < P) {
+                    const int e = A[j];
+                    bool st = (e & 0x8000) || j == 0;
+                    if (!st) st = y[e & 0x7fff] > y[A[j - 1] & 0x7fff];
+                    F[j] = st ? 1 : 0;
+                }
+            }
+            __syncwarp();
+            bool merged = false;
+            for (int base = 0; base < P; base += 32) {  // B: merge runs
+                const int j = base + lane;
+                if (j < P && F[j] == 1) merged |= pava_merge_run<T, uint16_t>(y, w, A, F, j, P);
+            }
+            merged = __any_sync(0xffffffffu, merged);
+            __syncwarp();
+            if (!merged) break;
+            int np = 0;
+            for (int base = 0; base < P; base += 32) {  // C: compact the survivors
+                const int j = base + lane;
+                const bool alive = j < P && F[j] != 2;
+                const unsigned m = __ballot_sync(0xffffffffu, alive);
+                if (alive) B[np + __popc(m & lt_mask)] = A[j];
+                np += __popc(m);
+            }
+            __syncwarp();
+            uint16_t *t = A;
+            A = B;
+            B = t;
+            P = np;
+        }
+        // ---- spread head values over their pools (isotonic_regression.h:50-57) -----------------
+        if (fl.update) {
+            for (int base = 0; base < P; base += 32) {
+                const int j = base + lane;
+                if (j < P) {
+                    const int p = A[j] & 0x7fff;
+                    const T v = y[p];
+                    const int stop = p + (int)w[p];
+                    for (int r = p + 1; r < stop; ++r) y[r] = v;
+                }
+            }
+            __syncwarp();
+        }
+        // ---- store ----------------------------------------------------------------------------------
+        for (int i = lane; i < nel; i += 32) {
+            T v = y[i];
+            if (fl.clip01) v = clip01(v);
+            yg[(size_t)lo + i] = v;
+            if (fl.has_weight) wg[(size_t)lo + i] = (int32_t)w[i];
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// one CTA per long block
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kPavaLargeThreads)
+pava_large_kernel(T *__restrict__ yg, int32_t *__restrict__ wg, const int32_t *__restrict__ starts,
+                  const int32_t *__restrict__ ids, int count, PavaFlags fl) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_cnt[kPavaLargeThreads / 32 + 1];
+    __shared__ int s_merged;
+    constexpr int NW = kPavaLargeThreads / 32;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    for (int it = blockIdx.x; it < count; it += gridDim.x) {
+        const int b = ids ? ids[it] : it;
+        const int lo = starts[b];
+        const int K = starts[b + 1] - lo;
+        T *y = reinterpret_cast<T *>(smem_raw);
+        int32_t *w = reinterpret_cast<int32_t *>(y + K + (K & 1));
+        uint16_t *A = reinterpret_cast<uint16_t *>(w + K);
+        uint16_t *B = A + K + (K & 1);
+        uint8_t *F = reinterpret_cast<uint8_t *>(B + K + (K & 1));
+        T *gy = yg + (size_t)lo;
+        int32_t *gw = wg ? wg + (size_t)lo : nullptr;
+        for (int i = tid; i < K; i += kPavaLargeThreads) {
+            y[i] = gy[i];
+            w[i] = fl.has_weight ? gw[i] : 1;
+            A[i] = (uint16_t)i;
+            F[i] = 0;
+        }
+        __syncthreads();
+        int P = K;
+        if (fl.has_weight) {  // warm start: heads are reached by i += weight[i]; serial, rare
+            if (tid == 0) {
+                int np = 0;
+                for (int i = 0; i < K; i += max(1, w[i])) B[np++] = (uint16_t)i;
+                s_cnt[NW] = np;
+            }
+            __syncthreads();
+            P = s_cnt[NW];
+            uint16_t *t = A;
+            A = B;
+            B = t;
+            __syncthreads();
+        }
+        for (;;) {
+            if (tid == 0) s_merged = 0;
+            for (int j = tid; j < P; j += kPavaLargeThreads) {
+                bool st = (j == 0);
+                if (!st) st = y[A[j]] > y[A[j - 1]];
+                F[j] = st ? 1 : 0;
+            }
+            __syncthreads();
+            bool merged = false;
+            for (int j = tid; j < P; j += kPavaLargeThreads)
+                if (F[j] == 1) merged |= pava_merge_run<T, int32_t>(y, w, A, F, j, P);
+            if (merged) s_merged = 1;
+            __syncthreads();
+            if (!s_merged) break;
+            // compaction: each warp owns a contiguous slice of the list
+            const int slice = ((P + NW - 1) / NW + 31) & ~31;
+            const int s0 = wid * slice, s1 = min(P, s0 + slice);
+            int cnt = 0;
+            for (int base = s0; base < s1; base += 32) {
+                const int j = base + lane;
+                cnt += __popc(__ballot_sync(0xffffffffu, j < s1 && F[j] != 2));
+            }
+            if (lane == 0) s_cnt[wid] = cnt;
+            __syncthreads();
+            int off = 0, total = 0;
+            for (int k = 0; k < NW; ++k) {
+                const int c = s_cnt[k];
+                if (k < wid) off += c;
+                total += c;
+            }
+            for (int base = s0; base < s1; base += 32) {
+                const int j = base + lane;
+                const bool alive = j < s1 && F[j] != 2;
+                const unsigned m = __ballot_sync(0xffffffffu, alive);
+                if (alive) B[off + __popc(m & lt_mask)] = A[j];
+                off += __popc(m);
+            }
+            __syncthreads();
+            uint16_t *t = A;
+            A = B;
+            B = t;
+            P = total;
+        }
+        if (fl.update) {
+            for (int j = tid; j < P; j += kPavaLargeThreads) {
+                const int p = A[j];
+                const T v = y[p];
+                const int stop = p + w[p];
+                for (int r = p + 1; r < stop; ++r) y[r] = v;
+            }
+            __syncthreads();
+        }
+        for (int i = tid; i < K; i += kPavaLargeThreads) {
+            T v = y[i];
+            if (fl.clip01) v = clip01(v);
+            gy[i] = v;
+            if (fl.has_weight) gw[i] = w[i];
+        }
+        __syncthreads();
+    }
+}
+
+inline size_t pava_large_smem(int K, size_t elem) {
+    const size_t kp = (size_t)K + (K & 1);
+    return kp * elem + (size_t)K * 4 + 2 * kp * 2 + (size_t)K + 64;
+}
+
+template <typename T>
+int launch_pava(T *y, int32_t *w, const int32_t *starts, const int32_t *win_first, int nwin, const int32_t *large_ids,
+                int nlarge, int max_large, PavaFlags fl, cudaStream_t stream) {
+    int dev = 0, num_sm = kNumSM;
+    BSLS_CUDA_TRY(cudaGetDevice(&dev));
+    BSLS_CUDA_TRY(cudaDeviceGetAttribute(&num_sm, cudaDevAttrMultiProcessorCount, dev));
+    if (nwin > 0) {
+        auto kern = pava_warp_kernel<T>;
+        static thread_local int per_sm = 0;
+        if (!per_sm) {
+            BSLS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPavaWarpsPerCta * 32, 0));
+            if (per_sm < 1) per_sm = 1;
+        }
+        const int want = (nwin + kPavaWarpsPerCta - 1) / kPavaWarpsPerCta;
+        const int grid = want < num_sm * per_sm ? want : num_sm * per_sm;
+        kern<<<grid, kPavaWarpsPerCta * 32, 0, stream>>>(y, w, starts, win_first, nwin, fl);
+        BSLS_LAUNCH_CHECK();
+    }
+    if (nlarge > 0) {
+        auto kern = pava_large_kernel<T>;
+        static thread_local bool attr_set = false;
+        if (!attr_set) {
+            BSLS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)pava_large_smem(kPavaLargeMaxBlock, sizeof(T))));
+            attr_set = true;
+        }
+        const int grid = nlarge < 2 * num_sm ? nlarge : 2 * num_sm;
+        kern<<<grid, kPavaLargeThreads, pava_large_smem(max_large, sizeof(T)), stream>>>(y, w, starts, large_ids, nlarge, fl);
+        BSLS_LAUNCH_CHECK();
+    }
+    return BSLS_OK;
+}
+
+}  // namespace bsls

@@ -1,0 +1,15 @@
+// pava_f32.cu -- float instantiation of the segmented isotonic regression kernels.
+#include "kernels.h"
+#include "pava.cuh"
+
+namespace bsls {
+int pava_f32(float *y, int32_t *w, const int32_t *starts, const int32_t *win_first, int nwin, const int32_t *large_ids,
+             int nlarge, int max_large, int update, int clip01, cudaStream_t stream) {
+    static_assert(kPavaPitch == kPlanPavaPitch && kPavaWarpMaxBlock == kPlanPavaWarpMax && kPavaLargeMaxBlock == kPlanPavaLargeMax, "plan constants");
+    PavaFlags fl;
+    fl.update = update;
+    fl.clip01 = clip01;
+    fl.has_weight = w != nullptr;
+    return launch_pava<float>(y, w, starts, win_first, nwin, large_ids, nlarge, max_large, fl, stream);
+}
+}  // namespace bsls

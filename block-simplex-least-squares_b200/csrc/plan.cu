@@ -38,20 +38,19 @@ int plan_layout_stats(const int32_t *starts, int nb, int n, LayoutStats *d_out, 
 }
 
 // tile_first[t] = first block whose start lies in tile t or later; tile_first[ntiles] = nb.
-__global__ void tile_first_kernel(const int32_t *__restrict__ starts, int nb, int first, int32_t *__restrict__ tile_first,
-                                  int ntiles) {
+__global__ void tile_first_kernel(const int32_t *__restrict__ starts, int nb, int first, int pitch,
+                                  int32_t *__restrict__ tile_first, int ntiles) {
     for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < nb; b += (long long)gridDim.x * blockDim.x) {
-        const int t_here = (starts[b] - first) / kPlanTileElems;
-        const int t_prev = b ? (starts[b - 1] - first) / kPlanTileElems : -1;
+        const int t_here = (starts[b] - first) / pitch;
+        const int t_prev = b ? (starts[b - 1] - first) / pitch : -1;
         for (int t = t_prev + 1; t <= t_here; ++t) tile_first[t] = (int)b;
         if (b == nb - 1)
             for (int t = t_here + 1; t <= ntiles; ++t) tile_first[t] = nb;
     }
 }
 
-int plan_tile_first(const int32_t *starts, int nb, int first, int n, int32_t *tile_first, int ntiles, cudaStream_t stream) {
-    (void)n;
-    tile_first_kernel<<<grid_for(nb, 256), 256, 0, stream>>>(starts, nb, first, tile_first, ntiles);
+int plan_tile_first(const int32_t *starts, int nb, int first, int pitch, int32_t *tile_first, int ntiles, cudaStream_t stream) {
+    tile_first_kernel<<<grid_for(nb, 256), 256, 0, stream>>>(starts, nb, first, pitch, tile_first, ntiles);
     BSLS_LAUNCH_CHECK();
     return BSLS_OK;
 }

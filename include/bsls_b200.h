@@ -61,6 +61,21 @@ BSLS_API int bsls_proj_multi_simplex(double *y, const int *blocks, int numblocks
 /* replaces proj_multi_ball         (python/c_extensions/proj_simplex.h:50-74) */
 BSLS_API int bsls_proj_multi_ball(double *y, const int *blocks, int numblocks, int n);
 
+/* replaces isotonic_regression     (python/c_extensions/isotonic_regression.h:13-58);
+ * weight = pool sizes at the pool heads, in/out (all ones unless warm-starting); NULL means
+ * "all ones in, result dropped", which is what the reference's Python layer does for
+ * weight=None (c_extensions.pyx:70-71). */
+BSLS_API int bsls_isotonic_regression(double *y, int start, int end, int *weight, int update);
+/* replaces isotonic_regression_multi (isotonic_regression.h:85-92) */
+BSLS_API int bsls_isotonic_regression_multi(double *y, const int *blocks, int numblocks, int n, int *weight, int update);
+/* replace isotonic_regression_2 / _multi_2 (isotonic_regression.h:61-82,95-102) and
+ * isotonic_regression_3 / _multi_3 (isotonic_regression.h:105-164): same regression, served
+ * by the variant-1 kernel (values equal to ~1e-15 relative; weights are variant 1's). */
+BSLS_API int bsls_isotonic_regression_2(double *y, int start, int end);
+BSLS_API int bsls_isotonic_regression_multi_2(double *y, const int *blocks, int numblocks, int n);
+BSLS_API int bsls_isotonic_regression_3(double *y, int start, int end, int *weight, int update);
+BSLS_API int bsls_isotonic_regression_multi_3(double *y, const int *blocks, int numblocks, int n, int *weight, int update);
+
 /* Pinned host memory for callers that want the host entry points to run at PCIe speed
  * (pageable buffers work too, through a staging copy). */
 BSLS_API int bsls_host_alloc(void **ptr, int64_t bytes);
@@ -87,6 +102,13 @@ BSLS_API int bsls_dev_proj_multi_simplex_f64(const bsls_plan *plan, double *y, b
 BSLS_API int bsls_dev_proj_multi_ball_f64(const bsls_plan *plan, double *y, bsls_stream_t stream);
 BSLS_API int bsls_dev_proj_multi_simplex_f32(const bsls_plan *plan, float *y, bsls_stream_t stream);
 BSLS_API int bsls_dev_proj_multi_ball_f32(const bsls_plan *plan, float *y, bsls_stream_t stream);
+
+
+/* segmented isotonic regression (a4-a6 of SURVEY section 8): weight may be NULL; clip01 != 0
+ * fuses the [0,1] clamp the z-space projection applies afterwards (python/main.py:65,
+ * python/algorithm_utils.py:223-224). */
+BSLS_API int bsls_dev_isotonic_regression_multi_f64(const bsls_plan *plan, double *y, int32_t *weight, int update, int clip01, bsls_stream_t stream);
+BSLS_API int bsls_dev_isotonic_regression_multi_f32(const bsls_plan *plan, float *y, int32_t *weight, int update, int clip01, bsls_stream_t stream);
 
 #ifdef __cplusplus
 }
