@@ -100,6 +100,12 @@ static int dev_pava(const bsls_plan *plan_, T *y, int32_t *weight, int update, i
         set_error("isotonic regression: a block of %d entries exceeds the %d-entry limit of this revision", plan->max_size, kPlanPavaLargeMax);
         return BSLS_ERR_ARG;
     }
+    if (plan->uniform > 0 && plan->uniform <= kPlanPavaSmallMax) {
+        if constexpr (sizeof(T) == 8)
+            return pava_small_f64((double *)y, weight, plan->first, plan->nb, plan->uniform, update, clip01, stream);
+        else
+            return pava_small_f32((float *)y, weight, plan->first, plan->nb, plan->uniform, update, clip01, stream);
+    }
     if (int rc = plan_ensure_pava(plan, stream)) return rc;
     if constexpr (sizeof(T) == 8)
         return pava_f64((double *)y, weight, plan->d_starts, plan->d_pava_first, plan->pava_windows, plan->d_pava_large,

@@ -32,6 +32,10 @@ constexpr int kPlanPavaLargeMax = 8192;   // == kPavaLargeMaxBlock
 // pava_f64.cu / pava_f32.cu: segmented isotonic regression (pava.cuh)
 int pava_f64(double *y, int32_t *w, const int32_t *starts, const int32_t *win_first, int nwin, const int32_t *large_ids,
              int nlarge, int max_large, int update, int clip01, cudaStream_t stream);
+// uniform layouts with K <= kPlanPavaSmallMax: one thread per block
+constexpr int kPlanPavaSmallMax = 64;
+int pava_small_f64(double *y, int32_t *w, long long first, int nb, int K, int update, int clip01, cudaStream_t stream);
+int pava_small_f32(float *y, int32_t *w, long long first, int nb, int K, int update, int clip01, cudaStream_t stream);
 int pava_f32(float *y, int32_t *w, const int32_t *starts, const int32_t *win_first, int nwin, const int32_t *large_ids,
              int nlarge, int max_large, int update, int clip01, cudaStream_t stream);
 

@@ -77,6 +77,141 @@ __device__ __forceinline__ bool pava_merge_run(T *y, W *w, const uint16_t *A, ui
 }
 
 // ---------------------------------------------------------------------------------------------
+// one THREAD per block: the reference loop verbatim, on shared-memory rows
+// ---------------------------------------------------------------------------------------------
+// y / w point at one block (K entries).  Statement for statement isotonic_regression.h:18-57.
+template <typename T, typename W>
+__device__ __forceinline__ void pava_block_serial(T *y, W *w, int K, int update) {
+    for (;;) {
+        bool pooled = false;
+        int i = 0;
+        while (i < K) {
+            int k = i + (int)w[i];
+            const T yi = y[i];
+            T yj = yi;
+            while (k < K) {
+                const T yk = y[k];
+                if (!(yk <= yj)) break;
+                yj = yk;
+                k += (int)w[k];
+            }
+            if (yi != yj) {
+                T num = T(0);
+                int den = 0;
+                for (int p = i; p < k;) {
+                    const int wp = (int)w[p];
+                    num += y[p] * (T)wp;
+                    den += wp;
+                    p += wp;
+                }
+                y[i] = num / (T)den;
+                w[i] = (W)den;
+                pooled = true;
+            }
+            i = k;
+        }
+        if (!pooled) break;
+    }
+    if (update) {
+        for (int i = 0; i < K;) {
+            const int wi = (int)w[i];
+            const T v = y[i];
+            for (int r = i + 1; r < i + wi; ++r) y[r] = v;
+            i += wi;
+        }
+    }
+}
+
+constexpr int kPavaSmallMaxBlock = 64;  // longest block of the thread-per-block kernel
+
+// Uniform layouts with K <= kPavaSmallMaxBlock: a CTA stages THREADS blocks in shared memory
+// (rows padded to an odd pitch so that lanes walking their own rows do not bank-conflict),
+// every thread regresses its own block, then the tile is written back coalesced.
+template <typename T, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+pava_small_kernel(T *__restrict__ yg, int32_t *__restrict__ wg, long long first, int nb, int K, FastDiv kdiv, PavaFlags fl) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int KS = K | 1;  // row pitch (elements)
+    T *ys = reinterpret_cast<T *>(smem_raw);
+    uint8_t *wsm = reinterpret_cast<uint8_t *>(ys + (size_t)THREADS * KS);
+    const int tid = threadIdx.x;
+    const int ntiles = (nb + THREADS - 1) / THREADS;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int nblk = min(THREADS, nb - tile * THREADS);
+        const int nel = nblk * K;
+        T *gy = yg + first + (size_t)tile * THREADS * K;
+        int32_t *gw = wg ? wg + first + (size_t)tile * THREADS * K : nullptr;
+        // coalesced load, scattered into padded rows; four loads in flight per thread
+        int i = tid;
+        for (; i + 3 * THREADS < nel; i += 4 * THREADS) {
+            T v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = gy[i + u * THREADS];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t e = (uint32_t)(i + u * THREADS), r = fdiv(e, kdiv);
+                ys[r * KS + (e - r * K)] = v[u];
+            }
+        }
+        for (; i < nel; i += THREADS) {
+            const uint32_t e = (uint32_t)i, r = fdiv(e, kdiv);
+            ys[r * KS + (e - r * K)] = gy[i];
+        }
+        if (fl.has_weight) {
+            for (int e2 = tid; e2 < nel; e2 += THREADS) {
+                const uint32_t e = (uint32_t)e2, r = fdiv(e, kdiv);
+                wsm[r * KS + (e - r * K)] = (uint8_t)gw[e2];
+            }
+        } else {
+            for (int e2 = tid; e2 < THREADS * KS; e2 += THREADS) wsm[e2] = 1;
+        }
+        __syncthreads();
+        if (tid < nblk) pava_block_serial<T, uint8_t>(ys + (size_t)tid * KS, wsm + (size_t)tid * KS, K, fl.update);
+        __syncthreads();
+        for (int e2 = tid; e2 < nel; e2 += THREADS) {
+            const uint32_t e = (uint32_t)e2, r = fdiv(e, kdiv);
+            T v = ys[r * KS + (e - r * K)];
+            if (fl.clip01) v = clip01(v);
+            gy[e2] = v;
+            if (fl.has_weight) gw[e2] = (int32_t)wsm[r * KS + (e - r * K)];
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T, int THREADS>
+int launch_pava_small_cfg(T *y, int32_t *w, long long first, int nb, int K, PavaFlags fl, cudaStream_t stream) {
+    auto kern = pava_small_kernel<T, THREADS>;
+    const int KS = K | 1;
+    const size_t smem = (size_t)THREADS * KS * (sizeof(T) + 1) + 16;
+    static thread_local size_t cached_smem = 0;
+    static thread_local int per_sm = 0, num_sm = 0;
+    if (cached_smem != smem) {
+        BSLS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int dev = 0;
+        BSLS_CUDA_TRY(cudaGetDevice(&dev));
+        BSLS_CUDA_TRY(cudaDeviceGetAttribute(&num_sm, cudaDevAttrMultiProcessorCount, dev));
+        BSLS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
+        if (per_sm < 1) {
+            set_error("pava_small: K=%d does not fit shared memory", K);
+            return BSLS_ERR_ARG;
+        }
+        cached_smem = smem;
+    }
+    const int ntiles = (nb + THREADS - 1) / THREADS;
+    const int grid = ntiles < num_sm * per_sm ? ntiles : num_sm * per_sm;
+    kern<<<grid, THREADS, smem, stream>>>(y, w, first, nb, K, make_fastdiv((uint32_t)K), fl);
+    BSLS_LAUNCH_CHECK();
+    return BSLS_OK;
+}
+
+template <typename T> int launch_pava_small(T *y, int32_t *w, long long first, int nb, int K, PavaFlags fl, cudaStream_t stream) {
+    if (nb <= 0) return BSLS_OK;
+    if (K <= 24) return launch_pava_small_cfg<T, 256>(y, w, first, nb, K, fl, stream);
+    return launch_pava_small_cfg<T, 128>(y, w, first, nb, K, fl, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
 // warp windows
 // ---------------------------------------------------------------------------------------------
 template <typename T>

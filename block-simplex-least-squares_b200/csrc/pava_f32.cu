@@ -12,4 +12,12 @@ int pava_f32(float *y, int32_t *w, const int32_t *starts, const int32_t *win_fir
     fl.has_weight = w != nullptr;
     return launch_pava<float>(y, w, starts, win_first, nwin, large_ids, nlarge, max_large, fl, stream);
 }
+
+int pava_small_f32(float *y, int32_t *w, long long first, int nb, int K, int update, int clip01, cudaStream_t stream) {
+    PavaFlags fl;
+    fl.update = update;
+    fl.clip01 = clip01;
+    fl.has_weight = w != nullptr;
+    return launch_pava_small<float>(y, w, first, nb, K, fl, stream);
+}
 }  // namespace bsls

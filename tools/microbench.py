@@ -59,3 +59,43 @@ if __name__ == "__main__":
         print(json.dumps(time_proj(K, nb)))
     print(json.dumps(time_proj(16, 10 ** 6, dtype=torch.float32)))
     print(json.dumps(time_proj(16, 10 ** 6, ball=True)))
+
+
+def time_pava(K, nb, kind="ref", reps=8, with_weight=False, clip=False):
+    n = nb * K
+    gen = torch.Generator(device="cuda").manual_seed(K)
+    starts = torch.arange(0, n, K, dtype=torch.int64, device="cuda")
+    plan = bsls_b200.BlockPlan(starts, n)
+
+    def make():
+        if kind == "ref":
+            ramp = 50.0 * torch.log1p(torch.arange(K, dtype=torch.float64, device="cuda"))
+            r = torch.randint(-50, 50, (nb, K), device="cuda", generator=gen).to(torch.float64)
+            return (r + ramp).reshape(-1)
+        if kind == "normal":
+            return torch.randn(n, dtype=torch.float64, device="cuda", generator=gen)
+        if kind == "zspace":
+            e = -torch.log(torch.rand(nb, K + 1, dtype=torch.float64, device="cuda", generator=gen))
+            x = e / e.sum(1, keepdim=True)
+            return (torch.cumsum(x, 1)[:, :K] + 0.05 * torch.randn(nb, K, dtype=torch.float64, device="cuda", generator=gen)).reshape(-1)
+        raise ValueError(kind)
+
+    bufs = [make() for _ in range(reps + 3)]
+    ws = [torch.ones(n, dtype=torch.int32, device="cuda") for _ in range(reps + 3)] if with_weight else [None] * (reps + 3)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for b, w in zip(bufs[:3], ws[:3]):
+        bsls_b200.isotonic_regression_multi_c(b, plan, w, 1, clip01=clip)
+    flush.zero_()
+    torch.cuda.synchronize()
+    evs = []
+    for b, w in zip(bufs[3:], ws[3:]):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        bsls_b200.isotonic_regression_multi_c(b, plan, w, 1, clip01=clip)
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    ms = np.array([a.elapsed_time(b) for a, b in evs])
+    bytes_ = 16 * n + 4 * nb + (8 * n if with_weight else 0)
+    return {"pava_K": K, "nb": nb, "kind": kind, "weights": with_weight, "ms_med": float(np.median(ms)),
+            "gvar_s": n / np.median(ms) / 1e6, "GBs": bytes_ / np.median(ms) / 1e6}
