@@ -21,7 +21,7 @@ from .plan import BlockPlan, plan_for
 __all__ = ["proj_simplex_c", "proj_multi_simplex_c", "proj_multi_ball_c",
            "isotonic_regression_c", "isotonic_regression_multi_c",
            "isotonic_regression_c_2", "isotonic_regression_multi_c_2",
-           "isotonic_regression_c_3", "isotonic_regression_multi_c_3"]
+           "isotonic_regression_c_3", "isotonic_regression_multi_c_3", "x2z_c", "z2x_c", "block_scale", "n_dot", "nt_dot"]
 
 
 def _stream(t):
@@ -201,3 +201,94 @@ def isotonic_regression_c_3(y, start, end, weight=None, update=1):
 
 def isotonic_regression_multi_c_3(y, blocks, weight=None, update=1):
     return _pava_multi(y, blocks, weight, update, False, 3)
+
+
+# ---------------------------------------------------------------------------------------------
+# x <-> z (reference: c_extensions.pyx:195-248) and the bidiagonal N (bsls_utils.py:139-162)
+# ---------------------------------------------------------------------------------------------
+def _host_x2z_blocks(blocks, n):
+    b = np.asarray(blocks.cpu() if torch.is_tensor(blocks) else blocks)
+    # c_extensions.pyx:202-203
+    assert False not in ((b[1:] - b[:-1]) > 0)
+    assert b[0] == 0 and b[-1] < n
+    return b
+
+
+def _z_plan(x, blocks):
+    n = x.shape[0]
+    if isinstance(blocks, BlockPlan):
+        assert blocks.first == 0 and blocks.n == n
+        return blocks
+    _host_x2z_blocks(blocks, n)
+    return plan_for(blocks, n, x.device)
+
+
+def x2z_c(x, z, blocks):
+    """z <- per-block running sums of x without every block's last entry; returns z
+    (c_extensions.pyx:195-220).  Device tensors, or NumPy arrays (copied through the GPU)."""
+    if isinstance(x, np.ndarray):
+        xd = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).cuda()
+        zd = torch.empty(z.shape[0], dtype=torch.float64, device=xd.device)
+        x2z_c(xd, zd, np.asarray(blocks))
+        z[:] = zd.cpu().numpy()
+        return z
+    _check_dev_vector(x, "x")
+    _check_dev_vector(z, "z")
+    plan = _z_plan(x, blocks)
+    assert z.shape[0] == x.shape[0] - plan.numblocks, "z must have n - numblocks entries"
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().bsls_dev_x2z_f64(plan.handle, x.data_ptr(), z.data_ptr(), _stream(x)), "x2z")
+    return z
+
+
+def z2x_c(x, z, blocks):
+    """x <- adjacent differences of z, last entry of a block = 1 - z_last; returns x
+    (c_extensions.pyx:223-248)."""
+    if isinstance(x, np.ndarray):
+        zd = torch.from_numpy(np.ascontiguousarray(z, dtype=np.float64)).cuda()
+        xd = torch.empty(x.shape[0], dtype=torch.float64, device=zd.device)
+        z2x_c(xd, zd, np.asarray(blocks))
+        x[:] = xd.cpu().numpy()
+        return x
+    _check_dev_vector(x, "x")
+    _check_dev_vector(z, "z")
+    plan = _z_plan(x, blocks)
+    assert z.shape[0] == x.shape[0] - plan.numblocks, "z must have n - numblocks entries"
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().bsls_dev_z2x_f64(plan.handle, x.data_ptr(), z.data_ptr(), _stream(x)), "z2x")
+    return x
+
+
+def n_dot(x, z, blocks, add_x0=False):
+    """x <- N z (+ x0): the change of variables of python/bsls_utils.py:139-162,327-328 as an
+    operator (x_l = z_l - z_{l-1} inside a block)."""
+    _check_dev_vector(x, "x")
+    _check_dev_vector(z, "z")
+    plan = _z_plan(x, blocks)
+    assert z.shape[0] == x.shape[0] - plan.numblocks
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().bsls_dev_nz_f64(plan.handle, x.data_ptr(), z.data_ptr(), int(bool(add_x0)), _stream(x)), "nz")
+    return x
+
+
+def nt_dot(zg, v, blocks):
+    """zg <- N^T v ((N^T v)_l = v_l - v_{l+1})."""
+    _check_dev_vector(zg, "zg")
+    _check_dev_vector(v, "v")
+    plan = _z_plan(v, blocks)
+    assert zg.shape[0] == v.shape[0] - plan.numblocks
+    with torch.cuda.device(v.device):
+        _lib.check(_lib.lib().bsls_dev_ntv_f64(plan.handle, zg.data_ptr(), v.data_ptr(), _stream(v)), "ntv")
+    return zg
+
+
+def block_scale(y, blocks, f, divide=False):
+    """y[block k] *= f[k] (or /= f[k]), in place: the per-block (de)normalisation that
+    get_solver_parts wraps around the projection when ``f`` is given (algorithm_utils.py:232-265)."""
+    _check_dev_vector(y, "y")
+    plan = plan_for(blocks, y.shape[0], y.device)
+    assert torch.is_tensor(f) and f.is_cuda and f.dtype == torch.float64 and f.is_contiguous() and f.shape[0] == plan.numblocks
+    with torch.cuda.device(y.device):
+        _lib.check(_lib.lib().bsls_dev_block_scale_f64(plan.handle, y.data_ptr(), f.data_ptr(), int(bool(divide)), _stream(y)),
+                   "block_scale")
+    return None

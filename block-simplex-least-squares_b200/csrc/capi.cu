@@ -22,7 +22,7 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
-static int device_ok() {
+int device_ok() {
     static thread_local int cached = -1;
     if (cached == BSLS_OK) return BSLS_OK;
     int count = 0;
@@ -47,21 +47,6 @@ static int device_ok() {
 
 using namespace bsls;
 
-struct bsls_plan {
-    int nb = 0, n = 0, first = 0;
-    int uniform = 0, min_size = 0, max_size = 0;
-    int32_t *d_starts = nullptr;      // nb + 1 entries, last = n
-    // ragged layouts only
-    int tiles = 0, large = 0;
-    int32_t *d_tile_first = nullptr;  // tiles + 1 entries
-    int32_t *d_large_ids = nullptr;   // `large` block indices (size > kPlanTileMaxBlock)
-    bool ragged = false;
-    // isotonic-regression windows (built on first use, any layout)
-    bool pava_ready = false;
-    int pava_windows = 0, pava_large = 0;
-    int32_t *d_pava_first = nullptr;  // pava_windows + 1 entries
-    int32_t *d_pava_large = nullptr;  // blocks longer than kPlanPavaWarpMax
-};
 
 // Window / long-block lists for the isotonic-regression kernels; built once, on first use.
 static int plan_ensure_pava(bsls_plan *p, cudaStream_t stream) {
@@ -270,6 +255,13 @@ int host_pava_single(double *y, int start, int end, int *weight, int update) {
 }
 
 }  // namespace
+
+namespace bsls {
+int project_f64(const bsls_plan *plan, double *y, int mode, cudaStream_t stream) { return dev_project<double>(plan, y, mode, stream); }
+int pava_clip_f64(const bsls_plan *plan, double *y, int32_t *weight, int update, int clip01, cudaStream_t stream) {
+    return dev_pava<double>(plan, y, weight, update, clip01, stream);
+}
+}  // namespace bsls
 
 extern "C" {
 

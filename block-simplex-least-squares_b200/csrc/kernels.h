@@ -39,4 +39,29 @@ int pava_small_f32(float *y, int32_t *w, long long first, int nb, int K, int upd
 int pava_f32(float *y, int32_t *w, const int32_t *starts, const int32_t *win_first, int nwin, const int32_t *large_ids,
              int nlarge, int max_large, int update, int clip01, cudaStream_t stream);
 
+int device_ok();  // BSLS_OK when an sm_100 device is current (capi.cu)
 }  // namespace bsls
+
+// The analysed block layout behind the opaque handle of the C ABI (built in capi.cu).
+struct bsls_plan {
+    int nb = 0, n = 0, first = 0;
+    int uniform = 0, min_size = 0, max_size = 0;
+    int32_t *d_starts = nullptr;      // nb + 1 entries, last = n
+    // ragged layouts only
+    int tiles = 0, large = 0;
+    int32_t *d_tile_first = nullptr;  // tiles + 1 entries
+    int32_t *d_large_ids = nullptr;   // `large` block indices (size > kPlanTileMaxBlock)
+    bool ragged = false;
+    // isotonic-regression windows (built on first use, any layout)
+    bool pava_ready = false;
+    int pava_windows = 0, pava_large = 0;
+    int32_t *d_pava_first = nullptr;  // pava_windows + 1 entries
+    int32_t *d_pava_large = nullptr;  // blocks longer than kPlanPavaWarpMax
+};
+
+namespace bsls {
+// capi.cu: the device entry points, for the solver translation units
+int project_f64(const bsls_plan *plan, double *y, int mode, cudaStream_t stream);
+int pava_clip_f64(const bsls_plan *plan, double *y, int32_t *weight, int update, int clip01, cudaStream_t stream);
+}  // namespace bsls
+

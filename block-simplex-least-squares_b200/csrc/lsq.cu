@@ -1,0 +1,705 @@
+// lsq.cu -- host side of the sparse least-squares path: the bsls_lsq handle, kernel
+// selection, the NCCL all-reduce of the link vector, and the x-space BATCH solver loop
+// (python/BATCH.py:7-106,217-250 of the reference) run without the interpreter.
+#include <dlfcn.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "kernels.h"
+#include "lsq.cuh"
+
+using namespace bsls;
+
+// ---------------------------------------------------------------------------------------------
+// NCCL, bound at run time (torch ships libnccl.so.2; no link-time dependency)
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct Id128 {  // ncclUniqueId, passed by value
+    char b[128];
+};
+struct NcclApi {
+    void *handle = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, Id128, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+constexpr int kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2;
+
+int nccl_load(const char *path) {
+    if (g_nccl.handle) return BSLS_OK;
+    const char *names[] = {path, "libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *nm : names) {
+        if (!nm || !*nm) continue;
+        h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) {
+        set_error("cannot load NCCL (%s)", dlerror());
+        return BSLS_ERR_ARG;
+    }
+    g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(h, "ncclCommInitRank");
+    g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(h, "ncclAllReduce");
+    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
+    g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
+        set_error("NCCL library lacks the expected symbols");
+        return BSLS_ERR_ARG;
+    }
+    g_nccl.handle = h;
+    return BSLS_OK;
+}
+#define BSLS_NCCL_TRY(expr)                                                                          \
+    do {                                                                                             \
+        int _r = (expr);                                                                             \
+        if (_r != 0) {                                                                               \
+            set_error("%s:%d %s -> NCCL error %d (%s)", __FILE__, __LINE__, #expr, _r,               \
+                      g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "?");                      \
+            return BSLS_ERR_CUDA;                                                                    \
+        }                                                                                            \
+    } while (0)
+}  // namespace
+
+struct bsls_comm {
+    void *comm = nullptr;
+    int nranks = 1, rank = 0;
+};
+
+// reduction scratch + device/host scalar block + communicator: everything a reducing kernel needs
+struct bsls_ws {
+    RedCtx red{};
+    double *d_scal = nullptr, *h_scal = nullptr;  // kScalCount each (h_scal pinned)
+    bsls_comm *comm = nullptr;
+    int launches = 0;
+};
+
+struct bsls_lsq {
+    int64_t m = 0, n = 0, nnz = 0;
+    const int64_t *a_ptr = nullptr, *t_ptr = nullptr;
+    const int32_t *a_idx = nullptr, *t_idx = nullptr;
+    const double *a_val = nullptr, *t_val = nullptr;
+    const double *b = nullptr;
+    int a_mode = 0, t_mode = 0;
+    double *r = nullptr;                          // m
+    double *wg = nullptr, *wxn = nullptr, *wgn = nullptr;  // n each, solver workspace
+    bsls_ws *ws = nullptr;                        // owned
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace {
+
+int pick_mode(int64_t nnz, int64_t rows) {
+    const double avg = rows > 0 ? (double)nnz / (double)rows : 0.0;
+    if (avg <= 32.0) return 1;
+    if (avg < 64.0) return 8;
+    if (avg < 128.0) return 16;
+    return 32;
+}
+
+int grid_elems(int64_t n) {
+    int64_t want = (n + 256 * 4 - 1) / (256 * 4);
+    if (want < 1) want = 1;
+    return (int)(want < kRedMaxGrid ? want : kRedMaxGrid);
+}
+
+template <class Epi>
+int launch_spmv(bsls_ws *w, int mode, int64_t rows, const int64_t *ptr, const int32_t *idx, const double *val, const double *v,
+                const Epi &epi, cudaStream_t st) {
+    constexpr int T = 256;
+    if (rows <= 0) return BSLS_OK;
+    if (mode == 1) {
+        const int64_t tiles = (rows + T - 1) / T;
+        const int grid = (int)(tiles < kRedMaxGrid ? tiles : kRedMaxGrid);
+        spmv_stream_kernel<Epi, T, 2048><<<grid, T, 0, st>>>(rows, ptr, idx, val, v, epi, w->red);
+    } else {
+        const int lanes = mode;
+        int64_t want = (rows * lanes + T - 1) / T;
+        // a few rows per group: enough CTAs to fill the machine, few enough to amortise the reduction
+        const int grid = (int)(want < kRedMaxGrid ? (want < 1 ? 1 : want) : kRedMaxGrid);
+        switch (lanes) {
+            case 4: spmv_vector_kernel<Epi, T, 4><<<grid, T, 0, st>>>(rows, ptr, idx, val, v, epi, w->red); break;
+            case 8: spmv_vector_kernel<Epi, T, 8><<<grid, T, 0, st>>>(rows, ptr, idx, val, v, epi, w->red); break;
+            case 16: spmv_vector_kernel<Epi, T, 16><<<grid, T, 0, st>>>(rows, ptr, idx, val, v, epi, w->red); break;
+            default: spmv_vector_kernel<Epi, T, 32><<<grid, T, 0, st>>>(rows, ptr, idx, val, v, epi, w->red); break;
+        }
+    }
+    BSLS_LAUNCH_CHECK();
+    w->launches++;
+    return BSLS_OK;
+}
+
+int allreduce(bsls_ws *w, double *buf, int64_t count, int op, cudaStream_t st) {
+    if (!w->comm || w->comm->nranks <= 1) return BSLS_OK;
+    BSLS_NCCL_TRY(g_nccl.AllReduce(buf, buf, (size_t)count, kNcclFloat64, op, w->comm->comm, st));
+    return BSLS_OK;
+}
+
+// r = A x - b (summed over ranks), scalar F = 0.5 <r, r>
+int residual(bsls_lsq *q, const double *x, double *r, const double *b, cudaStream_t st) {
+    bsls_ws *w = q->ws;
+    const bool dist = w->comm && w->comm->nranks > 1;
+    EpiResidual epi{r, (dist || !b) ? nullptr : b};
+    if (int rc = launch_spmv(w, q->a_mode, q->m, q->a_ptr, q->a_idx, q->a_val, x, epi, st)) return rc;
+    if (dist) {
+        if (int rc = allreduce(w, r, q->m, kNcclSum, st)) return rc;
+        if (b) {
+            residual_finish_kernel<<<grid_elems(q->m), 256, 0, st>>>(r, b, q->m, w->red);
+            BSLS_LAUNCH_CHECK();
+            w->launches++;
+        }
+    }
+    return BSLS_OK;
+}
+
+int ensure_workspace(bsls_lsq *q) {
+    if (q->wg) return BSLS_OK;
+    BSLS_CUDA_TRY(cudaMalloc(&q->wg, sizeof(double) * (size_t)q->n));
+    BSLS_CUDA_TRY(cudaMalloc(&q->wxn, sizeof(double) * (size_t)q->n));
+    BSLS_CUDA_TRY(cudaMalloc(&q->wgn, sizeof(double) * (size_t)q->n));
+    return BSLS_OK;
+}
+
+int fetch_scalars(bsls_ws *q, cudaStream_t st) {
+    BSLS_CUDA_TRY(cudaMemcpyAsync(q->h_scal, q->d_scal, sizeof(double) * kScalCount, cudaMemcpyDeviceToHost, st));
+    BSLS_CUDA_TRY(cudaStreamSynchronize(st));
+    return BSLS_OK;
+}
+
+BlockLayout layout_of(const bsls_plan *p) {
+    BlockLayout l;
+    l.starts = p->d_starts;
+    l.nb = p->nb;
+    l.uniform = p->uniform;
+    l.first = p->first;
+    return l;
+}
+
+int lanes_for(const bsls_plan *p) {
+    const int k = p->uniform > 0 ? p->uniform : (int)((p->n - p->first) / (p->nb > 0 ? p->nb : 1));
+    if (k <= 4) return 4;
+    if (k <= 8) return 8;
+    if (k <= 16) return 16;
+    return 32;
+}
+
+int grid_groups(int nb, int lanes) {
+    int64_t want = ((int64_t)nb * lanes + 255) / 256;
+    if (want < 1) want = 1;
+    return (int)(want < kRedMaxGrid ? want : kRedMaxGrid);
+}
+
+#define DISPATCH_LANES(lanes, KERNEL, grid, st, ...)                         \
+    switch (lanes) {                                                         \
+        case 4: KERNEL<4><<<grid, 256, 0, st>>>(__VA_ARGS__); break;         \
+        case 8: KERNEL<8><<<grid, 256, 0, st>>>(__VA_ARGS__); break;         \
+        case 16: KERNEL<16><<<grid, 256, 0, st>>>(__VA_ARGS__); break;       \
+        default: KERNEL<32><<<grid, 256, 0, st>>>(__VA_ARGS__); break;       \
+    }
+
+}  // namespace
+
+extern "C" {
+
+// ---------------------------------------------------------------------------------------------
+// communicator
+// ---------------------------------------------------------------------------------------------
+int bsls_comm_unique_id(const char *nccl_path, char id[128]) {
+    if (!id) return BSLS_ERR_ARG;
+    if (int rc = nccl_load(nccl_path)) return rc;
+    BSLS_NCCL_TRY(g_nccl.GetUniqueId(id));
+    return BSLS_OK;
+}
+
+int bsls_comm_create(const char *nccl_path, int nranks, int rank, const char id[128], bsls_comm **out) {
+    if (!out || !id || nranks < 1 || rank < 0 || rank >= nranks) return BSLS_ERR_ARG;
+    *out = nullptr;
+    if (int rc = device_ok()) return rc;
+    if (int rc = nccl_load(nccl_path)) return rc;
+    Id128 uid;
+    memcpy(uid.b, id, 128);
+    bsls_comm *c = new bsls_comm();
+    c->nranks = nranks;
+    c->rank = rank;
+    int r = g_nccl.CommInitRank(&c->comm, nranks, uid, rank);
+    if (r != 0) {
+        set_error("ncclCommInitRank -> %d (%s)", r, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+        delete c;
+        return BSLS_ERR_CUDA;
+    }
+    *out = c;
+    return BSLS_OK;
+}
+
+int bsls_comm_destroy(bsls_comm *c) {
+    if (!c) return BSLS_OK;
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    delete c;
+    return BSLS_OK;
+}
+
+int bsls_comm_allreduce_sum_f64(bsls_comm *c, double *buf, int64_t count, bsls_stream_t s) {
+    if (!c || !buf || count < 0) return BSLS_ERR_ARG;
+    if (c->nranks <= 1) return BSLS_OK;
+    BSLS_NCCL_TRY(g_nccl.AllReduce(buf, buf, (size_t)count, kNcclFloat64, kNcclSum, c->comm, (cudaStream_t)s));
+    return BSLS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// reduction workspace
+// ---------------------------------------------------------------------------------------------
+int bsls_ws_create(bsls_ws **out) {
+    if (!out) return BSLS_ERR_ARG;
+    *out = nullptr;
+    if (int rc = device_ok()) return rc;
+    bsls_ws *w = new bsls_ws();
+    auto fail = [&](int rc) {
+        bsls_ws_destroy(w);
+        return rc;
+    };
+#define TRY_OR_FAIL(expr)                                                                    \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return fail(BSLS_ERR_CUDA);                                                      \
+        }                                                                                    \
+    } while (0)
+    TRY_OR_FAIL(cudaMalloc(&w->red.partials, sizeof(double) * (size_t)kRedMaxGrid * kRedSlots));
+    TRY_OR_FAIL(cudaMalloc(&w->red.ticket, sizeof(unsigned)));
+    TRY_OR_FAIL(cudaMalloc(&w->d_scal, sizeof(double) * kScalCount));
+    TRY_OR_FAIL(cudaMemset(w->red.ticket, 0, sizeof(unsigned)));
+    TRY_OR_FAIL(cudaMemset(w->d_scal, 0, sizeof(double) * kScalCount));
+    TRY_OR_FAIL(cudaHostAlloc(&w->h_scal, sizeof(double) * kScalCount, cudaHostAllocDefault));
+#undef TRY_OR_FAIL
+    w->red.out = w->d_scal;
+    *out = w;
+    return BSLS_OK;
+}
+
+int bsls_ws_destroy(bsls_ws *w) {
+    if (!w) return BSLS_OK;
+    if (w->red.partials) cudaFree(w->red.partials);
+    if (w->red.ticket) cudaFree(w->red.ticket);
+    if (w->d_scal) cudaFree(w->d_scal);
+    if (w->h_scal) cudaFreeHost(w->h_scal);
+    delete w;
+    return BSLS_OK;
+}
+
+int bsls_ws_set_comm(bsls_ws *w, bsls_comm *c) {
+    if (!w) return BSLS_ERR_ARG;
+    w->comm = c;
+    return BSLS_OK;
+}
+
+double *bsls_ws_scalar_ptr(const bsls_ws *w) { return w ? w->d_scal : nullptr; }
+
+int bsls_ws_scalars(bsls_ws *w, double out[16], bsls_stream_t s) {
+    if (!w || !out) return BSLS_ERR_ARG;
+    if (int rc = fetch_scalars(w, (cudaStream_t)s)) return rc;
+    memcpy(out, w->h_scal, sizeof(double) * kScalCount);
+    return BSLS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// problem handle
+// ---------------------------------------------------------------------------------------------
+int bsls_lsq_create(int64_t m, int64_t n, int64_t nnz, const int64_t *a_ptr, const int32_t *a_idx, const double *a_val,
+                    const int64_t *at_ptr, const int32_t *at_idx, const double *at_val, const double *b, bsls_lsq **out) {
+    if (!out) return BSLS_ERR_ARG;
+    *out = nullptr;
+    if (int rc = device_ok()) return rc;
+    if (m <= 0 || n <= 0 || nnz < 0 || !a_ptr || !at_ptr || (nnz > 0 && (!a_idx || !at_idx))) {
+        set_error("lsq_create: need m, n > 0 and both CSR structures (A and A^T)");
+        return BSLS_ERR_ARG;
+    }
+    if (m >= (1LL << 31) || n >= (1LL << 31)) {
+        set_error("lsq_create: int32 indices as in the reference (m, n < 2^31)");
+        return BSLS_ERR_ARG;
+    }
+    bsls_lsq *q = new bsls_lsq();
+    q->m = m;
+    q->n = n;
+    q->nnz = nnz;
+    q->a_ptr = a_ptr;
+    q->a_idx = a_idx;
+    q->a_val = a_val;
+    q->t_ptr = at_ptr;
+    q->t_idx = at_idx;
+    q->t_val = at_val;
+    q->b = b;
+    q->a_mode = pick_mode(nnz, m);
+    q->t_mode = pick_mode(nnz, n);
+    if (const char *e = getenv("BSLS_SPMV_A")) q->a_mode = atoi(e);
+    if (const char *e = getenv("BSLS_SPMV_AT")) q->t_mode = atoi(e);
+    auto fail = [&](int rc) {
+        bsls_lsq_destroy(q);
+        return rc;
+    };
+#define TRY_OR_FAIL(expr)                                                                    \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return fail(BSLS_ERR_CUDA);                                                      \
+        }                                                                                    \
+    } while (0)
+    TRY_OR_FAIL(cudaMalloc(&q->r, sizeof(double) * (size_t)m));
+    TRY_OR_FAIL(cudaEventCreate(&q->ev0));
+    TRY_OR_FAIL(cudaEventCreate(&q->ev1));
+#undef TRY_OR_FAIL
+    if (int rc = bsls_ws_create(&q->ws)) return fail(rc);
+    *out = q;
+    return BSLS_OK;
+}
+
+int bsls_lsq_destroy(bsls_lsq *q) {
+    if (!q) return BSLS_OK;
+    if (q->r) cudaFree(q->r);
+    if (q->wg) cudaFree(q->wg);
+    if (q->wxn) cudaFree(q->wxn);
+    if (q->wgn) cudaFree(q->wgn);
+    bsls_ws_destroy(q->ws);
+    if (q->ev0) cudaEventDestroy(q->ev0);
+    if (q->ev1) cudaEventDestroy(q->ev1);
+    delete q;
+    return BSLS_OK;
+}
+
+int bsls_lsq_set_comm(bsls_lsq *q, bsls_comm *c) {
+    if (!q) return BSLS_ERR_ARG;
+    q->ws->comm = c;
+    return BSLS_OK;
+}
+
+bsls_ws *bsls_lsq_ws(bsls_lsq *q) { return q ? q->ws : nullptr; }
+
+int bsls_lsq_set_b(bsls_lsq *q, const double *b) {
+    if (!q) return BSLS_ERR_ARG;
+    q->b = b;
+    return BSLS_OK;
+}
+
+int bsls_lsq_set_modes(bsls_lsq *q, int a_mode, int at_mode) {
+    if (!q) return BSLS_ERR_ARG;
+    auto ok = [](int v) { return v == 0 || v == 1 || v == 4 || v == 8 || v == 16 || v == 32; };
+    if (!ok(a_mode) || !ok(at_mode)) {
+        set_error("lsq_set_modes: mode must be 0, 1, 4, 8, 16 or 32");
+        return BSLS_ERR_ARG;
+    }
+    q->a_mode = a_mode ? a_mode : pick_mode(q->nnz, q->m);
+    q->t_mode = at_mode ? at_mode : pick_mode(q->nnz, q->n);
+    return BSLS_OK;
+}
+
+const double *bsls_lsq_residual_ptr(const bsls_lsq *q) { return q ? q->r : nullptr; }
+double *bsls_lsq_scalar_ptr(const bsls_lsq *q) { return q ? q->ws->d_scal : nullptr; }
+
+int bsls_dev_lsq_residual_f64(bsls_lsq *q, const double *x, bsls_stream_t s) {
+    if (!q || !x || !q->b) {
+        set_error("lsq_residual: null handle, vector or b");
+        return BSLS_ERR_ARG;
+    }
+    return residual(q, x, q->r, q->b, (cudaStream_t)s);
+}
+
+int bsls_dev_lsq_gradient_f64(bsls_lsq *q, double *g, bsls_stream_t s) {
+    if (!q || !g) return BSLS_ERR_ARG;
+    EpiPlain epi{g};
+    return launch_spmv(q->ws, q->t_mode, q->n, q->t_ptr, q->t_idx, q->t_val, q->r, epi, (cudaStream_t)s);
+}
+
+int bsls_dev_lsq_matvec_f64(bsls_lsq *q, const double *v, double *out, bsls_stream_t s) {
+    if (!q || !v || !out) return BSLS_ERR_ARG;
+    return residual(q, v, out, nullptr, (cudaStream_t)s);
+}
+
+int bsls_dev_lsq_rmatvec_f64(bsls_lsq *q, const double *w, double *out, bsls_stream_t s) {
+    if (!q || !w || !out) return BSLS_ERR_ARG;
+    EpiPlain epi{out};
+    return launch_spmv(q->ws, q->t_mode, q->n, q->t_ptr, q->t_idx, q->t_val, w, epi, (cudaStream_t)s);
+}
+
+int bsls_lsq_scalars(bsls_lsq *q, double out[16], bsls_stream_t s) { return q ? bsls_ws_scalars(q->ws, out, s) : BSLS_ERR_ARG; }
+
+int bsls_lsq_obj_f64(bsls_lsq *q, const double *x, double *g, double *f_host, bsls_stream_t s) {
+    if (!q || !x || !g || !f_host) return BSLS_ERR_ARG;
+    if (int rc = bsls_dev_lsq_residual_f64(q, x, s)) return rc;
+    if (int rc = bsls_dev_lsq_gradient_f64(q, g, s)) return rc;
+    if (int rc = fetch_scalars(q->ws, (cudaStream_t)s)) return rc;
+    *f_host = q->ws->h_scal[kScalF];
+    return BSLS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// vector kernels
+// ---------------------------------------------------------------------------------------------
+int bsls_dev_axpby_f64(double *out, double a, const double *x, double b, const double *y, int64_t n, bsls_stream_t s) {
+    if (!out || !x || !y || n < 0) return BSLS_ERR_ARG;
+    if (int rc = device_ok()) return rc;
+    if (n == 0) return BSLS_OK;
+    axpby_kernel<<<grid_elems(n), 256, 0, (cudaStream_t)s>>>(out, a, x, b, y, n);
+    BSLS_LAUNCH_CHECK();
+    return BSLS_OK;
+}
+
+int bsls_ws_dots_f64(bsls_ws *q, int count, const double *const *x, const double *const *y, int64_t n, int want_max,
+                      double out[5], bsls_stream_t s) {
+    if (!q || count < 1 || count > 4 || !x || !y || !out || n <= 0) return BSLS_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)s;
+    DotArgs a{};
+    a.count = count;
+    a.want_max = want_max;
+    for (int k = 0; k < 4; ++k) {
+        a.x[k] = x[k < count ? k : 0];
+        a.y[k] = y[k < count ? k : 0];
+    }
+    RedCtx red = q->red;
+    red.out = q->d_scal + kScalDot0;  // slots 6..9, maximum in slot 10
+    dots_kernel<<<grid_elems(n), 256, 0, st>>>(a, n, red);
+    BSLS_LAUNCH_CHECK();
+    q->launches++;
+    if (int rc = allreduce(q, q->d_scal + kScalDot0, 4, kNcclSum, st)) return rc;
+    if (want_max)
+        if (int rc = allreduce(q, q->d_scal + kScalMax0, 1, kNcclMax, st)) return rc;
+    if (int rc = fetch_scalars(q, st)) return rc;
+    for (int k = 0; k < 5; ++k) out[k] = q->h_scal[kScalDot0 + k];
+    return BSLS_OK;
+}
+
+int bsls_dev_axpy_dot_f64(bsls_ws *q, double *d, double scale, const double *c0, const double *c1, const double *v,
+                          const double *w, double *out, int64_t n, bsls_stream_t s) {
+    if (!q || !d || n <= 0 || (w && !out)) return BSLS_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)s;
+    DevCoef c{c0, c1, scale};
+    RedCtx red = q->red;
+    red.out = w ? out : q->d_scal + (kScalCount - 1);  // slot 15 is scratch when no dot is wanted
+    axpy_dot_kernel<<<grid_elems(n), 256, 0, st>>>(d, c, v, w, n, red);
+    BSLS_LAUNCH_CHECK();
+    q->launches++;
+    if (w)
+        if (int rc = allreduce(q, out, 1, kNcclSum, st)) return rc;
+    return BSLS_OK;
+}
+
+int bsls_dev_md_update_f64(bsls_ws *q, const bsls_plan *plan, double *x_new, const double *x, const double *g, double step,
+                           int per_block_log, bsls_stream_t s) {
+    if (!q || !plan || !x_new || !x || !g) return BSLS_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)s;
+    const int lanes = lanes_for(plan);
+    const int grid = grid_groups(plan->nb, lanes);
+    DISPATCH_LANES(lanes, md_update_kernel, grid, st, x_new, x, g, step, per_block_log, layout_of(plan), q->red);
+    BSLS_LAUNCH_CHECK();
+    q->launches++;
+    return allreduce(q, q->d_scal + kScalMax0, 1, kNcclMax, st);
+}
+
+int bsls_dev_block_scale_f64(const bsls_plan *plan, double *y, const double *f, int divide, bsls_stream_t s) {
+    if (!plan || !y || !f) return BSLS_ERR_ARG;
+    if (int rc = device_ok()) return rc;
+    const int lanes = lanes_for(plan);
+    DISPATCH_LANES(lanes, block_scale_kernel, grid_groups(plan->nb, lanes), (cudaStream_t)s, y, f, divide, layout_of(plan));
+    BSLS_LAUNCH_CHECK();
+    return BSLS_OK;
+}
+
+int bsls_dev_nz_f64(const bsls_plan *plan, double *x, const double *z, int add_x0, bsls_stream_t s) {
+    if (!plan || !x || !z) return BSLS_ERR_ARG;
+    if (int rc = device_ok()) return rc;
+    const int lanes = lanes_for(plan);
+    DISPATCH_LANES(lanes, nz_kernel, grid_groups(plan->nb, lanes), (cudaStream_t)s, x, z, add_x0, layout_of(plan));
+    BSLS_LAUNCH_CHECK();
+    return BSLS_OK;
+}
+
+int bsls_dev_ntv_f64(const bsls_plan *plan, double *zg, const double *v, bsls_stream_t s) {
+    if (!plan || !zg || !v) return BSLS_ERR_ARG;
+    if (int rc = device_ok()) return rc;
+    const int lanes = lanes_for(plan);
+    DISPATCH_LANES(lanes, ntv_kernel, grid_groups(plan->nb, lanes), (cudaStream_t)s, zg, v, layout_of(plan));
+    BSLS_LAUNCH_CHECK();
+    return BSLS_OK;
+}
+
+int bsls_dev_x2z_f64(const bsls_plan *plan, const double *x, double *z, bsls_stream_t s) {
+    if (!plan || !x || !z) return BSLS_ERR_ARG;
+    if (int rc = device_ok()) return rc;
+    if (plan->first != 0) {  // c_extensions.pyx:203 asserts blocks[0] == 0
+        set_error("x2z: blocks[0] must be 0");
+        return BSLS_ERR_ARG;
+    }
+    x2z_kernel<<<grid_groups(plan->nb, 1), 256, 0, (cudaStream_t)s>>>(x, z, layout_of(plan));
+    BSLS_LAUNCH_CHECK();
+    return BSLS_OK;
+}
+
+int bsls_dev_z2x_f64(const bsls_plan *plan, double *x, const double *z, bsls_stream_t s) {
+    if (!plan || !x || !z) return BSLS_ERR_ARG;
+    if (int rc = device_ok()) return rc;
+    if (plan->first != 0) {
+        set_error("z2x: blocks[0] must be 0");
+        return BSLS_ERR_ARG;
+    }
+    z2x_kernel<<<grid_groups(plan->nb, 1), 256, 0, (cudaStream_t)s>>>(x, z, layout_of(plan));
+    BSLS_LAUNCH_CHECK();
+    return BSLS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// BATCH.solve / solve_BB / solve_MD, x-space, sparse objective
+// ---------------------------------------------------------------------------------------------
+// One objective evaluation at x_new, fused with everything the loop needs from it:
+//   r = A x_new - b, f_new = 0.5 <r,r>                               (kernel 1 [+ all-reduce])
+//   g_new = A^T r, <dx,dg>, <dg,dg>, <g,dx>, max|dx|                  (kernel 2)
+// and one 128-byte copy of the scalars to the host.
+static int eval_new(bsls_lsq *q, const double *x, const double *g, const double *x_new, double *g_new, cudaStream_t st) {
+    if (int rc = residual(q, x_new, q->r, q->b, st)) return rc;
+    EpiGradBB epi{g_new, g, x, x_new};
+    if (int rc = launch_spmv(q->ws, q->t_mode, q->n, q->t_ptr, q->t_idx, q->t_val, q->r, epi, st)) return rc;
+    if (int rc = allreduce(q->ws, q->ws->d_scal + kScalSxy, 4, kNcclSum, st)) return rc;
+    if (int rc = allreduce(q->ws, q->ws->d_scal + kScalStep, 1, kNcclMax, st)) return rc;
+    return fetch_scalars(q->ws, st);
+}
+
+int bsls_batch_solve_f64(bsls_lsq *q, const bsls_plan *plan, double *x, const bsls_batch_opts *o, bsls_batch_result *res,
+                         double *progress_f, double *progress_t, int progress_cap, bsls_stream_t s) {
+    if (!q || !plan || !x || !o || !res || !q->b) {
+        set_error("batch_solve: null argument");
+        return BSLS_ERR_ARG;
+    }
+    if (plan->n != q->n) {
+        set_error("batch_solve: plan covers %d variables, A has %lld columns", plan->n, (long long)q->n);
+        return BSLS_ERR_ARG;
+    }
+    if (o->method < 0 || o->method > 2) return BSLS_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)s;
+    if (int rc = ensure_workspace(q)) return rc;
+    const int64_t n = q->n;
+    double *xc = x, *g = q->wg, *xn = q->wxn, *gn = q->wgn;  // roles rotate by pointer swap; no vector is copied
+    const int launches0 = q->ws->launches;
+    int extra_launches = 0;
+    int evals = 0, backtracks = 0;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+
+    BSLS_CUDA_TRY(cudaEventRecord(q->ev0, st));
+    // f = obj(x, g)
+    double f = 0.0;
+    if (int rc = bsls_lsq_obj_f64(q, xc, g, &f, s)) return rc;
+    ++evals;
+    int np = 0;
+    if (progress_f && np < progress_cap) {
+        progress_f[np] = f;
+        if (progress_t) progress_t[np] = 0.0;
+        ++np;
+    }
+    const double t_start = now();
+    double f_old = INFINITY, sxy = 0.0, syy = 0.0;
+    int i = 1, stop_code = 0;
+    double stop_value = 0.0;
+    for (;;) {
+        // algorithm_utils.stopping (:158-172): later tests overwrite the reason of earlier ones
+        bool flag = false;
+        if (i == o->max_iter) {
+            stop_code = 1;
+            flag = true;
+        }
+        if (o->has_f_min && f - o->f_min < o->opt_tol) {
+            stop_code = 2;
+            stop_value = f - o->f_min;
+            flag = true;
+        }
+        if (std::fabs(f_old - f) < o->prog_tol) {
+            stop_code = 3;
+            stop_value = std::fabs(f_old - f);
+            flag = true;
+        }
+        if (flag) break;
+        // ---- trial point ---------------------------------------------------------------------
+        if (o->method == 2) {
+            const double t = 1.0 / (o->min_eig * i + 1.0);  // decreasing_step_size(i, 1.0, min_eig)
+            if (int rc = bsls_dev_md_update_f64(q->ws, plan, xn, xc, g, t, 0, s)) return rc;
+        } else {
+            double t;
+            if (o->method == 1)
+                t = (i == 1) ? 1.0 : sxy / syy;  // BATCH.py:87-91
+            else
+                t = 1.0 / (o->min_eig * i + 1.0);  // BATCH.py:38
+            axpby_kernel<<<grid_elems(n), 256, 0, st>>>(xn, 1.0, xc, -t, g, n);
+            BSLS_LAUNCH_CHECK();
+            ++extra_launches;
+            if (o->proj_mode == 2) {  // z-space: isotonic regression + clip to [0,1] (algorithm_utils.py:219-224)
+                if (int rc = pava_clip_f64(plan, xn, nullptr, 1, 1, st)) return rc;
+            } else {
+                if (int rc = project_f64(plan, xn, o->proj_mode, st)) return rc;
+            }
+            ++extra_launches;
+        }
+        if (int rc = eval_new(q, xc, g, xn, gn, st)) return rc;
+        ++evals;
+        double f_new = q->ws->h_scal[kScalF];
+        // ---- line_search_np (algorithm_utils.py:113-137) ------------------------------------------
+        const bool search = (o->method == 1) || (o->method == 0 && o->use_line_search);
+        if (search) {
+            double t = 1.0;
+            double upper = f + 1e-4 * q->ws->h_scal[kScalGd];
+            while (f_new > upper) {
+                t *= .8;
+                if (q->ws->h_scal[kScalStep] < 1e-12) {  // step too small: stay where we are
+                    f_new = f;
+                    BSLS_CUDA_TRY(cudaMemcpyAsync(gn, g, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+                    BSLS_CUDA_TRY(cudaMemcpyAsync(xn, xc, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+                    q->ws->h_scal[kScalSxy] = 0.0;
+                    q->ws->h_scal[kScalSyy] = 0.0;
+                    break;
+                }
+                axpby_kernel<<<grid_elems(n), 256, 0, st>>>(xn, 1.0 - t, xc, t, xn, n);
+                BSLS_LAUNCH_CHECK();
+                ++extra_launches;
+                if (int rc = eval_new(q, xc, g, xn, gn, st)) return rc;
+                ++evals;
+                ++backtracks;
+                f_new = q->ws->h_scal[kScalF];
+                upper = f + 1e-4 * q->ws->h_scal[kScalGd];
+            }
+        }
+        // ---- take the step: delta_x / delta_g only ever enter through their dot products -------------
+        sxy = q->ws->h_scal[kScalSxy];
+        syy = q->ws->h_scal[kScalSyy];
+        f_old = f;
+        f = f_new;
+        double *tx = xc, *tg = g;
+        xc = xn;
+        g = gn;
+        xn = tx;
+        gn = tg;
+        ++i;
+        if (progress_f && np < progress_cap) {
+            progress_f[np] = f;
+            if (progress_t) progress_t[np] = now() - t_start;
+            ++np;
+        }
+    }
+    if (xc != x) BSLS_CUDA_TRY(cudaMemcpyAsync(x, xc, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+    BSLS_CUDA_TRY(cudaEventRecord(q->ev1, st));
+    BSLS_CUDA_TRY(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    BSLS_CUDA_TRY(cudaEventElapsedTime(&ms, q->ev0, q->ev1));
+    res->f = f;
+    res->iterations = i;
+    res->stop_code = stop_code;
+    res->stop_value = stop_value;
+    res->obj_evals = evals;
+    res->backtracks = backtracks;
+    res->kernel_launches = (q->ws->launches - launches0) + extra_launches;
+    res->device_ms = ms;
+    return BSLS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,482 @@
+// lsq.cuh -- the sparse least-squares half of the hot path on sm_100a: the SpMV pair
+// r = A x - b, g = A^T r with the solver epilogues fused in, plus the vector and
+// per-block kernels the solver drivers are made of.
+//
+// Replaces, in the reference:
+//   sparse_least_squares_obj            python/algorithm_utils.py:88-94   (two scipy CSR mat-vecs + dot)
+//   BATCH.solve_BB update / deltas      python/BATCH.py:87-102
+//   BATCH.solve_MD / mirror_descent     python/BATCH.py:238-241, python/mirror_descent.py:39-47
+//   normalization                       python/algorithm_utils.py:175-179
+//   N z, N^T v (z-space)                python/main.py:53-54, python/bsls_utils.py:139-162
+//   x2z_c / z2x_c                       python/c_extensions/c_extensions.pyx:195-248
+//
+// Everything here is HBM/L2-bound: A is streamed once per product (12 B per non-zero, or
+// 4 B when the values are implicit ones), the gathered vector is served by L2.  No tensor
+// cores.  Two SpMV shapes, picked per matrix side from its mean row length:
+//   * STREAM (short rows: A^T has one row per route, a handful of links each): a CTA pulls
+//     the contiguous non-zero range of 256 rows through shared memory with coalesced loads,
+//     forming the products on the way; each thread then sums its own row LEFT TO RIGHT --
+//     the order scipy's csr_matvec uses, so the result is bit-identical to the reference.
+//   * VECTOR (long rows: A has one row per link, hundreds of routes each): LANES lanes per
+//     row, strided, four gathers in flight per lane, xor-shuffle tree.
+// Reductions (objective value, BB dot products) are deterministic: per-CTA partials, the
+// last CTA to finish adds them in a fixed order.
+#pragma once
+#include "common.cuh"
+
+namespace bsls {
+
+constexpr int kRedMaxGrid = 148 * 8;  // upper bound on any reducing kernel's grid
+constexpr int kRedSlots = 8;          // accumulators per CTA (sums first, maxima after)
+
+struct RedCtx {
+    double *partials;   // kRedMaxGrid * kRedSlots
+    unsigned *ticket;   // zero between launches
+    double *out;        // device scalars written by the finishing CTA
+};
+
+// ---- deterministic grid reduction ------------------------------------------------------
+// acc[0..NSUM) are added, acc[NSUM..NSUM+NMAX) are maximised.  FIN maps slot k and the grid
+// total to the value stored in red.out[FIN::slot(k)].
+template <int NSUM, int NMAX, int THREADS, class FIN>
+__device__ __forceinline__ void grid_reduce(double (&acc)[NSUM + NMAX], const RedCtx &red) {
+    constexpr int N = NSUM + NMAX;
+    static_assert(N <= kRedSlots, "too many accumulators");
+    __shared__ double s_w[THREADS / 32][N];
+    __shared__ bool s_last;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        double v = acc[k];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const double u = __shfl_xor_sync(0xffffffffu, v, o);
+            v = (k < NSUM) ? v + u : fmax(v, u);
+        }
+        if (lane == 0) s_w[wid][k] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            double v = s_w[0][k];
+            for (int w = 1; w < THREADS / 32; ++w) v = (k < NSUM) ? v + s_w[w][k] : fmax(v, s_w[w][k]);
+            red.partials[(size_t)blockIdx.x * kRedSlots + k] = v;
+        }
+        __threadfence();
+        const unsigned t = atomicAdd(red.ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // the finishing CTA: fixed assignment of partials to threads, then the same tree as above
+    double tot[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) tot[k] = 0.0;  // maxima are of absolute values (>= 0)
+    for (int b = tid; b < (int)gridDim.x; b += THREADS) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            const double u = __ldcg(&red.partials[(size_t)b * kRedSlots + k]);
+            tot[k] = (k < NSUM) ? tot[k] + u : fmax(tot[k], u);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        double v = tot[k];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const double u = __shfl_xor_sync(0xffffffffu, v, o);
+            v = (k < NSUM) ? v + u : fmax(v, u);
+        }
+        if (lane == 0) s_w[wid][k] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            double v = s_w[0][k];
+            for (int w = 1; w < THREADS / 32; ++w) v = (k < NSUM) ? v + s_w[w][k] : fmax(v, s_w[w][k]);
+            FIN::store(red.out, k, v);
+        }
+        *red.ticket = 0u;
+    }
+}
+
+// ---- device scalar slots (bsls_lsq::d_scal) -------------------------------------------------
+enum Scal {
+    kScalF = 0,     // 0.5 <r, r>
+    kScalSxy = 1,   // <x_new - x, g_new - g>
+    kScalSyy = 2,   // <g_new - g, g_new - g>
+    kScalGd = 3,    // <g, x_new - x>
+    kScalGnn = 4,   // <g_new, g_new>
+    kScalStep = 5,  // max |x_new - x|
+    kScalDot0 = 6,  // generic dot products: 6..9
+    kScalMax0 = 10, // generic maximum
+    kScalRR = 11,   // <r, r> (not halved)
+    kScalCount = 16
+};
+
+// ---- SpMV epilogues ----------------------------------------------------------------------------
+// An epilogue sees (row, dot) once per row and accumulates into acc[].
+struct EpiResidual {  // r = A x - b ; f = 0.5 <r, r>       (algorithm_utils.py:91,93)
+    static constexpr int NSUM = 1, NMAX = 0;
+    double *r;
+    const double *b;  // may be null (partial product of one rank: b is subtracted after the all-reduce)
+    __device__ __forceinline__ void apply(int64_t i, double dot, double (&acc)[1]) const {
+        const double v = b ? dot - b[i] : dot;
+        r[i] = v;
+        acc[0] += v * v;
+    }
+    static __device__ __forceinline__ void store(double *out, int k, double v) {
+        out[kScalF] = 0.5 * v;
+        out[kScalRR] = v;
+    }
+};
+struct EpiPlain {  // out = M v
+    static constexpr int NSUM = 1, NMAX = 0;
+    double *out;
+    __device__ __forceinline__ void apply(int64_t i, double dot, double (&acc)[1]) const {
+        out[i] = dot;
+        acc[0] += dot * dot;
+    }
+    static __device__ __forceinline__ void store(double *o, int k, double v) { o[kScalGnn] = v; }
+};
+struct EpiGradBB {  // g_new = A^T r and the Barzilai-Borwein / line-search dot products (BATCH.py:89,99-100; algorithm_utils.py:120)
+    static constexpr int NSUM = 4, NMAX = 1;
+    double *g_new;
+    const double *g, *x, *x_new;
+    __device__ __forceinline__ void apply(int64_t i, double dot, double (&acc)[5]) const {
+        const double go = g[i];
+        const double dx = x_new[i] - x[i];
+        const double dg = dot - go;
+        g_new[i] = dot;
+        acc[0] += dx * dg;
+        acc[1] += dg * dg;
+        acc[2] += go * dx;
+        acc[3] += dot * dot;
+        acc[4] = fmax(acc[4], fabs(dx));
+    }
+    static __device__ __forceinline__ void store(double *o, int k, double v) {
+        constexpr int slot[5] = {kScalSxy, kScalSyy, kScalGd, kScalGnn, kScalStep};
+        o[slot[k]] = v;
+    }
+};
+
+__device__ __forceinline__ int pad16(int k) { return k + (k >> 4); }  // one spare double per 128-byte row
+
+// ---- STREAM SpMV: thread per row, non-zeros staged through shared memory ----------------------
+template <class Epi, int THREADS, int CHUNK>
+__global__ void __launch_bounds__(THREADS)
+spmv_stream_kernel(int64_t rows, const int64_t *__restrict__ ptr, const int32_t *__restrict__ idx,
+                   const double *__restrict__ val, const double *__restrict__ v, Epi epi, RedCtx red) {
+    __shared__ double prod[CHUNK + CHUNK / 16 + 2];
+    __shared__ int64_t s_range[2];
+    constexpr int NA = Epi::NSUM + Epi::NMAX;
+    double acc[NA];
+#pragma unroll
+    for (int k = 0; k < NA; ++k) acc[k] = 0.0;
+    const int tid = threadIdx.x;
+    const int64_t ntiles = (rows + THREADS - 1) / THREADS;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t row = tile * THREADS + tid;
+        const bool valid = row < rows;
+        const int64_t p0 = valid ? ptr[row] : 0, p1 = valid ? ptr[row + 1] : 0;
+        const int64_t last = min(rows, (tile + 1) * THREADS) - 1;
+        if (tid == 0) s_range[0] = p0;
+        if (row == last) s_range[1] = p1;
+        __syncthreads();
+        const int64_t base = s_range[0], end = s_range[1];
+        __syncthreads();  // s_range may be rewritten for the next tile from here on
+        double sum = 0.0;
+        for (int64_t c = base; c < end; c += CHUNK) {
+            const int cnt = (int)min((int64_t)CHUNK, end - c);
+            const int32_t *ci = idx + c;
+            int k = tid;
+            for (; k + 3 * THREADS < cnt; k += 4 * THREADS) {  // four gathers in flight per thread
+                int32_t j[4];
+                double a[4], w[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) j[u] = __ldcs(ci + k + u * THREADS);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) a[u] = val ? __ldcs(val + c + k + u * THREADS) : 1.0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) w[u] = v[j[u]];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) prod[pad16(k + u * THREADS)] = a[u] * w[u];
+            }
+            for (; k < cnt; k += THREADS) {
+                const double a = val ? __ldcs(val + c + k) : 1.0;
+                prod[pad16(k)] = a * v[__ldcs(ci + k)];
+            }
+            __syncthreads();
+            const int64_t lo = max(p0, c), hi = min(p1, c + cnt);
+            for (int64_t p = lo; p < hi; ++p) sum += prod[pad16((int)(p - c))];  // left to right, as csr_matvec
+            __syncthreads();
+        }
+        if (valid) epi.apply(row, sum, acc);
+    }
+    grid_reduce<Epi::NSUM, Epi::NMAX, THREADS, Epi>(acc, red);
+}
+
+// ---- VECTOR SpMV: LANES lanes per row ------------------------------------------------------------
+template <class Epi, int THREADS, int LANES>
+__global__ void __launch_bounds__(THREADS)
+spmv_vector_kernel(int64_t rows, const int64_t *__restrict__ ptr, const int32_t *__restrict__ idx,
+                   const double *__restrict__ val, const double *__restrict__ v, Epi epi, RedCtx red) {
+    constexpr int NA = Epi::NSUM + Epi::NMAX;
+    double acc[NA];
+#pragma unroll
+    for (int k = 0; k < NA; ++k) acc[k] = 0.0;
+    const int sub = threadIdx.x & (LANES - 1);
+    const int64_t group = ((int64_t)blockIdx.x * THREADS + threadIdx.x) / LANES;
+    const int64_t ngroups = (int64_t)gridDim.x * THREADS / LANES;
+    const int64_t rounds = (rows + ngroups - 1) / ngroups;  // uniform trip count: shuffles stay converged
+    for (int64_t it = 0; it < rounds; ++it) {
+        const int64_t row = it * ngroups + group;
+        const bool valid = row < rows;
+        const int64_t p0 = valid ? ptr[row] : 0, p1 = valid ? ptr[row + 1] : 0;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int64_t p = p0 + sub;
+        for (; p + 3 * LANES < p1; p += 4 * LANES) {
+            const int32_t j0 = __ldcs(idx + p), j1 = __ldcs(idx + p + LANES), j2 = __ldcs(idx + p + 2 * LANES),
+                          j3 = __ldcs(idx + p + 3 * LANES);
+            double a0 = 1.0, a1 = 1.0, a2 = 1.0, a3 = 1.0;
+            if (val) {
+                a0 = __ldcs(val + p);
+                a1 = __ldcs(val + p + LANES);
+                a2 = __ldcs(val + p + 2 * LANES);
+                a3 = __ldcs(val + p + 3 * LANES);
+            }
+            const double w0 = v[j0], w1 = v[j1], w2 = v[j2], w3 = v[j3];
+            s0 += a0 * w0;
+            s1 += a1 * w1;
+            s2 += a2 * w2;
+            s3 += a3 * w3;
+        }
+        for (; p < p1; p += LANES) s0 += (val ? __ldcs(val + p) : 1.0) * v[__ldcs(idx + p)];
+        double sum = (s0 + s1) + (s2 + s3);
+#pragma unroll
+        for (int o = LANES / 2; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (valid && sub == 0) epi.apply(row, sum, acc);
+    }
+    grid_reduce<Epi::NSUM, Epi::NMAX, THREADS, Epi>(acc, red);
+}
+
+// ---- vector kernels -------------------------------------------------------------------------------
+// out = a x + b y, each product rounded on its own (np.add(x, -t*g, x_new); (1-t)*x + t*x_new)
+// `out` may alias x or y (element i is read before it is written).
+__global__ void __launch_bounds__(256) axpby_kernel(double *out, double a, const double *x, double b, const double *y, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const double u = a * x[i];
+        out[i] = u + b * y[i];
+    }
+}
+
+// out = a x + b y with a, b read from device scalars: a = sa * *pa (or sa), b = sb * (*pb0 - *pb1)
+struct DevCoef {
+    const double *p0, *p1;  // value = s * ((p0 ? *p0 : 1) - (p1 ? *p1 : 0))
+    double s;
+    __device__ __forceinline__ double get() const { return s * ((p0 ? *p0 : 1.0) - (p1 ? *p1 : 0.0)); }
+};
+
+struct FinDots {
+    static __device__ __forceinline__ void store(double *o, int k, double v) { o[k] = v; }
+};
+
+// up to four dot products <x_k, y_k> in one pass and max |x_0 - y_0| ; results to out[0..3], out[4]
+struct DotArgs {
+    const double *x[4], *y[4];
+    int count;
+    int want_max;  // 1: out[4] = max |x0 - y0|
+};
+__global__ void __launch_bounds__(256) dots_kernel(DotArgs a, int64_t n, RedCtx red) {
+    double acc[5] = {0, 0, 0, 0, 0};
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (k < a.count) acc[k] += a.x[k][i] * a.y[k][i];
+        if (a.want_max) acc[4] = fmax(acc[4], fabs(a.x[0][i] - a.y[0][i]));
+    }
+    grid_reduce<4, 1, 256, FinDots>(acc, red);
+}
+
+// d <- d + c * v  (c from device scalars) and, in the same pass, <w, d_new> -> out[0]  scaled by *scale
+// The L-BFGS two-loop recursion chains these without the host (LBFGS.py:60-71, BATCH.py:196-214).
+struct FinScaled {
+    static __device__ __forceinline__ void store(double *o, int k, double v) { o[k] = v; }
+};
+__global__ void __launch_bounds__(256) axpy_dot_kernel(double *__restrict__ d, DevCoef c, const double *v, const double *w, int64_t n,
+                                                        RedCtx red) {
+    const double cc = c.get();
+    double acc[1] = {0};
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        double di = d[i];
+        if (v) {
+            di = di + cc * v[i];
+            d[i] = di;
+        } else if (cc != 1.0) {
+            di = cc * di;
+            d[i] = di;
+        }
+        if (w) acc[0] += w[i] * di;
+    }
+    grid_reduce<1, 0, 256, FinScaled>(acc, red);
+}
+
+// r <- r - b ; f = 0.5 <r, r>   (after the all-reduce of the per-rank partial products)
+struct FinResidual {
+    static __device__ __forceinline__ void store(double *o, int k, double v) {
+        o[kScalF] = 0.5 * v;
+        o[kScalRR] = v;
+    }
+};
+__global__ void __launch_bounds__(256) residual_finish_kernel(double *__restrict__ r, const double *__restrict__ b, int64_t m, RedCtx red) {
+    double acc[1] = {0};
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < m; i += (int64_t)gridDim.x * 256) {
+        const double v = r[i] - b[i];
+        r[i] = v;
+        acc[0] += v * v;
+    }
+    grid_reduce<1, 0, 256, FinResidual>(acc, red);
+}
+
+// ---- per-block kernels: G lanes per block ---------------------------------------------------------
+struct BlockLayout {
+    const int32_t *starts;  // nb + 1 entries (last = n); ignored when uniform > 0
+    int nb;
+    int uniform;            // common block size or 0
+    int first;              // first index of block 0
+    __device__ __forceinline__ void range(int b, int &s, int &e) const {
+        if (uniform > 0) {
+            s = first + b * uniform;
+            e = s + uniform;
+        } else {
+            s = starts[b];
+            e = starts[b + 1];
+        }
+    }
+};
+
+// mirror-descent update: x_new = x * exp(-t g), then every block divided by its sum.
+//   per_block_log == 0: t = step                          (BATCH.py:239-241, algorithm_utils.py:175-179)
+//   per_block_log == 1: t = sqrt(2 ln K_block) / step     (mirror_descent.py:26-28,39-47; step = sqrt(k) * Lf)
+// out[kScalMax0] = max |x_new - x| (mirror_descent.py:50)
+struct FinMax {
+    static __device__ __forceinline__ void store(double *o, int k, double v) { o[kScalMax0] = v; }
+};
+template <int G>
+__global__ void __launch_bounds__(256) md_update_kernel(double *__restrict__ xn, const double *__restrict__ x, const double *__restrict__ g,
+                                                         double step, int per_block_log, BlockLayout lay, RedCtx red) {
+    const int sub = threadIdx.x & (G - 1);
+    const int64_t group = ((int64_t)blockIdx.x * 256 + threadIdx.x) / G;
+    const int64_t ngroups = (int64_t)gridDim.x * 256 / G;
+    const int64_t rounds = (lay.nb + ngroups - 1) / ngroups;
+    double acc[1] = {0};
+    for (int64_t it = 0; it < rounds; ++it) {
+        const int64_t b = it * ngroups + group;
+        const bool valid = b < lay.nb;
+        int s = 0, e = 0;
+        if (valid) lay.range((int)b, s, e);
+        double t = step;
+        if (per_block_log) t = sqrt(2.0 * log((double)(e - s > 0 ? e - s : 1))) / step;
+        double sum = 0.0;
+        for (int i = s + sub; i < e; i += G) {
+            const double up = per_block_log ? g[i] * t : -t * g[i];
+            const double w = x[i] * exp(per_block_log ? -up : up);
+            xn[i] = w;
+            sum += w;
+        }
+#pragma unroll
+        for (int o = G / 2; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        for (int i = s + sub; i < e; i += G) {
+            const double w = xn[i] / sum;
+            xn[i] = w;
+            acc[0] = fmax(acc[0], fabs(w - x[i]));
+        }
+    }
+    grid_reduce<0, 1, 256, FinMax>(acc, red);
+}
+
+// per-block scale: y[block k] <- y * f_k or y / f_k (get_solver_parts with f given, algorithm_utils.py:232-265)
+template <int G>
+__global__ void __launch_bounds__(256) block_scale_kernel(double *__restrict__ y, const double *__restrict__ f, int divide, BlockLayout lay) {
+    const int sub = threadIdx.x & (G - 1);
+    const int64_t group = ((int64_t)blockIdx.x * 256 + threadIdx.x) / G;
+    const int64_t ngroups = (int64_t)gridDim.x * 256 / G;
+    for (int64_t b = group; b < lay.nb; b += ngroups) {
+        int s, e;
+        lay.range((int)b, s, e);
+        const double k = f[b];
+        for (int i = s + sub; i < e; i += G) y[i] = divide ? y[i] / k : y[i] * k;
+    }
+}
+
+// x = x0 + N z: x_l = z_l - z_{l-1} inside a block (z_{-1} = 0, the last entry is -z_last [+ 1 when add_x0]).
+// Block b of x starts at s_b, the matching block of z at s_b - b (bsls_utils.py:139-162,327-328).
+template <int G>
+__global__ void __launch_bounds__(256) nz_kernel(double *__restrict__ x, const double *__restrict__ z, int add_x0, BlockLayout lay) {
+    const int sub = threadIdx.x & (G - 1);
+    const int64_t group = ((int64_t)blockIdx.x * 256 + threadIdx.x) / G;
+    const int64_t ngroups = (int64_t)gridDim.x * 256 / G;
+    for (int64_t b = group; b < lay.nb; b += ngroups) {
+        int s, e;
+        lay.range((int)b, s, e);
+        const int64_t zoff = (int64_t)b + lay.first;  // z index = x index - zoff
+        for (int i = s + sub; i < e; i += G) {
+            const double hi = (i < e - 1) ? z[i - zoff] : 0.0;
+            const double lo = (i > s) ? z[i - zoff - 1] : 0.0;
+            double v = hi - lo;
+            if (add_x0 && i == e - 1) v = 1.0 + v;
+            x[i] = v;
+        }
+    }
+}
+
+// z-gradient = N^T v: (N^T v)_l = v_l - v_{l+1} for l < K - 1
+template <int G>
+__global__ void __launch_bounds__(256) ntv_kernel(double *__restrict__ zg, const double *__restrict__ v, BlockLayout lay) {
+    const int sub = threadIdx.x & (G - 1);
+    const int64_t group = ((int64_t)blockIdx.x * 256 + threadIdx.x) / G;
+    const int64_t ngroups = (int64_t)gridDim.x * 256 / G;
+    for (int64_t b = group; b < lay.nb; b += ngroups) {
+        int s, e;
+        lay.range((int)b, s, e);
+        const int64_t zoff = (int64_t)b + lay.first;
+        for (int i = s + sub; i < e - 1; i += G) zg[i - zoff] = v[i] - v[i + 1];
+    }
+}
+
+// x -> z: running sums of a block without its last entry, summed left to right by one thread so
+// that the result is bit-identical to the reference (c_extensions.pyx:195-220, bsls_utils.py:267-287)
+__global__ void __launch_bounds__(256) x2z_kernel(const double *__restrict__ x, double *__restrict__ z, BlockLayout lay) {
+    for (int64_t b = (int64_t)blockIdx.x * 256 + threadIdx.x; b < lay.nb; b += (int64_t)gridDim.x * 256) {
+        int s, e;
+        lay.range((int)b, s, e);
+        const int64_t zoff = b + lay.first;
+        double run = 0.0;
+        for (int i = s; i < e - 1; ++i) {
+            run += x[i];
+            z[i - zoff] = run;
+        }
+    }
+}
+
+// z -> x: adjacent differences, last entry 1 - z_last (c_extensions.pyx:223-248)
+__global__ void __launch_bounds__(256) z2x_kernel(double *__restrict__ x, const double *__restrict__ z, BlockLayout lay) {
+    for (int64_t b = (int64_t)blockIdx.x * 256 + threadIdx.x; b < lay.nb; b += (int64_t)gridDim.x * 256) {
+        int s, e;
+        lay.range((int)b, s, e);
+        const int64_t zoff = b + lay.first;
+        double before = 0.0;
+        for (int i = s; i < e - 1; ++i) {
+            const double zi = z[i - zoff];
+            x[i] = zi - before;
+            before = zi;
+        }
+        x[e - 1] = 1.0 - before;
+    }
+}
+
+}  // namespace bsls

@@ -110,6 +110,122 @@ BSLS_API int bsls_dev_proj_multi_ball_f32(const bsls_plan *plan, float *y, bsls_
 BSLS_API int bsls_dev_isotonic_regression_multi_f64(const bsls_plan *plan, double *y, int32_t *weight, int update, int clip01, bsls_stream_t stream);
 BSLS_API int bsls_dev_isotonic_regression_multi_f32(const bsls_plan *plan, float *y, int32_t *weight, int update, int clip01, bsls_stream_t stream);
 
+
+/* x <-> z change of variables (a7): z = running sums of every block without its last entry,
+ * summed left to right; inverse = adjacent differences, last entry 1 - z_last.
+ * replaces x2z_c / z2x_c (python/c_extensions/c_extensions.pyx:195-248).  plan->first must be 0. */
+BSLS_API int bsls_dev_x2z_f64(const bsls_plan *plan, const double *x, double *z, bsls_stream_t stream);
+BSLS_API int bsls_dev_z2x_f64(const bsls_plan *plan, double *x, const double *z, bsls_stream_t stream);
+/* x = N z (+ x0 when add_x0 != 0) and zg = N^T v for the bidiagonal N of
+ * python/bsls_utils.py:139-162 (x0 = particular_x0, :327-328); the z-space closures of
+ * python/main.py:53-54 are built from these two and the SpMV pair below. */
+BSLS_API int bsls_dev_nz_f64(const bsls_plan *plan, double *x, const double *z, int add_x0, bsls_stream_t stream);
+BSLS_API int bsls_dev_ntv_f64(const bsls_plan *plan, double *zg, const double *v, bsls_stream_t stream);
+/* y[block k] *= f[k]  (divide == 0)  or  /= f[k]  (divide != 0): the f-scaled projections of
+ * get_solver_parts (python/algorithm_utils.py:232-265) */
+BSLS_API int bsls_dev_block_scale_f64(const bsls_plan *plan, double *y, const double *f, int divide, bsls_stream_t stream);
+
+/* ================================================================================== */
+/* sparse least-squares objective, solver steps (a9-a17 of SURVEY section 8)           */
+/* ================================================================================== */
+
+/* Multi-GPU: OD blocks (columns of A) are sharded over ranks; the partial link vector A_p x_p
+ * is summed with one ncclAllReduce per objective evaluation.  The communicator is NCCL's,
+ * loaded at run time from `nccl_path` (NULL: "libnccl.so.2"). */
+typedef struct bsls_comm bsls_comm;
+BSLS_API int bsls_comm_unique_id(const char *nccl_path, char id[128]);
+BSLS_API int bsls_comm_create(const char *nccl_path, int nranks, int rank, const char id[128], bsls_comm **out);
+BSLS_API int bsls_comm_destroy(bsls_comm *comm);
+BSLS_API int bsls_comm_allreduce_sum_f64(bsls_comm *comm, double *d_buf, int64_t count, bsls_stream_t stream);
+
+/* The problem 0.5 |A x - b|^2.  A is given as CSR with m rows and A^T as CSR with n rows -- the
+ * two matrices the reference keeps (python/algorithm_utils.py:199-200).  All arrays are DEVICE
+ * arrays owned by the caller and must outlive the handle.  a_val / at_val may be NULL: every
+ * stored entry is 1 (route-link incidence, python/bsls_utils.py:494-507).  The handle owns an
+ * m-vector for the residual, three n-vectors of solver workspace (allocated on first use) and
+ * the reduction scratch.  One stream at a time per handle. */
+typedef struct bsls_lsq bsls_lsq;
+/* Reduction workspace: scratch of the deterministic grid reductions, a block of 16 device
+ * scalars with a pinned host mirror, and (optionally) the communicator over which dot
+ * products and maxima are summed.  Every bsls_lsq owns one (bsls_lsq_ws); solver drivers that
+ * have no matrix create their own.  One stream at a time per workspace. */
+typedef struct bsls_ws bsls_ws;
+BSLS_API int bsls_ws_create(bsls_ws **out);
+BSLS_API int bsls_ws_destroy(bsls_ws *ws);
+BSLS_API int bsls_ws_set_comm(bsls_ws *ws, bsls_comm *comm);
+BSLS_API double *bsls_ws_scalar_ptr(const bsls_ws *ws);           /* device pointer, 16 entries */
+/* device scalars -> host (synchronises the stream): [0]=f [1]=<dx,dg> [2]=<dg,dg> [3]=<g,dx>
+ * [4]=<g_new,g_new> [5]=max|dx| [6..9]=generic dots [10]=generic max [11]=<r,r> */
+BSLS_API int bsls_ws_scalars(bsls_ws *ws, double out[16], bsls_stream_t stream);
+
+BSLS_API int bsls_lsq_create(int64_t m, int64_t n, int64_t nnz,
+                             const int64_t *a_ptr, const int32_t *a_idx, const double *a_val,
+                             const int64_t *at_ptr, const int32_t *at_idx, const double *at_val,
+                             const double *b, bsls_lsq **out);
+BSLS_API int bsls_lsq_destroy(bsls_lsq *lsq);
+BSLS_API int bsls_lsq_set_comm(bsls_lsq *lsq, bsls_comm *comm);   /* NULL: single GPU */
+BSLS_API bsls_ws *bsls_lsq_ws(bsls_lsq *lsq);
+BSLS_API int bsls_lsq_set_b(bsls_lsq *lsq, const double *b);
+/* kernel choice per side: 0 = from the mean row length, 1 = stream, 4/8/16/32 = lanes per row */
+BSLS_API int bsls_lsq_set_modes(bsls_lsq *lsq, int a_mode, int at_mode);
+
+/* replaces sparse_least_squares_obj (python/algorithm_utils.py:88-94): g <- A^T (A x - b),
+ * *f_host = 0.5 |A x - b|^2.  Blocks until f is on the host. */
+BSLS_API int bsls_lsq_obj_f64(bsls_lsq *lsq, const double *x, double *g, double *f_host, bsls_stream_t stream);
+/* the same in two asynchronous halves; the residual stays inside the handle */
+BSLS_API int bsls_dev_lsq_residual_f64(bsls_lsq *lsq, const double *x, bsls_stream_t stream);
+BSLS_API int bsls_dev_lsq_gradient_f64(bsls_lsq *lsq, double *g, bsls_stream_t stream);
+/* plain products: out = A v (m entries, summed over ranks) and out = A^T w (n entries) -- the
+ * `linop` / `linop_T` of DORE.solve (python/DORE.py:6, python/gradient_descent.py:62-63) */
+BSLS_API int bsls_dev_lsq_matvec_f64(bsls_lsq *lsq, const double *v, double *out, bsls_stream_t stream);
+BSLS_API int bsls_dev_lsq_rmatvec_f64(bsls_lsq *lsq, const double *w, double *out, bsls_stream_t stream);
+BSLS_API int bsls_lsq_scalars(bsls_lsq *lsq, double out[16], bsls_stream_t stream);
+BSLS_API const double *bsls_lsq_residual_ptr(const bsls_lsq *lsq);   /* device pointer, m entries */
+BSLS_API double *bsls_lsq_scalar_ptr(const bsls_lsq *lsq);           /* device pointer, 16 entries */
+
+/* vector kernels of the solver drivers (all on device buffers) */
+/* out = a x + b y, every product rounded separately (np.add(x, -t*g, x_new), python/BATCH.py:91) */
+BSLS_API int bsls_dev_axpby_f64(double *out, double a, const double *x, double b, const double *y, int64_t n, bsls_stream_t stream);
+/* count <= 4 dot products <x_k, y_k> in one pass (summed over ranks), and max |x_0 - y_0| when
+ * want_max; blocking, results in out[0..3] and out[4] */
+BSLS_API int bsls_ws_dots_f64(bsls_ws *ws, int count, const double *const *x, const double *const *y, int64_t n,
+                               int want_max, double out[5], bsls_stream_t stream);
+/* d <- d + c v with c = scale * ((c0 ? *c0 : 1) - (c1 ? *c1 : 0)) read from DEVICE scalars (v NULL:
+ * d <- c d), and *out (a DEVICE double, summed over ranks) <- <w, d> in the same pass (w NULL: no
+ * dot).  Chains the L-BFGS two-loop recursion without the host (python/LBFGS.py:60-71,
+ * python/BATCH.py:196-214). */
+BSLS_API int bsls_dev_axpy_dot_f64(bsls_ws *ws, double *d, double scale, const double *c0, const double *c1, const double *v,
+                                   const double *w, double *out, int64_t n, bsls_stream_t stream);
+/* mirror-descent step: x_new = x * exp(-t g), every block divided by its sum; scalar slot 10 =
+ * max |x_new - x|.  per_block_log == 0: t = step (python/BATCH.py:238-241);
+ * per_block_log != 0: t = sqrt(2 ln K_block) / step (python/mirror_descent.py:26-28,39-47). */
+BSLS_API int bsls_dev_md_update_f64(bsls_ws *ws, const bsls_plan *plan, double *x_new, const double *x, const double *g,
+                                    double step, int per_block_log, bsls_stream_t stream);
+
+/* The x-space BATCH solvers of the reference, run entirely by the library (no Python in the
+ * loop): method 0 = solve (projected gradient, step 1/(min_eig*i+1)), 1 = solve_BB, 2 = solve_MD
+ * (python/BATCH.py:7-106,217-250) with get_solver_parts' sparse objective, proj_multi_simplex_c
+ * (proj_mode 0) or proj_multi_ball_c (1) and line_search_np (python/algorithm_utils.py:113-137). */
+typedef struct {
+    int method;          /* 0 projected gradient, 1 Barzilai-Borwein, 2 mirror descent */
+    int proj_mode;       /* 0 simplex, 1 l1-ball, 2 isotonic regression + clip to [0,1] (problem posed in z) */
+    int use_line_search; /* BB always searches; solve() only when given one */
+    int has_f_min;
+    double f_min, opt_tol, prog_tol, min_eig;
+    int max_iter;
+} bsls_batch_opts;
+typedef struct {
+    double f;
+    int iterations;      /* the reference's counter `i` at exit */
+    int stop_code;       /* 1 max_iter, 2 f - f_min < opt_tol, 3 |f_old - f| < prog_tol */
+    double stop_value;   /* the number the reference formats into its stop string */
+    int obj_evals, backtracks, kernel_launches;
+    double device_ms;    /* CUDA-event time of the whole loop */
+} bsls_batch_result;
+BSLS_API int bsls_batch_solve_f64(bsls_lsq *lsq, const bsls_plan *plan, double *x, const bsls_batch_opts *opts,
+                                  bsls_batch_result *res, double *progress_f, double *progress_t, int progress_cap,
+                                  bsls_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

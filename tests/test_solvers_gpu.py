@@ -1,0 +1,402 @@
+"""GPU parity tests of the sparse least-squares / solver surface against (i) the golden
+fixtures produced by the reference's own modules and (ii) the pinned CPU oracle.
+
+Tolerances (BASELINE.json north_star): objective values and vectors within 1e-6 relative in
+fp64; the SpMV in STREAM mode keeps the reference's left-to-right row sums and is compared
+bit for bit."""
+import os
+from collections import deque
+
+import numpy as np
+import pytest
+import scipy.sparse as sps
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+TAGS = ("c1mini", "k16", "noisy", "noisy20")
+SHAPES = {"c1mini": (60, 5), "k16": (20, 16), "noisy": (80, 5), "noisy20": (30, 20)}
+
+
+@pytest.fixture(scope="module")
+def B():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    import bsls_b200
+    return bsls_b200
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "solvers.npz"))
+
+
+def problem(gold, tag):
+    m, n = gold[tag + "_shape"]
+    A = sps.csr_matrix((gold[tag + "_val"], gold[tag + "_idx"], gold[tag + "_ptr"]), shape=(m, n))
+    return A, gold[tag + "_b"], gold[tag + "_starts"], gold[tag + "_xinit"]
+
+
+def dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def random_problem(rng, nb, K, m, L, noise=0.1):
+    n = nb * K
+    rows = np.concatenate([rng.choice(m, L, replace=False) for _ in range(n)])
+    cols = np.repeat(np.arange(n), L)
+    A = sps.csr_matrix((np.ones(n * L), (rows, cols)), shape=(m, n))
+    x_true = rng.dirichlet(np.ones(K), size=nb).reshape(-1)
+    b = A.dot(x_true) + noise * rng.randn(m)
+    return A, b, np.arange(0, n, K, dtype=np.int64)
+
+
+# ---------------------------------------------------------------------------------------------
+# objective / gradient (a9)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", TAGS)
+@pytest.mark.parametrize("modes", [(1, 1), (0, 0), (8, 4), (32, 16)])
+@pytest.mark.parametrize("implicit", [False, True])
+def test_objective_matches_reference(B, gold, tag, modes, implicit):
+    A, b, starts, x0 = problem(gold, tag)
+    prob = B.LsqProblem(A, b, implicit_ones=implicit)
+    prob.set_modes(*modes)
+    x = dev(x0)
+    g = torch.zeros_like(x)
+    f = prob.obj(x, g)
+    assert f == pytest.approx(float(gold[tag + "_f0"]), rel=1e-13)
+    if modes == (1, 1):
+        # left-to-right row sums, no FMA: identical to scipy's csr_matvec
+        assert np.array_equal(host(g), gold[tag + "_g0"])
+        assert np.array_equal(host(prob.residual()), A.dot(x0) - b)
+    else:
+        np.testing.assert_allclose(host(g), gold[tag + "_g0"], rtol=1e-12, atol=1e-13)
+
+
+@pytest.mark.parametrize("shape", [(2000, 5, 700, 6), (500, 20, 300, 10), (37, 3, 11, 2), (1, 2, 1, 1), (300, 64, 5000, 12)])
+def test_objective_matches_oracle_random(B, shape):
+    from oracle import solvers_np as S
+    rng = np.random.RandomState(4242 + shape[0])
+    A, b, starts = random_problem(rng, *shape)
+    A.data[:] = rng.rand(A.nnz) + 0.5          # general values, not only an incidence matrix
+    x0 = rng.rand(A.shape[1])
+    _, _, _, obj = S.get_solver_parts(A, b, starts, 0.1)
+    g_ref = np.zeros_like(x0)
+    f_ref = obj(x0, g_ref)
+    for modes in ((1, 1), (0, 0), (32, 32), (4, 4)):
+        prob = B.LsqProblem(A, b)
+        prob.set_modes(*modes)
+        g = torch.zeros(A.shape[1], dtype=torch.float64, device="cuda")
+        f = prob.obj(dev(x0), g)
+        assert f == pytest.approx(f_ref, rel=1e-12)
+        np.testing.assert_allclose(host(g), g_ref, rtol=1e-11, atol=1e-12)
+        if modes == (1, 1):
+            assert np.array_equal(host(g), g_ref)
+        out = host(prob.matvec(dev(x0)))
+        np.testing.assert_allclose(out, A.dot(x0), rtol=1e-12, atol=1e-13)
+        w = rng.randn(A.shape[0])
+        np.testing.assert_allclose(host(prob.rmatvec(dev(w))), A.T.dot(w), rtol=1e-11, atol=1e-12)
+
+
+def test_empty_rows_and_columns(B):
+    rng = np.random.RandomState(5)
+    A = sps.random(50, 120, density=0.02, random_state=rng, format="csr")
+    b = rng.randn(50)
+    x0 = rng.rand(120)
+    r = A.dot(x0) - b
+    for modes in ((1, 1), (8, 8)):
+        prob = B.LsqProblem(A, b)
+        prob.set_modes(*modes)
+        g = torch.zeros(120, dtype=torch.float64, device="cuda")
+        f = prob.obj(dev(x0), g)
+        assert f == pytest.approx(.5 * r.dot(r), rel=1e-13)
+        np.testing.assert_allclose(host(g), A.T.dot(r), rtol=1e-12, atol=1e-14)
+
+
+# ---------------------------------------------------------------------------------------------
+# vector kernels
+# ---------------------------------------------------------------------------------------------
+def test_vector_kernels(B):
+    from bsls_b200.sparse import axpby, default_workspace
+    rng = np.random.RandomState(11)
+    for n in (1, 7, 1000, 300001):
+        x, y, z = rng.randn(n), rng.randn(n), rng.randn(n)
+        out = axpby(torch.empty(n, dtype=torch.float64, device="cuda"), 1.0, dev(x), -0.37, dev(y))
+        assert np.array_equal(host(out), x + (-0.37) * y)
+        t = 0.8 * 0.8
+        xn = dev(y)
+        axpby(xn, 1.0 - t, dev(x), t, xn)          # in place, as the line search does
+        assert np.array_equal(host(xn), (1.0 - t) * x + t * y)
+        ws = default_workspace("cuda")
+        d = ws.dots([(dev(x), dev(y)), (dev(y), dev(y)), (dev(x), dev(z))], want_max=True)
+        np.testing.assert_allclose(d[:3], [x.dot(y), y.dot(y), x.dot(z)], rtol=1e-11, atol=1e-11)
+        assert d[3] == np.max(np.abs(x - y))
+        # deterministic: same bits on every run
+        assert d == ws.dots([(dev(x), dev(y)), (dev(y), dev(y)), (dev(x), dev(z))], want_max=True)
+
+
+def test_lbfgs_helper_matches_oracle(B):
+    from oracle import solvers_np as S
+    from bsls_b200.BATCH import LBFGS_helper
+    rng = np.random.RandomState(3)
+    n, m = 500, 7
+    ys = [rng.randn(n) for _ in range(m)]
+    ss = [rng.randn(n) for _ in range(m)]
+    rho = [1.0 / y.dot(s) for y, s in zip(ys, ss)]
+    g = rng.randn(n)
+    d_ref = np.zeros(n)
+    S.LBFGS_helper(deque(ys), deque(ss), deque(rho), g, d_ref, np.zeros(50))
+    d = torch.zeros(n, dtype=torch.float64, device="cuda")
+    alpha = torch.zeros(104, dtype=torch.float64, device="cuda")
+    LBFGS_helper(deque(dev(y) for y in ys), deque(dev(s) for s in ss), deque(rho), dev(g), d, alpha)
+    np.testing.assert_allclose(host(d), d_ref, rtol=1e-9, atol=1e-10)
+
+
+# ---------------------------------------------------------------------------------------------
+# change of variables (a7) and the N operator (a10)
+# ---------------------------------------------------------------------------------------------
+def test_x2z_z2x_golden(B, golden_dir):
+    d = np.load(os.path.join(golden_dir, "x2z.npz"))
+    for k in range(int(d["count"])):
+        x, starts, z, xback = d["x%d" % k], d["starts%d" % k], d["z%d" % k], d["xback%d" % k]
+        zd = torch.empty(len(z), dtype=torch.float64, device="cuda")
+        B.x2z_c(dev(x), zd, starts)
+        assert np.array_equal(host(zd), z)
+        xd = torch.empty(len(x), dtype=torch.float64, device="cuda")
+        B.z2x_c(xd, dev(z), starts)
+        assert np.array_equal(host(xd), xback)
+        assert np.array_equal(host(B.bsls_utils.x2z(dev(x), block_starts=starts)), z)
+    with pytest.raises(AssertionError):
+        B.x2z_c(dev(np.ones(4)), torch.empty(2, dtype=torch.float64, device="cuda"), np.array([1, 2]))
+    with pytest.raises(AssertionError):
+        B.x2z_c(dev(np.ones(4)), torch.empty(2, dtype=torch.float64, device="cuda"), np.array([0, 2, 2]))
+
+
+def test_x2z_matches_oracle_ragged(B):
+    from oracle import cpu
+    rng = np.random.RandomState(8)
+    sizes = rng.randint(1, 40, size=3000)
+    sizes[::97] = 300
+    starts = np.concatenate(([0], np.cumsum(sizes)[:-1]))
+    n = int(sizes.sum())
+    x = rng.rand(n)
+    z_ref = np.empty(n - len(sizes))
+    cpu.port().x2z(x, z_ref, starts)
+    z = B.bsls_utils.x2z(dev(x), block_sizes=sizes)
+    assert np.array_equal(host(z), z_ref)
+    x_ref = np.empty(n)
+    cpu.port().z2x(x_ref, z_ref, starts)
+    assert np.array_equal(host(B.bsls_utils.z2x(dev(z_ref), block_sizes=sizes)), x_ref)
+
+
+@pytest.mark.parametrize("sizes", [[5] * 40, [2, 3, 7, 2, 30, 4, 64, 2], [1, 4, 1, 1, 6], [16] * 1000])
+def test_N_operator(B, sizes):
+    from oracle import solvers_np as S
+    sizes = np.asarray(sizes)
+    n = int(sizes.sum())
+    m = 9
+    rng = np.random.RandomState(2)
+    A = sps.random(m, n, density=0.3, random_state=rng, format="csr")
+    Nref, x0ref, *_ = S.z_space_closures(A, rng.randn(m), sizes)
+    N = B.bsls_utils.block_sizes_to_N(sizes)
+    assert N.shape == Nref.shape
+    z = rng.randn(Nref.shape[1])
+    v = rng.randn(n)
+    assert np.array_equal(host(N.dot(dev(z))), Nref.dot(z))
+    assert np.array_equal(host(N.T.dot(dev(v))), Nref.T.dot(v))
+    assert np.array_equal(host(B.bsls_utils.particular_x0(sizes)), x0ref)
+
+
+# ---------------------------------------------------------------------------------------------
+# BATCH solvers (a13, a14)
+# ---------------------------------------------------------------------------------------------
+def run_batch(B, name, parts, starts, x0, native):
+    step_size, proj, line_search, obj = parts
+    if not native:  # strip the handles: forces the generic (closure-driven) loop
+        obj_ = lambda x, g=None: obj(x, g)
+        proj_ = lambda x: proj(x)
+        ls_ = lambda *a: line_search(*a)
+        ss_ = lambda i: step_size(i)
+    else:
+        obj_, proj_, ls_, ss_ = obj, proj, line_search, step_size
+    if name == "bb":
+        return B.BATCH.solve_BB(obj_, proj_, ls_, x0, max_iter=300)
+    if name == "pg":
+        return B.BATCH.solve(obj_, proj_, ss_, x0, ls_, max_iter=100)
+    if name == "md":
+        return B.BATCH.solve_MD(obj_, starts, ss_, x0, max_iter=100)
+    return B.BATCH.solve_LBFGS(obj_, proj_, ls_, x0, max_iter=150)
+
+
+@pytest.mark.parametrize("tag", TAGS)
+@pytest.mark.parametrize("name", ["bb", "pg", "md", "lbfgs"])
+@pytest.mark.parametrize("native", [True, False])
+def test_batch_solvers_match_reference(B, gold, tag, name, native):
+    A, b, starts, x0 = problem(gold, tag)
+    parts = B.algorithm_utils.get_solver_parts((A, b), starts, 0.1, is_sparse=True)
+    parts[3].problem.set_modes(1, 1)
+    sol = run_batch(B, name, parts, starts, dev(x0), native)
+    key = "%s_%s_" % (tag, name)
+    f_ref = float(gold[key + "f"])
+    trace = np.array([p[1] for p in sol["progress"]])
+    ref_trace = gold[key + "ftrace"]
+    if native and name != "lbfgs":
+        assert "kernel_launches" in sol and sol["kernel_launches"] > 0
+    # objective of the full solve: 1e-6 relative (north_star); a noiseless problem converges to f = 0
+    assert sol["f"] == pytest.approx(f_ref, rel=1e-6, abs=1e-10)
+    # the first iterations follow the reference's trajectory closely
+    k = min(6, len(trace), len(ref_trace))
+    np.testing.assert_allclose(trace[:k], ref_trace[:k], rtol=1e-9, atol=1e-12)
+    if name in ("pg", "md"):
+        # no chaotic step rule: whole trajectory, iteration count, stop reason and solution agree
+        assert sol["iterations"] == int(gold[key + "iters"])
+        assert sol["stop"].split("=")[0] == str(gold[key + "stop"]).split("=")[0]
+        np.testing.assert_allclose(trace, ref_trace, rtol=1e-8, atol=1e-12)
+        np.testing.assert_allclose(host(sol["x"]), gold[key + "x"], atol=1e-7)
+    xs = host(sol["x"])
+    K = SHAPES[tag][1]
+    np.testing.assert_allclose(xs.reshape(-1, K).sum(1), 1.0, atol=1e-9)
+    assert xs.min() >= 0.0
+
+
+def test_small_qp_known_answer(B, gold):
+    """tests/fast/test_BATCH.py of the reference: 2-variable QP, solution [.25, .75], f_min 1.875."""
+    Q, c, x_true, f_min, min_eig = B.bsls_utils.generate_small_qp()
+    step_size, proj, line_search, obj = B.algorithm_utils.get_solver_parts((Q, c), np.array([0]), min_eig)
+    x0 = dev([.5, .5])
+    sol = B.BATCH.solve_BB(obj, proj, line_search, x0)
+    np.testing.assert_allclose(host(sol["x"]), x_true, atol=1e-3)
+    assert sol["stop"].split("=")[0] == str(gold["qp_bb_stop"]).split("=")[0]
+    np.testing.assert_allclose(host(sol["x"]), gold["qp_bb_x"], atol=1e-9)
+    sol = B.BATCH.solve_BB(obj, proj, line_search, x0, f_min=f_min)
+    assert sol["stop"].split("=")[0] == str(gold["qp_bb_fmin_stop"]).split("=")[0]
+    sol = B.BATCH.solve(obj, proj, step_size, x0, line_search)
+    np.testing.assert_allclose(host(sol["x"]), x_true, atol=1e-3)
+    sol = B.BATCH.solve_LBFGS(obj, proj, line_search, x0)
+    np.testing.assert_allclose(host(sol["x"]), x_true, atol=1e-3)
+    sol = B.BATCH.solve_MD(obj, np.array([0]), step_size, x0)
+    np.testing.assert_allclose(host(sol["x"]), x_true, atol=1e-2)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_batch_random_least_squares_vs_oracle(B, seed):
+    """The reference's own solver test shape (tests/fast/test_BATCH.py: random_least_squares(10, 7)
+    generalised): GPU and oracle reach the same objective from the same start."""
+    from oracle import solvers_np as S
+    rng = np.random.RandomState(100 + seed)
+    A, b, starts = random_problem(rng, 150, 7, 260, 5, noise=0.2)
+    x0 = np.ones(A.shape[1]) / 7
+    ref = S.solve_BB(*[S.get_solver_parts(A, b, starts, 0.1)[k] for k in (3, 1, 2)], x0, max_iter=400)
+    parts = B.algorithm_utils.get_solver_parts((A, b), starts, 0.1, is_sparse=True)
+    sol = B.BATCH.solve_BB(parts[3], parts[1], parts[2], dev(x0), max_iter=400)
+    assert sol["f"] == pytest.approx(ref["f"], rel=1e-6)
+    # lasso (l1-ball) feasible set
+    ref = S.solve_BB(*[S.get_solver_parts(A, b, starts, 0.1, lasso=True)[k] for k in (3, 1, 2)], x0, max_iter=400)
+    parts = B.algorithm_utils.get_solver_parts((A, b), starts, 0.1, is_sparse=True, lasso=True)
+    sol = B.BATCH.solve_BB(parts[3], parts[1], parts[2], dev(x0), max_iter=400)
+    assert sol["f"] == pytest.approx(ref["f"], rel=1e-6)
+
+
+def test_batch_in_z_and_scaled(B):
+    """get_solver_parts(in_z=True) (PAVA + clip) and f-scaled projections (algorithm_utils.py:219-265)."""
+    from oracle import solvers_np as S
+    rng = np.random.RandomState(77)
+    nb, K = 40, 6
+    A, b, starts = random_problem(rng, nb, K, 90, 4, noise=0.2)
+    # problem posed in z: Az = A N, bz = b - A x0  (ls_to_ls_in_z, bsls_utils.py:251-264)
+    sizes = np.full(nb, K)
+    N, x0p, *_ = S.z_space_closures(A, b, sizes)
+    Az = sps.csr_matrix(A.dot(N))
+    bz = b - A.dot(x0p)
+    z0 = np.concatenate([np.cumsum(np.ones(K) / K)[:-1] for _ in range(nb)])
+    ref_parts = S.get_solver_parts(Az, bz, starts, 0.1, in_z=True)
+    ref = S.solve_BB(ref_parts[3], ref_parts[1], ref_parts[2], z0, max_iter=300)
+    for native in (True, False):
+        parts = B.algorithm_utils.get_solver_parts((Az, bz), starts, 0.1, is_sparse=True, in_z=True)
+        sol = run_batch(B, "bb", parts, starts, dev(z0), native)
+        assert sol["f"] == pytest.approx(ref["f"], rel=1e-6)
+    # f-scaled simplex: blocks sum to f_k
+    fk = rng.rand(nb) + 0.5
+    parts = B.algorithm_utils.get_solver_parts((A, b), starts, 0.1, is_sparse=True, f=fk)
+    y = rng.randn(nb * K)
+    yd = dev(y)
+    parts[1](yd)
+    from oracle import cpu
+    want = y.copy()
+    for k in range(nb):
+        want[k * K:(k + 1) * K] /= fk[k]
+    cpu.port().proj_multi_simplex(want, starts)
+    for k in range(nb):
+        want[k * K:(k + 1) * K] *= fk[k]
+    np.testing.assert_allclose(host(yd), want, rtol=1e-14, atol=1e-15)
+
+
+# ---------------------------------------------------------------------------------------------
+# functional drivers in z (a10-a12, a15, a16, a19) and mirror descent (a17)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", TAGS)
+def test_z_space_drivers_match_reference(B, gold, tag):
+    A, b, starts, xinit = problem(gold, tag)
+    nb, K = SHAPES[tag]
+    sizes = np.full(nb, K, dtype=np.int64)
+    z0, target, f, nabla_f, proj, prob, N = B.main.z_space_parts(A, b, host(B.bsls_utils.particular_x0(sizes)), None, sizes)
+    # the fixtures start from x2z(x_init), not from x0
+    z_init = B.bsls_utils.x2z(dev(xinit), block_sizes=sizes)
+    np.testing.assert_allclose(host(z_init), gold[tag + "_z0"], rtol=0, atol=0)
+    log = lambda it, state, dur: 0.0
+    opts = {"max_iter": 200, "opt_tol": 1e-30, "verbose": 0}
+    zbb = B.BB.solve(z_init.clone(), f, nabla_f, B.solvers.stopping, proj=proj, log=log, options=opts)
+    assert f(zbb) == pytest.approx(float(gold[tag + "_zbb_f"]), rel=1e-6, abs=1e-10)
+    ones = torch.ones_like(z_init)
+    zl = B.LBFGS.solve(z_init + ones, f, nabla_f, B.solvers.stopping, proj=proj, log=log,
+                       options={"max_iter": 40, "opt_tol": 1e-30, "verbose": 0})
+    assert f(zl) == pytest.approx(float(gold[tag + "_zlbfgs_f"]), rel=1e-6, abs=1e-10)
+    lsv = B.bsls_utils.lsv_operator(prob, N)
+    assert lsv == pytest.approx(float(gold[tag + "_lsv"]), rel=1e-9)
+    gd = B.gradient_descent.GradientDescent(z0=z_init.clone(), f=f, nabla_f=nabla_f, proj=proj, method="DORE",
+                                            options={"max_iter": 150, "opt_tol": 1e-30, "verbose": 0}, A=prob, N=N, target=target)
+    iters, times, states = gd.run()
+    assert f(states[-1]) == pytest.approx(float(gold[tag + "_zdore_f"]), rel=1e-6, abs=1e-10)
+    np.testing.assert_allclose(host(states[-1]), gold[tag + "_zdore_z"], atol=1e-6)
+
+
+@pytest.mark.parametrize("tag", TAGS)
+def test_mirror_descent_least_squares(B, gold, tag):
+    A, b, starts, xinit = problem(gold, tag)
+    nb, K = SHAPES[tag]
+    Lf = float(gold[tag + "_Lf"])
+    x = B.mirror_descent.least_squares(A, b, [K] * nb, iters=60, tolerance=1e-9, Lf=Lf)
+    np.testing.assert_allclose(host(x), gold[tag + "_md_ls_x"], rtol=1e-9, atol=1e-12)
+    # the library's own Lanczos estimate of sigma_max(A) agrees with ARPACK's
+    assert B.bsls_utils.largest_singular_value(A) == pytest.approx(Lf, rel=1e-9)
+
+
+def test_mirror_descent_ragged_blocks(B):
+    from oracle import solvers_np as S
+    rng = np.random.RandomState(31)
+    sizes = [2, 5, 3, 17, 40, 2, 2, 9] * 20
+    n = sum(sizes)
+    A = sps.random(60, n, density=0.05, random_state=rng, format="csr")
+    A.data[:] = 1.0
+    b = rng.rand(60)
+    Lf = float(sps.linalg.svds(A, 1, return_singular_vectors=False)[0])
+    ref = S.md_least_squares(A, b, sizes, iters=40, Lf=Lf)
+    x = B.mirror_descent.least_squares(A, b, sizes, iters=40, Lf=Lf)
+    np.testing.assert_allclose(host(x), ref, rtol=1e-9, atol=1e-13)
+
+
+def test_block_isotonic_regression_drop_in(B):
+    from oracle import cpu
+    rng = np.random.RandomState(9)
+    sizes = rng.randint(2, 30, size=200)
+    starts = np.concatenate(([0], np.cumsum(sizes)[:-1]))
+    y = rng.randn(int(sizes.sum()))
+    want = y.copy()
+    cpu.port().pava_multi(want, starts)
+    yd = dev(y)
+    B.block_isotonic_regression.block_isotonic_regression_2(yd, starts)
+    assert np.array_equal(host(yd), want)
