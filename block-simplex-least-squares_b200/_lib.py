@@ -85,6 +85,7 @@ def lib():
         L.bsls_lsq_ws.restype = c_void_p
         L.bsls_lsq_set_b.argtypes = [c_void_p, c_void_p]
         L.bsls_lsq_set_modes.argtypes = [c_void_p, c_int, c_int]
+        L.bsls_lsq_set_panels.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p]
         L.bsls_lsq_obj_f64.argtypes = [c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_dbl), c_void_p]
         L.bsls_dev_lsq_residual_f64.argtypes = [c_void_p, c_void_p, c_void_p]
         L.bsls_dev_lsq_gradient_f64.argtypes = [c_void_p, c_void_p, c_void_p]

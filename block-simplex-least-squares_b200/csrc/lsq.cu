@@ -87,6 +87,14 @@ struct bsls_lsq {
     const double *a_val = nullptr, *t_val = nullptr;
     const double *b = nullptr;
     int a_mode = 0, t_mode = 0;
+    // column-panelled copy of A (optional): `panels` CSR matrices of m rows stacked into one of
+    // panels*m rows; panel p holds the columns of its slice, so the gathered part of x stays in L2
+    int panels = 0;
+    const int64_t *p_ptr = nullptr;
+    const int32_t *p_idx = nullptr;
+    const double *p_val = nullptr;
+    double *partial = nullptr;                    // panels * m (owned)
+    int p_mode = 0;
     double *r = nullptr;                          // m
     double *wg = nullptr, *wxn = nullptr, *wgn = nullptr;  // n each, solver workspace
     bsls_ws *ws = nullptr;                        // owned
@@ -109,25 +117,45 @@ int grid_elems(int64_t n) {
     return (int)(want < kRedMaxGrid ? want : kRedMaxGrid);
 }
 
+// Grid of a persistent kernel: every CTA resident at once (one wave), never more than the
+// reduction scratch holds.
+template <class K> int resident_grid(K kern, int threads) {
+    int dev = 0, sms = kNumSM, per = 1;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, threads, 0) != cudaSuccess || per < 1) per = 1;
+    const int g = sms * per;
+    return g < kRedMaxGrid ? g : kRedMaxGrid;
+}
+
+template <class Epi, int LANES>
+int launch_vector(bsls_ws *w, int64_t rows, const int64_t *ptr, const int32_t *idx, const double *val, const double *v,
+                  const Epi &epi, cudaStream_t st) {
+    constexpr int T = 256;
+    static thread_local int full = 0;
+    if (!full) full = resident_grid(spmv_vector_kernel<Epi, T, LANES>, T);
+    int64_t want = (rows * LANES + T - 1) / T;
+    const int grid = (int)(want < full ? (want < 1 ? 1 : want) : full);
+    spmv_vector_kernel<Epi, T, LANES><<<grid, T, 0, st>>>(rows, ptr, idx, val, v, epi, w->red);
+    return 0;
+}
+
 template <class Epi>
 int launch_spmv(bsls_ws *w, int mode, int64_t rows, const int64_t *ptr, const int32_t *idx, const double *val, const double *v,
                 const Epi &epi, cudaStream_t st) {
     constexpr int T = 256;
     if (rows <= 0) return BSLS_OK;
     if (mode == 1) {
+        static thread_local int full = 0;
+        if (!full) full = resident_grid(spmv_stream_kernel<Epi, T, 2048>, T);
         const int64_t tiles = (rows + T - 1) / T;
-        const int grid = (int)(tiles < kRedMaxGrid ? tiles : kRedMaxGrid);
+        const int grid = (int)(tiles < full ? tiles : full);
         spmv_stream_kernel<Epi, T, 2048><<<grid, T, 0, st>>>(rows, ptr, idx, val, v, epi, w->red);
     } else {
-        const int lanes = mode;
-        int64_t want = (rows * lanes + T - 1) / T;
-        // a few rows per group: enough CTAs to fill the machine, few enough to amortise the reduction
-        const int grid = (int)(want < kRedMaxGrid ? (want < 1 ? 1 : want) : kRedMaxGrid);
-        switch (lanes) {
-            case 4: spmv_vector_kernel<Epi, T, 4><<<grid, T, 0, st>>>(rows, ptr, idx, val, v, epi, w->red); break;
-            case 8: spmv_vector_kernel<Epi, T, 8><<<grid, T, 0, st>>>(rows, ptr, idx, val, v, epi, w->red); break;
-            case 16: spmv_vector_kernel<Epi, T, 16><<<grid, T, 0, st>>>(rows, ptr, idx, val, v, epi, w->red); break;
-            default: spmv_vector_kernel<Epi, T, 32><<<grid, T, 0, st>>>(rows, ptr, idx, val, v, epi, w->red); break;
+        switch (mode) {
+            case 4: launch_vector<Epi, 4>(w, rows, ptr, idx, val, v, epi, st); break;
+            case 8: launch_vector<Epi, 8>(w, rows, ptr, idx, val, v, epi, st); break;
+            case 16: launch_vector<Epi, 16>(w, rows, ptr, idx, val, v, epi, st); break;
+            default: launch_vector<Epi, 32>(w, rows, ptr, idx, val, v, epi, st); break;
         }
     }
     BSLS_LAUNCH_CHECK();
@@ -145,8 +173,20 @@ int allreduce(bsls_ws *w, double *buf, int64_t count, int op, cudaStream_t st) {
 int residual(bsls_lsq *q, const double *x, double *r, const double *b, cudaStream_t st) {
     bsls_ws *w = q->ws;
     const bool dist = w->comm && w->comm->nranks > 1;
-    EpiResidual epi{r, (dist || !b) ? nullptr : b};
-    if (int rc = launch_spmv(w, q->a_mode, q->m, q->a_ptr, q->a_idx, q->a_val, x, epi, st)) return rc;
+    if (q->panels > 1) {
+        // one launch per panel: the kernel boundary keeps all CTAs inside the same slice of x, which
+        // therefore stays L2-resident (a single launch lets CTAs drift several panels apart)
+        for (int p = 0; p < q->panels; ++p) {
+            EpiResidual epi{q->partial + (size_t)p * q->m, nullptr};
+            if (int rc = launch_spmv(w, q->p_mode, q->m, q->p_ptr + (size_t)p * q->m, q->p_idx, q->p_val, x, epi, st)) return rc;
+        }
+        panel_reduce_kernel<<<grid_elems(q->m), 256, 0, st>>>(r, q->partial, dist ? nullptr : b, q->m, q->panels, w->red);
+        BSLS_LAUNCH_CHECK();
+        w->launches++;
+    } else {
+        EpiResidual epi{r, (dist || !b) ? nullptr : b};
+        if (int rc = launch_spmv(w, q->a_mode, q->m, q->a_ptr, q->a_idx, q->a_val, x, epi, st)) return rc;
+    }
     if (dist) {
         if (int rc = allreduce(w, r, q->m, kNcclSum, st)) return rc;
         if (b) {
@@ -363,6 +403,7 @@ int bsls_lsq_create(int64_t m, int64_t n, int64_t nnz, const int64_t *a_ptr, con
 int bsls_lsq_destroy(bsls_lsq *q) {
     if (!q) return BSLS_OK;
     if (q->r) cudaFree(q->r);
+    if (q->partial) cudaFree(q->partial);
     if (q->wg) cudaFree(q->wg);
     if (q->wxn) cudaFree(q->wxn);
     if (q->wgn) cudaFree(q->wgn);
@@ -396,6 +437,26 @@ int bsls_lsq_set_modes(bsls_lsq *q, int a_mode, int at_mode) {
     }
     q->a_mode = a_mode ? a_mode : pick_mode(q->nnz, q->m);
     q->t_mode = at_mode ? at_mode : pick_mode(q->nnz, q->n);
+    return BSLS_OK;
+}
+
+int bsls_lsq_set_panels(bsls_lsq *q, int panels, const int64_t *ptr, const int32_t *idx, const double *val) {
+    if (!q || panels < 0) return BSLS_ERR_ARG;
+    if (q->partial) cudaFree(q->partial);
+    q->partial = nullptr;
+    q->panels = 0;
+    if (panels <= 1) return BSLS_OK;
+    if (!ptr || !idx) {
+        set_error("lsq_set_panels: null structure");
+        return BSLS_ERR_ARG;
+    }
+    BSLS_CUDA_TRY(cudaMalloc(&q->partial, sizeof(double) * (size_t)q->m * (size_t)panels));
+    q->panels = panels;
+    q->p_ptr = ptr;
+    q->p_idx = idx;
+    q->p_val = val;
+    q->p_mode = pick_mode(q->nnz, q->m * panels);
+    if (const char *e = getenv("BSLS_SPMV_P")) q->p_mode = atoi(e);
     return BSLS_OK;
 }
 

@@ -342,6 +342,21 @@ __global__ void __launch_bounds__(256) residual_finish_kernel(double *__restrict
     grid_reduce<1, 0, 256, FinResidual>(acc, red);
 }
 
+// r_i = sum_p partial[p m + i] (- b_i), panels added in ascending order; f = 0.5 <r, r>.
+// Closes the column-panelled product A x (see bsls_lsq_set_panels).
+__global__ void __launch_bounds__(256) panel_reduce_kernel(double *__restrict__ r, const double *__restrict__ partial,
+                                                            const double *__restrict__ b, int64_t m, int panels, RedCtx red) {
+    double acc[1] = {0};
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < m; i += (int64_t)gridDim.x * 256) {
+        double v = partial[i];
+        for (int p = 1; p < panels; ++p) v += partial[(int64_t)p * m + i];
+        if (b) v -= b[i];
+        r[i] = v;
+        acc[0] += v * v;
+    }
+    grid_reduce<1, 0, 256, FinResidual>(acc, red);
+}
+
 // ---- per-block kernels: G lanes per block ---------------------------------------------------------
 struct BlockLayout {
     const int32_t *starts;  // nb + 1 entries (last = n); ignored when uniform > 0

@@ -275,6 +275,47 @@ class LsqProblem:
         assert self.b.shape[0] == self.m
         _lib.check(_lib.lib().bsls_lsq_set_b(self._handle, self.b.data_ptr()))
 
+    def set_panels(self, panel_cols=None, l2_budget_bytes=32 << 20):
+        """Build the column-panelled copy of A (``bsls_lsq_set_panels``) so that the slice of x a
+        panel gathers from stays L2-resident.  ``panel_cols`` columns per panel (default: as many
+        as fit ``l2_budget_bytes``); a single panel removes the copy.  Set-up work, done once per
+        matrix with torch's sort on the device; the per-iteration products use only library kernels."""
+        L = _lib.lib()
+        if panel_cols is None:
+            panel_cols = max(1, l2_budget_bytes // 8)
+        P = (self.n + panel_cols - 1) // panel_cols
+        if P <= 1:
+            _lib.check(L.bsls_lsq_set_panels(self._handle, 0, None, None, None))
+            self.p_ptr = self.p_idx = self.p_val = None
+            self.panels = 1
+            return 1
+        dev = self.device
+        ptrs, idxs, vals = [], [], []
+        base = 0
+        for p in range(P):
+            lo, hi = p * panel_cols, min(self.n, (p + 1) * panel_cols)
+            n0, n1 = int(self.t_ptr[lo]), int(self.t_ptr[hi])
+            rows = self.t_idx[n0:n1]
+            counts = (self.t_ptr[lo + 1:hi + 1] - self.t_ptr[lo:hi])
+            cols = torch.repeat_interleave(torch.arange(lo, hi, device=dev, dtype=torch.int32), counts)
+            order = torch.argsort(rows.to(torch.int64), stable=True)
+            idxs.append(cols[order])
+            if self.t_val is not None:
+                vals.append(self.t_val[n0:n1][order])
+            rc = torch.bincount(rows, minlength=self.m)
+            ptrs.append(base + torch.cumsum(rc, 0) - rc)          # starts of the m rows of this panel
+            base += n1 - n0
+            del rows, counts, cols, order, rc
+        ptrs.append(torch.tensor([base], dtype=torch.int64, device=dev))
+        self.p_ptr = torch.cat(ptrs).to(torch.int64).contiguous()
+        self.p_idx = torch.cat(idxs).contiguous()
+        self.p_val = torch.cat(vals).contiguous() if vals else None
+        assert self.p_ptr.shape[0] == P * self.m + 1 and base == self.nnz
+        _lib.check(L.bsls_lsq_set_panels(self._handle, P, self.p_ptr.data_ptr(), self.p_idx.data_ptr(),
+                                         None if self.p_val is None else self.p_val.data_ptr()), "lsq_set_panels")
+        self.panels = P
+        return P
+
     def set_modes(self, a_mode=0, at_mode=0):
         _lib.check(_lib.lib().bsls_lsq_set_modes(self._handle, int(a_mode), int(at_mode)), "lsq_set_modes")
 

@@ -166,6 +166,12 @@ BSLS_API int bsls_lsq_destroy(bsls_lsq *lsq);
 BSLS_API int bsls_lsq_set_comm(bsls_lsq *lsq, bsls_comm *comm);   /* NULL: single GPU */
 BSLS_API bsls_ws *bsls_lsq_ws(bsls_lsq *lsq);
 BSLS_API int bsls_lsq_set_b(bsls_lsq *lsq, const double *b);
+/* Optional column-panelled copy of A for problems whose x does not fit the 126 MB L2: the columns
+ * are cut into `panels` contiguous slices, slice p is stored as a CSR matrix with m rows (column
+ * ids global), and the `panels` matrices are stacked row-wise: ptr has panels*m + 1 entries.
+ * A x is then formed panel after panel (the gathered slice of x stays L2-resident) and the
+ * per-panel partial sums are added in ascending panel order.  panels <= 1 removes the copy. */
+BSLS_API int bsls_lsq_set_panels(bsls_lsq *lsq, int panels, const int64_t *ptr, const int32_t *idx, const double *val);
 /* kernel choice per side: 0 = from the mean row length, 1 = stream, 4/8/16/32 = lanes per row */
 BSLS_API int bsls_lsq_set_modes(bsls_lsq *lsq, int a_mode, int at_mode);
 

@@ -102,6 +102,30 @@ def test_objective_matches_oracle_random(B, shape):
         np.testing.assert_allclose(host(prob.rmatvec(dev(w))), A.T.dot(w), rtol=1e-11, atol=1e-12)
 
 
+@pytest.mark.parametrize("panel_cols", [1, 7, 64, 1000])
+def test_column_panelled_product(B, panel_cols):
+    """bsls_lsq_set_panels: A x formed panel by panel equals the plain product."""
+    rng = np.random.RandomState(21)
+    A, b, starts = random_problem(rng, 60, 5, 40, 4)
+    A.data[:] = rng.rand(A.nnz) + 0.5
+    x0 = rng.rand(A.shape[1])
+    r = A.dot(x0) - b
+    for implicit in (False, True):
+        Ause = A.copy()
+        if implicit:
+            Ause.data[:] = 1.0
+            r = Ause.dot(x0) - b
+        prob = B.LsqProblem(Ause, b, implicit_ones=implicit)
+        P = prob.set_panels(panel_cols)
+        assert P == -(-A.shape[1] // panel_cols)
+        g = torch.zeros(A.shape[1], dtype=torch.float64, device="cuda")
+        f = prob.obj(dev(x0), g)
+        assert f == pytest.approx(.5 * r.dot(r), rel=1e-12)
+        np.testing.assert_allclose(host(prob.residual()), r, rtol=1e-12, atol=1e-13)
+        np.testing.assert_allclose(host(g), Ause.T.dot(r), rtol=1e-11, atol=1e-12)
+        np.testing.assert_allclose(host(prob.matvec(dev(x0))), Ause.dot(x0), rtol=1e-12, atol=1e-13)
+
+
 def test_empty_rows_and_columns(B):
     rng = np.random.RandomState(5)
     A = sps.random(50, 120, density=0.02, random_state=rng, format="csr")

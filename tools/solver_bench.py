@@ -24,6 +24,8 @@ def main():
     ap.add_argument("--explicit", action="store_true", help="store fp64 values instead of implicit ones")
     ap.add_argument("--scale", type=float, default=1.0, help="scale nb (and m) of the config")
     ap.add_argument("--modes", default="0,0")
+    ap.add_argument("--panel-mb", type=int, default=32, help="L2 budget of one column panel of x (0: no panels)")
+    ap.add_argument("--noise", type=float, default=0.1)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -39,7 +41,8 @@ def main():
         nb, K, m, Lk = CONFIGS[name]
         nb, m = max(world, int(nb * args.scale)), max(Lk, int(m * args.scale))
         t0 = time.time()
-        sp = SyntheticProblem(nb, K, m, Lk, rank=rank, world=world, comm=comm, implicit_ones=not args.explicit)
+        sp = SyntheticProblem(nb, K, m, Lk, rank=rank, world=world, comm=comm, implicit_ones=not args.explicit, noise=args.noise)
+        panels = sp.problem.set_panels(l2_budget_bytes=args.panel_mb << 20) if args.panel_mb > 0 and sp.n * 8 > (48 << 20) else 1
         torch.cuda.synchronize()
         gen_s = time.time() - t0
         a_mode, t_mode = [int(v) for v in args.modes.split(",")]
@@ -73,7 +76,7 @@ def main():
         if rank == 0:
             print(json.dumps({
                 "config": name, "world": world, "nb": nb, "K": K, "m": m, "L": Lk, "n_local": sp.n, "nnz_local": sp.nnz,
-                "explicit_values": args.explicit, "gen_s": round(gen_s, 2),
+                "explicit_values": args.explicit, "panels": panels, "gen_s": round(gen_s, 2),
                 "residual_ms": float(np.median(tr)), "gradient_ms": float(np.median(tg)),
                 "residual_GBs_stored": bytes_r / np.median(tr) / 1e6, "gradient_GBs_stored": bytes_g / np.median(tg) / 1e6,
                 "bb_iters": its, "bb_f": sol["f"], "bb_backtracks": sol["backtracks"], "bb_evals": sol["obj_evals"],
