@@ -181,6 +181,136 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+
+# --------------------------------------------------------------------------------------------
+# secondary workloads reported beside the headline (same JSON line, own sub-objects)
+# --------------------------------------------------------------------------------------------
+def power_law_sizes(total, lo=2, hi=4096, alpha=1.5, seed=SEED + 2):
+    """C3 layout: sizes floor(lo * u^(-1/alpha)) clipped to [lo, hi], drawn until they
+    sum to `total` (last block trimmed, never below 2)."""
+    rng = np.random.RandomState(seed)
+    sizes = []
+    left = total
+    while left > 0:
+        k = np.floor(lo * rng.rand(65536) ** (-1.0 / alpha)).clip(lo, hi).astype(np.int64)
+        c = np.cumsum(k)
+        cut = int(np.searchsorted(c, left, side="left"))
+        if cut >= len(k):
+            sizes.append(k)
+            left -= int(c[-1])
+            continue
+        take = k[:cut + 1].copy()
+        take[-1] -= int(c[cut] - left)
+        if take[-1] < 2:                      # fold a 0/1-sized tail into the previous block
+            extra = int(take[-1])
+            take = take[:-1]
+            take[-1] += extra
+        sizes.append(take)
+        left = 0
+    return np.concatenate(sizes)
+
+
+def bench_c3(bsls_b200, torch, dev, peak, steps=5):
+    """BASELINE config 3: power-law blocks 2..4096, 10^7 variables: projection and segmented PAVA
+    (values only, and with the pool-size array) on fresh inputs; CUDA events."""
+    sizes = power_law_sizes(10 ** 7)
+    n, nb = int(sizes.sum()), len(sizes)
+    starts = torch.as_tensor(np.concatenate(([0], np.cumsum(sizes)[:-1]))).to(dev)
+    plan = bsls_b200.BlockPlan(starts, n)
+    gen = torch.Generator(device=dev).manual_seed(SEED + 3)
+    pos = torch.arange(n, device=dev) - torch.repeat_interleave(starts, torch.as_tensor(sizes).to(dev))
+    ramp = 50.0 * torch.log1p(pos.to(torch.float64))       # the reference's PAVA test input (test_isotonic_regression.py:43)
+    out = {"workload": "C3: power-law block sizes 2..4096, %d variables in %d blocks, fp64" % (n, nb)}
+
+    def timed(make, run, bytes_):
+        bufs = [make() for _ in range(steps + 3)]
+        for b in bufs[:3]:
+            run(b)
+        torch.cuda.synchronize()
+        evs = []
+        for b in bufs[3:]:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            run(b)
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+        return {"avg_ms": ms, "var_per_s": n / ms * 1e3, "algorithmic_bytes": bytes_, "GBs": bytes_ / ms / 1e6,
+                "frac": bytes_ / ms / 1e6 / peak}
+
+    out["projection"] = timed(lambda: torch.randn(n, dtype=torch.float64, device=dev, generator=gen),
+                              lambda y: bsls_b200.proj_multi_simplex_c(y, plan), 16 * n + 4 * nb)
+    mk = lambda: torch.randint(-50, 50, (n,), device=dev, generator=gen).to(torch.float64) + ramp
+    out["pava"] = timed(mk, lambda y: bsls_b200.isotonic_regression_multi_c(y, plan, None, 1), 16 * n + 4 * nb)
+    w = torch.ones(n, dtype=torch.int32, device=dev)
+
+    def run_w(y):
+        w.fill_(1)
+        bsls_b200.isotonic_regression_multi_c(y, plan, w, 1)
+    out["pava_with_pool_sizes"] = timed(mk, run_w, 16 * n + 4 * nb + 4 * n)
+    return out
+
+
+def cpu_bb_sample(seconds=12.0):
+    """The reference's BATCH.solve_BB (oracle restatement: scipy CSR products + the reference's C++
+    projection) on a reduced C5-shaped problem, one host thread."""
+    import scipy.sparse as sps
+    from oracle import solvers_np as S
+    nb, K, m, L = 100000, 16, 10000, 8
+    rng = np.random.RandomState(SEED + 5)
+    n = nb * K
+    base = np.sort(rng.randint(0, m - L + 1, size=(n, L)), axis=1) + np.arange(L)
+    A = sps.csr_matrix((np.ones(n * L), (base.reshape(-1), np.repeat(np.arange(n), L))), shape=(m, n))
+    x_true = rng.dirichlet(np.ones(K), size=nb).reshape(-1)
+    b = A.dot(x_true) + 0.1 * rng.randn(m)
+    starts = np.arange(0, n, K)
+    step_size, proj, line_search, obj = S.get_solver_parts(A, b, starts, 0.1)
+    t0 = time.perf_counter()
+    sol = S.solve_BB(obj, proj, line_search, np.ones(n) / K, max_iter=12)
+    dt = time.perf_counter() - t0
+    its = sol["iterations"] - 1
+    return {"value": its / dt, "unit": "iter/s", "cores": 1, "kind": "port",
+            "sample": "BATCH.solve_BB, %d iterations on a 1/100-size C5 (nb=%d, K=%d, m=%d, L=%d: nnz=%.3g)" % (its, nb, K, m, L, n * L),
+            "seconds": dt, "nnz_iter_per_s": its * n * L / dt}
+
+
+def bench_bb_c5(bsls_b200, torch, dist, dev, rank, world, peak, max_iter=40):
+    """BASELINE config 5: 10^7 OD blocks x 16 routes, 10^6 links, L = 8 links per route; OD blocks
+    sharded over ranks, A x summed by one NCCL all-reduce per objective evaluation; the whole BB
+    loop (BATCH.solve_BB semantics) runs inside the library.  Strong scaling."""
+    from bsls_b200.generate import SyntheticProblem
+    comm = bsls_b200.Communicator() if world > 1 else None
+    sp = SyntheticProblem.config("C5", rank=rank, world=world, comm=comm, noise=0.1)
+    panels = sp.problem.set_panels() if sp.n * 8 > (64 << 20) else 1
+    step_size, proj, line_search, obj = sp.solver_parts()
+    bsls_b200.BATCH.solve_BB(obj, proj, line_search, sp.x_init, max_iter=4)          # warm-up
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sol = bsls_b200.BATCH.solve_BB(obj, proj, line_search, sp.x_init, max_iter=max_iter)
+    ms = torch.tensor([sol["device_ms"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    its = sol["iterations"] - 1
+    nnz, n, m, nb = 1280000000, 160000000, 1000000, 10000000
+    b_bb = 24 * nnz + 72 * n + 32 * m + 4 * nb                     # SURVEY 8d, fp64 values + int32 indices
+    stored = 8 * nnz + 72 * n + 32 * m + 4 * nb + 16 * (n + m)     # what this build moves: index-only A, both sides
+    evals = sol["obj_evals"]
+    return {"workload": "C5: BB solve, 10^7 OD blocks x 16 routes, 10^6 links, nnz=1.28e9, sharded by OD block over %d GPU(s)" % world,
+            "iter_per_s": its / ms * 1e3, "iterations": its, "objective_evaluations": evals, "backtracks": sol["backtracks"],
+            "ms_per_iteration": ms / max(1, its), "ms_per_evaluation": ms / max(1, evals), "f_final": sol["f"],
+            "stop": sol["stop"], "scaling": "strong", "n_gpus": world, "panels_per_gpu": panels,
+            "kernel_launches": sol["kernel_launches"],
+            "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peak * world,
+                         "algorithmic_bytes_per_iteration": b_bb,
+                         "achieved": b_bb * evals / ms / 1e6, "frac": b_bb * evals / ms / 1e6 / (peak * world),
+                         "stored_bytes_per_iteration": stored, "achieved_stored": stored * evals / ms / 1e6,
+                         "note": "per objective evaluation (a back-track repeats the SpMV pair); A is held index-only "
+                                 "(values are implicit ones): `achieved` uses SURVEY 8d's fp64-value formula, "
+                                 "`achieved_stored` the bytes actually moved"}}
+
 # --------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------
@@ -257,9 +387,18 @@ def run_ours(args, rank, world, local_rank):
     nvar_step = NB * sum(SIZES)
     value = world * nvar_step * steps / (ms * 1e-3)
 
+    # ---- BB solve on config 5 (all ranks take part; strong scaling) -------------------------------
+    peak, peak_src = peaks()
+    extras = {}
+    if not args.skip_extras:
+        for b in bufs:
+            b.clear()
+        del bufs
+        torch.cuda.empty_cache()
+        extras["bb_c5"] = bench_bb_c5(bsls_b200, torch, dist, dev, rank, world, peak)
+        torch.cuda.empty_cache()
     if rank != 0:
         return
-    peak, peak_src = peaks()
     kern = {}
     for K in SIZES:
         d = np.array([a.elapsed_time(b) for a, b in events[K]])
@@ -303,6 +442,9 @@ def run_ours(args, rank, world, local_rank):
            "api": "bsls_proj_multi_simplex(double*, const int*, int, int) on pinned host buffers via ctypes"}
 
     cpu_base = cpu_baseline_sample(threads=1, reps=2) if world == 1 else None
+    extras["c3"] = bench_c3(bsls_b200, torch, dev, peak) if not args.skip_extras else None
+    if cpu_base is not None and not args.skip_extras:
+        extras["bb_c5"]["cpu_baseline"] = cpu_bb_sample()
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -312,6 +454,11 @@ def run_ours(args, rank, world, local_rank):
             "roofline": roofline, "e2e": e2e, "gpu_launches": 3 * steps, "clocks": clocks}
     if cpu_base is not None:
         line["cpu_baseline"] = cpu_base
+    for k, v in extras.items():
+        if v is not None:
+            line[k] = v
+    if "bb_c5" in line:
+        line["gpu_launches"] += line["bb_c5"]["kernel_launches"]
     print(json.dumps(line))
 
 
@@ -322,6 +469,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--skip-extras", action="store_true", help="headline (C2 projection) only: no BB-on-C5 / C3 sub-objects")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
 

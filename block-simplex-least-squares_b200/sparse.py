@@ -275,7 +275,7 @@ class LsqProblem:
         assert self.b.shape[0] == self.m
         _lib.check(_lib.lib().bsls_lsq_set_b(self._handle, self.b.data_ptr()))
 
-    def set_panels(self, panel_cols=None, l2_budget_bytes=32 << 20):
+    def set_panels(self, panel_cols=None, l2_budget_bytes=48 << 20):
         """Build the column-panelled copy of A (``bsls_lsq_set_panels``) so that the slice of x a
         panel gathers from stays L2-resident.  ``panel_cols`` columns per panel (default: as many
         as fit ``l2_budget_bytes``); a single panel removes the copy.  Set-up work, done once per
