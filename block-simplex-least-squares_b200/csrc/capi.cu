@@ -103,6 +103,14 @@ static int dev_pava(const bsls_plan *plan_, T *y, int32_t *weight, int update, i
 // ------------------------------------------------------------------------------------
 // device entry points: projections
 // ------------------------------------------------------------------------------------
+// scratch of the selection kernels (queue of dense blocks), allocated on first use
+static int ensure_slow_queue(const bsls_plan *plan) {
+    if (plan->d_slow) return BSLS_OK;
+    bsls_plan *p = const_cast<bsls_plan *>(plan);
+    BSLS_CUDA_TRY(cudaMalloc(&p->d_slow, sizeof(int32_t) * ((size_t)plan->nb + 1)));
+    return BSLS_OK;
+}
+
 template <typename T> static int dev_project(const bsls_plan *plan, T *y, int mode, cudaStream_t stream) {
     if (int rc = device_ok()) return rc;
     if (!plan || !y) {
@@ -110,10 +118,12 @@ template <typename T> static int dev_project(const bsls_plan *plan, T *y, int mo
         return BSLS_ERR_ARG;
     }
     if (plan->uniform > 0 && plan->uniform <= 512) {
+        if (plan->uniform > 16)
+            if (int rc = ensure_slow_queue(plan)) return rc;
         if constexpr (sizeof(T) == 8)
-            return proj_uniform_f64((double *)y, plan->first, plan->nb, plan->uniform, mode, stream);
+            return proj_uniform_f64((double *)y, plan->first, plan->nb, plan->uniform, mode, plan->d_slow, stream);
         else
-            return proj_uniform_f32((float *)y, plan->first, plan->nb, plan->uniform, mode, stream);
+            return proj_uniform_f32((float *)y, plan->first, plan->nb, plan->uniform, mode, plan->d_slow, stream);
     }
     if (plan->max_size > kPlanLargeMaxBlock) {
         set_error("projection: a block of %d entries exceeds the %d-entry limit of this revision", plan->max_size, kPlanLargeMaxBlock);
@@ -122,10 +132,13 @@ template <typename T> static int dev_project(const bsls_plan *plan, T *y, int mo
     const int ntiles = plan->ragged ? plan->tiles : 0;
     const int32_t *ids = plan->ragged ? plan->d_large_ids : nullptr;  // uniform large blocks: all of them
     const int nlarge = plan->ragged ? plan->large : plan->nb;
+    if (int rc = ensure_slow_queue(plan)) return rc;
     if constexpr (sizeof(T) == 8)
-        return proj_ragged_f64((double *)y, plan->d_starts, plan->d_tile_first, ntiles, ids, nlarge, plan->max_size, mode, stream);
+        return proj_ragged_f64((double *)y, plan->d_starts, plan->d_tile_first, ntiles, ids, nlarge, plan->max_size, mode, plan->d_slow,
+                               plan->nb, stream);
     else
-        return proj_ragged_f32((float *)y, plan->d_starts, plan->d_tile_first, ntiles, ids, nlarge, plan->max_size, mode, stream);
+        return proj_ragged_f32((float *)y, plan->d_starts, plan->d_tile_first, ntiles, ids, nlarge, plan->max_size, mode, plan->d_slow,
+                               plan->nb, stream);
 }
 
 
@@ -357,6 +370,7 @@ int bsls_plan_destroy(bsls_plan *plan) {
     if (plan->d_large_ids) cudaFree(plan->d_large_ids);
     if (plan->d_pava_first) cudaFree(plan->d_pava_first);
     if (plan->d_pava_large) cudaFree(plan->d_pava_large);
+    if (plan->d_slow) cudaFree(plan->d_slow);
     delete plan;
     return BSLS_OK;
 }

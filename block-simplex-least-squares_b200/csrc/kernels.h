@@ -5,15 +5,16 @@
 namespace bsls {
 
 // proj_f64.cu / proj_f32.cu: all blocks have K entries, first block starts at `first`.
-int proj_uniform_f64(double *y, long long first, int nb, int K, int mode, cudaStream_t stream);
-int proj_uniform_f32(float *y, long long first, int nb, int K, int mode, cudaStream_t stream);
+// `slow`: nb + 1 int32 of scratch for the blocks the selection kernel hands to the sorter (may be null: sorting kernels only)
+int proj_uniform_f64(double *y, long long first, int nb, int K, int mode, int32_t *slow, cudaStream_t stream);
+int proj_uniform_f32(float *y, long long first, int nb, int K, int mode, int32_t *slow, cudaStream_t stream);
 
 
 // ragged layouts: tile kernel + one-CTA-per-large-block kernel (proj_ragged.cuh)
 int proj_ragged_f64(double *y, const int32_t *starts, const int32_t *tile_first, int ntiles, const int32_t *large_ids,
-                    int nlarge, int max_large, int mode, cudaStream_t stream);
+                    int nlarge, int max_large, int mode, int32_t *slow, int nb, cudaStream_t stream);
 int proj_ragged_f32(float *y, const int32_t *starts, const int32_t *tile_first, int ntiles, const int32_t *large_ids,
-                    int nlarge, int max_large, int mode, cudaStream_t stream);
+                    int nlarge, int max_large, int mode, int32_t *slow, int nb, cudaStream_t stream);
 
 // plan.cu: layout analysis on the device
 struct LayoutStats {
@@ -57,6 +58,7 @@ struct bsls_plan {
     int pava_windows = 0, pava_large = 0;
     int32_t *d_pava_first = nullptr;  // pava_windows + 1 entries
     int32_t *d_pava_large = nullptr;  // blocks longer than kPlanPavaWarpMax
+    int32_t *d_slow = nullptr;        // nb + 1: queue of dense blocks between the selection kernel and the sorter
 };
 
 namespace bsls {

@@ -3,15 +3,15 @@
 #include "proj_ragged.cuh"
 
 namespace bsls {
-int proj_uniform_f32(float *y, long long first, int nb, int K, int mode, cudaStream_t stream) {
-    return mode == kBall ? launch_proj_uniform<float, kBall>(y, first, nb, K, stream)
-                         : launch_proj_uniform<float, kSimplex>(y, first, nb, K, stream);
+int proj_uniform_f32(float *y, long long first, int nb, int K, int mode, int32_t *slow, cudaStream_t stream) {
+    return mode == kBall ? launch_proj_uniform<float, kBall>(y, first, nb, K, slow, stream)
+                         : launch_proj_uniform<float, kSimplex>(y, first, nb, K, slow, stream);
 }
 
 int proj_ragged_f32(float *y, const int32_t *starts, const int32_t *tile_first, int ntiles, const int32_t *large_ids,
-                    int nlarge, int max_large, int mode, cudaStream_t stream) {
+                    int nlarge, int max_large, int mode, int32_t *slow, int nb, cudaStream_t stream) {
     static_assert(kTileElems == kPlanTileElems && kTileMaxBlock == kPlanTileMaxBlock && kLargeMaxBlock == kPlanLargeMaxBlock, "plan constants");
-    return mode == kBall ? launch_proj_ragged<float, kBall>(y, starts, tile_first, ntiles, large_ids, nlarge, max_large, stream)
-                         : launch_proj_ragged<float, kSimplex>(y, starts, tile_first, ntiles, large_ids, nlarge, max_large, stream);
+    return mode == kBall ? launch_proj_ragged<float, kBall>(y, starts, tile_first, ntiles, large_ids, nlarge, max_large, slow, nb, stream)
+                         : launch_proj_ragged<float, kSimplex>(y, starts, tile_first, ntiles, large_ids, nlarge, max_large, slow, nb, stream);
 }
 }  // namespace bsls

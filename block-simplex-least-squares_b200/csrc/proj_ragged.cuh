@@ -6,14 +6,19 @@
 // Work split (decided once per layout, see plan.cu):
 //   * TILE kernel: the element range is cut into fixed tiles of kTileElems; a CTA owns the
 //     blocks that START in its tile (at most kTileMaxBlock long, so they fit the CTA's
-//     shared-memory window of kTileElems + kTileMaxBlock values).  Inside the CTA blocks
-//     are binned by size class and every class is processed by the register code of
-//     simplex_core.cuh with G = 1..32 lanes per block.  HBM traffic: read y once, write y
-//     once, read the int32 starts once.
-//   * LARGE kernel: one CTA per block longer than kTileMaxBlock (up to kLargeMaxBlock):
-//     bitonic sort in shared memory, the reference's left-to-right running sum by one
-//     thread, candidates tested by all threads.
-// Both reproduce the reference's arithmetic order, so results are bit-identical to it.
+//     shared-memory window of kTileElems + kTileMaxBlock values).  Inside the CTA the blocks
+//     are binned by size class (so that the lanes of a warp do similar work) and then
+//       - blocks of at most 8 values: one thread, sorting network in registers;
+//       - 9..32 values: one thread, candidate selection (select_core.cuh);
+//       - longer blocks, and the few whose support is too dense for one thread: one warp,
+//         candidate selection with up to 128 candidates in the warp's registers;
+//       - blocks even a warp cannot settle are queued for the LARGE kernel.
+//     Results are written into the window in place; the tile goes back with coalesced stores.
+//     HBM traffic: read y once, write y once, read the int32 starts once.
+//   * LARGE kernel: one CTA per block longer than kTileMaxBlock (up to kLargeMaxBlock) and per
+//     queued block: the block is staged in shared memory, warp 0 tries candidate selection,
+//     and only a dense support falls back to a bitonic sort with the reference's serial sum.
+// All paths reproduce the reference's arithmetic order, so results are bit-identical to it.
 #pragma once
 #include "proj_uniform.cuh"
 
@@ -21,7 +26,7 @@ namespace bsls {
 
 constexpr int kTileElems = 2048;     // tile grid pitch (elements)
 constexpr int kTileMaxBlock = 512;   // longest block the tile kernel handles
-constexpr int kTileThreads = 256;
+constexpr int kTileThreads = 128;
 constexpr int kLargeMaxBlock = 8192; // longest block the one-CTA kernel handles
 constexpr int kLargeThreads = 512;
 constexpr int kNumClasses = 8;
@@ -31,72 +36,62 @@ __device__ __forceinline__ int size_class(int K) {
     return K <= 4 ? 0 : (30 - __clz(K - 1));  // ceil(log2 K) - 2 for K > 4
 }
 
-// One size class: G lanes per block, E registers per lane.
-template <typename T, int E, int G, int MODE>
-__device__ __noinline__ void process_class(T *ybuf, const int *sstart, const uint16_t *list, int count, int tile_lo) {
-    constexpr int GROUPS = kTileThreads / G;
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int sub = lane & (G - 1);
-    const int grp = tid / G;
-    for (int base = 0; base < count; base += GROUPS) {  // uniform trip count across the CTA
-        const int idx = base + grp;
-        const bool live = idx < count;
-        int K = 1;
-        T *blkp = ybuf;
-        if (live) {
-            const int b = list[idx];
-            const int s = sstart[b];
-            K = sstart[b + 1] - s;
-            blkp = ybuf + (s - tile_lo);
-        }
-        bool project = true;
-        if (MODE == kBall) {
-            T total = T(0);
-            if (live && sub == 0)
-                for (int k = 0; k < K; ++k) {
-                    const T x = blkp[k];
-                    if (!(x < T(0))) total += x;
-                }
-            if (G > 1) total = __shfl_sync(0xffffffffu, total, lane & ~(G - 1));
-            project = total > T(1);
-        }
-        T v[E];
-        load_block_regs<T, E, G, MODE>(v, blkp, K, lane, live, false);
-        sort_desc_group<T, E, G>(v, lane);
-        T shift = simplex_shift_sorted<T, E, G>(v, K, lane);
-        if (MODE == kBall && !project) shift = T(0);
-        // every lane rewrites exactly the elements it loaded (same rotation as the load)
-        if (live) {
-            int q = lane % K;
-            const int step = G % K;
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-                const int slot = e * G + sub;
-                if (slot < K) {
-                    T x = blkp[q];
-                    if (MODE == kBall) x = clip_neg(x);
-                    x = shift + x;
-                    blkp[q] = (x < T(0)) ? T(0) : x;
-                }
-                q += step;
-                if (q >= K) q -= K;
-            }
-        }
+// y <- max(y + shift, 0) over one block held in shared memory, by one thread
+template <typename T, int MODE> __device__ __forceinline__ void apply_shift_thread(T *blk, int K, T shift) {
+    for (int j = 0; j < K; ++j) {
+        T x = blk[j];
+        if (MODE == kBall) x = clip_neg(x);
+        x = shift + x;
+        blk[j] = (x < T(0)) ? T(0) : x;
     }
 }
 
-// tile_first[t] = index of the first block whose start lies in tile t (tile_first[ntiles] = nb)
-template <typename T, int MODE>
-__global__ void __launch_bounds__(kTileThreads, 2)
-proj_tile_kernel(T *__restrict__ y, const int32_t *__restrict__ starts /* nb+1, last = n */,
-                 const int32_t *__restrict__ tile_first, int ntiles) {
-    __shared__ __align__(16) T ybuf[kTileElems + kTileMaxBlock];
-    __shared__ int sstart[kTileElems + 1];
-    __shared__ uint16_t list[kTileElems];
-    __shared__ int cnt[kNumClasses], off[kNumClasses + 1], fill[kNumClasses];
+// l1-ball: clip, and project only when the clipped block sums to more than one; the sum runs in
+// index order as in the reference (proj_simplex.h:54-62).  Returns false when the block is final.
+template <typename T> __device__ __forceinline__ bool ball_needs_projection(T *blk, int K) {
+    T total = T(0);
+    for (int k = 0; k < K; ++k) {
+        const T x = blk[k];
+        if (!(x < T(0))) total += x;
+    }
+    return total > T(1);
+}
 
-    const int tid = threadIdx.x;
+// Blocks of at most E values: registers, sorting network, the reference's loop.
+template <typename T, int E, int MODE> __device__ __forceinline__ void tiny_block(T *blk, int K) {
+    T v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        T x = Num<T>::neg_inf();
+        if (e < K) {
+            x = blk[e];
+            if (MODE == kBall) x = clip_neg(x);
+        }
+        v[e] = x;
+    }
+    sort_desc_regs<T, E>(v);
+    const T shift = simplex_shift_sorted<T, E, 1>(v, K, 0);
+    apply_shift_thread<T, MODE>(blk, K, shift);
+}
+
+// tile_first[t] = index of the first block whose start lies in tile t (tile_first[ntiles] = nb)
+// slow: queue of block ids for the LARGE kernel, count at slow[nb]
+template <typename T, int MODE>
+__global__ void __launch_bounds__(kTileThreads)
+proj_tile_kernel(T *__restrict__ y, const int32_t *__restrict__ starts /* nb+1, last = n */,
+                 const int32_t *__restrict__ tile_first, int ntiles, int32_t *__restrict__ slow, int nb) {
+    constexpr int NW = kTileThreads / 32;
+    __shared__ __align__(16) T ybuf[kTileElems + kTileMaxBlock];
+    __shared__ uint16_t sstart[kTileElems + 2];       // block starts relative to the window
+    __shared__ uint16_t list[kTileElems];
+    __shared__ uint16_t wlist[(kTileElems + kTileMaxBlock) / 17 + 8];  // single-thread failures (17..32 values only)
+    __shared__ __align__(16) T tcand[kSelMaxCand * kTileThreads];      // thread phase; reused by the warp phase
+    static_assert(kSelMaxCand * kTileThreads >= NW * kSelWarpCand, "warp candidate lists alias the thread slots");
+    T(*wcand)[kSelWarpCand] = reinterpret_cast<T(*)[kSelWarpCand]>(tcand);
+    __shared__ int cnt[kNumClasses], off[kNumClasses + 1], fill[kNumClasses];
+    __shared__ int s_nwarp;
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int fb = tile_first[tile];
         const int nblk = tile_first[tile + 1] - fb;
@@ -105,13 +100,13 @@ proj_tile_kernel(T *__restrict__ y, const int32_t *__restrict__ starts /* nb+1, 
             cnt[tid] = 0;
             fill[tid] = 0;
         }
-        for (int i = tid; i <= nblk; i += kTileThreads) sstart[i] = starts[fb + i];
+        if (tid == 0) s_nwarp = 0;
+        const int tile_lo = starts[fb];
+        // relative starts; a "large" last block (it ends the window) is clamped, it is never touched here
+        for (int i = tid; i <= nblk; i += kTileThreads) sstart[i] = (uint16_t)min(starts[fb + i] - tile_lo, 65535);
         __syncthreads();
-        const int tile_lo = sstart[0];
-        // the window ends with the last block that is not "large"
-        int tile_hi = sstart[nblk];
-        if (tile_hi - sstart[nblk - 1] > kTileMaxBlock) tile_hi = sstart[nblk - 1];
-        const int nel = tile_hi - tile_lo;
+        int nel = sstart[nblk];
+        if (nel - sstart[nblk - 1] > kTileMaxBlock) nel = sstart[nblk - 1];
         for (int i = tid; i < nel; i += kTileThreads) ybuf[i] = y[(size_t)tile_lo + i];
         // ---- bin the blocks by size class (counting sort on shared counters) ---------------
         for (int i = tid; i < nblk; i += kTileThreads) {
@@ -136,15 +131,59 @@ proj_tile_kernel(T *__restrict__ y, const int32_t *__restrict__ starts /* nb+1, 
             }
         }
         __syncthreads();
-        // ---- per class ------------------------------------------------------------------------
-        process_class<T, 4, 1, MODE>(ybuf, sstart, list + off[0], cnt[0], tile_lo);
-        process_class<T, 8, 1, MODE>(ybuf, sstart, list + off[1], cnt[1], tile_lo);
-        process_class<T, 16, 1, MODE>(ybuf, sstart, list + off[2], cnt[2], tile_lo);
-        process_class<T, 32, 1, MODE>(ybuf, sstart, list + off[3], cnt[3], tile_lo);
-        process_class<T, 16, 4, MODE>(ybuf, sstart, list + off[4], cnt[4], tile_lo);
-        process_class<T, 16, 8, MODE>(ybuf, sstart, list + off[5], cnt[5], tile_lo);
-        process_class<T, 16, 16, MODE>(ybuf, sstart, list + off[6], cnt[6], tile_lo);
-        process_class<T, 16, 32, MODE>(ybuf, sstart, list + off[7], cnt[7], tile_lo);
+        // ---- thread per block: classes 0..3 (at most 32 values) ------------------------------
+        const int nthread = off[4];
+        for (int p = tid; p < nthread; p += kTileThreads) {
+            const int b = list[p];
+            const int s = sstart[b];
+            const int K = sstart[b + 1] - s;
+            T *blk = ybuf + s;
+            if (MODE == kBall && !ball_needs_projection<T>(blk, K)) {
+                for (int j = 0; j < K; ++j) blk[j] = clip_neg(blk[j]);
+                continue;
+            }
+            if (K <= 4) {
+                tiny_block<T, 4, MODE>(blk, K);
+            } else if (K <= 8) {
+                tiny_block<T, 8, MODE>(blk, K);
+            } else {
+                T shift;
+                if (select_shift_thread<T, MODE == kBall, 0>(blk, K, lane, false, tcand + tid, kTileThreads, shift))
+                    apply_shift_thread<T, MODE>(blk, K, shift);
+                else
+                    wlist[atomicAdd(&s_nwarp, 1)] = (uint16_t)b;
+            }
+        }
+        __syncthreads();
+        // ---- warp per block: classes 4..7 and the blocks a single thread gave up on ----------------
+        const int nlong = off[kNumClasses] - nthread;
+        const int nwork = nlong + s_nwarp;
+        for (int p = wid; p < nwork; p += NW) {
+            const int b = (p < nlong) ? list[nthread + p] : wlist[p - nlong];
+            const int s = sstart[b];
+            const int K = sstart[b + 1] - s;
+            T *blk = ybuf + s;
+            bool project = true;
+            if (MODE == kBall) {
+                int flag = 0;
+                if (lane == 0) flag = ball_needs_projection<T>(blk, K) ? 1 : 0;
+                project = __shfl_sync(0xffffffffu, flag, 0) != 0;
+            }
+            T shift = T(0);
+            bool ok = true;
+            if (project) ok = select_shift_warp<T, MODE == kBall>(blk, K, lane, wcand[wid], shift);
+            if (ok) {
+                for (int j = lane; j < K; j += 32) {
+                    T x = blk[j];
+                    if (MODE == kBall) x = clip_neg(x);
+                    x = shift + x;
+                    blk[j] = (x < T(0)) ? T(0) : x;
+                }
+            } else if (lane == 0) {
+                slow[atomicAdd(&slow[nb], 1)] = fb + b;  // dense support: the LARGE kernel sorts it (block left untouched)
+            }
+            __syncwarp();
+        }
         __syncthreads();
         // ---- coalesced write-back (large blocks inside the window are rewritten unchanged;
         //      the LARGE kernel runs afterwards on the same stream) ----------------------------
@@ -156,11 +195,14 @@ proj_tile_kernel(T *__restrict__ y, const int32_t *__restrict__ starts /* nb+1, 
 // ---- one CTA per large block ---------------------------------------------------------------------
 template <typename T, int MODE>
 __global__ void __launch_bounds__(kLargeThreads)
-proj_large_kernel(T *__restrict__ y, const int32_t *__restrict__ starts, const int32_t *__restrict__ ids, int count) {
+proj_large_kernel(T *__restrict__ y, const int32_t *__restrict__ starts, const int32_t *__restrict__ ids, int count_host,
+                  const int32_t *__restrict__ count_dev) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int s_last;
+    __shared__ int s_last, s_done;
     __shared__ T s_shift, s_total;
+    __shared__ __align__(16) T wcand[kSelWarpCand];
     const int tid = threadIdx.x;
+    const int count = count_dev ? *count_dev : count_host;
     for (int it = blockIdx.x; it < count; it += gridDim.x) {
         const int b = ids ? ids[it] : it;
         const int lo = starts[b];
@@ -192,8 +234,20 @@ proj_large_kernel(T *__restrict__ y, const int32_t *__restrict__ starts, const i
         }
         __syncthreads();
         const bool project = (MODE == kBall) ? (s_total > T(1)) : true;
+        // candidate selection by warp 0 on the staged copy (srt[0..K) is still in input order)
         if (project) {
-            // bitonic sort, descending, -inf sentinels at the tail
+            if (tid < 32) {
+                T shift;
+                const bool ok = select_shift_warp<T, false>(srt, K, tid, wcand, shift);  // srt is already clipped in ball mode
+                if (tid == 0) {
+                    s_done = ok ? 1 : 0;
+                    if (ok) s_shift = shift;
+                }
+            }
+            __syncthreads();
+        }
+        if (project && !s_done) {
+            // dense support: bitonic sort, descending, -inf sentinels at the tail
             for (int size = 2; size <= KP; size <<= 1) {
                 for (int stride = size >> 1; stride > 0; stride >>= 1) {
                     for (int t = tid; t < (KP >> 1); t += kLargeThreads) {
@@ -245,10 +299,16 @@ proj_large_kernel(T *__restrict__ y, const int32_t *__restrict__ starts, const i
 
 template <typename T, int MODE>
 int launch_proj_ragged(T *y, const int32_t *starts, const int32_t *tile_first, int ntiles, const int32_t *large_ids,
-                       int nlarge, int max_large, cudaStream_t stream) {
+                       int nlarge, int max_large, int32_t *slow, int nb, cudaStream_t stream) {
     int dev = 0, num_sm = kNumSM;
     BSLS_CUDA_TRY(cudaGetDevice(&dev));
     BSLS_CUDA_TRY(cudaDeviceGetAttribute(&num_sm, cudaDevAttrMultiProcessorCount, dev));
+    auto large = proj_large_kernel<T, MODE>;
+    static thread_local bool attr_set = false;
+    if (!attr_set) {
+        BSLS_CUDA_TRY(cudaFuncSetAttribute(large, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kLargeMaxBlock * sizeof(T))));
+        attr_set = true;
+    }
     if (ntiles > 0) {
         auto kern = proj_tile_kernel<T, MODE>;
         static thread_local int per_sm = 0;
@@ -257,21 +317,19 @@ int launch_proj_ragged(T *y, const int32_t *starts, const int32_t *tile_first, i
             if (per_sm < 1) per_sm = 1;
         }
         const int grid = ntiles < num_sm * per_sm ? ntiles : num_sm * per_sm;
-        kern<<<grid, kTileThreads, 0, stream>>>(y, starts, tile_first, ntiles);
+        BSLS_CUDA_TRY(cudaMemsetAsync(slow + nb, 0, sizeof(int32_t), stream));
+        kern<<<grid, kTileThreads, 0, stream>>>(y, starts, tile_first, ntiles, slow, nb);
+        BSLS_LAUNCH_CHECK();
+        // blocks whose support was too dense for a warp (count known only on the device; usually zero)
+        large<<<num_sm, kLargeThreads, (size_t)2 * kTileMaxBlock * sizeof(T), stream>>>(y, starts, slow, 0, slow + nb);
         BSLS_LAUNCH_CHECK();
     }
     if (nlarge > 0) {
-        auto kern = proj_large_kernel<T, MODE>;
         int KP = 1;
         while (KP < max_large) KP <<= 1;
         const size_t smem = (size_t)2 * KP * sizeof(T);
-        static thread_local bool attr_set = false;
-        if (!attr_set) {
-            BSLS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kLargeMaxBlock * sizeof(T))));
-            attr_set = true;
-        }
         const int grid = nlarge < 2 * num_sm ? nlarge : 2 * num_sm;
-        kern<<<grid, kLargeThreads, smem, stream>>>(y, starts, large_ids, nlarge);
+        large<<<grid, kLargeThreads, smem, stream>>>(y, starts, large_ids, nlarge, nullptr);
         BSLS_LAUNCH_CHECK();
     }
     return BSLS_OK;

@@ -14,7 +14,7 @@
 #pragma once
 #include <cstdlib>
 
-#include "simplex_core.cuh"
+#include "select_core.cuh"
 
 namespace bsls {
 
@@ -30,7 +30,6 @@ template <> struct Vec16<float> {
     using type = float4;
 };
 
-template <typename T> __device__ __forceinline__ T clip_neg(T v) { return (v < T(0)) ? T(0) : v; }
 
 // Loads the K values of one block (at blkp, in shared memory) into the registers of its G
 // lanes.  Which lane/register receives which element is irrelevant to the sort, so the
@@ -240,6 +239,228 @@ proj_uniform_kernel(T *__restrict__ y, long long first, int nb, int Krt, FastDiv
     }
 }
 
+// ---- SELECT kernel: one thread per block, no full sort (select_core.cuh) -----------------------------
+// Same streaming skeleton as proj_uniform_kernel (persistent CTAs, one bulk copy per tile, coalesced
+// 128-bit output pass); a tile holds THREADS blocks and every thread finds the shift of its own
+// block by candidate selection.  Blocks with a dense support (more than kSelMaxCand candidates)
+// are left untouched and queued in `slow` (ids from slow[0], count in slow[nb]); proj_list_kernel
+// sorts them afterwards.  Keeping the sorter out of this kernel keeps its register count low.
+template <typename T, int THREADS, int MINB, int STAGES, int KC, int MODE>
+__global__ void __launch_bounds__(THREADS, MINB)
+proj_select_kernel(T *__restrict__ y, long long first, int nb, int Krt, FastDiv kdiv, int aligned, int32_t *__restrict__ slow) {
+    constexpr int TB = THREADS;  // blocks per tile
+    constexpr int VN = Vec16<T>::N;
+    using VT = typename Vec16<T>::type;
+    const int K = KC ? KC : Krt;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tile_elems = TB * K;
+    T *stage0 = reinterpret_cast<T *>(smem_raw);
+    T *stage1 = stage0 + (STAGES == 2 ? tile_elems : 0);
+    T *lam = stage1 + tile_elems;
+    T *cand = lam + TB;                                     // kSelMaxCand x THREADS, slot-major
+    uint64_t *bar = reinterpret_cast<uint64_t *>(cand + (size_t)kSelMaxCand * THREADS + ((TB & 1) ? 1 : 0));
+    __shared__ int s_nslow, s_base;
+    __shared__ uint16_t s_slow[THREADS];
+    __shared__ uint8_t s_keep[THREADS];                     // 1: block goes to the sorter, write it back unchanged
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int ntiles = (nb + TB - 1) / TB;
+    T *ybase = y + first;
+    const bool vec_ok = (K % VN) == 0;
+
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        if (STAGES == 2) mbar_init(&bar[1], 1);
+        mbar_init_fence();
+        s_nslow = 0;
+    }
+    __syncthreads();
+    auto issue = [&](int t, int s) {
+        if (aligned && (nb - t * TB) >= TB) {
+            const uint32_t bytes = (uint32_t)(tile_elems * sizeof(T));
+            mbar_expect_tx(&bar[s], bytes);
+            bulk_g2s(s ? stage1 : stage0, ybase + (size_t)t * tile_elems, bytes, &bar[s]);
+        }
+    };
+    auto kdivide = [&](uint32_t e) -> uint32_t { return KC ? e / (uint32_t)(KC ? KC : 1) : fdiv(e, kdiv); };
+    int tile = blockIdx.x;
+    if (STAGES == 2 && tile < ntiles && tid == 0) issue(tile, 0);
+    for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+        const int s = (STAGES == 2) ? (it & 1) : 0;
+        if (STAGES == 2) {
+            const int nxt = tile + gridDim.x;
+            if (nxt < ntiles && tid == 0) issue(nxt, s ^ 1);
+        } else if (tid == 0) {
+            issue(tile, 0);
+        }
+        const int nblk = min(TB, nb - tile * TB);
+        const int nel = nblk * K;
+        T *buf = s ? stage1 : stage0;
+        T *gy = ybase + (size_t)tile * tile_elems;
+        if (aligned && nblk == TB) {
+            mbar_wait(&bar[s], (STAGES == 2) ? ((it >> 1) & 1) : (it & 1));
+        } else {
+            for (int i = tid; i < nel; i += THREADS) buf[i] = gy[i];
+            __syncthreads();
+        }
+        // ---- shift of every block: thread per block ---------------------------------------------------
+        if (tid < nblk) {
+            const T *blkp = buf + tid * K;
+            bool project = true;
+            if (MODE == kBall) {
+                T total = T(0);  // in index order, as the reference sums (proj_simplex.h:54-62)
+                for (int k = 0; k < K; ++k) {
+                    const T x = blkp[k];
+                    if (!(x < T(0))) total += x;
+                }
+                project = total > T(1);
+            }
+            T shift = T(0);
+            bool ok = true;
+            if (project) ok = select_shift_thread<T, MODE == kBall, KC>(blkp, K, lane, vec_ok, cand + tid, THREADS, shift);
+            if (!ok) s_slow[atomicAdd(&s_nslow, 1)] = (uint16_t)tid;
+            s_keep[tid] = ok ? 0 : 1;
+            lam[tid] = shift;
+        }
+        __syncthreads();
+        const int nslow = s_nslow;
+        if (nslow > 0) {  // hand the dense blocks to the sorter: one global atomic per tile
+            if (tid == 0) s_base = atomicAdd(&slow[nb], nslow);
+            __syncthreads();
+            for (int i = tid; i < nslow; i += THREADS) slow[s_base + i] = tile * TB + (int)s_slow[i];
+        }
+        // ---- output pass ----------------------------------------------------------------------------------------
+        if (aligned) {
+            const int nvec = nel / VN;
+            for (int i = tid; i < nvec; i += THREADS) {
+                const VT g = reinterpret_cast<const VT *>(buf)[i];
+                T x[VN];
+                if constexpr (VN == 2) {
+                    x[0] = g.x;
+                    x[1] = g.y;
+                } else {
+                    x[0] = g.x;
+                    x[1] = g.y;
+                    x[2] = g.z;
+                    x[3] = g.w;
+                }
+                const uint32_t e0 = (uint32_t)i * VN;
+                const uint32_t b0 = kdivide(e0);
+#pragma unroll
+                for (int j = 0; j < VN; ++j) {
+                    const uint32_t b = vec_ok ? b0 : kdivide(e0 + j);
+                    T t = x[j];
+                    if (MODE == kBall) t = clip_neg(t);
+                    t = lam[b] + t;
+                    t = (t < T(0)) ? T(0) : t;
+                    x[j] = s_keep[b] ? x[j] : t;
+                }
+                if constexpr (VN == 2)
+                    st_stream_v2(gy + e0, x[0], x[1]);
+                else
+                    st_stream_v4(gy + e0, x[0], x[1], x[2], x[3]);
+            }
+            for (int i = nvec * VN + tid; i < nel; i += THREADS) {
+                const T x = buf[i];
+                const uint32_t b = kdivide((uint32_t)i);
+                T t = x;
+                if (MODE == kBall) t = clip_neg(t);
+                t = lam[b] + t;
+                t = (t < T(0)) ? T(0) : t;
+                gy[i] = s_keep[b] ? x : t;
+            }
+        } else {
+            for (int i = tid; i < nel; i += THREADS) {
+                const T x = buf[i];
+                const uint32_t b = kdivide((uint32_t)i);
+                T t = x;
+                if (MODE == kBall) t = clip_neg(t);
+                t = lam[b] + t;
+                t = (t < T(0)) ? T(0) : t;
+                gy[i] = s_keep[b] ? x : t;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) s_nslow = 0;
+    }
+}
+
+// The sorter for the blocks proj_select_kernel queued: G lanes per block, values straight from
+// global memory into registers, full sort, reference replay, result written in place.
+template <typename T, int E, int G, int THREADS, int MODE>
+__global__ void __launch_bounds__(THREADS)
+proj_list_kernel(T *__restrict__ y, long long first, int K, const int32_t *__restrict__ slow, int nb) {
+    const int count = slow[nb];
+    if (count == 0) return;
+    constexpr int GROUPS = THREADS / G;
+    const int tid = threadIdx.x, lane = tid & 31, sub = tid & (G - 1), grp = tid / G;
+    const T ninf = Num<T>::neg_inf();
+    for (int base = blockIdx.x * GROUPS; base < count; base += gridDim.x * GROUPS) {  // uniform trip count per warp
+        const int idx = base + grp;
+        const bool live = idx < count;
+        T *blk = y + first + (size_t)(live ? slow[idx] : 0) * K;
+        T v[E], raw[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int pos = e * G + sub;  // lane-interleaved: consecutive lanes read consecutive values
+            T x = ninf;
+            if (live && pos < K) x = blk[pos];
+            raw[e] = x;
+            v[e] = (MODE == kBall && x < T(0)) ? T(0) : x;
+        }
+        sort_desc_group<T, E, G>(v, lane);
+        const T shift = simplex_shift_sorted<T, E, G>(v, K, lane);
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int pos = e * G + sub;
+            if (live && pos < K) {
+                T t = raw[e];
+                if (MODE == kBall) t = clip_neg(t);
+                t = shift + t;
+                blk[pos] = (t < T(0)) ? T(0) : t;
+            }
+        }
+    }
+}
+
+template <typename T, int E, int G, int THREADS, int MINB, int STAGES, int KC, int MODE>
+int launch_proj_select_cfg(T *y, long long first, int nb, int K, int32_t *slow, cudaStream_t stream) {
+    constexpr int TB = THREADS;
+    auto kern = proj_select_kernel<T, THREADS, MINB, STAGES, KC, MODE>;
+    const size_t smem = (size_t)STAGES * TB * K * sizeof(T) + (size_t)TB * sizeof(T) + (size_t)kSelMaxCand * THREADS * sizeof(T) +
+                        sizeof(T) + 2 * sizeof(uint64_t);
+    static thread_local int cached_blocks_per_sm = -1;
+    static thread_local size_t cached_smem = 0;
+    static thread_local int num_sm = 0;
+    if (cached_blocks_per_sm < 0 || cached_smem != smem) {
+        BSLS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int dev = 0;
+        BSLS_CUDA_TRY(cudaGetDevice(&dev));
+        BSLS_CUDA_TRY(cudaDeviceGetAttribute(&num_sm, cudaDevAttrMultiProcessorCount, dev));
+        int per = 0;
+        BSLS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, THREADS, smem));
+        if (per < 1) {
+            set_error("proj_select: block size K=%d does not fit shared memory (%zu B)", K, smem);
+            return BSLS_ERR_ARG;
+        }
+        cached_blocks_per_sm = per;
+        cached_smem = smem;
+    }
+    const int ntiles = (nb + TB - 1) / TB;
+    const int grid = ntiles < num_sm * cached_blocks_per_sm ? ntiles : num_sm * cached_blocks_per_sm;
+    const int aligned = ((reinterpret_cast<uintptr_t>(y + first) % 16) == 0) ? 1 : 0;
+    BSLS_CUDA_TRY(cudaMemsetAsync(slow + nb, 0, sizeof(int32_t), stream));
+    kern<<<grid, THREADS, smem, stream>>>(y, first, nb, K, make_fastdiv((uint32_t)K), aligned, slow);
+    BSLS_LAUNCH_CHECK();
+    // the sorter reads the count on the device: no host round trip; an empty queue costs one tiny launch
+    constexpr int LT = 128;
+    const int lgrid = num_sm * 4;
+    proj_list_kernel<T, E, G, LT, MODE><<<lgrid, LT, 0, stream>>>(y, first, K, slow, nb);
+    BSLS_LAUNCH_CHECK();
+    return BSLS_OK;
+}
+
 // ---- host side: pick a configuration for K and launch ------------------------------------------
 template <typename T, int E, int G, int THREADS, int MINB, int BPT, int STAGES, int KC, int MODE>
 int launch_proj_uniform_cfg(T *y, long long first, int nb, int K, cudaStream_t stream) {
@@ -283,11 +504,20 @@ inline int tune_variant() {
     return v;
 }
 
-template <typename T, int MODE> int launch_proj_uniform(T *y, long long first, int nb, int K, cudaStream_t stream) {
+template <typename T, int MODE> int launch_proj_uniform(T *y, long long first, int nb, int K, int32_t *slow, cudaStream_t stream) {
     if (nb <= 0) return BSLS_OK;
     const int tv = tune_variant();
     // sizes the BASELINE configs name, with K known at compile time
 #define CFG(E, G, TH, MINB, BPT, ST, KC) return launch_proj_uniform_cfg<T, E, G, TH, MINB, BPT, ST, KC, MODE>(y, first, nb, K, stream)
+#define SEL(E, G, TH, MINB, ST, KC) return launch_proj_select_cfg<T, E, G, TH, MINB, ST, KC, MODE>(y, first, nb, K, slow, stream)
+    // candidate selection instead of a full sort (BSLS_TUNE=100 keeps the sorting kernels everywhere)
+    if (tv != 100 && slow != nullptr && K >= 32 && K <= 128) {
+        if (K == 32) SEL(32, 1, 128, 5, 1, 32);
+        if (K == 64) SEL(16, 4, 64, 5, 1, 64);
+        if (K == 128) SEL(16, 8, 64, 3, 1, 128);
+        if (K <= 64) SEL(16, 4, 64, 4, 1, 0);
+        SEL(16, 8, 64, 2, 1, 0);
+    }
     if (K == 4) CFG(4, 1, 256, 4, 4, 2, 4);
     if (K == 16) {
         if (tv == 1) CFG(16, 1, 128, 6, 1, 1, 16);
@@ -317,6 +547,7 @@ template <typename T, int MODE> int launch_proj_uniform(T *y, long long first, i
     if (K <= 256) CFG(16, 16, 256, 2, 1, 2, 0);
     if (K <= 512) CFG(16, 32, 256, 2, 1, 2, 0);
 #undef CFG
+#undef SEL
     set_error("launch_proj_uniform: K=%d above %d", K, kUniformMaxK);
     return BSLS_ERR_ARG;
 }

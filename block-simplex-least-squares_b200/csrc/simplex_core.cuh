@@ -17,6 +17,8 @@
 
 namespace bsls {
 
+template <typename T> __device__ __forceinline__ T clip_neg(T v) { return (v < T(0)) ? T(0) : v; }
+
 // compare-exchange, larger value first.  fp64: one DSETP + four 32-bit SELs (sm_100a has no
 // native fp64 min/max: fmax() expands to DSETP + SEL + FSEL + NaN fix-up + moves, which is
 // slower).  fp32: FMNMX pairs.  Inputs are never NaN.

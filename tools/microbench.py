@@ -13,12 +13,24 @@ pass
 import bsls_b200
 
 
-def time_proj(K, nb, reps=10, dtype=torch.float64, ball=False):
+def make_input(n, K, kind, dtype, gen):
+    if kind == "normal":        # BASELINE config 2
+        return torch.randn(n, dtype=dtype, device="cuda", generator=gen)
+    if kind == "uniform":       # the reference's own stress input (test_stress_proj_simplex.py:28)
+        return torch.rand(n, dtype=dtype, device="cuda", generator=gen)
+    if kind == "near":          # a solver iterate: a feasible point with a dense support, slightly perturbed
+        e = -torch.log(torch.rand(n // K, K, dtype=dtype, device="cuda", generator=gen))
+        x = e / e.sum(1, keepdim=True)
+        return (x + 0.01 / K * torch.randn(n // K, K, dtype=dtype, device="cuda", generator=gen)).reshape(-1)
+    raise ValueError(kind)
+
+
+def time_proj(K, nb, reps=10, dtype=torch.float64, ball=False, kind="normal"):
     n = nb * K
     gen = torch.Generator(device="cuda").manual_seed(K)
     starts = torch.arange(0, n, K, dtype=torch.int64, device="cuda")
     plan = bsls_b200.BlockPlan(starts, n)
-    bufs = [torch.randn(n, dtype=dtype, device="cuda", generator=gen) for _ in range(reps + 3)]
+    bufs = [make_input(n, K, kind, dtype, gen) for _ in range(reps + 3)]
     fn = bsls_b200.proj_multi_ball_c if ball else bsls_b200.proj_multi_simplex_c
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     for b in bufs[:3]:
