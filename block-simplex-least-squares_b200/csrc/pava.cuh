@@ -79,38 +79,52 @@ __device__ __forceinline__ bool pava_merge_run(T *y, W *w, const uint16_t *A, ui
 // ---------------------------------------------------------------------------------------------
 // one THREAD per block: the reference loop verbatim, on shared-memory rows
 // ---------------------------------------------------------------------------------------------
-// y / w point at one block (K entries).  Statement for statement isotonic_regression.h:18-57.
+// y / w point at one block (K entries).  The reference's sweeps (isotonic_regression.h:18-49) as
+// ONE flat loop per sweep: every iteration looks at exactly one pool head and either absorbs it
+// into the open run (the running numerator / denominator are formed on the way, in the same
+// left-to-right order as the reference's second loop: 0 + y*w == y*w) or closes the run
+// (merging it if its first and last value differ) and opens the next.  The lanes of a warp then
+// iterate in near lock step, whereas the reference's nested loops serialise under SIMT.
+// Branch-free body: the next state is selected, not branched to; merged pools first receive
+// their numerator and a mark in `dirty`, and the divisions of a sweep are done together after
+// it (the quotient is not needed before the next sweep).  K <= 64.
 template <typename T, typename W>
 __device__ __forceinline__ void pava_block_serial(T *y, W *w, int K, int update) {
     for (;;) {
-        bool pooled = false;
+        unsigned long long dirty = 0ull;
         int i = 0;
-        while (i < K) {
-            int k = i + (int)w[i];
-            const T yi = y[i];
-            T yj = yi;
-            while (k < K) {
-                const T yk = y[k];
-                if (!(yk <= yj)) break;
-                yj = yk;
-                k += (int)w[k];
-            }
-            if (yi != yj) {
-                T num = T(0);
-                int den = 0;
-                for (int p = i; p < k;) {
-                    const int wp = (int)w[p];
-                    num += y[p] * (T)wp;
-                    den += wp;
-                    p += wp;
-                }
-                y[i] = num / (T)den;
+        int den = (int)w[0];
+        T yi = y[0];
+        T yj = yi;
+        T num = yi * (T)den;
+        int k = den;
+        bool run = true;
+        while (run) {
+            const bool in = k < K;
+            const int kk = in ? k : 0;
+            const T yk = y[kk];
+            const int wk = (int)w[kk];
+            const bool absorb = in && (yk <= yj);
+            const T prod = yk * (T)wk;
+            if (!absorb && yi != yj) {  // close a run that pooled something
+                y[i] = num;
                 w[i] = (W)den;
-                pooled = true;
+                dirty |= 1ull << i;
             }
-            i = k;
+            run = in;
+            num = absorb ? num + prod : prod;
+            den = absorb ? den + wk : wk;
+            yi = absorb ? yi : yk;
+            i = absorb ? i : k;
+            yj = yk;
+            k += wk;
         }
-        if (!pooled) break;
+        if (!dirty) break;
+        while (dirty) {
+            const int p = __ffsll((long long)dirty) - 1;
+            dirty &= dirty - 1ull;
+            y[p] = y[p] / (T)(int)w[p];
+        }
     }
     if (update) {
         for (int i = 0; i < K;) {

@@ -194,7 +194,7 @@ __device__ __forceinline__ bool select_shift_thread(const T *blk, int K, int rot
 // registers of the warp (E_W per lane) and are consumed in descending order with shuffles.
 constexpr int kSelWarpRegs = 4;                      // candidate registers per lane
 constexpr int kSelWarpCand = 32 * kSelWarpRegs;      // 128 candidates per block at most
-constexpr int kSelWarpRounds = 8;
+constexpr int kSelWarpRounds = 12;
 
 template <typename T> __device__ __forceinline__ T warp_max(T v) {
 #pragma unroll
@@ -222,7 +222,7 @@ __device__ __forceinline__ bool select_shift_warp(const T *blk, int K, int lane,
     umax = warp_max(umax);
     const T delta = select_delta<T>(K, umax);
     T tau = (umax - T(1)) - delta;
-    int c = 0;
+    int c = 0, c_prev = K + 1;
 #pragma unroll 1
     for (int round = 0; round < kSelWarpRounds; ++round) {
         T s = T(0);
@@ -237,7 +237,9 @@ __device__ __forceinline__ bool select_shift_warp(const T *blk, int K, int lane,
         }
         s = warp_sum(s);
         c = __reduce_add_sync(0xffffffffu, cl);
-        if (c <= kSelWarpCand) break;
+        // keep tightening while it pays: every candidate less saves a round of shuffles below
+        if (c <= 8 || c >= c_prev) break;
+        c_prev = c;
         const T t2 = (s - T(1)) / (T)c - delta;
         if (!(t2 > tau)) break;
         tau = t2;
@@ -276,6 +278,9 @@ __device__ __forceinline__ bool select_shift_warp(const T *blk, int K, int lane,
 #pragma unroll
         for (int e = 1; e < kSelWarpRegs; ++e) lm = (r[e] > lm) ? r[e] : lm;
         const T v = warp_max(lm);
+        // (S_{i-1} - 1)/i bounds the threshold from below: a value more than delta under it, and
+        // every later one, is rejected by the reference -- stop (multiplied out: no division)
+        if (i > 0 && fma(v, (T)i, delta * (T)i) < sum - T(1)) break;
         // exactly one holder gives its copy up (lowest lane, lowest register)
         const unsigned holders = __ballot_sync(0xffffffffu, lm == v);
         if (lane == __ffs(holders) - 1) {
