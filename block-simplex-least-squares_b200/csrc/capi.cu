@@ -91,6 +91,46 @@ static int dev_pava(const bsls_plan *plan_, T *y, int32_t *weight, int update, i
         else
             return pava_small_f32((float *)y, weight, plan->first, plan->nb, plan->uniform, update, clip01, stream);
     }
+    if (plan->ragged) {
+        // tile grid of the projection: blocks of at most kPlanMidMin values by one thread each inside
+        // tiles, up to kPlanTileMaxBlock by one warp each (d_mid_ids), longer ones by one CTA each
+        // (d_large_ids).  The three kernels own disjoint blocks: fork onto two auxiliary streams, join.
+        if (!plan->ev_fork) {
+            BSLS_CUDA_TRY(cudaEventCreateWithFlags(&plan->ev_fork, cudaEventDisableTiming));
+            for (int k = 0; k < 2; ++k) {
+                BSLS_CUDA_TRY(cudaStreamCreateWithFlags(&plan->aux[k], cudaStreamNonBlocking));
+                BSLS_CUDA_TRY(cudaEventCreateWithFlags(&plan->ev_join[k], cudaEventDisableTiming));
+            }
+        }
+        BSLS_CUDA_TRY(cudaEventRecord(plan->ev_fork, stream));
+        int rc = BSLS_OK;
+        if (plan->mid > 0) {
+            BSLS_CUDA_TRY(cudaStreamWaitEvent(plan->aux[0], plan->ev_fork, 0));
+            if constexpr (sizeof(T) == 8)
+                rc = pava_mid_f64((double *)y, weight, plan->d_starts, plan->d_mid_ids, plan->mid, update, clip01, plan->aux[0]);
+            else
+                rc = pava_mid_f32((float *)y, weight, plan->d_starts, plan->d_mid_ids, plan->mid, update, clip01, plan->aux[0]);
+            if (rc) return rc;
+            BSLS_CUDA_TRY(cudaEventRecord(plan->ev_join[0], plan->aux[0]));
+        }
+        if (plan->large > 0) {
+            BSLS_CUDA_TRY(cudaStreamWaitEvent(plan->aux[1], plan->ev_fork, 0));
+            if constexpr (sizeof(T) == 8)
+                rc = pava_f64((double *)y, weight, plan->d_starts, nullptr, 0, plan->d_large_ids, plan->large, plan->max_size, update, clip01, plan->aux[1]);
+            else
+                rc = pava_f32((float *)y, weight, plan->d_starts, nullptr, 0, plan->d_large_ids, plan->large, plan->max_size, update, clip01, plan->aux[1]);
+            if (rc) return rc;
+            BSLS_CUDA_TRY(cudaEventRecord(plan->ev_join[1], plan->aux[1]));
+        }
+        if constexpr (sizeof(T) == 8)
+            rc = pava_tile_f64((double *)y, weight, plan->d_starts, plan->d_tile_first, plan->tiles, update, clip01, stream);
+        else
+            rc = pava_tile_f32((float *)y, weight, plan->d_starts, plan->d_tile_first, plan->tiles, update, clip01, stream);
+        if (rc) return rc;
+        if (plan->mid > 0) BSLS_CUDA_TRY(cudaStreamWaitEvent(stream, plan->ev_join[0], 0));
+        if (plan->large > 0) BSLS_CUDA_TRY(cudaStreamWaitEvent(stream, plan->ev_join[1], 0));
+        return BSLS_OK;
+    }
     if (int rc = plan_ensure_pava(plan, stream)) return rc;
     if constexpr (sizeof(T) == 8)
         return pava_f64((double *)y, weight, plan->d_starts, plan->d_pava_first, plan->pava_windows, plan->d_pava_large,
@@ -305,6 +345,7 @@ int bsls_plan_create(const int32_t *d_blocks, int numblocks, int n, bsls_stream_
         if (p->d_starts) cudaFree(p->d_starts);
         if (p->d_tile_first) cudaFree(p->d_tile_first);
         if (p->d_large_ids) cudaFree(p->d_large_ids);
+        if (p->d_mid_ids) cudaFree(p->d_mid_ids);
         delete p;
         return rc;
     };
@@ -355,6 +396,19 @@ int bsls_plan_create(const int32_t *d_blocks, int numblocks, int n, bsls_stream_
             if (int rc = plan_large_list(p->d_starts, numblocks, kPlanTileMaxBlock, p->d_large_ids, d_count, stream)) return fail(rc);
             p->large = h_count;
         }
+        if (p->max_size > kPlanMidMin) {
+            int h_mid = 0;
+            TRY_OR_FAIL(cudaMemsetAsync(d_count, 0, sizeof(int), stream));
+            if (int rc = plan_large_list(p->d_starts, numblocks, kPlanMidMin, nullptr, d_count, stream, kPlanTileMaxBlock)) return fail(rc);
+            TRY_OR_FAIL(cudaMemcpyAsync(&h_mid, d_count, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            TRY_OR_FAIL(cudaStreamSynchronize(stream));
+            if (h_mid > 0) {
+                TRY_OR_FAIL(cudaMalloc(&p->d_mid_ids, sizeof(int32_t) * (size_t)h_mid));
+                TRY_OR_FAIL(cudaMemsetAsync(d_count, 0, sizeof(int), stream));
+                if (int rc = plan_large_list(p->d_starts, numblocks, kPlanMidMin, p->d_mid_ids, d_count, stream, kPlanTileMaxBlock)) return fail(rc);
+            }
+            p->mid = h_mid;
+        }
         TRY_OR_FAIL(cudaStreamSynchronize(stream));
         cudaFree(d_count);
     }
@@ -371,6 +425,12 @@ int bsls_plan_destroy(bsls_plan *plan) {
     if (plan->d_pava_first) cudaFree(plan->d_pava_first);
     if (plan->d_pava_large) cudaFree(plan->d_pava_large);
     if (plan->d_slow) cudaFree(plan->d_slow);
+    if (plan->d_mid_ids) cudaFree(plan->d_mid_ids);
+    if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
+    for (int k = 0; k < 2; ++k) {
+        if (plan->ev_join[k]) cudaEventDestroy(plan->ev_join[k]);
+        if (plan->aux[k]) cudaStreamDestroy(plan->aux[k]);
+    }
     delete plan;
     return BSLS_OK;
 }

@@ -22,7 +22,9 @@ struct LayoutStats {
 };
 int plan_layout_stats(const int32_t *starts /* nb+1 */, int nb, int n, LayoutStats *d_out, cudaStream_t stream);
 int plan_tile_first(const int32_t *starts, int nb, int first, int pitch, int32_t *tile_first, int ntiles, cudaStream_t stream);
-int plan_large_list(const int32_t *starts, int nb, int threshold, int32_t *ids, int *d_count, cudaStream_t stream);
+int plan_large_list(const int32_t *starts, int nb, int threshold, int32_t *ids, int *d_count, cudaStream_t stream,
+                    int upper = 0x7fffffff);
+constexpr int kPlanMidMin = 32;           // ragged layouts: blocks of kPlanMidMin < size <= kPlanTileMaxBlock get a warp each
 constexpr int kPlanTileElems = 2048;      // == kTileElems (proj_ragged.cuh)
 constexpr int kPlanTileMaxBlock = 512;    // == kTileMaxBlock
 constexpr int kPlanLargeMaxBlock = 8192;  // == kLargeMaxBlock
@@ -39,6 +41,15 @@ int pava_small_f64(double *y, int32_t *w, long long first, int nb, int K, int up
 int pava_small_f32(float *y, int32_t *w, long long first, int nb, int K, int update, int clip01, cudaStream_t stream);
 int pava_f32(float *y, int32_t *w, const int32_t *starts, const int32_t *win_first, int nwin, const int32_t *large_ids,
              int nlarge, int max_large, int update, int clip01, cudaStream_t stream);
+
+// ragged layouts: tiles of whole blocks (thread / warp per block); longer blocks go to pava_f64 with nwin = 0
+int pava_tile_f64(double *y, int32_t *w, const int32_t *starts, const int32_t *tile_first, int ntiles, int update, int clip01,
+                  cudaStream_t stream);
+int pava_tile_f32(float *y, int32_t *w, const int32_t *starts, const int32_t *tile_first, int ntiles, int update, int clip01,
+                  cudaStream_t stream);
+// blocks of kPlanMidMin < size <= kPlanTileMaxBlock: one warp each
+int pava_mid_f64(double *y, int32_t *w, const int32_t *starts, const int32_t *mid_ids, int nmid, int update, int clip01, cudaStream_t stream);
+int pava_mid_f32(float *y, int32_t *w, const int32_t *starts, const int32_t *mid_ids, int nmid, int update, int clip01, cudaStream_t stream);
 
 int device_ok();  // BSLS_OK when an sm_100 device is current (capi.cu)
 }  // namespace bsls
@@ -58,6 +69,11 @@ struct bsls_plan {
     int pava_windows = 0, pava_large = 0;
     int32_t *d_pava_first = nullptr;  // pava_windows + 1 entries
     int32_t *d_pava_large = nullptr;  // blocks longer than kPlanPavaWarpMax
+    int mid = 0;
+    int32_t *d_mid_ids = nullptr;     // ragged: blocks with kPlanMidMin < size <= kPlanTileMaxBlock
+    // fork/join inside one call: the tile, mid and large kernels own disjoint blocks and run side by side
+    cudaStream_t aux[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     int32_t *d_slow = nullptr;        // nb + 1: queue of dense blocks between the selection kernel and the sorter
 };
 

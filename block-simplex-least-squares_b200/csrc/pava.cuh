@@ -353,6 +353,229 @@ pava_warp_kernel(T *__restrict__ yg, int32_t *__restrict__ wg, const int32_t *__
 }
 
 // ---------------------------------------------------------------------------------------------
+// ragged layouts: tiles of whole blocks (the projection's tile grid, plan.cu)
+// ---------------------------------------------------------------------------------------------
+constexpr int kPavaTileElems = 2048;     // == kPlanTileElems
+constexpr int kPavaTileMaxBlock = 512;   // == kPlanTileMaxBlock
+constexpr int kPavaTileThreads = 128;
+constexpr int kPavaThreadMax = 32;       // longest block one thread takes in a tile (== kPlanMidMin)
+
+// One WARP regresses one block of K <= kPavaTileMaxBlock values held in shared memory: the
+// parallel replay of the reference's sweeps (flag run starts, merge runs, compact heads).
+// A / B: head lists (K entries each), F: flags (K entries) -- scratch owned by the warp.
+template <typename T>
+__device__ __forceinline__ void pava_warp_block(T *y, uint16_t *w, int K, int lane, uint16_t *A, uint16_t *B, uint8_t *F,
+                                                bool warm, int update) {
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int P = K;
+    if (!warm) {
+        for (int i = lane; i < K; i += 32) A[i] = (uint16_t)i;
+        __syncwarp();
+    } else {  // heads are reached by i += weight[i] (isotonic_regression.h:22): serial, rare
+        if (lane == 0) {
+            int np = 0;
+            for (int i = 0; i < K; i += max(1, (int)w[i])) A[np++] = (uint16_t)i;
+            B[0] = (uint16_t)np;
+        }
+        __syncwarp();
+        P = B[0];
+        __syncwarp();
+    }
+    for (;;) {
+        for (int base = 0; base < P; base += 32) {  // run starts
+            const int j = base + lane;
+            if (j < P) F[j] = (j == 0 || y[A[j]] > y[A[j - 1]]) ? 1 : 0;
+        }
+        __syncwarp();
+        bool merged = false;
+        for (int base = 0; base < P; base += 32) {  // merge runs
+            const int j = base + lane;
+            if (j < P && F[j] == 1) merged |= pava_merge_run<T, uint16_t>(y, w, A, F, j, P);
+        }
+        merged = __any_sync(0xffffffffu, merged);
+        __syncwarp();
+        if (!merged) break;
+        int np = 0;
+        for (int base = 0; base < P; base += 32) {  // compact the survivors
+            const int j = base + lane;
+            const bool alive = j < P && F[j] != 2;
+            const unsigned m = __ballot_sync(0xffffffffu, alive);
+            if (alive) B[np + __popc(m & lt_mask)] = A[j];
+            np += __popc(m);
+        }
+        __syncwarp();
+        uint16_t *t = A;
+        A = B;
+        B = t;
+        P = np;
+    }
+    if (update) {
+        for (int base = 0; base < P; base += 32) {
+            const int j = base + lane;
+            if (j < P) {
+                const int p = A[j];
+                const T v = y[p];
+                const int stop = p + (int)w[p];
+                for (int r = p + 1; r < stop; ++r) y[r] = v;
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// tile_first[t] = index of the first block whose start lies in tile t (tile_first[ntiles] = nb).
+// Blocks longer than kPavaTileMaxBlock are left to pava_large_kernel.
+template <typename T>
+__global__ void __launch_bounds__(kPavaTileThreads)
+pava_tile_kernel(T *__restrict__ yg, int32_t *__restrict__ wg, const int32_t *__restrict__ starts,
+                 const int32_t *__restrict__ tile_first, int ntiles, PavaFlags fl) {
+    constexpr int WIN = kPavaTileElems + kPavaTileMaxBlock;
+    __shared__ __align__(16) T ybuf[WIN];
+    __shared__ uint16_t wbuf[WIN];
+    __shared__ uint16_t sstart[kPavaTileElems + 2];
+    __shared__ uint16_t list[kPavaTileElems];
+    __shared__ uint8_t skip[WIN];  // 1: element of a block another kernel owns (not written back)
+    constexpr int NC = 6;  // size classes of the thread path: <=1, 2, <=4, <=8, <=16, <=32
+    __shared__ int cnt[NC], off[NC + 1], fill[NC];
+    auto cls = [](int K) { return K <= 1 ? 0 : 32 - __clz(K - 1); };  // ceil(log2 K) + (K > 1)
+
+    const int tid = threadIdx.x;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int fb = tile_first[tile];
+        const int nblk = tile_first[tile + 1] - fb;
+        if (nblk <= 0) continue;
+        if (tid < NC) {
+            cnt[tid] = 0;
+            fill[tid] = 0;
+        }
+        const int tile_lo = starts[fb];
+        for (int i = tid; i <= nblk; i += kPavaTileThreads) sstart[i] = (uint16_t)min(starts[fb + i] - tile_lo, 65535);
+        __syncthreads();
+        int nel = sstart[nblk];
+        if (nel - sstart[nblk - 1] > kPavaTileMaxBlock) nel = sstart[nblk - 1];
+        for (int i = tid; i < nel; i += kPavaTileThreads) {
+            ybuf[i] = yg[(size_t)tile_lo + i];
+            wbuf[i] = fl.has_weight ? (uint16_t)wg[(size_t)tile_lo + i] : (uint16_t)1;
+            skip[i] = 0;
+        }
+        __syncthreads();
+        // work lists: short blocks binned by size class (lanes of a warp then do similar work) from the
+        // front of list[], longer ones from its back
+        for (int i = tid; i < nblk; i += kPavaTileThreads) {
+            const int K = sstart[i + 1] - sstart[i];
+            if (K <= kPavaThreadMax) atomicAdd(&cnt[cls(K)], 1);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int acc = 0;
+            for (int c = 0; c < NC; ++c) {
+                off[c] = acc;
+                acc += cnt[c];
+            }
+            off[NC] = acc;
+        }
+        __syncthreads();
+        for (int i = tid; i < nblk; i += kPavaTileThreads) {
+            const int K = sstart[i + 1] - sstart[i];
+            if (K <= kPavaThreadMax) {
+                const int c = cls(K);
+                list[off[c] + atomicAdd(&fill[c], 1)] = (uint16_t)i;
+            } else {  // a block of pava_mid_kernel / pava_large_kernel: never written back from here
+                const int e1 = min((int)sstart[i + 1], nel);
+                for (int e = sstart[i]; e < e1; ++e) skip[e] = 1;
+            }
+        }
+        __syncthreads();
+        const int nthread = off[NC];
+        for (int p = tid; p < nthread; p += kPavaTileThreads) {
+            const int b = list[p];
+            const int s0 = sstart[b];
+            pava_block_serial<T, uint16_t>(ybuf + s0, wbuf + s0, sstart[b + 1] - s0, fl.update);
+        }
+        __syncthreads();
+        for (int i = tid; i < nel; i += kPavaTileThreads) {
+            if (skip[i]) continue;
+            T v = ybuf[i];
+            if (fl.clip01) v = clip01(v);
+            yg[(size_t)tile_lo + i] = v;
+            if (fl.has_weight) wg[(size_t)tile_lo + i] = (int32_t)wbuf[i];
+        }
+        __syncthreads();
+    }
+}
+
+// Blocks of kPavaThreadMax < K <= kPavaTileMaxBlock: one WARP per block, staged in the warp's own
+// slice of shared memory.  A separate launch (instead of a phase of the tile kernel) puts every
+// such block in flight at once; inside a tile only a handful exist and the other warps would idle.
+constexpr int kPavaMidWarps = 4;
+template <typename T>
+__global__ void __launch_bounds__(kPavaMidWarps * 32)
+pava_mid_kernel(T *__restrict__ yg, int32_t *__restrict__ wg, const int32_t *__restrict__ starts, const int32_t *__restrict__ ids,
+                int count, PavaFlags fl) {
+    __shared__ __align__(16) T ys[kPavaMidWarps][kPavaTileMaxBlock];
+    __shared__ uint16_t ws[kPavaMidWarps][kPavaTileMaxBlock];
+    __shared__ uint16_t la[kPavaMidWarps][kPavaTileMaxBlock], lb[kPavaMidWarps][kPavaTileMaxBlock];
+    __shared__ uint8_t lf[kPavaMidWarps][kPavaTileMaxBlock];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int it = blockIdx.x * kPavaMidWarps + wid; it < count; it += gridDim.x * kPavaMidWarps) {
+        const int b = ids[it];
+        const int lo = starts[b];
+        const int K = starts[b + 1] - lo;
+        T *gy = yg + (size_t)lo;
+        int32_t *gw = wg ? wg + (size_t)lo : nullptr;
+        for (int i = lane; i < K; i += 32) {
+            ys[wid][i] = gy[i];
+            ws[wid][i] = fl.has_weight ? (uint16_t)gw[i] : (uint16_t)1;
+        }
+        __syncwarp();
+        pava_warp_block<T>(ys[wid], ws[wid], K, lane, la[wid], lb[wid], lf[wid], fl.has_weight != 0, fl.update);
+        for (int i = lane; i < K; i += 32) {
+            T v = ys[wid][i];
+            if (fl.clip01) v = clip01(v);
+            gy[i] = v;
+            if (fl.has_weight) gw[i] = (int32_t)ws[wid][i];
+        }
+        __syncwarp();
+    }
+}
+
+template <typename T>
+int launch_pava_mid(T *y, int32_t *w, const int32_t *starts, const int32_t *mid_ids, int nmid, PavaFlags fl, cudaStream_t stream) {
+    if (nmid > 0) {
+        auto mid = pava_mid_kernel<T>;
+        static thread_local int mid_full = 0;
+        if (!mid_full) {
+            int dev = 0, num_sm = kNumSM, per_sm = 1;
+            BSLS_CUDA_TRY(cudaGetDevice(&dev));
+            BSLS_CUDA_TRY(cudaDeviceGetAttribute(&num_sm, cudaDevAttrMultiProcessorCount, dev));
+            BSLS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mid, kPavaMidWarps * 32, 0));
+            mid_full = num_sm * (per_sm < 1 ? 1 : per_sm);
+        }
+        const int want = (nmid + kPavaMidWarps - 1) / kPavaMidWarps;
+        mid<<<want < mid_full ? want : mid_full, kPavaMidWarps * 32, 0, stream>>>(y, w, starts, mid_ids, nmid, fl);
+        BSLS_LAUNCH_CHECK();
+    }
+    return BSLS_OK;
+}
+
+template <typename T>
+int launch_pava_tile(T *y, int32_t *w, const int32_t *starts, const int32_t *tile_first, int ntiles, PavaFlags fl, cudaStream_t stream) {
+    if (ntiles <= 0) return BSLS_OK;
+    auto kern = pava_tile_kernel<T>;
+    static thread_local int grid_full = 0;
+    if (!grid_full) {
+        int dev = 0, num_sm = kNumSM, per_sm = 1;
+        BSLS_CUDA_TRY(cudaGetDevice(&dev));
+        BSLS_CUDA_TRY(cudaDeviceGetAttribute(&num_sm, cudaDevAttrMultiProcessorCount, dev));
+        BSLS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPavaTileThreads, 0));
+        grid_full = num_sm * (per_sm < 1 ? 1 : per_sm);
+    }
+    kern<<<ntiles < grid_full ? ntiles : grid_full, kPavaTileThreads, 0, stream>>>(y, w, starts, tile_first, ntiles, fl);
+    BSLS_LAUNCH_CHECK();
+    return BSLS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // one CTA per long block
 // ---------------------------------------------------------------------------------------------
 template <typename T>
@@ -491,7 +714,9 @@ int launch_pava(T *y, int32_t *w, const int32_t *starts, const int32_t *win_firs
                                                (int)pava_large_smem(kPavaLargeMaxBlock, sizeof(T))));
             attr_set = true;
         }
-        const int grid = nlarge < 2 * num_sm ? nlarge : 2 * num_sm;
+        int per = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, kPavaLargeThreads, pava_large_smem(max_large, sizeof(T))) != cudaSuccess || per < 1) per = 1;
+        const int grid = nlarge < per * num_sm ? nlarge : per * num_sm;
         kern<<<grid, kPavaLargeThreads, pava_large_smem(max_large, sizeof(T)), stream>>>(y, w, starts, large_ids, nlarge, fl);
         BSLS_LAUNCH_CHECK();
     }

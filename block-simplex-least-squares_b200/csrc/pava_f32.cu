@@ -20,4 +20,22 @@ int pava_small_f32(float *y, int32_t *w, long long first, int nb, int K, int upd
     fl.has_weight = w != nullptr;
     return launch_pava_small<float>(y, w, first, nb, K, fl, stream);
 }
+
+int pava_tile_f32(float *y, int32_t *w, const int32_t *starts, const int32_t *tile_first, int ntiles, int update, int clip01,
+                  cudaStream_t stream) {
+    static_assert(kPavaTileElems == kPlanTileElems && kPavaTileMaxBlock == kPlanTileMaxBlock && kPavaThreadMax == kPlanMidMin, "plan constants");
+    PavaFlags fl;
+    fl.update = update;
+    fl.clip01 = clip01;
+    fl.has_weight = w != nullptr;
+    return launch_pava_tile<float>(y, w, starts, tile_first, ntiles, fl, stream);
+}
+
+int pava_mid_f32(float *y, int32_t *w, const int32_t *starts, const int32_t *mid_ids, int nmid, int update, int clip01, cudaStream_t stream) {
+    PavaFlags fl;
+    fl.update = update;
+    fl.clip01 = clip01;
+    fl.has_weight = w != nullptr;
+    return launch_pava_mid<float>(y, w, starts, mid_ids, nmid, fl, stream);
+}
 }  // namespace bsls

@@ -55,17 +55,19 @@ int plan_tile_first(const int32_t *starts, int nb, int first, int pitch, int32_t
     return BSLS_OK;
 }
 
-__global__ void large_list_kernel(const int32_t *__restrict__ starts, int nb, int threshold, int32_t *__restrict__ ids, int *count) {
+// blocks with threshold < size <= upper
+__global__ void large_list_kernel(const int32_t *__restrict__ starts, int nb, int threshold, int upper, int32_t *__restrict__ ids, int *count) {
     for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < nb; b += (long long)gridDim.x * blockDim.x) {
-        if (starts[b + 1] - starts[b] > threshold) {
+        const int sz = starts[b + 1] - starts[b];
+        if (sz > threshold && sz <= upper) {
             const int slot = atomicAdd(count, 1);
             if (ids) ids[slot] = (int)b;
         }
     }
 }
 
-int plan_large_list(const int32_t *starts, int nb, int threshold, int32_t *ids, int *d_count, cudaStream_t stream) {
-    large_list_kernel<<<grid_for(nb, 256), 256, 0, stream>>>(starts, nb, threshold, ids, d_count);
+int plan_large_list(const int32_t *starts, int nb, int threshold, int32_t *ids, int *d_count, cudaStream_t stream, int upper) {
+    large_list_kernel<<<grid_for(nb, 256), 256, 0, stream>>>(starts, nb, threshold, upper, ids, d_count);
     BSLS_LAUNCH_CHECK();
     return BSLS_OK;
 }
