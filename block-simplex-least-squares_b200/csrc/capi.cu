@@ -73,6 +73,8 @@ static int plan_ensure_pava(bsls_plan *p, cudaStream_t stream) {
     return BSLS_OK;
 }
 
+static int ensure_streams(bsls_plan *plan);
+
 template <typename T>
 static int dev_pava(const bsls_plan *plan_, T *y, int32_t *weight, int update, int clip01, cudaStream_t stream) {
     if (int rc = device_ok()) return rc;
@@ -95,13 +97,7 @@ static int dev_pava(const bsls_plan *plan_, T *y, int32_t *weight, int update, i
         // tile grid of the projection: blocks of at most kPlanMidMin values by one thread each inside
         // tiles, up to kPlanTileMaxBlock by one warp each (d_mid_ids), longer ones by one CTA each
         // (d_large_ids).  The three kernels own disjoint blocks: fork onto two auxiliary streams, join.
-        if (!plan->ev_fork) {
-            BSLS_CUDA_TRY(cudaEventCreateWithFlags(&plan->ev_fork, cudaEventDisableTiming));
-            for (int k = 0; k < 2; ++k) {
-                BSLS_CUDA_TRY(cudaStreamCreateWithFlags(&plan->aux[k], cudaStreamNonBlocking));
-                BSLS_CUDA_TRY(cudaEventCreateWithFlags(&plan->ev_join[k], cudaEventDisableTiming));
-            }
-        }
+        if (int rc = ensure_streams(plan)) return rc;
         BSLS_CUDA_TRY(cudaEventRecord(plan->ev_fork, stream));
         int rc = BSLS_OK;
         if (plan->mid > 0) {
@@ -151,6 +147,17 @@ static int ensure_slow_queue(const bsls_plan *plan) {
     return BSLS_OK;
 }
 
+// auxiliary streams / events of a plan (fork-join of kernels that own disjoint blocks), created on first use
+static int ensure_streams(bsls_plan *plan) {
+    if (plan->ev_fork) return BSLS_OK;
+    BSLS_CUDA_TRY(cudaEventCreateWithFlags(&plan->ev_fork, cudaEventDisableTiming));
+    for (int k = 0; k < 2; ++k) {
+        BSLS_CUDA_TRY(cudaStreamCreateWithFlags(&plan->aux[k], cudaStreamNonBlocking));
+        BSLS_CUDA_TRY(cudaEventCreateWithFlags(&plan->ev_join[k], cudaEventDisableTiming));
+    }
+    return BSLS_OK;
+}
+
 template <typename T> static int dev_project(const bsls_plan *plan, T *y, int mode, cudaStream_t stream) {
     if (int rc = device_ok()) return rc;
     if (!plan || !y) {
@@ -173,12 +180,14 @@ template <typename T> static int dev_project(const bsls_plan *plan, T *y, int mo
     const int32_t *ids = plan->ragged ? plan->d_large_ids : nullptr;  // uniform large blocks: all of them
     const int nlarge = plan->ragged ? plan->large : plan->nb;
     if (int rc = ensure_slow_queue(plan)) return rc;
+    if (int rc = ensure_streams(const_cast<bsls_plan *>(plan))) return rc;
+    const RaggedStreams rs = {{plan->aux[0], plan->aux[1]}, plan->ev_fork, {plan->ev_join[0], plan->ev_join[1]}};
     if constexpr (sizeof(T) == 8)
-        return proj_ragged_f64((double *)y, plan->d_starts, plan->d_tile_first, ntiles, ids, nlarge, plan->max_size, mode, plan->d_slow,
-                               plan->nb, stream);
+        return proj_ragged_f64((double *)y, plan->d_starts, plan->d_tile_first, ntiles, plan->d_mid_ids, plan->mid, ids, nlarge,
+                               plan->max_size, mode, plan->d_slow, plan->nb, rs, stream);
     else
-        return proj_ragged_f32((float *)y, plan->d_starts, plan->d_tile_first, ntiles, ids, nlarge, plan->max_size, mode, plan->d_slow,
-                               plan->nb, stream);
+        return proj_ragged_f32((float *)y, plan->d_starts, plan->d_tile_first, ntiles, plan->d_mid_ids, plan->mid, ids, nlarge,
+                               plan->max_size, mode, plan->d_slow, plan->nb, rs, stream);
 }
 
 

@@ -10,11 +10,18 @@ int proj_uniform_f64(double *y, long long first, int nb, int K, int mode, int32_
 int proj_uniform_f32(float *y, long long first, int nb, int K, int mode, int32_t *slow, cudaStream_t stream);
 
 
-// ragged layouts: tile kernel + one-CTA-per-large-block kernel (proj_ragged.cuh)
-int proj_ragged_f64(double *y, const int32_t *starts, const int32_t *tile_first, int ntiles, const int32_t *large_ids,
-                    int nlarge, int max_large, int mode, int32_t *slow, int nb, cudaStream_t stream);
-int proj_ragged_f32(float *y, const int32_t *starts, const int32_t *tile_first, int ntiles, const int32_t *large_ids,
-                    int nlarge, int max_large, int mode, int32_t *slow, int nb, cudaStream_t stream);
+// fork/join inside one call: the tile, mid and large kernels own disjoint blocks and run side by side
+struct RaggedStreams {
+    cudaStream_t aux[2];
+    cudaEvent_t fork, join[2];
+};
+// ragged layouts: tile kernel (thread per block) + warp-per-block kernel + one-CTA-per-large-block kernel (proj_ragged.cuh)
+int proj_ragged_f64(double *y, const int32_t *starts, const int32_t *tile_first, int ntiles, const int32_t *mid_ids, int nmid,
+                    const int32_t *large_ids, int nlarge, int max_large, int mode, int32_t *slow, int nb, const RaggedStreams &rs,
+                    cudaStream_t stream);
+int proj_ragged_f32(float *y, const int32_t *starts, const int32_t *tile_first, int ntiles, const int32_t *mid_ids, int nmid,
+                    const int32_t *large_ids, int nlarge, int max_large, int mode, int32_t *slow, int nb, const RaggedStreams &rs,
+                    cudaStream_t stream);
 
 // plan.cu: layout analysis on the device
 struct LayoutStats {

@@ -8,10 +8,12 @@ int proj_uniform_f64(double *y, long long first, int nb, int K, int mode, int32_
                          : launch_proj_uniform<double, kSimplex>(y, first, nb, K, slow, stream);
 }
 
-int proj_ragged_f64(double *y, const int32_t *starts, const int32_t *tile_first, int ntiles, const int32_t *large_ids,
-                    int nlarge, int max_large, int mode, int32_t *slow, int nb, cudaStream_t stream) {
-    static_assert(kTileElems == kPlanTileElems && kTileMaxBlock == kPlanTileMaxBlock && kLargeMaxBlock == kPlanLargeMaxBlock, "plan constants");
-    return mode == kBall ? launch_proj_ragged<double, kBall>(y, starts, tile_first, ntiles, large_ids, nlarge, max_large, slow, nb, stream)
-                         : launch_proj_ragged<double, kSimplex>(y, starts, tile_first, ntiles, large_ids, nlarge, max_large, slow, nb, stream);
+int proj_ragged_f64(double *y, const int32_t *starts, const int32_t *tile_first, int ntiles, const int32_t *mid_ids, int nmid,
+                    const int32_t *large_ids, int nlarge, int max_large, int mode, int32_t *slow, int nb, const RaggedStreams &rs,
+                    cudaStream_t stream) {
+    static_assert(kTileElems == kPlanTileElems && kTileMaxBlock == kPlanTileMaxBlock && kLargeMaxBlock == kPlanLargeMaxBlock &&
+                      kTileThreadMax == kPlanMidMin, "plan constants");
+    return mode == kBall ? launch_proj_ragged<double, kBall>(y, starts, tile_first, ntiles, mid_ids, nmid, large_ids, nlarge, max_large, slow, nb, rs, stream)
+                         : launch_proj_ragged<double, kSimplex>(y, starts, tile_first, ntiles, mid_ids, nmid, large_ids, nlarge, max_large, slow, nb, rs, stream);
 }
 }  // namespace bsls

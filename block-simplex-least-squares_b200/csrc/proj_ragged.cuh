@@ -27,6 +27,7 @@ namespace bsls {
 constexpr int kTileElems = 2048;     // tile grid pitch (elements)
 constexpr int kTileMaxBlock = 512;   // longest block the tile kernel handles
 constexpr int kTileThreads = 128;
+constexpr int kTileThreadMax = 32;   // longest block one thread takes inside a tile (== kPlanMidMin)
 constexpr int kLargeMaxBlock = 8192; // longest block the one-CTA kernel handles
 constexpr int kLargeThreads = 512;
 constexpr int kNumClasses = 8;
@@ -90,6 +91,7 @@ proj_tile_kernel(T *__restrict__ y, const int32_t *__restrict__ starts /* nb+1, 
     T(*wcand)[kSelWarpCand] = reinterpret_cast<T(*)[kSelWarpCand]>(tcand);
     __shared__ int cnt[kNumClasses], off[kNumClasses + 1], fill[kNumClasses];
     __shared__ int s_nwarp;
+    __shared__ uint8_t skip[kTileElems + kTileMaxBlock];  // 1: element of a block another kernel owns (not written back)
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -107,11 +109,20 @@ proj_tile_kernel(T *__restrict__ y, const int32_t *__restrict__ starts /* nb+1, 
         __syncthreads();
         int nel = sstart[nblk];
         if (nel - sstart[nblk - 1] > kTileMaxBlock) nel = sstart[nblk - 1];
-        for (int i = tid; i < nel; i += kTileThreads) ybuf[i] = y[(size_t)tile_lo + i];
+        for (int i = tid; i < nel; i += kTileThreads) {
+            ybuf[i] = y[(size_t)tile_lo + i];
+            skip[i] = 0;
+        }
+        __syncthreads();
         // ---- bin the blocks by size class (counting sort on shared counters) ---------------
         for (int i = tid; i < nblk; i += kTileThreads) {
             const int K = sstart[i + 1] - sstart[i];
-            if (K <= kTileMaxBlock) atomicAdd(&cnt[size_class(K)], 1);
+            if (K <= kTileThreadMax) {
+                atomicAdd(&cnt[size_class(K)], 1);
+            } else {  // a block of proj_mid_kernel / proj_large_kernel
+                const int e1 = min((int)sstart[i + 1], nel);
+                for (int e = sstart[i]; e < e1; ++e) skip[e] = 1;
+            }
         }
         __syncthreads();
         if (tid == 0) {
@@ -125,7 +136,7 @@ proj_tile_kernel(T *__restrict__ y, const int32_t *__restrict__ starts /* nb+1, 
         __syncthreads();
         for (int i = tid; i < nblk; i += kTileThreads) {
             const int K = sstart[i + 1] - sstart[i];
-            if (K <= kTileMaxBlock) {
+            if (K <= kTileThreadMax) {
                 const int c = size_class(K);
                 list[off[c] + atomicAdd(&fill[c], 1)] = (uint16_t)i;
             }
@@ -155,11 +166,10 @@ proj_tile_kernel(T *__restrict__ y, const int32_t *__restrict__ starts /* nb+1, 
             }
         }
         __syncthreads();
-        // ---- warp per block: classes 4..7 and the blocks a single thread gave up on ----------------
-        const int nlong = off[kNumClasses] - nthread;
-        const int nwork = nlong + s_nwarp;
+        // ---- warp per block: the few blocks a single thread gave up on (dense support) -------------------
+        const int nwork = s_nwarp;
         for (int p = wid; p < nwork; p += NW) {
-            const int b = (p < nlong) ? list[nthread + p] : wlist[p - nlong];
+            const int b = wlist[p];
             const int s = sstart[b];
             const int K = sstart[b + 1] - s;
             T *blk = ybuf + s;
@@ -187,8 +197,52 @@ proj_tile_kernel(T *__restrict__ y, const int32_t *__restrict__ starts /* nb+1, 
         __syncthreads();
         // ---- coalesced write-back (large blocks inside the window are rewritten unchanged;
         //      the LARGE kernel runs afterwards on the same stream) ----------------------------
-        for (int i = tid; i < nel; i += kTileThreads) y[(size_t)tile_lo + i] = ybuf[i];
+        for (int i = tid; i < nel; i += kTileThreads)
+            if (!skip[i]) y[(size_t)tile_lo + i] = ybuf[i];
         __syncthreads();
+    }
+}
+
+// Blocks of kTileThreadMax < K <= kTileMaxBlock: one WARP per block (ids from the plan), staged in the
+// warp's slice of shared memory, candidate selection with up to 128 candidates in registers.  Its own
+// launch puts all of them in flight at once (inside a tile there are only a handful).  Dense supports
+// are queued for proj_large_kernel.
+constexpr int kMidWarps = 4;
+template <typename T, int MODE>
+__global__ void __launch_bounds__(kMidWarps * 32)
+proj_mid_kernel(T *__restrict__ y, const int32_t *__restrict__ starts, const int32_t *__restrict__ ids, int count,
+                int32_t *__restrict__ slow, int nb) {
+    __shared__ __align__(16) T ys[kMidWarps][kTileMaxBlock];
+    __shared__ __align__(16) T wcand[kMidWarps][kSelWarpCand];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int it = blockIdx.x * kMidWarps + wid; it < count; it += gridDim.x * kMidWarps) {
+        const int b = ids[it];
+        const int lo = starts[b];
+        const int K = starts[b + 1] - lo;
+        T *gy = y + (size_t)lo;
+        T *blk = ys[wid];
+        for (int i = lane; i < K; i += 32) blk[i] = gy[i];
+        __syncwarp();
+        bool project = true;
+        if (MODE == kBall) {
+            int flag = 0;
+            if (lane == 0) flag = ball_needs_projection<T>(blk, K) ? 1 : 0;
+            project = __shfl_sync(0xffffffffu, flag, 0) != 0;
+        }
+        T shift = T(0);
+        bool ok = true;
+        if (project) ok = select_shift_warp<T, MODE == kBall>(blk, K, lane, wcand[wid], shift);
+        if (ok) {
+            for (int j = lane; j < K; j += 32) {
+                T x = blk[j];
+                if (MODE == kBall) x = clip_neg(x);
+                x = shift + x;
+                gy[j] = (x < T(0)) ? T(0) : x;
+            }
+        } else if (lane == 0) {
+            slow[atomicAdd(&slow[nb], 1)] = b;
+        }
+        __syncwarp();
     }
 }
 
@@ -298,8 +352,9 @@ proj_large_kernel(T *__restrict__ y, const int32_t *__restrict__ starts, const i
 }
 
 template <typename T, int MODE>
-int launch_proj_ragged(T *y, const int32_t *starts, const int32_t *tile_first, int ntiles, const int32_t *large_ids,
-                       int nlarge, int max_large, int32_t *slow, int nb, cudaStream_t stream) {
+int launch_proj_ragged(T *y, const int32_t *starts, const int32_t *tile_first, int ntiles, const int32_t *mid_ids, int nmid,
+                       const int32_t *large_ids, int nlarge, int max_large, int32_t *slow, int nb, const RaggedStreams &rs,
+                       cudaStream_t stream) {
     int dev = 0, num_sm = kNumSM;
     BSLS_CUDA_TRY(cudaGetDevice(&dev));
     BSLS_CUDA_TRY(cudaDeviceGetAttribute(&num_sm, cudaDevAttrMultiProcessorCount, dev));
@@ -309,7 +364,36 @@ int launch_proj_ragged(T *y, const int32_t *starts, const int32_t *tile_first, i
         BSLS_CUDA_TRY(cudaFuncSetAttribute(large, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kLargeMaxBlock * sizeof(T))));
         attr_set = true;
     }
-    if (ntiles > 0) {
+    const bool tiled = ntiles > 0;
+    if (tiled) BSLS_CUDA_TRY(cudaMemsetAsync(slow + nb, 0, sizeof(int32_t), stream));
+    BSLS_CUDA_TRY(cudaEventRecord(rs.fork, stream));
+    if (tiled && nmid > 0) {
+        BSLS_CUDA_TRY(cudaStreamWaitEvent(rs.aux[0], rs.fork, 0));
+        auto mid = proj_mid_kernel<T, MODE>;
+        static thread_local int mid_full = 0;
+        if (!mid_full) {
+            int per = 1;
+            BSLS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, mid, kMidWarps * 32, 0));
+            mid_full = num_sm * (per < 1 ? 1 : per);
+        }
+        const int want = (nmid + kMidWarps - 1) / kMidWarps;
+        mid<<<want < mid_full ? want : mid_full, kMidWarps * 32, 0, rs.aux[0]>>>(y, starts, mid_ids, nmid, slow, nb);
+        BSLS_LAUNCH_CHECK();
+        BSLS_CUDA_TRY(cudaEventRecord(rs.join[0], rs.aux[0]));
+    }
+    if (nlarge > 0) {
+        BSLS_CUDA_TRY(cudaStreamWaitEvent(rs.aux[1], rs.fork, 0));
+        int KP = 1;
+        while (KP < max_large) KP <<= 1;
+        const size_t smem = (size_t)2 * KP * sizeof(T);
+        int per = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, large, kLargeThreads, smem) != cudaSuccess || per < 1) per = 1;
+        const int grid = nlarge < per * num_sm ? nlarge : per * num_sm;
+        large<<<grid, kLargeThreads, smem, rs.aux[1]>>>(y, starts, large_ids, nlarge, nullptr);
+        BSLS_LAUNCH_CHECK();
+        BSLS_CUDA_TRY(cudaEventRecord(rs.join[1], rs.aux[1]));
+    }
+    if (tiled) {
         auto kern = proj_tile_kernel<T, MODE>;
         static thread_local int per_sm = 0;
         if (!per_sm) {
@@ -317,19 +401,14 @@ int launch_proj_ragged(T *y, const int32_t *starts, const int32_t *tile_first, i
             if (per_sm < 1) per_sm = 1;
         }
         const int grid = ntiles < num_sm * per_sm ? ntiles : num_sm * per_sm;
-        BSLS_CUDA_TRY(cudaMemsetAsync(slow + nb, 0, sizeof(int32_t), stream));
         kern<<<grid, kTileThreads, 0, stream>>>(y, starts, tile_first, ntiles, slow, nb);
         BSLS_LAUNCH_CHECK();
+    }
+    if (tiled && nmid > 0) BSLS_CUDA_TRY(cudaStreamWaitEvent(stream, rs.join[0], 0));
+    if (nlarge > 0) BSLS_CUDA_TRY(cudaStreamWaitEvent(stream, rs.join[1], 0));
+    if (tiled) {
         // blocks whose support was too dense for a warp (count known only on the device; usually zero)
         large<<<num_sm, kLargeThreads, (size_t)2 * kTileMaxBlock * sizeof(T), stream>>>(y, starts, slow, 0, slow + nb);
-        BSLS_LAUNCH_CHECK();
-    }
-    if (nlarge > 0) {
-        int KP = 1;
-        while (KP < max_large) KP <<= 1;
-        const size_t smem = (size_t)2 * KP * sizeof(T);
-        const int grid = nlarge < 2 * num_sm ? nlarge : 2 * num_sm;
-        large<<<grid, kLargeThreads, smem, stream>>>(y, starts, large_ids, nlarge, nullptr);
         BSLS_LAUNCH_CHECK();
     }
     return BSLS_OK;
