@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <vector>
 
 #include "kernels.h"
@@ -250,6 +251,71 @@ int validate_blocks(const int *blocks, int numblocks, int n) {
     return BSLS_OK;
 }
 
+// common block size of a layout, or 0 (host side)
+int uniform_size(const int *blocks, int numblocks, int n) {
+    const int K = (numblocks > 1 ? blocks[1] : n) - blocks[0];
+    for (int i = 1; i < numblocks; ++i)
+        if (blocks[i] - blocks[i - 1] != K) return 0;
+    return (n - blocks[numblocks - 1] == K) ? K : 0;
+}
+
+// Uniform layouts need no plan, which lets the host entry points pipeline: the span is cut into
+// chunks of whole blocks and chunk c's upload, kernel and download run on stream c mod 3, so the
+// two copy engines and the SMs work at the same time (PCIe is the bound of these entry points).
+constexpr int kPipeStreams = 3;
+struct HostPipeline {
+    cudaStream_t s[kPipeStreams] = {nullptr, nullptr, nullptr};
+    int32_t *slow[kPipeStreams] = {nullptr, nullptr, nullptr};
+    size_t slow_cap = 0;
+    int prepare(size_t chunk_blocks) {
+        for (int k = 0; k < kPipeStreams; ++k)
+            if (!s[k]) BSLS_CUDA_TRY(cudaStreamCreateWithFlags(&s[k], cudaStreamNonBlocking));
+        if (chunk_blocks + 1 > slow_cap) {
+            for (int k = 0; k < kPipeStreams; ++k) {
+                if (slow[k]) cudaFree(slow[k]);
+                slow[k] = nullptr;
+                BSLS_CUDA_TRY(cudaMalloc(&slow[k], (chunk_blocks + 1) * sizeof(int32_t)));
+            }
+            slow_cap = chunk_blocks + 1;
+        }
+        return BSLS_OK;
+    }
+    int sync() {
+        for (int k = 0; k < kPipeStreams; ++k) BSLS_CUDA_TRY(cudaStreamSynchronize(s[k]));
+        return BSLS_OK;
+    }
+};
+thread_local HostPipeline g_pipe;
+
+size_t pipeline_chunk_blocks(int K, int numblocks) {
+    size_t cb = ((size_t)32 << 20) / ((size_t)K * sizeof(double));  // ~32 MB of values per chunk
+    if (cb < 1024) cb = 1024;
+    if (cb > (size_t)numblocks) cb = (size_t)numblocks;
+    return cb;
+}
+
+int host_project_uniform(double *y, int first, int numblocks, int K, int mode) {
+    const size_t span = (size_t)numblocks * K;
+    if (int rc = g_ws.reserve(span, 1)) return rc;
+    const size_t cb = pipeline_chunk_blocks(K, numblocks);
+    if (int rc = g_pipe.prepare(cb)) return rc;
+    int c = 0;
+    for (size_t b0 = 0; b0 < (size_t)numblocks; b0 += cb, ++c) {
+        const size_t nbc = std::min(cb, (size_t)numblocks - b0);
+        const size_t off = b0 * K, cnt = nbc * K;
+        cudaStream_t st = g_pipe.s[c % kPipeStreams];
+        BSLS_CUDA_TRY(cudaMemcpyAsync(g_ws.d_y + off, y + first + off, cnt * sizeof(double), cudaMemcpyHostToDevice, st));
+        if (K <= 512) {
+            if (int rc = proj_uniform_f64(g_ws.d_y, (long long)off, (int)nbc, K, mode, g_pipe.slow[c % kPipeStreams], st)) return rc;
+        } else {
+            set_error("internal: uniform host path called with K > 512");
+            return BSLS_ERR_ARG;
+        }
+        BSLS_CUDA_TRY(cudaMemcpyAsync(y + first + off, g_ws.d_y + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    return g_pipe.sync();
+}
+
 int host_project(double *y, const int *blocks, int numblocks, int n, int mode) {
     if (int rc = device_ok()) return rc;
     if (!y) {
@@ -259,6 +325,7 @@ int host_project(double *y, const int *blocks, int numblocks, int n, int mode) {
     if (int rc = validate_blocks(blocks, numblocks, n)) return rc;
     const int first = blocks[0];
     const size_t span = (size_t)n - first;  // entries before blocks[0] never leave the host
+    if (const int K = uniform_size(blocks, numblocks, n); K > 0 && K <= 512) return host_project_uniform(y, first, numblocks, K, mode);
     if (int rc = g_ws.reserve(span, (size_t)numblocks)) return rc;
     cudaStream_t st = g_ws.stream;
     BSLS_CUDA_TRY(cudaMemcpyAsync(g_ws.d_y, y + first, span * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -289,6 +356,23 @@ int host_pava(double *y, const int *blocks, int numblocks, int n, int *weight, i
     if (int rc = g_ws.reserve(span, (size_t)numblocks)) return rc;
     if (weight)
         if (int rc = g_ws.reserve_w(span)) return rc;
+    if (const int K = uniform_size(blocks, numblocks, n); K > 0 && K <= kPlanPavaSmallMax) {
+        // pipelined like host_project_uniform: chunks of whole blocks on three streams
+        const size_t cb = pipeline_chunk_blocks(K, numblocks);
+        if (int rc = g_pipe.prepare(cb)) return rc;
+        int c = 0;
+        for (size_t b0 = 0; b0 < (size_t)numblocks; b0 += cb, ++c) {
+            const size_t nbc = std::min(cb, (size_t)numblocks - b0);
+            const size_t off = b0 * K, cnt = nbc * K;
+            cudaStream_t st = g_pipe.s[c % kPipeStreams];
+            BSLS_CUDA_TRY(cudaMemcpyAsync(g_ws.d_y + off, y + first + off, cnt * sizeof(double), cudaMemcpyHostToDevice, st));
+            if (weight) BSLS_CUDA_TRY(cudaMemcpyAsync(g_ws.d_w + off, weight + first + off, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+            if (int rc = pava_small_f64(g_ws.d_y, weight ? g_ws.d_w : nullptr, (long long)off, (int)nbc, K, update, 0, st)) return rc;
+            BSLS_CUDA_TRY(cudaMemcpyAsync(y + first + off, g_ws.d_y + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, st));
+            if (weight) BSLS_CUDA_TRY(cudaMemcpyAsync(weight + first + off, g_ws.d_w + off, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        }
+        return g_pipe.sync();
+    }
     cudaStream_t st = g_ws.stream;
     BSLS_CUDA_TRY(cudaMemcpyAsync(g_ws.d_y, y + first, span * sizeof(double), cudaMemcpyHostToDevice, st));
     if (weight) BSLS_CUDA_TRY(cudaMemcpyAsync(g_ws.d_w, weight + first, span * sizeof(int32_t), cudaMemcpyHostToDevice, st));
