@@ -297,3 +297,51 @@ def test_adversarial_near_ties(api, K):
     want = y2.copy()
     cpu_port().proj_multi_simplex(want, starts2)
     assert np.array_equal(gpu_project(api, y2, starts2), want)
+
+
+@pytest.mark.parametrize("K", [32, 33, 64, 100, 128, 300])
+def test_selection_path_mixed_scales(api, K):
+    """Inputs that stress the rounding margin of the candidate selection (select_core.cuh): values
+    spread over many orders of magnitude and signs, huge negative tails, blocks of equal values,
+    supports of every density.  Uniform layout (thread-per-block selection + sorter fallback) and
+    the same blocks in a ragged layout (thread / warp / CTA paths).  Bit-exact."""
+    rng = np.random.RandomState(SEED + 977 * K)
+    blocks = []
+    for trial in range(1500):
+        kind = trial % 6
+        if kind == 0:      # wide dynamic range
+            blk = rng.randn(K) * 10.0 ** rng.randint(-8, 9, size=K)
+        elif kind == 1:    # a few O(1) values over a huge negative tail
+            blk = -rng.rand(K) * 1e12
+            blk[rng.choice(K, 3, replace=False)] = rng.rand(3) * 2
+        elif kind == 2:    # all equal / two levels
+            blk = np.full(K, rng.randn())
+            blk[: rng.randint(0, K)] += rng.choice([0.0, 1e-16, 1e-9, 0.5])
+        elif kind == 3:    # support of a prescribed size, the rest barely below the threshold
+            s = rng.randint(1, K + 1)
+            x = np.zeros(K)
+            x[:s] = rng.dirichlet(np.ones(s))
+            theta = rng.randn() * 3
+            blk = x + theta
+            blk[s:] -= rng.rand(K - s) * rng.choice([1e-15, 1e-12, 1e-9, 1e-3])
+        elif kind == 4:    # large common offset
+            blk = 1e6 + rng.rand(K)
+        else:              # tiny values
+            blk = rng.randn(K) * 1e-12
+        rng.shuffle(blk)
+        blocks.append(blk)
+    y = np.concatenate(blocks)
+    starts = np.arange(0, len(blocks) * K, K, dtype=np.int64)
+    for ball in (False, True):
+        want = y.copy()
+        (cpu_port().proj_multi_ball if ball else cpu_port().proj_multi_simplex)(want, starts)
+        got = gpu_project(api, y, starts, ball=ball)
+        bad = np.flatnonzero(got != want)
+        assert bad.size == 0, (ball, bad[:5] // K, got[bad[:3]], want[bad[:3]])
+    starts2 = np.concatenate(([0, 1], 3 + starts))
+    y2 = np.concatenate((rng.randn(3), y))
+    want = y2.copy()
+    cpu_port().proj_multi_simplex(want, starts2)
+    got = gpu_project(api, y2, starts2)
+    bad = np.flatnonzero(got != want)
+    assert bad.size == 0, (bad[:5], got[bad[:3]], want[bad[:3]])

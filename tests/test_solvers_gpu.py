@@ -424,3 +424,94 @@ def test_block_isotonic_regression_drop_in(B):
     yd = dev(y)
     B.block_isotonic_regression.block_isotonic_regression_2(yd, starts)
     assert np.array_equal(host(yd), want)
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE configs as parity cases: C1 at full size, C4 / C5 shapes reduced in size
+# ---------------------------------------------------------------------------------------------
+def config_problem(nb, K, m, L, seed, noise=0.1):
+    rng = np.random.RandomState(seed)
+    n = nb * K
+    base = np.sort(rng.randint(0, m - L + 1, size=(n, L)), axis=1) + np.arange(L)   # L distinct links per route
+    A = sps.csr_matrix((np.ones(n * L), (base.reshape(-1), np.repeat(np.arange(n), L))), shape=(m, n))
+    x_true = rng.dirichlet(np.ones(K), size=nb).reshape(-1)
+    b = A.dot(x_true) + noise * rng.randn(m)
+    return A, b, np.arange(0, n, K, dtype=np.int64)
+
+
+def test_config1_bb_full_size(B):
+    """BASELINE config 1: 1,000 OD blocks x 5 routes, 2,000 links, BB with proj_simplex (the reference path)."""
+    from oracle import solvers_np as S
+    A, b, starts = config_problem(1000, 5, 2000, 10, 237423433 + 1)
+    x0 = np.ones(5000) / 5
+    ref_parts = S.get_solver_parts(A, b, starts, 0.1)
+    ref = S.solve_BB(ref_parts[3], ref_parts[1], ref_parts[2], x0, max_iter=2000)
+    for implicit in (False, True):
+        parts = B.algorithm_utils.get_solver_parts((A, b), starts, 0.1, is_sparse=True, implicit_ones=implicit)
+        sol = B.BATCH.solve_BB(parts[3], parts[1], parts[2], dev(x0), max_iter=2000)
+        assert sol["f"] == pytest.approx(ref["f"], rel=1e-6)
+        k = min(8, len(sol["progress"]), len(ref["progress"]))
+        np.testing.assert_allclose([p[1] for p in sol["progress"][:k]], [p[1] for p in ref["progress"][:k]], rtol=1e-9)
+        xs = host(sol["x"])
+        np.testing.assert_allclose(xs.reshape(-1, 5).sum(1), 1.0, atol=1e-9)
+
+
+def test_config4_shape_md_and_lbfgs(B):
+    """BASELINE config 4 shape (K = 20, L = 10; 1/10 of the blocks and links): mirror descent and L-BFGS."""
+    from oracle import solvers_np as S
+    nb, K, m, L = 10000, 20, 5000, 10
+    A, b, starts = config_problem(nb, K, m, L, 237423433 + 4)
+    Lf = float(sps.linalg.svds(A, 1, return_singular_vectors=False)[0])
+    ref = S.md_least_squares(A, b, [K] * nb, iters=15, Lf=Lf)
+    x = B.mirror_descent.least_squares(A, b, [K] * nb, iters=15, Lf=Lf)
+    np.testing.assert_allclose(host(x), ref, rtol=1e-9, atol=1e-14)
+    assert B.bsls_utils.largest_singular_value(A) == pytest.approx(Lf, rel=1e-8)
+    x0 = np.ones(nb * K) / K
+    ref_parts = S.get_solver_parts(A, b, starts, 0.1)
+    ref = S.solve_LBFGS(ref_parts[3], ref_parts[1], ref_parts[2], x0, max_iter=12)
+    parts = B.algorithm_utils.get_solver_parts((A, b), starts, 0.1, is_sparse=True)
+    sol = B.BATCH.solve_LBFGS(parts[3], parts[1], parts[2], dev(x0), max_iter=12)
+    np.testing.assert_allclose([p[1] for p in sol["progress"]], [p[1] for p in ref["progress"]], rtol=1e-7)
+    ref = S.solve_MD(ref_parts[3], starts, ref_parts[0], x0, max_iter=10)
+    sol = B.BATCH.solve_MD(parts[3], starts, parts[0], dev(x0), max_iter=10)
+    np.testing.assert_allclose([p[1] for p in sol["progress"]], [p[1] for p in ref["progress"]], rtol=1e-9)
+    np.testing.assert_allclose(host(sol["x"]), ref["x"], rtol=1e-9, atol=1e-14)
+
+
+def test_config5_shape_bb_with_panels(B):
+    """BASELINE config 5 shape (K = 16, L = 8; 1/500 of the blocks): the BB solve with the column-panelled
+    product of A (several panels) reaches the objective of the oracle's BATCH.solve_BB."""
+    from oracle import solvers_np as S
+    nb, K, m, L = 20000, 16, 2000, 8
+    A, b, starts = config_problem(nb, K, m, L, 237423433 + 5)
+    x0 = np.ones(nb * K) / K
+    ref_parts = S.get_solver_parts(A, b, starts, 0.1)
+    ref = S.solve_BB(ref_parts[3], ref_parts[1], ref_parts[2], x0, max_iter=200)
+    prob = B.LsqProblem(A, b, implicit_ones=True)
+    assert prob.set_panels(panel_cols=50000) == 7
+    parts = B.algorithm_utils.get_solver_parts(prob, starts, 0.1)
+    sol = B.BATCH.solve_BB(parts[3], parts[1], parts[2], dev(x0), max_iter=200)
+    assert sol["f"] == pytest.approx(ref["f"], rel=1e-6)
+    k = min(6, len(sol["progress"]), len(ref["progress"]))
+    np.testing.assert_allclose([p[1] for p in sol["progress"][:k]], [p[1] for p in ref["progress"][:k]], rtol=1e-9)
+
+
+def test_synthetic_generator_matches_its_own_matrix(B):
+    """generate.SyntheticProblem builds CSR(A) and CSR(A^T) on the device: the two sides describe the
+    same matrix, columns have L distinct links, b = A x_true."""
+    from bsls_b200.generate import SyntheticProblem
+    sp = SyntheticProblem(300, 16, 500, 8, implicit_ones=True)
+    a_ptr, a_idx = host_i(sp.problem.a_ptr), host_i(sp.problem.a_idx)
+    t_ptr, t_idx = host_i(sp.problem.t_ptr), host_i(sp.problem.t_idx)
+    n, m = sp.n, sp.m
+    A1 = sps.csr_matrix((np.ones(len(a_idx)), a_idx, a_ptr), shape=(m, n))
+    A2 = sps.csr_matrix((np.ones(len(t_idx)), t_idx, t_ptr), shape=(n, m)).T.tocsr()
+    assert (A1 != A2).nnz == 0
+    assert np.all(np.diff(t_ptr) == 8) and A1.max() == 1.0
+    np.testing.assert_allclose(host(sp.b), A1.dot(host(sp.x_true)), rtol=1e-12)
+    xs = host(sp.x_true).reshape(-1, 16)
+    np.testing.assert_allclose(xs.sum(1), 1.0, atol=1e-12)
+
+
+def host_i(t):
+    return t.detach().cpu().numpy()
