@@ -50,7 +50,7 @@ def _check_host_vector(y, name="y"):
 def _host_blocks(blocks):
     b = np.asarray(blocks)
     # c_extensions.pyx:33-34
-    assert False not in ((b[1:] - b[:-1]) > 0)
+    assert bool(np.all(b[1:] > b[:-1]))
     return np.ascontiguousarray(b, dtype=np.int32)
 
 

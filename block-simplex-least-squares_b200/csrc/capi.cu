@@ -243,20 +243,23 @@ int validate_blocks(const int *blocks, int numblocks, int n) {
         set_error("block starts out of range");
         return BSLS_ERR_ARG;
     }
-    for (int i = 1; i < numblocks; ++i)
-        if (blocks[i] <= blocks[i - 1]) {
-            set_error("block starts not strictly increasing at %d", i);
-            return BSLS_ERR_ARG;
-        }
+    int bad = 0;  // branch-free scan (vectorised); the position is looked up only on failure
+    for (int i = 1; i < numblocks; ++i) bad |= (blocks[i] <= blocks[i - 1]);
+    if (bad) {
+        int i = 1;
+        while (i < numblocks && blocks[i] > blocks[i - 1]) ++i;
+        set_error("block starts not strictly increasing at %d", i);
+        return BSLS_ERR_ARG;
+    }
     return BSLS_OK;
 }
 
 // common block size of a layout, or 0 (host side)
 int uniform_size(const int *blocks, int numblocks, int n) {
     const int K = (numblocks > 1 ? blocks[1] : n) - blocks[0];
-    for (int i = 1; i < numblocks; ++i)
-        if (blocks[i] - blocks[i - 1] != K) return 0;
-    return (n - blocks[numblocks - 1] == K) ? K : 0;
+    int diff = 0;  // branch-free so that the compiler vectorises the scan
+    for (int i = 1; i < numblocks; ++i) diff |= (blocks[i] - blocks[i - 1]) ^ K;
+    return (diff == 0 && n - blocks[numblocks - 1] == K) ? K : 0;
 }
 
 // Uniform layouts need no plan, which lets the host entry points pipeline: the span is cut into
@@ -288,7 +291,7 @@ struct HostPipeline {
 thread_local HostPipeline g_pipe;
 
 size_t pipeline_chunk_blocks(int K, int numblocks) {
-    size_t cb = ((size_t)32 << 20) / ((size_t)K * sizeof(double));  // ~32 MB of values per chunk
+    size_t cb = ((size_t)8 << 20) / ((size_t)K * sizeof(double));  // ~8 MB of values per chunk: short fill / drain
     if (cb < 1024) cb = 1024;
     if (cb > (size_t)numblocks) cb = (size_t)numblocks;
     return cb;
@@ -404,6 +407,13 @@ int host_pava_single(double *y, int start, int end, int *weight, int update) {
 
 namespace bsls {
 int project_f64(const bsls_plan *plan, double *y, int mode, cudaStream_t stream) { return dev_project<double>(plan, y, mode, stream); }
+int project_step_f64(const bsls_plan *plan, const double *x, const double *g, double t, double *x_new, int mode, cudaStream_t stream, bool *fused) {
+    *fused = false;
+    if (!plan || !x || !g || !x_new) return BSLS_ERR_ARG;
+    if (plan->first != 0 || plan->uniform <= 0 || plan->uniform > 512 || !proj_step_fuses(plan->uniform)) return BSLS_OK;
+    *fused = true;
+    return proj_step_uniform_f64(x, g, t, x_new, 0, plan->nb, plan->uniform, mode, stream);
+}
 int pava_clip_f64(const bsls_plan *plan, double *y, int32_t *weight, int update, int clip01, cudaStream_t stream) {
     return dev_pava<double>(plan, y, weight, update, clip01, stream);
 }

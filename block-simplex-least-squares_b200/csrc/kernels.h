@@ -8,6 +8,10 @@ namespace bsls {
 // `slow`: nb + 1 int32 of scratch for the blocks the selection kernel hands to the sorter (may be null: sorting kernels only)
 int proj_uniform_f64(double *y, long long first, int nb, int K, int mode, int32_t *slow, cudaStream_t stream);
 int proj_uniform_f32(float *y, long long first, int nb, int K, int mode, int32_t *slow, cudaStream_t stream);
+// fused projected-gradient step x_new = proj(x - t g), uniform layouts whose K the sorting kernels take
+bool proj_step_fuses(int K);
+int proj_step_uniform_f64(const double *x, const double *g, double t, double *x_new, long long first, int nb, int K, int mode,
+                          cudaStream_t stream);
 
 
 // fork/join inside one call: the tile, mid and large kernels own disjoint blocks and run side by side
@@ -88,5 +92,7 @@ namespace bsls {
 // capi.cu: the device entry points, for the solver translation units
 int project_f64(const bsls_plan *plan, double *y, int mode, cudaStream_t stream);
 int pava_clip_f64(const bsls_plan *plan, double *y, int32_t *weight, int update, int clip01, cudaStream_t stream);
+// x_new = proj(x - t g): one fused kernel where the layout allows it, else returns 1 ("not fused") and does nothing
+int project_step_f64(const bsls_plan *plan, const double *x, const double *g, double t, double *x_new, int mode, cudaStream_t stream, bool *fused);
 }  // namespace bsls
 

@@ -692,13 +692,18 @@ int bsls_batch_solve_f64(bsls_lsq *q, const bsls_plan *plan, double *x, const bs
                 t = (i == 1) ? 1.0 : sxy / syy;  // BATCH.py:87-91
             else
                 t = 1.0 / (o->min_eig * i + 1.0);  // BATCH.py:38
-            axpby_kernel<<<grid_elems(n), 256, 0, st>>>(xn, 1.0, xc, -t, g, n);
-            BSLS_LAUNCH_CHECK();
-            ++extra_launches;
-            if (o->proj_mode == 2) {  // z-space: isotonic regression + clip to [0,1] (algorithm_utils.py:219-224)
-                if (int rc = pava_clip_f64(plan, xn, nullptr, 1, 1, st)) return rc;
-            } else {
-                if (int rc = project_f64(plan, xn, o->proj_mode, st)) return rc;
+            bool fused = false;
+            if (o->proj_mode != 2)  // x_new = proj(x - t g) in ONE kernel where the layout allows it
+                if (int rc = project_step_f64(plan, xc, g, t, xn, o->proj_mode, st, &fused)) return rc;
+            if (!fused) {
+                axpby_kernel<<<grid_elems(n), 256, 0, st>>>(xn, 1.0, xc, -t, g, n);
+                BSLS_LAUNCH_CHECK();
+                ++extra_launches;
+                if (o->proj_mode == 2) {  // z-space: isotonic regression + clip to [0,1] (algorithm_utils.py:219-224)
+                    if (int rc = pava_clip_f64(plan, xn, nullptr, 1, 1, st)) return rc;
+                } else {
+                    if (int rc = project_f64(plan, xn, o->proj_mode, st)) return rc;
+                }
             }
             ++extra_launches;
         }

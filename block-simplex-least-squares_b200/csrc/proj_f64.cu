@@ -8,6 +8,15 @@ int proj_uniform_f64(double *y, long long first, int nb, int K, int mode, int32_
                          : launch_proj_uniform<double, kSimplex>(y, first, nb, K, slow, stream);
 }
 
+bool proj_step_fuses(int K) { return proj_uniform_fuses(K); }
+
+int proj_step_uniform_f64(const double *x, const double *g, double t, double *x_new, long long first, int nb, int K, int mode,
+                          cudaStream_t stream) {
+    double *xin = const_cast<double *>(x);
+    return mode == kBall ? launch_proj_uniform<double, kBall>(xin, first, nb, K, nullptr, stream, g, t, x_new)
+                         : launch_proj_uniform<double, kSimplex>(xin, first, nb, K, nullptr, stream, g, t, x_new);
+}
+
 int proj_ragged_f64(double *y, const int32_t *starts, const int32_t *tile_first, int ntiles, const int32_t *mid_ids, int nmid,
                     const int32_t *large_ids, int nlarge, int max_large, int mode, int32_t *slow, int nb, const RaggedStreams &rs,
                     cudaStream_t stream) {

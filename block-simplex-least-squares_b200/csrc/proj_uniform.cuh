@@ -101,7 +101,12 @@ __device__ __forceinline__ void load_block_regs(T (&v)[E], const T *blkp, int K,
 //   KC       block size when known at compile time (0: runtime K <= E*G, -inf padded)
 template <typename T, int E, int G, int THREADS, int MINB, int BPT, int STAGES, int KC, int MODE>
 __global__ void __launch_bounds__(THREADS, MINB)
-proj_uniform_kernel(T *__restrict__ y, long long first, int nb, int Krt, FastDiv kdiv, int aligned) {
+proj_uniform_kernel(T *__restrict__ y, long long first, int nb, int Krt, FastDiv kdiv, int aligned, const T *__restrict__ gsrc,
+                    T tstep, T *__restrict__ yout) {
+    // gsrc != null: FUSED projected-gradient step: the tile is formed as y + (-tstep) * gsrc on the
+    // way in (np.add(x, -t*g, x_new), python/BATCH.py:91: product and sum rounded separately) and the
+    // result goes to yout -- x, g are read once, x_new written once, no intermediate vector.
+    const bool fused = gsrc != nullptr;
     constexpr int GROUPS = THREADS / G;
     constexpr int TB = GROUPS * BPT;  // blocks per tile
     constexpr int VN = Vec16<T>::N;
@@ -131,7 +136,7 @@ proj_uniform_kernel(T *__restrict__ y, long long first, int nb, int Krt, FastDiv
     __syncthreads();
 
     auto issue = [&](int t, int s) {  // thread 0: start the bulk copy of a full tile
-        if (aligned && (nb - t * TB) >= TB) {
+        if (!fused && aligned && (nb - t * TB) >= TB) {
             const uint32_t bytes = (uint32_t)(tile_elems * sizeof(T));
             mbar_expect_tx(&bar[s], bytes);
             bulk_g2s(s ? stage1 : stage0, ybase + (size_t)t * tile_elems, bytes, &bar[s]);
@@ -154,12 +159,18 @@ proj_uniform_kernel(T *__restrict__ y, long long first, int nb, int Krt, FastDiv
         const int nblk = min(TB, nb - tile * TB);
         const int nel = nblk * K;
         T *buf = s ? stage1 : stage0;
-        T *gy = ybase + (size_t)tile * tile_elems;
+        const T *gin = ybase + (size_t)tile * tile_elems;
+        T *gy = (fused && yout ? yout + first : ybase) + (size_t)tile * tile_elems;
 
-        if (aligned && nblk == TB) {
+        if (fused) {
+            const T *gg = gsrc + first + (size_t)tile * tile_elems;
+            const T nt = -tstep;
+            for (int i = tid; i < nel; i += THREADS) buf[i] = gin[i] + nt * gg[i];
+            __syncthreads();
+        } else if (aligned && nblk == TB) {
             mbar_wait(&bar[s], (STAGES == 2) ? ((it >> 1) & 1) : (it & 1));
         } else {  // ragged last tile or unaligned base: plain coalesced loads
-            for (int i = tid; i < nel; i += THREADS) buf[i] = gy[i];
+            for (int i = tid; i < nel; i += THREADS) buf[i] = gin[i];
             __syncthreads();
         }
 
@@ -463,7 +474,8 @@ int launch_proj_select_cfg(T *y, long long first, int nb, int K, int32_t *slow, 
 
 // ---- host side: pick a configuration for K and launch ------------------------------------------
 template <typename T, int E, int G, int THREADS, int MINB, int BPT, int STAGES, int KC, int MODE>
-int launch_proj_uniform_cfg(T *y, long long first, int nb, int K, cudaStream_t stream) {
+int launch_proj_uniform_cfg(T *y, long long first, int nb, int K, cudaStream_t stream, const T *gsrc = nullptr, T tstep = T(0),
+                            T *yout = nullptr) {
     constexpr int TB = THREADS / G * BPT;
     auto kern = proj_uniform_kernel<T, E, G, THREADS, MINB, BPT, STAGES, KC, MODE>;
     const size_t smem = (size_t)STAGES * TB * K * sizeof(T) + (size_t)(TB + (TB & 1)) * sizeof(T) + 2 * sizeof(uint64_t);
@@ -486,8 +498,8 @@ int launch_proj_uniform_cfg(T *y, long long first, int nb, int K, cudaStream_t s
     }
     const int ntiles = (nb + TB - 1) / TB;
     const int grid = ntiles < num_sm * cached_blocks_per_sm ? ntiles : num_sm * cached_blocks_per_sm;
-    const int aligned = ((reinterpret_cast<uintptr_t>(y + first) % 16) == 0) ? 1 : 0;
-    kern<<<grid, THREADS, smem, stream>>>(y, first, nb, K, make_fastdiv((uint32_t)K), aligned);
+    const int aligned = ((reinterpret_cast<uintptr_t>((gsrc && yout ? yout : y) + first) % 16) == 0) ? 1 : 0;
+    kern<<<grid, THREADS, smem, stream>>>(y, first, nb, K, make_fastdiv((uint32_t)K), aligned, gsrc, tstep, yout);
     BSLS_LAUNCH_CHECK();
     return BSLS_OK;
 }
@@ -504,11 +516,18 @@ inline int tune_variant() {
     return v;
 }
 
-template <typename T, int MODE> int launch_proj_uniform(T *y, long long first, int nb, int K, int32_t *slow, cudaStream_t stream) {
+// gsrc != null: fused step yout = proj(y - tstep * gsrc); only the sorting kernels fuse (the caller
+// checks proj_uniform_fuses(K) first)
+inline bool proj_uniform_fuses(int K) { return K < 32 || K > 128; }
+
+template <typename T, int MODE>
+int launch_proj_uniform(T *y, long long first, int nb, int K, int32_t *slow, cudaStream_t stream, const T *gsrc = nullptr, T tstep = T(0),
+                        T *yout = nullptr) {
     if (nb <= 0) return BSLS_OK;
     const int tv = tune_variant();
+    if (gsrc) slow = nullptr;  // fused mode: sorting kernels only
     // sizes the BASELINE configs name, with K known at compile time
-#define CFG(E, G, TH, MINB, BPT, ST, KC) return launch_proj_uniform_cfg<T, E, G, TH, MINB, BPT, ST, KC, MODE>(y, first, nb, K, stream)
+#define CFG(E, G, TH, MINB, BPT, ST, KC) return launch_proj_uniform_cfg<T, E, G, TH, MINB, BPT, ST, KC, MODE>(y, first, nb, K, stream, gsrc, tstep, yout)
 #define SEL(E, G, TH, MINB, ST, KC) return launch_proj_select_cfg<T, E, G, TH, MINB, ST, KC, MODE>(y, first, nb, K, slow, stream)
     // candidate selection instead of a full sort (BSLS_TUNE=100 keeps the sorting kernels everywhere)
     if (tv != 100 && slow != nullptr && K >= 32 && K <= 128) {
