@@ -334,9 +334,10 @@ def run_ours(args, rank, world, local_rank):
     starts = {K: torch.arange(0, NB * K, K, dtype=torch.int64, device=dev) for K in SIZES}
     plans = {K: bsls_b200.BlockPlan(starts[K], NB * K) for K in SIZES}
     # a fresh, never-touched input set for every step (672 MB each; aggregate >> 126 MB L2)
+    ksteps = min(steps, 10)   # extra, separately timed passes for the per-kernel numbers
     bufs = [{K: torch.randn(NB * K, dtype=torch.float64, device=dev, generator=gen) for K in SIZES}
-            for _ in range(steps + warmup)]
-    keep = {K: bufs[-1][K][: 1024 * K].clone() for K in SIZES}  # for the post-run spot check
+            for _ in range(steps + warmup + ksteps)]
+    keep = {K: bufs[warmup + steps - 1][K][: 1024 * K].clone() for K in SIZES}  # for the post-run spot check
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 
     def step(b, events=None):
@@ -366,10 +367,15 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.profiler.start()      # ncu --profile-from-start off: only the timed regions are listed
     ev0.record()
     for i in range(steps):
-        step(bufs[warmup + i], events)
+        step(bufs[warmup + i])
     ev1.record()
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
+    # per-kernel durations: the same launches on further fresh inputs, each bracketed by its own events
+    # (kept out of the headline region: an event pair costs a few microseconds per launch)
+    for i in range(ksteps):
+        step(bufs[warmup + steps + i], events)
+    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t_wall1 = time.time()
@@ -385,7 +391,7 @@ def run_ours(args, rank, world, local_rank):
     for K in SIZES:
         want = keep[K].cpu().numpy().copy()
         cpu.port().proj_multi_simplex(want, np.arange(0, want.size, K))
-        got = bufs[-1][K][: 1024 * K].cpu().numpy()
+        got = bufs[warmup + steps - 1][K][: 1024 * K].cpu().numpy()
         assert np.array_equal(got, want), "bench output differs from the oracle (K=%d)" % K
 
     nvar_step = NB * sum(SIZES)
@@ -455,7 +461,7 @@ def run_ours(args, rank, world, local_rank):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "l2": "fresh input buffers every step (inputs larger than L2); L2 flushed before timing",
                        "per_gpu_variables_per_step": nvar_step},
-            "roofline": roofline, "e2e": e2e, "gpu_launches": 3 * steps, "clocks": clocks}
+            "roofline": roofline, "e2e": e2e, "gpu_launches": 4 * steps, "clocks": clocks}
     if cpu_base is not None:
         line["cpu_baseline"] = cpu_base
     for k, v in extras.items():

@@ -86,6 +86,8 @@ def time_pava(K, nb, kind="ref", reps=8, with_weight=False, clip=False):
             return (r + ramp).reshape(-1)
         if kind == "normal":
             return torch.randn(n, dtype=torch.float64, device="cuda", generator=gen)
+        if kind == "sorted":     # already isotonic: one sweep, nothing pools (the kernel's floor)
+            return torch.sort(torch.randn(nb, K, dtype=torch.float64, device="cuda", generator=gen), dim=1)[0].reshape(-1)
         if kind == "zspace":
             e = -torch.log(torch.rand(nb, K + 1, dtype=torch.float64, device="cuda", generator=gen))
             x = e / e.sum(1, keepdim=True)
