@@ -252,6 +252,41 @@ def bench_c3(bsls_b200, torch, dev, peak, steps=5):
     return out
 
 
+def bench_1e8(bsls_b200, torch, dev, peak, reps=4):
+    """north_star's target size: projection and PAVA on 10^8-variable problems (uniform blocks of 4 / 16 / 64,
+    fp64, fresh inputs every launch, CUDA events)."""
+    gen = torch.Generator(device=dev).manual_seed(SEED + 9)
+    out = {"workload": "10^8 variables in uniform blocks of K = 4, 16, 64; fp64; one launch per measurement on a fresh input"}
+    for K in SIZES:
+        nb = 10 ** 8 // K
+        n = nb * K
+        plan = bsls_b200.BlockPlan(torch.arange(0, n, K, dtype=torch.int64, device=dev), n)
+        ramp = 50.0 * torch.log1p(torch.arange(K, dtype=torch.float64, device=dev))
+        for name, make, run in (
+                ("projection", lambda: torch.randn(n, dtype=torch.float64, device=dev, generator=gen),
+                 lambda y: bsls_b200.proj_multi_simplex_c(y, plan)),
+                ("pava", lambda: (torch.randint(-50, 50, (nb, K), device=dev, generator=gen).to(torch.float64) + ramp).reshape(-1),
+                 lambda y: bsls_b200.isotonic_regression_multi_c(y, plan, None, 1))):
+            ms = []
+            for r in range(reps + 1):
+                y = make()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                run(y)
+                e1.record()
+                torch.cuda.synchronize()
+                if r > 0:
+                    ms.append(e0.elapsed_time(e1))
+                del y
+            t = float(np.mean(ms))
+            bytes_ = 16 * n + 4 * nb
+            out["%s_K%d" % (name, K)] = {"avg_ms": t, "var_per_s": n / t * 1e3, "algorithmic_bytes": bytes_, "GBs": bytes_ / t / 1e6,
+                                         "frac": bytes_ / t / 1e6 / peak}
+        del plan
+        torch.cuda.empty_cache()
+    return out
+
+
 def cpu_bb_sample(seconds=12.0):
     """The reference's BATCH.solve_BB (oracle restatement: scipy CSR products + the reference's C++
     projection) on a reduced C5-shaped problem, one host thread."""
@@ -453,6 +488,7 @@ def run_ours(args, rank, world, local_rank):
 
     cpu_base = cpu_baseline_sample(threads=1, reps=2) if world == 1 else None
     extras["c3"] = bench_c3(bsls_b200, torch, dev, peak) if not args.skip_extras else None
+    extras["n1e8"] = bench_1e8(bsls_b200, torch, dev, peak) if not args.skip_extras else None
     if cpu_base is not None and not args.skip_extras:
         extras["bb_c5"]["cpu_baseline"] = cpu_bb_sample()
 

@@ -85,6 +85,14 @@ __device__ __forceinline__ bool pava_merge_run(T *y, W *w, const uint16_t *A, ui
 // left-to-right order as the reference's second loop: 0 + y*w == y*w) or closes the run
 // (merging it if its first and last value differ) and opens the next.  The lanes of a warp then
 // iterate in near lock step, whereas the reference's nested loops serialise under SIMT.
+// Small non-negative integer -> floating point without the conversion unit: I2F.F64 issues at a
+// quarter of the fp64 add rate on sm_100a and sat on the critical path of the sweep loop; 2^52 + w
+// assembled from bits, minus 2^52, is exact for 0 <= w < 2^31.
+__device__ __forceinline__ double small_int_to(double, int w) {
+    return __hiloint2double(0x43300000, w) - 4503599627370496.0;
+}
+__device__ __forceinline__ float small_int_to(float, int w) { return (float)w; }
+
 // Branch-free body: the next state is selected, not branched to; merged pools first receive
 // their numerator and a mark in `dirty`, and the divisions of a sweep are done together after
 // it (the quotient is not needed before the next sweep).  K <= 64.
@@ -96,7 +104,7 @@ __device__ __forceinline__ void pava_block_serial(T *y, W *w, int K, int update)
         int den = (int)w[0];
         T yi = y[0];
         T yj = yi;
-        T num = yi * (T)den;
+        T num = yi * small_int_to(T(0), den);
         int k = den;
         bool run = true;
         while (run) {
@@ -105,7 +113,7 @@ __device__ __forceinline__ void pava_block_serial(T *y, W *w, int K, int update)
             const T yk = y[kk];
             const int wk = (int)w[kk];
             const bool absorb = in && (yk <= yj);
-            const T prod = yk * (T)wk;
+            const T prod = yk * small_int_to(T(0), wk);
             if (!absorb && yi != yj) {  // close a run that pooled something
                 y[i] = num;
                 w[i] = (W)den;
@@ -123,7 +131,7 @@ __device__ __forceinline__ void pava_block_serial(T *y, W *w, int K, int update)
         while (dirty) {
             const int p = __ffsll((long long)dirty) - 1;
             dirty &= dirty - 1ull;
-            y[p] = y[p] / (T)(int)w[p];
+            y[p] = y[p] / small_int_to(T(0), (int)w[p]);
         }
     }
     if (update) {
@@ -143,18 +151,19 @@ constexpr int kPavaSmallMaxBlock = 64;  // longest block of the thread-per-block
 // every thread regresses its own block, then the tile is written back coalesced.
 template <typename T, int THREADS>
 __global__ void __launch_bounds__(THREADS)
-pava_small_kernel(T *__restrict__ yg, int32_t *__restrict__ wg, long long first, int nb, int K, FastDiv kdiv, PavaFlags fl) {
+pava_small_kernel(T *__restrict__ yg, int32_t *__restrict__ wg, long long first, int nb, int K, FastDiv kdiv, PavaFlags fl, int bpt) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int KS = K | 1;  // row pitch (elements)
+    const int TB = THREADS * bpt;  // blocks per tile: short blocks come several to a thread so that a tile stays large
     T *ys = reinterpret_cast<T *>(smem_raw);
-    uint8_t *wsm = reinterpret_cast<uint8_t *>(ys + (size_t)THREADS * KS);
+    uint8_t *wsm = reinterpret_cast<uint8_t *>(ys + (size_t)TB * KS);
     const int tid = threadIdx.x;
-    const int ntiles = (nb + THREADS - 1) / THREADS;
+    const int ntiles = (nb + TB - 1) / TB;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int nblk = min(THREADS, nb - tile * THREADS);
+        const int nblk = min(TB, nb - tile * TB);
         const int nel = nblk * K;
-        T *gy = yg + first + (size_t)tile * THREADS * K;
-        int32_t *gw = wg ? wg + first + (size_t)tile * THREADS * K : nullptr;
+        T *gy = yg + first + (size_t)tile * TB * K;
+        int32_t *gw = wg ? wg + first + (size_t)tile * TB * K : nullptr;
         // coalesced load, scattered into padded rows; four loads in flight per thread
         int i = tid;
         for (; i + 3 * THREADS < nel; i += 4 * THREADS) {
@@ -177,10 +186,13 @@ pava_small_kernel(T *__restrict__ yg, int32_t *__restrict__ wg, long long first,
                 wsm[r * KS + (e - r * K)] = (uint8_t)gw[e2];
             }
         } else {
-            for (int e2 = tid; e2 < THREADS * KS; e2 += THREADS) wsm[e2] = 1;
+            // all ones, four bytes per store (wsm is 4-byte aligned: it follows TB*KS values of 4 or 8 bytes)
+            uint32_t *w4 = reinterpret_cast<uint32_t *>(wsm);
+            for (int e2 = tid; e2 < (TB * KS + 3) / 4; e2 += THREADS) w4[e2] = 0x01010101u;
         }
         __syncthreads();
-        if (tid < nblk) pava_block_serial<T, uint8_t>(ys + (size_t)tid * KS, wsm + (size_t)tid * KS, K, fl.update);
+        for (int b = tid; b < nblk; b += THREADS)
+            pava_block_serial<T, uint8_t>(ys + (size_t)b * KS, wsm + (size_t)b * KS, K, fl.update);
         __syncthreads();
         for (int e2 = tid; e2 < nel; e2 += THREADS) {
             const uint32_t e = (uint32_t)e2, r = fdiv(e, kdiv);
@@ -197,7 +209,8 @@ template <typename T, int THREADS>
 int launch_pava_small_cfg(T *y, int32_t *w, long long first, int nb, int K, PavaFlags fl, cudaStream_t stream) {
     auto kern = pava_small_kernel<T, THREADS>;
     const int KS = K | 1;
-    const size_t smem = (size_t)THREADS * KS * (sizeof(T) + 1) + 16;
+    const int bpt = K >= 16 ? 1 : (K >= 8 ? 2 : 4);
+    const size_t smem = (size_t)THREADS * bpt * KS * (sizeof(T) + 1) + 16;
     static thread_local size_t cached_smem = 0;
     static thread_local int per_sm = 0, num_sm = 0;
     if (cached_smem != smem) {
@@ -212,9 +225,9 @@ int launch_pava_small_cfg(T *y, int32_t *w, long long first, int nb, int K, Pava
         }
         cached_smem = smem;
     }
-    const int ntiles = (nb + THREADS - 1) / THREADS;
+    const int ntiles = (nb + THREADS * bpt - 1) / (THREADS * bpt);
     const int grid = ntiles < num_sm * per_sm ? ntiles : num_sm * per_sm;
-    kern<<<grid, THREADS, smem, stream>>>(y, w, first, nb, K, make_fastdiv((uint32_t)K), fl);
+    kern<<<grid, THREADS, smem, stream>>>(y, w, first, nb, K, make_fastdiv((uint32_t)K), fl, bpt);
     BSLS_LAUNCH_CHECK();
     return BSLS_OK;
 }
