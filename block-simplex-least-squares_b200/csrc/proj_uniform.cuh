@@ -270,7 +270,7 @@ proj_select_kernel(T *__restrict__ y, long long first, int nb, int Krt, FastDiv 
     T *lam = stage1 + tile_elems;
     T *cand = lam + TB;                                     // kSelMaxCand x THREADS, slot-major
     uint64_t *bar = reinterpret_cast<uint64_t *>(cand + (size_t)kSelMaxCand * THREADS + ((TB & 1) ? 1 : 0));
-    __shared__ int s_nslow, s_base;
+    __shared__ int s_nslow2[2], s_base;               // queue counters, one per tile parity (see the reset below)
     __shared__ uint16_t s_slow[THREADS];
     __shared__ uint8_t s_keep[THREADS];                     // 1: block goes to the sorter, write it back unchanged
 
@@ -284,7 +284,8 @@ proj_select_kernel(T *__restrict__ y, long long first, int nb, int Krt, FastDiv 
         mbar_init(&bar[0], 1);
         if (STAGES == 2) mbar_init(&bar[1], 1);
         mbar_init_fence();
-        s_nslow = 0;
+        s_nslow2[0] = 0;
+        s_nslow2[1] = 0;
     }
     __syncthreads();
     auto issue = [&](int t, int s) {
@@ -298,6 +299,7 @@ proj_select_kernel(T *__restrict__ y, long long first, int nb, int Krt, FastDiv 
     int tile = blockIdx.x;
     if (STAGES == 2 && tile < ntiles && tid == 0) issue(tile, 0);
     for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+        int &s_nslow = s_nslow2[it & 1];
         const int s = (STAGES == 2) ? (it & 1) : 0;
         if (STAGES == 2) {
             const int nxt = tile + gridDim.x;
@@ -336,6 +338,10 @@ proj_select_kernel(T *__restrict__ y, long long first, int nb, int Krt, FastDiv 
         }
         __syncthreads();
         const int nslow = s_nslow;
+        // the NEXT tile's counter is cleared here, between two barriers of this tile: its first increment
+        // comes after this tile's closing barrier, and nobody reads it before then (a full tile is awaited
+        // on the mbarrier, without a CTA barrier, so clearing "at the top of the loop" would race)
+        if (tid == 0) s_nslow2[(it + 1) & 1] = 0;
         if (nslow > 0) {  // hand the dense blocks to the sorter: one global atomic per tile
             if (tid == 0) s_base = atomicAdd(&slow[nb], nslow);
             __syncthreads();
@@ -393,7 +399,6 @@ proj_select_kernel(T *__restrict__ y, long long first, int nb, int Krt, FastDiv 
             }
         }
         __syncthreads();
-        if (tid == 0) s_nslow = 0;
     }
 }
 
