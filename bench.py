@@ -287,6 +287,84 @@ def bench_1e8(bsls_b200, torch, dev, peak, reps=4):
     return out
 
 
+def bench_c1_c4(bsls_b200, torch, dev, with_cpu):
+    """BASELINE configs 1 and 4 on one GPU: the BB solve on the reference's own CPU-sized problem (C1: 1,000
+    OD blocks x 5 routes, 2,000 links) and mirror descent / L-BFGS on C4 (10^5 blocks x 20 routes, 5*10^4
+    links, nnz = 2*10^7).  CPU columns: the oracle's restatement of the same reference functions, one thread
+    (C4 on a 1/10-size problem)."""
+    import scipy.sparse as sps
+    from bsls_b200.generate import SyntheticProblem
+    out = {}
+    # ---- C1: BATCH.solve_BB, reference defaults (max_iter 2000, prog_tol 1e-12) ------------------------
+    sp = SyntheticProblem.config("C1", noise=0.1, implicit_ones=False)
+    parts = sp.solver_parts()
+    bsls_b200.BATCH.solve_BB(parts[3], parts[1], parts[2], sp.x_init, max_iter=50)
+    sol = bsls_b200.BATCH.solve_BB(parts[3], parts[1], parts[2], sp.x_init, max_iter=2000)
+    its = sol["iterations"] - 1
+    out["c1"] = {"workload": "C1: BATCH.solve_BB, 1,000 OD blocks x 5 routes, 2,000 links, 10 links per route (latency-bound: 1.6 MB per iteration)",
+                 "iter_per_s": its / sol["device_ms"] * 1e3, "iterations": its, "objective_evaluations": sol["obj_evals"],
+                 "f_final": sol["f"], "stop": sol["stop"], "us_per_evaluation": 1e3 * sol["device_ms"] / max(1, sol["obj_evals"])}
+    if with_cpu:
+        from oracle import solvers_np as S
+        A = sps.csr_matrix((np.ones(sp.nnz), sp.problem.a_idx.cpu().numpy(), sp.problem.a_ptr.cpu().numpy()), shape=(sp.m, sp.n))
+        b = sp.b.cpu().numpy()
+        starts = sp.starts.cpu().numpy()
+        cp = S.get_solver_parts(A, b, starts, 0.1)
+        t0 = time.perf_counter()
+        ref = S.solve_BB(cp[3], cp[1], cp[2], sp.x_init.cpu().numpy(), max_iter=2000)
+        dt = time.perf_counter() - t0
+        out["c1"]["cpu_baseline"] = {"value": (ref["iterations"] - 1) / dt, "unit": "iter/s", "cores": 1, "kind": "port",
+                                     "sample": "the same problem and call, %d iterations" % (ref["iterations"] - 1), "f_final": ref["f"]}
+    del sp, parts
+    # ---- C4: mirror descent and L-BFGS -----------------------------------------------------------------------
+    sp = SyntheticProblem.config("C4", noise=0.1)
+    nb, K = sp.nb, sp.K
+    Lf = bsls_b200.bsls_utils.largest_singular_value(sp.problem)
+    bsls_b200.mirror_descent.least_squares(sp.problem, None, [K] * nb, iters=5, Lf=Lf)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 200
+    e0.record()
+    bsls_b200.mirror_descent.least_squares(sp.problem, None, [K] * nb, iters=iters, tolerance=0.0, Lf=Lf)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    b_md = 24 * sp.nnz + 48 * sp.n + 32 * sp.m + 4 * sp.nb
+    out["c4_mirror_descent"] = {"workload": "C4: mirror_descent.least_squares, 10^5 OD blocks x 20 routes, 5*10^4 links, nnz=2e7",
+                                "iter_per_s": iters / ms * 1e3, "iterations": iters, "ms_per_iteration": ms / iters, "Lf": Lf,
+                                "algorithmic_bytes_per_iteration": b_md, "GBs": b_md * iters / ms / 1e6}
+    parts = sp.solver_parts()
+    bsls_b200.BATCH.solve_LBFGS(parts[3], parts[1], parts[2], sp.x_init, max_iter=8)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    sol = bsls_b200.BATCH.solve_LBFGS(parts[3], parts[1], parts[2], sp.x_init, max_iter=60)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    its = sol["iterations"] - 1
+    out["c4_lbfgs"] = {"workload": "C4: BATCH.solve_LBFGS (corrections=50), same problem; wall clock around the call (host-driven loop)",
+                       "iter_per_s": its / dt, "iterations": its, "ms_per_iteration": 1e3 * dt / max(1, its), "f_final": sol["f"]}
+    if with_cpu:
+        from oracle import solvers_np as S
+        rng = np.random.RandomState(SEED + 4)
+        nbs, ms_, L = 10000, 5000, 10
+        n = nbs * K
+        base = np.sort(rng.randint(0, ms_ - L + 1, size=(n, L)), axis=1) + np.arange(L)
+        A = sps.csr_matrix((np.ones(n * L), (base.reshape(-1), np.repeat(np.arange(n), L))), shape=(ms_, n))
+        b = A.dot(rng.dirichlet(np.ones(K), size=nbs).reshape(-1)) + 0.1 * rng.randn(ms_)
+        t0 = time.perf_counter()
+        S.md_least_squares(A, b, [K] * nbs, iters=20, tolerance=0.0, Lf=10.0)
+        dt = time.perf_counter() - t0
+        out["c4_mirror_descent"]["cpu_baseline"] = {"value": 20 / dt, "unit": "iter/s", "cores": 1, "kind": "port",
+                                                    "sample": "20 iterations on a 1/10-size C4 (nnz=2e6)", "nnz_iter_per_s": 20 * n * L / dt}
+        cp = S.get_solver_parts(A, b, np.arange(0, n, K), 0.1)
+        t0 = time.perf_counter()
+        ref = S.solve_LBFGS(cp[3], cp[1], cp[2], np.ones(n) / K, max_iter=20)
+        dt = time.perf_counter() - t0
+        out["c4_lbfgs"]["cpu_baseline"] = {"value": (ref["iterations"] - 1) / dt, "unit": "iter/s", "cores": 1, "kind": "port",
+                                           "sample": "%d iterations on a 1/10-size C4 (nnz=2e6)" % (ref["iterations"] - 1)}
+    return out
+
+
 def cpu_bb_sample(seconds=12.0):
     """The reference's BATCH.solve_BB (oracle restatement: scipy CSR products + the reference's C++
     projection) on a reduced C5-shaped problem, one host thread."""
@@ -489,6 +567,8 @@ def run_ours(args, rank, world, local_rank):
     cpu_base = cpu_baseline_sample(threads=1, reps=2) if world == 1 else None
     extras["c3"] = bench_c3(bsls_b200, torch, dev, peak) if not args.skip_extras else None
     extras["n1e8"] = bench_1e8(bsls_b200, torch, dev, peak) if not args.skip_extras else None
+    if not args.skip_extras:
+        extras.update(bench_c1_c4(bsls_b200, torch, dev, with_cpu=(world == 1)))
     if cpu_base is not None and not args.skip_extras:
         extras["bb_c5"]["cpu_baseline"] = cpu_bb_sample()
 

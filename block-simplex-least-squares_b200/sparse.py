@@ -134,9 +134,10 @@ class Workspace:
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().bsls_ws_dots_f64(self._handle, len(pairs), ctypes.byref(xs), ctypes.byref(ys), n,
                                                    int(bool(want_max)), ctypes.byref(out), _stream(self.device)), "ws_dots")
-        res = [out[k] for k in range(len(pairs))]
+        # NumPy scalars, as the reference's x.dot(y) returns: 0/0 and 1/0 give nan / inf, not exceptions
+        res = [np.float64(out[k]) for k in range(len(pairs))]
         if want_max:
-            res.append(out[4])
+            res.append(np.float64(out[4]))
         return res
 
     def dot(self, x, y):
