@@ -173,8 +173,9 @@ template <typename T> static int dev_project(const bsls_plan *plan, T *y, int mo
         else
             return proj_uniform_f32((float *)y, plan->first, plan->nb, plan->uniform, mode, plan->d_slow, stream);
     }
-    if (plan->max_size > kPlanLargeMaxBlock) {
-        set_error("projection: a block of %d entries exceeds the %d-entry limit of this revision", plan->max_size, kPlanLargeMaxBlock);
+    if (plan->max_size > kPlanLargeMaxBlock && sizeof(T) != 8) {
+        // longer blocks stage only their candidates; the rounding margin of that selection is too wide in fp32
+        set_error("projection (fp32): a block of %d entries exceeds the %d-entry limit", plan->max_size, kPlanLargeMaxBlock);
         return BSLS_ERR_ARG;
     }
     const int ntiles = plan->ragged ? plan->tiles : 0;
@@ -182,13 +183,22 @@ template <typename T> static int dev_project(const bsls_plan *plan, T *y, int mo
     const int nlarge = plan->ragged ? plan->large : plan->nb;
     if (int rc = ensure_slow_queue(plan)) return rc;
     if (int rc = ensure_streams(const_cast<bsls_plan *>(plan))) return rc;
+    if (plan->max_size > kPlanLargeMaxBlock && !plan->d_huge) {
+        bsls_plan *p = const_cast<bsls_plan *>(plan);
+        int cap = 1;
+        while (cap < plan->max_size) cap <<= 1;
+        BSLS_CUDA_TRY(cudaMalloc(&p->d_huge, (size_t)2 * cap * sizeof(double)));
+        BSLS_CUDA_TRY(cudaMalloc(&p->d_huge_lock, sizeof(int)));
+        BSLS_CUDA_TRY(cudaMemsetAsync(p->d_huge_lock, 0, sizeof(int), stream));
+        p->huge_cap = cap;
+    }
     const RaggedStreams rs = {{plan->aux[0], plan->aux[1]}, plan->ev_fork, {plan->ev_join[0], plan->ev_join[1]}};
     if constexpr (sizeof(T) == 8)
         return proj_ragged_f64((double *)y, plan->d_starts, plan->d_tile_first, ntiles, plan->d_mid_ids, plan->mid, ids, nlarge,
-                               plan->max_size, mode, plan->d_slow, plan->nb, rs, stream);
+                               plan->max_size, mode, plan->d_slow, plan->nb, rs, plan->d_huge, plan->huge_cap, plan->d_huge_lock, stream);
     else
         return proj_ragged_f32((float *)y, plan->d_starts, plan->d_tile_first, ntiles, plan->d_mid_ids, plan->mid, ids, nlarge,
-                               plan->max_size, mode, plan->d_slow, plan->nb, rs, stream);
+                               plan->max_size, mode, plan->d_slow, plan->nb, rs, plan->d_huge, plan->huge_cap, plan->d_huge_lock, stream);
 }
 
 
@@ -528,6 +538,8 @@ int bsls_plan_destroy(bsls_plan *plan) {
     if (plan->d_pava_first) cudaFree(plan->d_pava_first);
     if (plan->d_pava_large) cudaFree(plan->d_pava_large);
     if (plan->d_slow) cudaFree(plan->d_slow);
+    if (plan->d_huge) cudaFree(plan->d_huge);
+    if (plan->d_huge_lock) cudaFree(plan->d_huge_lock);
     if (plan->d_mid_ids) cudaFree(plan->d_mid_ids);
     if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
     for (int k = 0; k < 2; ++k) {

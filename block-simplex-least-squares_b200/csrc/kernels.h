@@ -22,10 +22,10 @@ struct RaggedStreams {
 // ragged layouts: tile kernel (thread per block) + warp-per-block kernel + one-CTA-per-large-block kernel (proj_ragged.cuh)
 int proj_ragged_f64(double *y, const int32_t *starts, const int32_t *tile_first, int ntiles, const int32_t *mid_ids, int nmid,
                     const int32_t *large_ids, int nlarge, int max_large, int mode, int32_t *slow, int nb, const RaggedStreams &rs,
-                    cudaStream_t stream);
+                    void *huge_buf, int huge_cap, int *huge_lock, cudaStream_t stream);
 int proj_ragged_f32(float *y, const int32_t *starts, const int32_t *tile_first, int ntiles, const int32_t *mid_ids, int nmid,
                     const int32_t *large_ids, int nlarge, int max_large, int mode, int32_t *slow, int nb, const RaggedStreams &rs,
-                    cudaStream_t stream);
+                    void *huge_buf, int huge_cap, int *huge_lock, cudaStream_t stream);
 
 // plan.cu: layout analysis on the device
 struct LayoutStats {
@@ -85,6 +85,9 @@ struct bsls_plan {
     // fork/join inside one call: the tile, mid and large kernels own disjoint blocks and run side by side
     cudaStream_t aux[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    void *d_huge = nullptr;           // blocks longer than kPlanLargeMaxBlock: global scratch for their candidates (2 * huge_cap values)
+    int huge_cap = 0;
+    int *d_huge_lock = nullptr;
     int32_t *d_slow = nullptr;        // nb + 1: queue of dense blocks between the selection kernel and the sorter
 };
 

@@ -19,10 +19,10 @@ int proj_step_uniform_f64(const double *x, const double *g, double t, double *x_
 
 int proj_ragged_f64(double *y, const int32_t *starts, const int32_t *tile_first, int ntiles, const int32_t *mid_ids, int nmid,
                     const int32_t *large_ids, int nlarge, int max_large, int mode, int32_t *slow, int nb, const RaggedStreams &rs,
-                    cudaStream_t stream) {
+                    void *huge_buf, int huge_cap, int *huge_lock, cudaStream_t stream) {
     static_assert(kTileElems == kPlanTileElems && kTileMaxBlock == kPlanTileMaxBlock && kLargeMaxBlock == kPlanLargeMaxBlock &&
                       kTileThreadMax == kPlanMidMin, "plan constants");
-    return mode == kBall ? launch_proj_ragged<double, kBall>(y, starts, tile_first, ntiles, mid_ids, nmid, large_ids, nlarge, max_large, slow, nb, rs, stream)
-                         : launch_proj_ragged<double, kSimplex>(y, starts, tile_first, ntiles, mid_ids, nmid, large_ids, nlarge, max_large, slow, nb, rs, stream);
+    return mode == kBall ? launch_proj_ragged<double, kBall>(y, starts, tile_first, ntiles, mid_ids, nmid, large_ids, nlarge, max_large, slow, nb, rs, huge_buf, huge_cap, huge_lock, stream)
+                         : launch_proj_ragged<double, kSimplex>(y, starts, tile_first, ntiles, mid_ids, nmid, large_ids, nlarge, max_large, slow, nb, rs, huge_buf, huge_cap, huge_lock, stream);
 }
 }  // namespace bsls

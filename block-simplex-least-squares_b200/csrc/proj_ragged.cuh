@@ -20,6 +20,8 @@
 //     and only a dense support falls back to a bitonic sort with the reference's serial sum.
 // All paths reproduce the reference's arithmetic order, so results are bit-identical to it.
 #pragma once
+#include <cstdio>
+
 #include "proj_uniform.cuh"
 
 namespace bsls {
@@ -247,39 +249,143 @@ proj_mid_kernel(T *__restrict__ y, const int32_t *__restrict__ starts, const int
 }
 
 // ---- one CTA per large block ---------------------------------------------------------------------
+// block-wide reductions for kLargeThreads threads (result to every thread)
+template <typename T> __device__ __forceinline__ T cta_reduce_max(T v, T *s_red) {
+    v = warp_max(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    T r = s_red[0];
+    for (int w = 1; w < kLargeThreads / 32; ++w) r = (s_red[w] > r) ? s_red[w] : r;
+    return r;
+}
+template <typename T> __device__ __forceinline__ T cta_reduce_sum(T v, T *s_red) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    T r = s_red[0];
+    for (int w = 1; w < kLargeThreads / 32; ++w) r += s_red[w];
+    return r;
+}
+
+// Blocks longer than kLargeMaxBlock never fit shared memory.  Only their CANDIDATES are staged: the
+// whole CTA scans the block in global memory for its maximum, tightens the threshold bound with
+// Michelot rounds (select_core.cuh) and compacts the survivors into srt[]; everything not staged is
+// provably inactive, so the reference's algorithm run on the staged values alone yields the same
+// shift.  Returns the number of staged values (traps when they exceed `cap`: a support that dense in a
+// block that long is outside this revision).
+// Scratch in global memory for long blocks whose candidates do not even fit the shared-memory window
+// (e.g. 10^6 uniform random values: the rounding margin of the selection keeps ~2 % of them).  One
+// such block at a time: `lock` serialises the CTAs that need it.
+template <typename T> struct HugeScratch {
+    T *buf;        // 2 * cap values
+    int cap;       // power of two
+    int *lock;     // 0 = free
+};
+
+template <typename T, int MODE>
+__device__ int stage_candidates(const T *gy, int K, T *&srt, int cap, const HugeScratch<T> &huge, bool &used_scratch, T *s_red,
+                                int *s_cnt) {
+    const int tid = threadIdx.x;
+    T umax = Num<T>::neg_inf();
+    for (int i = tid; i < K; i += kLargeThreads) {
+        T x = gy[i];
+        if (MODE == kBall) x = clip_neg(x);
+        umax = (x > umax) ? x : umax;
+    }
+    umax = cta_reduce_max<T>(umax, s_red);
+    const T delta = select_delta<T>(K, umax);
+    T tau = (umax - T(1)) - delta;
+    int c = K, c_prev = K + 1;
+    for (int round = 0; round < 24; ++round) {
+        T sl = T(0), cl = T(0);
+        for (int i = tid; i < K; i += kLargeThreads) {
+            T x = gy[i];
+            if (MODE == kBall) x = clip_neg(x);
+            if (x >= tau) {
+                sl += x;
+                cl += T(1);
+            }
+        }
+        const T ssum = cta_reduce_sum<T>(sl, s_red);
+        c = (int)cta_reduce_sum<T>(cl, s_red);  // exact: counts stay far below 2^24
+        if (c <= 8 || c >= c_prev) break;
+        c_prev = c;
+        const T t2 = (ssum - T(1)) / (T)c - delta;
+        if (!(t2 > tau)) break;
+        tau = t2;
+    }
+    used_scratch = false;
+    if (c > cap) {
+        if (!huge.buf || c > huge.cap) {
+            if (tid == 0)
+                printf("libbsls_b200: a block of %d values keeps %d candidates (limit %d): support too dense for the long-block path\n", K, c,
+                       huge.buf ? huge.cap : cap);
+            __syncthreads();
+            asm volatile("trap;");
+        }
+        if (tid == 0) {
+            while (atomicCAS(huge.lock, 0, 1) != 0) __nanosleep(200);
+            __threadfence();
+        }
+        __syncthreads();
+        srt = huge.buf;
+        used_scratch = true;
+    }
+    if (tid == 0) *s_cnt = 0;
+    __syncthreads();
+    for (int i = tid; i < K; i += kLargeThreads) {
+        T x = gy[i];
+        if (MODE == kBall) x = clip_neg(x);
+        if (x >= tau) srt[atomicAdd(s_cnt, 1)] = x;  // order is irrelevant: the values are sorted next
+    }
+    __syncthreads();
+    return *s_cnt;
+}
+
 template <typename T, int MODE>
 __global__ void __launch_bounds__(kLargeThreads)
 proj_large_kernel(T *__restrict__ y, const int32_t *__restrict__ starts, const int32_t *__restrict__ ids, int count_host,
-                  const int32_t *__restrict__ count_dev) {
+                  const int32_t *__restrict__ count_dev, HugeScratch<T> huge) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int s_last, s_done;
+    __shared__ int s_last, s_done, s_cnt;
     __shared__ T s_shift, s_total;
+    __shared__ T s_red[kLargeThreads / 32];
     __shared__ __align__(16) T wcand[kSelWarpCand];
     const int tid = threadIdx.x;
     const int count = count_dev ? *count_dev : count_host;
     for (int it = blockIdx.x; it < count; it += gridDim.x) {
         const int b = ids ? ids[it] : it;
         const int lo = starts[b];
-        const int K = starts[b + 1] - lo;
-        int KP = 1;
-        while (KP < K) KP <<= 1;
-        T *srt = reinterpret_cast<T *>(smem_raw);  // KP sorted values
-        T *pre = srt + KP;                         // KP running sums
+        const int Kfull = starts[b + 1] - lo;
         T *gy = y + (size_t)lo;
         const T ninf = Num<T>::neg_inf();
-        for (int i = tid; i < KP; i += kLargeThreads) {
-            T x = ninf;
-            if (i < K) {
-                x = gy[i];
-                if (MODE == kBall) x = clip_neg(x);
+        T *srt = reinterpret_cast<T *>(smem_raw);  // staged values (sorted later)
+        // K: number of staged values -- the whole block, or only its candidates when it is too long
+        int K = Kfull;
+        bool used_scratch = false;
+        if (Kfull > kLargeMaxBlock) K = stage_candidates<T, MODE>(gy, Kfull, srt, kLargeMaxBlock, huge, used_scratch, s_red, &s_cnt);
+        int KP = 1;
+        while (KP < K) KP <<= 1;
+        T *pre = srt + KP;                         // KP running sums
+        if (Kfull > kLargeMaxBlock) {
+            for (int i = K + tid; i < KP; i += kLargeThreads) srt[i] = ninf;
+        } else {
+            for (int i = tid; i < KP; i += kLargeThreads) {
+                T x = ninf;
+                if (i < K) {
+                    x = gy[i];
+                    if (MODE == kBall) x = clip_neg(x);
+                }
+                srt[i] = x;
             }
-            srt[i] = x;
         }
         if (tid == 0) s_last = 0;
         if (MODE == kBall) {
             if (tid == 0) {  // the reference's left-to-right sum over the kept entries
                 T total = T(0);
-                for (int k = 0; k < K; ++k) {
+                for (int k = 0; k < Kfull; ++k) {
                     const T x = gy[k];
                     if (!(x < T(0))) total += x;
                 }
@@ -341,20 +447,25 @@ proj_large_kernel(T *__restrict__ y, const int32_t *__restrict__ starts, const i
             __syncthreads();
         }
         const T shift = project ? s_shift : T(0);
-        for (int i = tid; i < K; i += kLargeThreads) {
+        for (int i = tid; i < Kfull; i += kLargeThreads) {
             T x = gy[i];
             if (MODE == kBall) x = clip_neg(x);
             x = shift + x;
             gy[i] = (x < T(0)) ? T(0) : x;
         }
         __syncthreads();
+        if (used_scratch && tid == 0) {
+            __threadfence();
+            atomicExch(huge.lock, 0);
+        }
     }
 }
 
 template <typename T, int MODE>
 int launch_proj_ragged(T *y, const int32_t *starts, const int32_t *tile_first, int ntiles, const int32_t *mid_ids, int nmid,
                        const int32_t *large_ids, int nlarge, int max_large, int32_t *slow, int nb, const RaggedStreams &rs,
-                       cudaStream_t stream) {
+                       void *huge_buf, int huge_cap, int *huge_lock, cudaStream_t stream) {
+    const HugeScratch<T> huge = {reinterpret_cast<T *>(huge_buf), huge_cap, huge_lock};
     int dev = 0, num_sm = kNumSM;
     BSLS_CUDA_TRY(cudaGetDevice(&dev));
     BSLS_CUDA_TRY(cudaDeviceGetAttribute(&num_sm, cudaDevAttrMultiProcessorCount, dev));
@@ -384,12 +495,12 @@ int launch_proj_ragged(T *y, const int32_t *starts, const int32_t *tile_first, i
     if (nlarge > 0) {
         BSLS_CUDA_TRY(cudaStreamWaitEvent(rs.aux[1], rs.fork, 0));
         int KP = 1;
-        while (KP < max_large) KP <<= 1;
+        while (KP < max_large && KP < kLargeMaxBlock) KP <<= 1;   // longer blocks stage only their candidates
         const size_t smem = (size_t)2 * KP * sizeof(T);
         int per = 1;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, large, kLargeThreads, smem) != cudaSuccess || per < 1) per = 1;
         const int grid = nlarge < per * num_sm ? nlarge : per * num_sm;
-        large<<<grid, kLargeThreads, smem, rs.aux[1]>>>(y, starts, large_ids, nlarge, nullptr);
+        large<<<grid, kLargeThreads, smem, rs.aux[1]>>>(y, starts, large_ids, nlarge, nullptr, huge);
         BSLS_LAUNCH_CHECK();
         BSLS_CUDA_TRY(cudaEventRecord(rs.join[1], rs.aux[1]));
     }
@@ -408,7 +519,7 @@ int launch_proj_ragged(T *y, const int32_t *starts, const int32_t *tile_first, i
     if (nlarge > 0) BSLS_CUDA_TRY(cudaStreamWaitEvent(stream, rs.join[1], 0));
     if (tiled) {
         // blocks whose support was too dense for a warp (count known only on the device; usually zero)
-        large<<<num_sm, kLargeThreads, (size_t)2 * kTileMaxBlock * sizeof(T), stream>>>(y, starts, slow, 0, slow + nb);
+        large<<<num_sm, kLargeThreads, (size_t)2 * kTileMaxBlock * sizeof(T), stream>>>(y, starts, slow, 0, slow + nb, HugeScratch<T>{nullptr, 0, nullptr});
         BSLS_LAUNCH_CHECK();
     }
     return BSLS_OK;

@@ -345,3 +345,37 @@ def test_selection_path_mixed_scales(api, K):
     got = gpu_project(api, y2, starts2)
     bad = np.flatnonzero(got != want)
     assert bad.size == 0, (bad[:5], got[bad[:3]], want[bad[:3]])
+
+
+@pytest.mark.parametrize("n", [8193, 20000, 10 ** 5, 10 ** 6])
+def test_blocks_longer_than_shared_memory(api, n):
+    """The reference's own stress shape (python/experiments/test_stress_proj_simplex.py:27: ONE block of
+    10^3 .. 10^6 values): blocks beyond the 8192-value shared-memory window stage only their candidates."""
+    rng = np.random.RandomState(SEED + n % 1000)
+    for kind in ("normal", "uniform", "sparse_support"):
+        if kind == "normal":
+            y = rng.randn(n)
+        elif kind == "uniform":
+            y = rng.rand(n)
+        else:
+            y = -rng.rand(n)
+            idx = rng.choice(n, 200, replace=False)
+            y[idx] = rng.dirichlet(np.ones(200)) + 0.3
+        want = y.copy()
+        cpu_port().proj_simplex(want, 0, n)
+        got = torch_vec(y)
+        api.proj_simplex_c(got, 0, n)
+        assert np.array_equal(got.cpu().numpy(), want), kind
+    # the same long block inside a ragged layout, between short blocks, and the l1-ball variant
+    sizes = np.array([3, 7, n, 2, 40, 600])
+    starts = np.concatenate(([0], np.cumsum(sizes)[:-1]))
+    y = rng.randn(int(sizes.sum()))
+    for ball in (False, True):
+        want = y.copy()
+        (cpu_port().proj_multi_ball if ball else cpu_port().proj_multi_simplex)(want, starts)
+        assert np.array_equal(gpu_project(api, y, starts, ball=ball), want), ball
+
+
+def torch_vec(a):
+    import torch
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).cuda()
