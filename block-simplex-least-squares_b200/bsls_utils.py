@@ -9,7 +9,7 @@ from . import c_extensions as cx
 from .plan import BlockPlan
 from .sparse import LsqProblem, axpby, default_workspace
 
-__all__ = ["x2z", "z2x", "block_sizes_to_N", "block_starts_to_N", "block_starts_to_x0", "particular_x0", "lsv_operator",
+__all__ = ["generate_data", "x2z", "z2x", "block_sizes_to_N", "block_starts_to_N", "block_starts_to_x0", "particular_x0", "lsv_operator",
            "largest_singular_value", "generate_small_qp", "random_least_squares", "block_starts_to_block_sizes"]
 
 
@@ -226,3 +226,53 @@ def random_least_squares(m, n, block_starts, sparsity=0.0, in_z=False, lasso=Fal
     f_min = .5 * x_true.T.dot(g + c)
     min_eig = w[-1]
     return {'Q': Q, 'c': c, 'x_true': x_true, 'f_min': f_min, 'min_eig': min_eig, 'A': A, 'b': b}
+
+
+def generate_data(fname=None, n=100, m1=5, m2=10, A_sparse=0.5, alpha=1.0, tolerance=1e-10, permute=False, scale=True,
+                  in_z=False, distribution='uniform'):
+    """The reference's synthetic traffic data (bsls_utils.py:590-655), host arrays as there: A (m1 x n, 0/1),
+    U (m2 x n block indicator), x_true ~ Dirichlet(alpha) per block (scaled by f when ``scale``), b = A x."""
+    import scipy.linalg as ssla
+    if distribution == 'uniform':
+        A = (np.random.random((m1, n)) > A_sparse).astype(float)
+    elif distribution == 'affine':
+        tmp = 2 * (1 - A_sparse)
+        line = (1 - tmp) + tmp * np.arange(n) / (n - 1)
+        lines = []
+        for i in range(m1):
+            j = np.random.randint(n)
+            lines.append(np.append(line[j:], line[:j]))
+        A = (np.random.random((m1, n)) > np.array(lines)).astype(float)
+    elif distribution == 'aggregated':
+        num_zeros = int(n * A_sparse)
+        line = np.array([0.1] * num_zeros + [.9] * (n - num_zeros))
+        lines = []
+        for i in range(m1):
+            j = np.random.randint(n)
+            lines.append(np.append(line[j:], line[:j]))
+        A = (np.random.random((m1, n)) > np.array(lines)).astype(float)
+    else:
+        raise ValueError(distribution)
+    block_sizes = (np.random.multinomial(n - m2, np.ones(m2) / m2) + np.ones(m2)).astype(int)
+    assert sum(block_sizes) == n, 'all-zero row present!'
+    block_starts = np.append([0], np.cumsum(block_sizes[:-1])).astype(int)
+    x = np.concatenate([np.random.dirichlet(alpha * np.ones(bs)) for bs in block_sizes])
+    U = ssla.block_diag(*[np.ones(bs) for bs in block_sizes])
+    if scale:
+        f = np.floor(np.random.random(m2) * 1000)
+        x = U.T.dot(f) * x
+    else:
+        f = np.ones(len(U))
+    b = A.dot(x)
+    assert np.linalg.norm(U.dot(x) - f) < tolerance, "Ux!=f"
+    assert np.linalg.norm(A.dot(x) - b) < tolerance, "Ax!=b"
+    if permute:
+        reorder = np.random.permutation(n)
+        A = A[:, reorder]
+        U = U[:, reorder]
+        x = x[reorder]
+    data = {'A': A, 'b': b, 'x_true': x, 'U': U, 'f': f, 'block_starts': block_starts, 'block_sizes': block_sizes}
+    if fname:
+        import scipy.io
+        scipy.io.savemat(fname, data, oned_as='column')
+    return data

@@ -515,3 +515,24 @@ def test_synthetic_generator_matches_its_own_matrix(B):
 
 def host_i(t):
     return t.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("n,m1,m2", [(100, 5, 10), (100, 20, 10), (1000, 50, 100)])
+def test_solve_in_z_on_generate_data(B, n, m1, m2):
+    """The reference's end-to-end tests (tests/fast/test_main.py:31-47, tests/slow/test_main.py:32-36):
+    generate_data -> solve_in_z with BB drives 0.5 |A x - b|^2 to (numerically) zero."""
+    np.random.seed(237423433)
+    data = B.bsls_utils.generate_data(n=n, m1=m1, m2=m2, scale=False)
+    A, b, sizes = sps.csr_matrix(data['A']), data['b'], data['block_sizes']
+    x0 = host(B.bsls_utils.particular_x0(sizes))
+    iters, times, states = B.main.solve_in_z(A, b, x0, None, sizes, 'BB',
+                                             options={'max_iter': 30000, 'opt_tol': 1e-30, 'verbose': 0})
+    z = states[-1]
+    N = B.bsls_utils.block_sizes_to_N(sizes)
+    x = host(N.dot(z)) + x0
+    assert np.all(x >= -1e-12)
+    np.testing.assert_allclose(x.reshape(-1)[np.cumsum(sizes) - 1] + 0, x[np.cumsum(sizes) - 1])
+    r = A.dot(x) - b
+    assert 0.5 * r.dot(r) < 1e-12
+    for s, e in zip(data['block_starts'], np.append(data['block_starts'][1:], n)):
+        assert abs(x[s:e].sum() - 1.0) < 1e-9
