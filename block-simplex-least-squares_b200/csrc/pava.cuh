@@ -20,6 +20,9 @@
 // Small blocks (<= kPavaWarpMaxBlock): one WARP owns a window of whole blocks in shared
 // memory and needs no block-wide barrier.  Longer blocks: one CTA per block.
 #pragma once
+#include <math.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace bsls {
@@ -77,87 +80,223 @@ __device__ __forceinline__ bool pava_merge_run(T *y, W *w, const uint16_t *A, ui
 }
 
 // ---------------------------------------------------------------------------------------------
-// one THREAD per block: the reference loop verbatim, on shared-memory rows
+// one THREAD per block: the reference's sweeps replayed run by run, driven by bit masks
 // ---------------------------------------------------------------------------------------------
-// y / w point at one block (K entries).  The reference's sweeps (isotonic_regression.h:18-49) as
-// ONE flat loop per sweep: every iteration looks at exactly one pool head and either absorbs it
-// into the open run (the running numerator / denominator are formed on the way, in the same
-// left-to-right order as the reference's second loop: 0 + y*w == y*w) or closes the run
-// (merging it if its first and last value differ) and opens the next.  The lanes of a warp then
-// iterate in near lock step, whereas the reference's nested loops serialise under SIMT.
 // Small non-negative integer -> floating point without the conversion unit: I2F.F64 issues at a
-// quarter of the fp64 add rate on sm_100a and sat on the critical path of the sweep loop; 2^52 + w
-// assembled from bits, minus 2^52, is exact for 0 <= w < 2^31.
-__device__ __forceinline__ double small_int_to(double, int w) {
-    return __hiloint2double(0x43300000, w) - 4503599627370496.0;
+// quarter of the fp64 add rate on sm_100a; 2^52 + w assembled from bits, minus 2^52, is exact
+// for 0 <= w < 2^31.
+// The routines of this section also compile for the host (tools/pava_host_check.cu runs this very
+// source against the oracle on the CPU); intrinsics get plain-C stand-ins there.
+#define BSLS_HD __host__ __device__ __forceinline__
+BSLS_HD double bits_to_double(unsigned hi, unsigned lo) {
+#ifdef __CUDA_ARCH__
+    return __hiloint2double((int)hi, (int)lo);
+#else
+    const unsigned long long b = ((unsigned long long)hi << 32) | lo;
+    double d;
+    memcpy(&d, &b, 8);
+    return d;
+#endif
 }
-__device__ __forceinline__ float small_int_to(float, int w) { return (float)w; }
+BSLS_HD unsigned double_hi(double d) {
+#ifdef __CUDA_ARCH__
+    return (unsigned)__double2hiint(d);
+#else
+    unsigned long long b;
+    memcpy(&b, &d, 8);
+    return (unsigned)(b >> 32);
+#endif
+}
+BSLS_HD double small_int_to(double, int w) { return bits_to_double(0x43300000u, (unsigned)w) - 4503599627370496.0; }
+BSLS_HD float small_int_to(float, int w) { return (float)w; }
 
-// Branch-free body: the next state is selected, not branched to; merged pools first receive
-// their numerator and a mark in `dirty`, and the divisions of a sweep are done together after
-// it (the quotient is not needed before the next sweep).  K <= 64.
-template <typename T, typename W>
-__device__ __forceinline__ void pava_block_serial(T *y, W *w, int K, int update) {
-    for (;;) {
-        unsigned long long dirty = 0ull;
-        int i = 0;
-        int den = (int)w[0];
-        T yi = y[0];
-        T yj = yi;
-        T num = yi * small_int_to(T(0), den);
-        int k = den;
-        bool run = true;
-        while (run) {
-            const bool in = k < K;
-            const int kk = in ? k : 0;
-            const T yk = y[kk];
-            const int wk = (int)w[kk];
-            const bool absorb = in && (yk <= yj);
-            const T prod = yk * small_int_to(T(0), wk);
-            if (!absorb && yi != yj) {  // close a run that pooled something
-                y[i] = num;
-                w[i] = (W)den;
-                dirty |= 1ull << i;
-            }
-            run = in;
-            num = absorb ? num + prod : prod;
-            den = absorb ? den + wk : wk;
-            yi = absorb ? yi : yk;
-            i = absorb ? i : k;
-            yj = yk;
-            k += wk;
+#ifdef __CUDA_ARCH__
+BSLS_HD int bit_lo(uint32_t m) { return __ffs((int)m) - 1; }
+BSLS_HD int bit_lo(uint64_t m) { return __ffsll((long long)m) - 1; }
+BSLS_HD int bit_hi(uint32_t m) { return 31 - __clz((int)m); }
+BSLS_HD int bit_hi(uint64_t m) { return 63 - __clzll((long long)m); }
+#else
+BSLS_HD int bit_lo(uint32_t m) { return __builtin_ctz(m); }
+BSLS_HD int bit_lo(uint64_t m) { return __builtin_ctzll(m); }
+BSLS_HD int bit_hi(uint32_t m) { return 31 - __builtin_clz(m); }
+BSLS_HD int bit_hi(uint64_t m) { return 63 - __builtin_clzll(m); }
+#endif
+
+// num / den for a small positive integer den, correctly rounded (== the reference's
+// `numerator / denominator`, isotonic_regression.h:40) without the generic division sequence:
+// with y = RN(1/den) from a table, q0 = RN(num*y), two residual corrections
+// q <- fma(fma(-den, q, num), y, q) give RN(num/den) (Markstein: a faithful q and a correctly
+// rounded reciprocal make the corrected quotient correctly rounded; the residuals are exact
+// while nothing under- or overflows).  Zero, subnormal-range, huge and non-finite numerators
+// -- where a residual could underflow or the sign of zero would be lost -- take the true
+// division.  tools/divtest.c compares 10^9 quotients (random and near-midpoint) bit for bit.
+BSLS_HD double div_small(double num, int den, const double *rcp, int rcp_n) {
+    const double d = small_int_to(double(0), den);
+    const unsigned hi = double_hi(num) & 0x7fffffffu;
+    // 2^-900 <= |num| < 2^1001  (biased exponent 123 .. 2023)
+    if (hi - 0x07b00000u < 0x76d00000u && (unsigned)den < (unsigned)rcp_n) {
+        const double y = rcp[den];
+        double q = num * y;
+        double r = fma(-d, q, num);
+        q = fma(r, y, q);
+        r = fma(-d, q, num);
+        return fma(r, y, q);
+    }
+    return num / d;
+}
+BSLS_HD float div_small(float num, int den, const float *, int) { return num / (float)den; }
+
+// y / w point at one block of K <= 8*sizeof(M) entries in shared memory.
+//
+// State: `alive` = bit k set when entry k is a pool head; S = bit k set when head k STARTS a
+// run of the current sweep, i.e. !(y[k] <= y[previous head]) on the values the sweep began
+// with (isotonic_regression.h:23-28 reads only values the sweep has not rewritten yet).  Heads
+// that start a run and are followed by another run start are singleton runs: the reference
+// leaves them alone, and so they cost nothing here.  Every run with followers is summed
+// exactly as the reference does (:33-39: 0 + y*w products left to right, integer weights) and,
+// if its first and last value differ, replaced by the quotient at its head (:40-42); followers
+// keep their stale value / weight as in the reference.  A merge changes the run-start bit of
+// only two heads (the merged head against its predecessor, the successor against the merged
+// head): those are re-evaluated into Snext, which becomes S for the next sweep.  The loop ends
+// after a sweep that merged nothing (:46).  Lanes do not wait for each other between sweeps.
+//
+// WMEM = false: cold start (all weights 1 on entry): pool sizes are the gaps between head bits
+//               and w[] is only written (when `wout`), never read.
+// WMEM = true:  warm start: weights are read from w[] as the reference does.
+// Returns the final head mask.
+template <typename T, typename W, typename M, bool WMEM>
+BSLS_HD M pava_block_runs(T *y, W *w, int K, M alive, bool wout, const T *rcp, int rcp_n) {
+    const M one = 1;
+    M S;
+    if (!WMEM) {
+        S = one;
+        T prev = y[0];
+        for (int r = 1; r < K; ++r) {
+            const T v = y[r];
+            S |= (M)(!(v <= prev)) << r;
+            prev = v;
         }
-        if (!dirty) break;
-        while (dirty) {
-            const int p = __ffsll((long long)dirty) - 1;
-            dirty &= dirty - 1ull;
-            y[p] = y[p] / small_int_to(T(0), (int)w[p]);
+    } else {
+        M rem = alive;
+        int k = bit_lo(rem);
+        rem &= rem - 1;
+        S = one << k;
+        T prev = y[k];
+        while (rem) {
+            k = bit_lo(rem);
+            rem &= rem - 1;
+            const T v = y[k];
+            if (!(v <= prev)) S |= one << k;
+            prev = v;
         }
     }
-    if (update) {
-        for (int i = 0; i < K;) {
-            const int wi = (int)w[i];
-            const T v = y[i];
-            for (int r = i + 1; r < i + wi; ++r) y[r] = v;
-            i += wi;
+    M Snext = S;
+    M NS = alive & ~S;  // followers not yet consumed by this sweep
+    bool any = false;
+    for (;;) {
+        if (NS == 0) {
+            if (!any) break;
+            S = Snext;
+            NS = alive & ~S;
+            any = false;
+            if (NS == 0) break;
         }
+        const M fb = NS & (~NS + 1);              // lowest follower
+        const M low = alive & (fb - 1);           // heads below it: the highest is its run's head
+        const int p = bit_hi(low);
+        const M pb = one << p;
+        const M above = (~one) << p;              // positions above p
+        const M Sab = S & alive & above;
+        const M eb = Sab & (~Sab + 1);            // next run start (0: the run reaches the end of the block)
+        const M fol = alive & (eb - 1) & above;   // the run's followers
+        const int e = eb ? bit_lo(eb) : K;
+        const M lowp = low ^ pb;                  // heads below p
+        // the two neighbours whose run-start bit a merge re-evaluates; fetched early, next to `first`
+        const T first = y[p];
+        const T yprev = y[lowp ? bit_hi(lowp) : p];
+        const T ynext = y[eb ? e : p];
+        NS &= ~fol;
+        // first follower (always there), then the rare longer tail
+        M rem = fol;
+        int k = bit_lo(rem);
+        rem &= rem - 1;
+        int wp = WMEM ? (int)w[p] : k - p;
+        int den = wp;
+        T num = T(0) + first * small_int_to(T(0), wp);  // -fmad=false: product and sum round separately
+        T vprev = y[k];
+        int kprev = k;
+        while (rem) {
+            k = bit_lo(rem);
+            rem &= rem - 1;
+            wp = WMEM ? (int)w[kprev] : k - kprev;
+            num += vprev * small_int_to(T(0), wp);
+            den += wp;
+            kprev = k;
+            vprev = y[k];
+        }
+        wp = WMEM ? (int)w[kprev] : e - kprev;
+        num += vprev * small_int_to(T(0), wp);
+        den += wp;
+        if (first != vprev) {
+            const T val = div_small(num, den, rcp, rcp_n);
+            y[p] = val;
+            if (WMEM || wout) w[p] = (W)den;
+            alive &= ~fol;
+            any = true;
+            const bool sp = !lowp || !(val <= yprev);
+            const bool sq = !(ynext <= val);
+            Snext = sp ? (Snext | pb) : (Snext & ~pb);
+            Snext = (eb && !sq) ? (Snext & ~eb) : (Snext | eb);
+        }
+    }
+    return alive;
+}
+
+// heads of a warm-started block: the entries reached by i += weight[i] (isotonic_regression.h:22)
+template <typename W, typename M> BSLS_HD M pava_heads_from_weights(const W *w, int K) {
+    M alive = 0;
+    for (int i = 0; i < K; i += ((int)w[i] > 1 ? (int)w[i] : 1)) alive |= (M)1 << i;
+    return alive;
+}
+
+// copy each head value over its pool (isotonic_regression.h:50-57), pools given by the head mask
+template <typename T, typename M> BSLS_HD void pava_spread(T *y, int K, M alive) {
+    M rem = alive;
+    while (rem) {
+        const int k = bit_lo(rem);
+        rem &= rem - 1;
+        const int stop = rem ? bit_lo(rem) : K;
+        const T v = y[k];
+        for (int r = k + 1; r < stop; ++r) y[r] = v;
     }
 }
 
 constexpr int kPavaSmallMaxBlock = 64;  // longest block of the thread-per-block kernel
 
-// Uniform layouts with K <= kPavaSmallMaxBlock: a CTA stages THREADS blocks in shared memory
+// Uniform layouts with K <= kPavaSmallMaxBlock: a CTA stages THREADS*bpt blocks in shared memory
 // (rows padded to an odd pitch so that lanes walking their own rows do not bank-conflict),
-// every thread regresses its own block, then the tile is written back coalesced.
-template <typename T, int THREADS>
+// every thread regresses its own block(s) and leaves the head mask, then the tile is written
+// back coalesced -- every element fetches the value of the head its mask names.
+// FAST = the hot configuration (cold start, no weight array, update = 1; main.py:64): the
+// loops carry no run-time flags.  CLIP is the [0,1] clamp of python/main.py:65.
+template <typename T, int THREADS, typename M, bool FAST, bool CLIP>
 __global__ void __launch_bounds__(THREADS)
 pava_small_kernel(T *__restrict__ yg, int32_t *__restrict__ wg, long long first, int nb, int K, FastDiv kdiv, PavaFlags fl, int bpt) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int KS = K | 1;  // row pitch (elements)
+    const int pad = KS - K;  // 1 for even K: element e of the tile sits at e + row
     const int TB = THREADS * bpt;  // blocks per tile: short blocks come several to a thread so that a tile stays large
-    T *ys = reinterpret_cast<T *>(smem_raw);
-    uint8_t *wsm = reinterpret_cast<uint8_t *>(ys + (size_t)TB * KS);
+    constexpr int RCPN = kPavaSmallMaxBlock + 1;
+    T *rcp = reinterpret_cast<T *>(smem_raw);
+    M *masks = reinterpret_cast<M *>(smem_raw + ((RCPN * sizeof(T) + 15) & ~size_t(15)));
+    T *ys = reinterpret_cast<T *>(masks + TB + (TB & 1));
+    uint8_t *wsm = reinterpret_cast<uint8_t *>(ys + (size_t)TB * KS);  // only with a weight array
     const int tid = threadIdx.x;
+    const bool has_weight = !FAST && fl.has_weight;
+    const bool update = FAST || fl.update;
+    const bool clip = FAST ? CLIP : (fl.clip01 != 0);
+    for (int i = tid + 1; i < RCPN; i += THREADS) rcp[i] = T(1) / (T)i;
+    const M full = K == (int)(8 * sizeof(M)) ? ~M(0) : (((M)1 << K) - 1);
     const int ntiles = (nb + TB - 1) / TB;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int nblk = min(TB, nb - tile * TB);
@@ -172,45 +311,54 @@ pava_small_kernel(T *__restrict__ yg, int32_t *__restrict__ wg, long long first,
             for (int u = 0; u < 4; ++u) v[u] = gy[i + u * THREADS];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const uint32_t e = (uint32_t)(i + u * THREADS), r = fdiv(e, kdiv);
-                ys[r * KS + (e - r * K)] = v[u];
+                const uint32_t e = (uint32_t)(i + u * THREADS);
+                ys[e + (pad ? fdiv(e, kdiv) : 0u)] = v[u];
             }
         }
         for (; i < nel; i += THREADS) {
-            const uint32_t e = (uint32_t)i, r = fdiv(e, kdiv);
-            ys[r * KS + (e - r * K)] = gy[i];
+            const uint32_t e = (uint32_t)i;
+            ys[e + (pad ? fdiv(e, kdiv) : 0u)] = gy[i];
         }
-        if (fl.has_weight) {
+        if (has_weight) {
             for (int e2 = tid; e2 < nel; e2 += THREADS) {
-                const uint32_t e = (uint32_t)e2, r = fdiv(e, kdiv);
-                wsm[r * KS + (e - r * K)] = (uint8_t)gw[e2];
+                const uint32_t e = (uint32_t)e2;
+                wsm[e + (pad ? fdiv(e, kdiv) : 0u)] = (uint8_t)gw[e2];
             }
-        } else {
-            // all ones, four bytes per store (wsm is 4-byte aligned: it follows TB*KS values of 4 or 8 bytes)
-            uint32_t *w4 = reinterpret_cast<uint32_t *>(wsm);
-            for (int e2 = tid; e2 < (TB * KS + 3) / 4; e2 += THREADS) w4[e2] = 0x01010101u;
         }
         __syncthreads();
-        for (int b = tid; b < nblk; b += THREADS)
-            pava_block_serial<T, uint8_t>(ys + (size_t)b * KS, wsm + (size_t)b * KS, K, fl.update);
+        for (int b = tid; b < nblk; b += THREADS) {
+            T *yb = ys + (size_t)b * KS;
+            if (has_weight) {
+                uint8_t *wb = wsm + (size_t)b * KS;
+                masks[b] = pava_block_runs<T, uint8_t, M, true>(yb, wb, K, pava_heads_from_weights<uint8_t, M>(wb, K), true, rcp, RCPN);
+            } else {
+                masks[b] = pava_block_runs<T, uint8_t, M, false>(yb, nullptr, K, full, false, rcp, RCPN);
+            }
+        }
         __syncthreads();
+        // coalesced store; with `update` every element takes the value of the head its mask names
+#pragma unroll 4
         for (int e2 = tid; e2 < nel; e2 += THREADS) {
-            const uint32_t e = (uint32_t)e2, r = fdiv(e, kdiv);
-            T v = ys[r * KS + (e - r * K)];
-            if (fl.clip01) v = clip01(v);
+            const uint32_t e = (uint32_t)e2, r = fdiv(e, kdiv), c = e - r * K;
+            uint32_t src = c;
+            if (update) src = (uint32_t)bit_hi((M)(masks[r] & ((((M)2) << c) - 1)));
+            T v = ys[r * KS + src];
+            if (clip) v = clip01(v);
             gy[e2] = v;
-            if (fl.has_weight) gw[e2] = (int32_t)wsm[r * KS + (e - r * K)];
+            if (has_weight) gw[e2] = (int32_t)wsm[r * KS + c];
         }
         __syncthreads();
     }
 }
 
-template <typename T, int THREADS>
+template <typename T, int THREADS, typename M, bool FAST, bool CLIP>
 int launch_pava_small_cfg(T *y, int32_t *w, long long first, int nb, int K, PavaFlags fl, cudaStream_t stream) {
-    auto kern = pava_small_kernel<T, THREADS>;
+    auto kern = pava_small_kernel<T, THREADS, M, FAST, CLIP>;
     const int KS = K | 1;
     const int bpt = K >= 16 ? 1 : (K >= 8 ? 2 : 4);
-    const size_t smem = (size_t)THREADS * bpt * KS * (sizeof(T) + 1) + 16;
+    const int TB = THREADS * bpt;
+    const size_t smem = (((kPavaSmallMaxBlock + 1) * sizeof(T) + 15) & ~size_t(15)) + (size_t)(TB + (TB & 1)) * sizeof(M) +
+                        (size_t)TB * KS * (sizeof(T) + (fl.has_weight ? 1 : 0)) + 16;
     static thread_local size_t cached_smem = 0;
     static thread_local int per_sm = 0, num_sm = 0;
     if (cached_smem != smem) {
@@ -225,17 +373,27 @@ int launch_pava_small_cfg(T *y, int32_t *w, long long first, int nb, int K, Pava
         }
         cached_smem = smem;
     }
-    const int ntiles = (nb + THREADS * bpt - 1) / (THREADS * bpt);
+    const int ntiles = (nb + TB - 1) / TB;
     const int grid = ntiles < num_sm * per_sm ? ntiles : num_sm * per_sm;
     kern<<<grid, THREADS, smem, stream>>>(y, w, first, nb, K, make_fastdiv((uint32_t)K), fl, bpt);
     BSLS_LAUNCH_CHECK();
     return BSLS_OK;
 }
 
+template <typename T, int THREADS, typename M>
+int launch_pava_small_flags(T *y, int32_t *w, long long first, int nb, int K, PavaFlags fl, cudaStream_t stream) {
+    if (!fl.has_weight && fl.update) {
+        if (fl.clip01) return launch_pava_small_cfg<T, THREADS, M, true, true>(y, w, first, nb, K, fl, stream);
+        return launch_pava_small_cfg<T, THREADS, M, true, false>(y, w, first, nb, K, fl, stream);
+    }
+    return launch_pava_small_cfg<T, THREADS, M, false, false>(y, w, first, nb, K, fl, stream);
+}
+
 template <typename T> int launch_pava_small(T *y, int32_t *w, long long first, int nb, int K, PavaFlags fl, cudaStream_t stream) {
     if (nb <= 0) return BSLS_OK;
-    if (K <= 24) return launch_pava_small_cfg<T, 256>(y, w, first, nb, K, fl, stream);
-    return launch_pava_small_cfg<T, 128>(y, w, first, nb, K, fl, stream);
+    if (K <= 24) return launch_pava_small_flags<T, 256, uint32_t>(y, w, first, nb, K, fl, stream);
+    if (K <= 32) return launch_pava_small_flags<T, 128, uint32_t>(y, w, first, nb, K, fl, stream);
+    return launch_pava_small_flags<T, 128, uint64_t>(y, w, first, nb, K, fl, stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -450,6 +608,8 @@ pava_tile_kernel(T *__restrict__ yg, int32_t *__restrict__ wg, const int32_t *__
     __shared__ uint8_t skip[WIN];  // 1: element of a block another kernel owns (not written back)
     constexpr int NC = 6;  // size classes of the thread path: <=1, 2, <=4, <=8, <=16, <=32
     __shared__ int cnt[NC], off[NC + 1], fill[NC];
+    __shared__ T rcp[kPavaThreadMax + 1];
+    for (int i = threadIdx.x + 1; i <= kPavaThreadMax; i += kPavaTileThreads) rcp[i] = T(1) / (T)i;
     auto cls = [](int K) { return K <= 1 ? 0 : 32 - __clz(K - 1); };  // ceil(log2 K) + (K > 1)
 
     const int tid = threadIdx.x;
@@ -503,7 +663,15 @@ pava_tile_kernel(T *__restrict__ yg, int32_t *__restrict__ wg, const int32_t *__
         for (int p = tid; p < nthread; p += kPavaTileThreads) {
             const int b = list[p];
             const int s0 = sstart[b];
-            pava_block_serial<T, uint16_t>(ybuf + s0, wbuf + s0, sstart[b + 1] - s0, fl.update);
+            const int Kb = sstart[b + 1] - s0;
+            uint32_t heads;
+            if (fl.has_weight)
+                heads = pava_block_runs<T, uint16_t, uint32_t, true>(ybuf + s0, wbuf + s0, Kb, pava_heads_from_weights<uint16_t, uint32_t>(wbuf + s0, Kb),
+                                                                     true, rcp, kPavaThreadMax + 1);
+            else
+                heads = pava_block_runs<T, uint16_t, uint32_t, false>(ybuf + s0, nullptr, Kb, Kb == 32 ? ~0u : ((1u << Kb) - 1u), false, rcp,
+                                                                      kPavaThreadMax + 1);
+            if (fl.update) pava_spread(ybuf + s0, Kb, heads);
         }
         __syncthreads();
         for (int i = tid; i < nel; i += kPavaTileThreads) {
