@@ -21,6 +21,8 @@
 // memory and needs no block-wide barrier.  Longer blocks: one CTA per block.
 #pragma once
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -164,23 +166,39 @@ BSLS_HD float div_small(float num, int den, const float *, int) { return num / (
 //               and w[] is only written (when `wout`), never read.
 // WMEM = true:  warm start: weights are read from w[] as the reference does.
 // Returns the final head mask.
+// bst: positions that always start a run -- bit 0, and the first entry of every further block when
+// one thread takes several short blocks as one row (runs then never cross a block boundary).
 template <typename T, typename W, typename M, bool WMEM>
-BSLS_HD M pava_block_runs(T *y, W *w, int K, M alive, bool wout, const T *rcp, int rcp_n) {
+BSLS_HD M pava_block_runs(T *y, W *w, int K, M alive, M bst, bool wout, const T *rcp, int rcp_n) {
     const M one = 1;
     M S;
     if (!WMEM) {
-        S = one;
         T prev = y[0];
-        for (int r = 1; r < K; ++r) {
-            const T v = y[r];
-            S |= (M)(!(v <= prev)) << r;
-            prev = v;
+#ifdef __CUDA_ARCH__
+        if (sizeof(M) == 4) {
+            // compare bits shifted in from the top (one funnel shift per entry), aligned afterwards
+            uint32_t acc = 0x80000000u;  // entry 0
+            for (int r = 1; r < K; ++r) {
+                const T v = y[r];
+                acc = __funnelshift_r(acc, (uint32_t)(!(v <= prev)), 1);
+                prev = v;
+            }
+            S = (M)(acc >> (32 - K)) | bst;
+        } else
+#endif
+        {
+            S = bst;
+            for (int r = 1; r < K; ++r) {
+                const T v = y[r];
+                S |= (M)(!(v <= prev)) << r;
+                prev = v;
+            }
         }
     } else {
         M rem = alive;
         int k = bit_lo(rem);
         rem &= rem - 1;
-        S = one << k;
+        S = (one << k) | (bst & alive);
         T prev = y[k];
         while (rem) {
             k = bit_lo(rem);
@@ -243,10 +261,10 @@ BSLS_HD M pava_block_runs(T *y, W *w, int K, M alive, bool wout, const T *rcp, i
             if (WMEM || wout) w[p] = (W)den;
             alive &= ~fol;
             any = true;
-            const bool sp = !lowp || !(val <= yprev);
-            const bool sq = !(ynext <= val);
+            const bool sp = (pb & bst) || !(val <= yprev);
+            const bool sq = (eb & bst) || !(ynext <= val);
             Snext = sp ? (Snext | pb) : (Snext & ~pb);
-            Snext = (eb && !sq) ? (Snext & ~eb) : (Snext | eb);
+            Snext = sq ? (Snext | eb) : (Snext & ~eb);
         }
     }
     return alive;
@@ -277,88 +295,128 @@ constexpr int kPavaSmallMaxBlock = 64;  // longest block of the thread-per-block
 // (rows padded to an odd pitch so that lanes walking their own rows do not bank-conflict),
 // every thread regresses its own block(s) and leaves the head mask, then the tile is written
 // back coalesced -- every element fetches the value of the head its mask names.
+template <int BYTES> __device__ __forceinline__ void cp_async_elem(void *dst_smem, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_addr(dst_smem)), "l"(src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// A ROW is what one thread regresses: G consecutive blocks of K entries (KR = G*K <= bits of M),
+// G > 1 for short blocks so that a lane has enough work to stay in step with its warp.
+// A tile is THREADS rows, staged in shared memory with rows padded to an odd pitch (lanes walking
+// their own rows then do not bank-conflict).  Tiles are fetched with per-element cp.async
+// (LDGSTS: global -> padded shared address, no registers).  CTAs are small (64 threads) and a
+// tile is single-buffered: measured on B200, many resident CTAs in different phases hide the
+// load latency better than a two-buffer pipeline with half the warps (tools/pava_cfg_sweep.py,
+// K = 16: 0.45 ms against 0.50 ms for 10^8 values).
 // FAST = the hot configuration (cold start, no weight array, update = 1; main.py:64): the
 // loops carry no run-time flags.  CLIP is the [0,1] clamp of python/main.py:65.
 template <typename T, int THREADS, typename M, bool FAST, bool CLIP>
 __global__ void __launch_bounds__(THREADS)
-pava_small_kernel(T *__restrict__ yg, int32_t *__restrict__ wg, long long first, int nb, int K, FastDiv kdiv, PavaFlags fl, int bpt) {
+pava_small_kernel(T *__restrict__ yg, int32_t *__restrict__ wg, long long first, int nb, int K, int G, FastDiv rdiv, PavaFlags fl) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int KS = K | 1;  // row pitch (elements)
-    const int pad = KS - K;  // 1 for even K: element e of the tile sits at e + row
-    const int TB = THREADS * bpt;  // blocks per tile: short blocks come several to a thread so that a tile stays large
+    const int KR = K * G;     // row length (elements)
+    const int KS = KR | 1;    // row pitch
+    const int pad = KS - KR;  // 1 for even KR: element e of the tile sits at e + row
     constexpr int RCPN = kPavaSmallMaxBlock + 1;
     T *rcp = reinterpret_cast<T *>(smem_raw);
     M *masks = reinterpret_cast<M *>(smem_raw + ((RCPN * sizeof(T) + 15) & ~size_t(15)));
-    T *ys = reinterpret_cast<T *>(masks + TB + (TB & 1));
-    uint8_t *wsm = reinterpret_cast<uint8_t *>(ys + (size_t)TB * KS);  // only with a weight array
+    T *ys = reinterpret_cast<T *>(masks + THREADS);
+    uint8_t *wsm = reinterpret_cast<uint8_t *>(ys + (((size_t)THREADS * KS + 1) & ~size_t(1)));  // only with a weight array
     const int tid = threadIdx.x;
     const bool has_weight = !FAST && fl.has_weight;
     const bool update = FAST || fl.update;
     const bool clip = FAST ? CLIP : (fl.clip01 != 0);
     for (int i = tid + 1; i < RCPN; i += THREADS) rcp[i] = T(1) / (T)i;
-    const M full = K == (int)(8 * sizeof(M)) ? ~M(0) : (((M)1 << K) - 1);
-    const int ntiles = (nb + TB - 1) / TB;
+    M bst = 0;  // first entry of every block of a row
+    for (int g = 0; g < G; ++g) bst |= (M)1 << (g * K);
+    const int nrows = (nb + G - 1) / G;
+    const int ntiles = (nrows + THREADS - 1) / THREADS;
+    const long long ntot = (long long)nb * K;
+    const int tile_elems = THREADS * KR;
+    // two entries per thread and 16-byte stores when rows hold an even number of entries and the span is aligned
+    const bool pairs = FAST && sizeof(T) == 8 && pad == 1 && ((reinterpret_cast<uintptr_t>(yg + first) & 15) == 0);
+
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int nblk = min(TB, nb - tile * TB);
-        const int nel = nblk * K;
-        T *gy = yg + first + (size_t)tile * TB * K;
-        int32_t *gw = wg ? wg + first + (size_t)tile * TB * K : nullptr;
-        // coalesced load, scattered into padded rows; four loads in flight per thread
-        int i = tid;
-        for (; i + 3 * THREADS < nel; i += 4 * THREADS) {
-            T v[4];
+        const long long e0 = (long long)tile * tile_elems;
+        const int nel = (int)min((long long)tile_elems, ntot - e0);
+        T *gy = yg + first + e0;
+        int32_t *gw = wg ? wg + first + e0 : nullptr;
+        {
+            int i = tid;
+            for (; i + 3 * THREADS < nel; i += 4 * THREADS) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = gy[i + u * THREADS];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const uint32_t e = (uint32_t)(i + u * THREADS);
-                ys[e + (pad ? fdiv(e, kdiv) : 0u)] = v[u];
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t e = (uint32_t)(i + u * THREADS);
+                    cp_async_elem<sizeof(T)>(&ys[e + (pad ? fdiv(e, rdiv) : 0u)], gy + e);
+                }
             }
-        }
-        for (; i < nel; i += THREADS) {
-            const uint32_t e = (uint32_t)i;
-            ys[e + (pad ? fdiv(e, kdiv) : 0u)] = gy[i];
+            for (; i < nel; i += THREADS) {
+                const uint32_t e = (uint32_t)i;
+                cp_async_elem<sizeof(T)>(&ys[e + (pad ? fdiv(e, rdiv) : 0u)], gy + e);
+            }
+            cp_async_commit();
         }
         if (has_weight) {
             for (int e2 = tid; e2 < nel; e2 += THREADS) {
                 const uint32_t e = (uint32_t)e2;
-                wsm[e + (pad ? fdiv(e, kdiv) : 0u)] = (uint8_t)gw[e2];
+                wsm[e + (pad ? fdiv(e, rdiv) : 0u)] = (uint8_t)gw[e2];
             }
         }
+        cp_async_wait<0>();
         __syncthreads();
-        for (int b = tid; b < nblk; b += THREADS) {
-            T *yb = ys + (size_t)b * KS;
-            if (has_weight) {
-                uint8_t *wb = wsm + (size_t)b * KS;
-                masks[b] = pava_block_runs<T, uint8_t, M, true>(yb, wb, K, pava_heads_from_weights<uint8_t, M>(wb, K), true, rcp, RCPN);
-            } else {
-                masks[b] = pava_block_runs<T, uint8_t, M, false>(yb, nullptr, K, full, false, rcp, RCPN);
+        {
+            const int len = min(KR, nel - tid * KR);  // the very last row may hold fewer blocks
+            if (len > 0) {
+                T *yb = ys + (size_t)tid * KS;
+                const M full = len == (int)(8 * sizeof(M)) ? ~M(0) : (((M)1 << len) - 1);
+                if (has_weight) {
+                    uint8_t *wb = wsm + (size_t)tid * KS;
+                    masks[tid] = pava_block_runs<T, uint8_t, M, true>(yb, wb, len, pava_heads_from_weights<uint8_t, M>(wb, len), (M)(bst & full), true, rcp, RCPN);
+                } else {
+                    masks[tid] = pava_block_runs<T, uint8_t, M, false>(yb, nullptr, len, full, (M)(bst & full), false, rcp, RCPN);
+                }
             }
         }
         __syncthreads();
         // coalesced store; with `update` every element takes the value of the head its mask names
+        if (pairs) {
+#pragma unroll 2
+            for (int e2 = 2 * tid; e2 < nel; e2 += 2 * THREADS) {  // nel is even (KR is)
+                const uint32_t e = (uint32_t)e2, r = fdiv(e, rdiv), c = e - r * KR;
+                const M m = masks[r];
+                const uint32_t h0 = (uint32_t)bit_hi((M)(m & ((((M)2) << c) - 1)));
+                const uint32_t h1 = ((m >> (c + 1)) & 1) ? c + 1 : h0;
+                T v0 = ys[r * KS + h0], v1 = ys[r * KS + h1];
+                if (clip) {
+                    v0 = clip01(v0);
+                    v1 = clip01(v1);
+                }
+                st_stream_v2(reinterpret_cast<double *>(gy + e2), (double)v0, (double)v1);
+            }
+        } else {
 #pragma unroll 4
-        for (int e2 = tid; e2 < nel; e2 += THREADS) {
-            const uint32_t e = (uint32_t)e2, r = fdiv(e, kdiv), c = e - r * K;
-            uint32_t src = c;
-            if (update) src = (uint32_t)bit_hi((M)(masks[r] & ((((M)2) << c) - 1)));
-            T v = ys[r * KS + src];
-            if (clip) v = clip01(v);
-            gy[e2] = v;
-            if (has_weight) gw[e2] = (int32_t)wsm[r * KS + c];
+            for (int e2 = tid; e2 < nel; e2 += THREADS) {
+                const uint32_t e = (uint32_t)e2, r = fdiv(e, rdiv), c = e - r * KR;
+                uint32_t src = c;
+                if (update) src = (uint32_t)bit_hi((M)(masks[r] & ((((M)2) << c) - 1)));
+                T v = ys[r * KS + src];
+                if (clip) v = clip01(v);
+                gy[e2] = v;
+                if (has_weight) gw[e2] = (int32_t)wsm[r * KS + c];
+            }
         }
         __syncthreads();
     }
 }
 
 template <typename T, int THREADS, typename M, bool FAST, bool CLIP>
-int launch_pava_small_cfg(T *y, int32_t *w, long long first, int nb, int K, PavaFlags fl, cudaStream_t stream) {
+int launch_pava_small_cfg(T *y, int32_t *w, long long first, int nb, int K, int G, PavaFlags fl, cudaStream_t stream) {
     auto kern = pava_small_kernel<T, THREADS, M, FAST, CLIP>;
-    const int KS = K | 1;
-    const int bpt = K >= 16 ? 1 : (K >= 8 ? 2 : 4);
-    const int TB = THREADS * bpt;
-    const size_t smem = (((kPavaSmallMaxBlock + 1) * sizeof(T) + 15) & ~size_t(15)) + (size_t)(TB + (TB & 1)) * sizeof(M) +
-                        (size_t)TB * KS * (sizeof(T) + (fl.has_weight ? 1 : 0)) + 16;
+    const int KR = K * G, KS = KR | 1;
+    const size_t buf_elems = ((size_t)THREADS * KS + 1) & ~size_t(1);
+    const size_t smem = (((kPavaSmallMaxBlock + 1) * sizeof(T) + 15) & ~size_t(15)) + (size_t)THREADS * sizeof(M) + buf_elems * sizeof(T) +
+                        (fl.has_weight ? (size_t)THREADS * KS : 0) + 16;
     static thread_local size_t cached_smem = 0;
     static thread_local int per_sm = 0, num_sm = 0;
     if (cached_smem != smem) {
@@ -373,27 +431,38 @@ int launch_pava_small_cfg(T *y, int32_t *w, long long first, int nb, int K, Pava
         }
         cached_smem = smem;
     }
-    const int ntiles = (nb + TB - 1) / TB;
+    const int nrows = (nb + G - 1) / G;
+    const int ntiles = (nrows + THREADS - 1) / THREADS;
     const int grid = ntiles < num_sm * per_sm ? ntiles : num_sm * per_sm;
-    kern<<<grid, THREADS, smem, stream>>>(y, w, first, nb, K, make_fastdiv((uint32_t)K), fl, bpt);
+    kern<<<grid, THREADS, smem, stream>>>(y, w, first, nb, K, G, make_fastdiv((uint32_t)KR), fl);
     BSLS_LAUNCH_CHECK();
     return BSLS_OK;
 }
 
 template <typename T, int THREADS, typename M>
-int launch_pava_small_flags(T *y, int32_t *w, long long first, int nb, int K, PavaFlags fl, cudaStream_t stream) {
-    if (!fl.has_weight && fl.update) {
-        if (fl.clip01) return launch_pava_small_cfg<T, THREADS, M, true, true>(y, w, first, nb, K, fl, stream);
-        return launch_pava_small_cfg<T, THREADS, M, true, false>(y, w, first, nb, K, fl, stream);
+int launch_pava_small_flags(T *y, int32_t *w, long long first, int nb, int K, int G, PavaFlags fl, cudaStream_t stream) {
+    if (!fl.has_weight && fl.update) {  // hot configuration
+        if (fl.clip01) return launch_pava_small_cfg<T, THREADS, M, true, true>(y, w, first, nb, K, G, fl, stream);
+        return launch_pava_small_cfg<T, THREADS, M, true, false>(y, w, first, nb, K, G, fl, stream);
     }
-    return launch_pava_small_cfg<T, THREADS, M, false, false>(y, w, first, nb, K, fl, stream);
+    return launch_pava_small_cfg<T, THREADS, M, false, false>(y, w, first, nb, K, 1, fl, stream);
 }
 
 template <typename T> int launch_pava_small(T *y, int32_t *w, long long first, int nb, int K, PavaFlags fl, cudaStream_t stream) {
     if (nb <= 0) return BSLS_OK;
-    if (K <= 24) return launch_pava_small_flags<T, 256, uint32_t>(y, w, first, nb, K, fl, stream);
-    if (K <= 32) return launch_pava_small_flags<T, 128, uint32_t>(y, w, first, nb, K, fl, stream);
-    return launch_pava_small_flags<T, 128, uint64_t>(y, w, first, nb, K, fl, stream);
+    if (K <= 32) {
+        int G = K <= 8 ? 16 / K : 1;  // short blocks: several to a row (<= 16 entries)
+        int th = 64;
+        if (const char *cfg = getenv("BSLS_PAVA_CFG")) {  // tuning experiments: "<threads>,<G>"
+            int g = G;
+            sscanf(cfg, "%d,%d", &th, &g);
+            if (g >= 1 && g * K <= 32) G = g;
+        }
+        if (th == 128) return launch_pava_small_flags<T, 128, uint32_t>(y, w, first, nb, K, G, fl, stream);
+        if (th == 32) return launch_pava_small_flags<T, 32, uint32_t>(y, w, first, nb, K, G, fl, stream);
+        return launch_pava_small_flags<T, 64, uint32_t>(y, w, first, nb, K, G, fl, stream);
+    }
+    return launch_pava_small_flags<T, 64, uint64_t>(y, w, first, nb, K, 1, fl, stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -667,9 +736,9 @@ pava_tile_kernel(T *__restrict__ yg, int32_t *__restrict__ wg, const int32_t *__
             uint32_t heads;
             if (fl.has_weight)
                 heads = pava_block_runs<T, uint16_t, uint32_t, true>(ybuf + s0, wbuf + s0, Kb, pava_heads_from_weights<uint16_t, uint32_t>(wbuf + s0, Kb),
-                                                                     true, rcp, kPavaThreadMax + 1);
+                                                                     1u, true, rcp, kPavaThreadMax + 1);
             else
-                heads = pava_block_runs<T, uint16_t, uint32_t, false>(ybuf + s0, nullptr, Kb, Kb == 32 ? ~0u : ((1u << Kb) - 1u), false, rcp,
+                heads = pava_block_runs<T, uint16_t, uint32_t, false>(ybuf + s0, nullptr, Kb, Kb == 32 ? ~0u : ((1u << Kb) - 1u), 1u, false, rcp,
                                                                       kPavaThreadMax + 1);
             if (fl.update) pava_spread(ybuf + s0, Kb, heads);
         }

@@ -48,7 +48,7 @@ template <typename M> static long run_case(int K, int kind, int warm, int update
         // first a cold pass on BOTH sides with update = 0 leaves a consistent warm state; perturb the values and run again
         orc_pava(yr.data(), 0, K, wr.data(), 0);
         std::vector<uint16_t> ww(K, 1);
-        heads = bsls::pava_block_runs<double, uint16_t, M, false>(y.data(), ww.data(), K, full, true, rcp, 65);
+        heads = bsls::pava_block_runs<double, uint16_t, M, false>(y.data(), ww.data(), K, full, (M)1, true, rcp, 65);
         for (int i = 0; i < K; ++i)
             if (memcmp(&y[i], &yr[i], 8) || ww[i] != (uint16_t)wr[i]) return 1 + i;
         for (int i = 0; i < K; ++i) {
@@ -58,10 +58,10 @@ template <typename M> static long run_case(int K, int kind, int warm, int update
         }
         w = ww;
         orc_pava(yr.data(), 0, K, wr.data(), update);
-        heads = bsls::pava_block_runs<double, uint16_t, M, true>(y.data(), w.data(), K, bsls::pava_heads_from_weights<uint16_t, M>(w.data(), K), true, rcp, 65);
+        heads = bsls::pava_block_runs<double, uint16_t, M, true>(y.data(), w.data(), K, bsls::pava_heads_from_weights<uint16_t, M>(w.data(), K), (M)1, true, rcp, 65);
     } else {
         orc_pava(yr.data(), 0, K, wr.data(), update);
-        heads = bsls::pava_block_runs<double, uint16_t, M, false>(y.data(), w.data(), K, full, true, rcp, 65);
+        heads = bsls::pava_block_runs<double, uint16_t, M, false>(y.data(), w.data(), K, full, (M)1, true, rcp, 65);
     }
     if (update) bsls::pava_spread(y.data(), K, heads);
     for (int i = 0; i < K; ++i)
@@ -79,6 +79,43 @@ template <typename M> static long run_case(int K, int kind, int warm, int update
     return 0;
 }
 
+// several short blocks regressed as one row with forced run starts at the block boundaries (cold start)
+template <typename M> static long run_group(int K, int G, int kind) {
+    const int KR = K * G;
+    std::vector<double> y(KR), yr(KR);
+    std::vector<int32_t> wr(KR, 1);
+    std::vector<uint16_t> w(KR, 1);
+    for (int i = 0; i < KR; ++i) {
+        double v;
+        switch (kind) {
+            case 0: v = uni() * 2 - 1; break;
+            case 1: v = (double)(int)(rnd() % 5); break;
+            case 2: v = (double)((int)(rnd() % 100) - 50) + 50.0 * log(1.0 + (i % K)); break;
+            case 4: v = -(double)i * 0.1; break;   // decreasing ACROSS block boundaries: runs must stop there
+            case 5: v = (rnd() % 3 == 0) ? 0.0 : (double)((int)(rnd() % 3) - 1); break;
+            default: v = uni() * 1e-3 + (double)(rnd() % 4) / 3.0; break;
+        }
+        y[i] = v;
+    }
+    yr = y;
+    static double rcp[65];
+    for (int i = 1; i <= 64; ++i) rcp[i] = 1.0 / i;
+    M bst = 0;
+    for (int g = 0; g < G; ++g) {
+        bst |= (M)1 << (g * K);
+        orc_pava(yr.data(), g * K, (g + 1) * K, wr.data(), 1);
+    }
+    const M full = KR == (int)(8 * sizeof(M)) ? ~M(0) : (((M)1 << KR) - 1);
+    const M heads = bsls::pava_block_runs<double, uint16_t, M, false>(y.data(), w.data(), KR, full, bst, true, rcp, 65);
+    bsls::pava_spread(y.data(), KR, heads);
+    for (int i = 0; i < KR; ++i)
+        if (memcmp(&y[i], &yr[i], 8) || w[i] != (uint16_t)wr[i]) {
+            fprintf(stderr, "group mismatch K=%d G=%d kind=%d at %d\n", K, G, kind, i);
+            return 1 + i;
+        }
+    return 0;
+}
+
 int main(int argc, char **argv) {
     const long reps = argc > 1 ? atol(argv[1]) : 20000;
     long cases = 0;
@@ -91,11 +128,18 @@ int main(int argc, char **argv) {
                     if (run_case<uint64_t>(K64, kind, warm, update)) return 1;
                     cases += 2;
                 }
+        for (int kind = 0; kind < 7; ++kind) {
+            const int K = 1 + (int)(rnd() % 16), G32 = 1 + (int)(rnd() % (32 / K)), G64 = 1 + (int)(rnd() % (64 / K));
+            if (run_group<uint32_t>(K, G32, kind) || run_group<uint64_t>(K, G64, kind)) return 1;
+            cases += 2;
+        }
     }
+    for (int once = 0; once < 1; ++once) {
     // full-width blocks
     for (int kind = 0; kind < 7; ++kind) {
         if (run_case<uint32_t>(32, kind, 0, 1) || run_case<uint64_t>(64, kind, 0, 1) || run_case<uint32_t>(32, kind, 1, 1) || run_case<uint64_t>(64, kind, 1, 0)) return 1;
         cases += 4;
+    }
     }
     printf("ok %ld cases\n", cases);
     return 0;
