@@ -343,17 +343,19 @@ pava_small_kernel(T *__restrict__ yg, int32_t *__restrict__ wg, long long first,
         T *gy = yg + first + e0;
         int32_t *gw = wg ? wg + first + e0 : nullptr;
         {
+            // thread-relative pointer + constant offsets: no 64-bit address arithmetic per element
+            const T *src = gy + tid;
             int i = tid;
-            for (; i + 3 * THREADS < nel; i += 4 * THREADS) {
+            for (; i + 3 * THREADS < nel; i += 4 * THREADS, src += 4 * THREADS) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const uint32_t e = (uint32_t)(i + u * THREADS);
-                    cp_async_elem<sizeof(T)>(&ys[e + (pad ? fdiv(e, rdiv) : 0u)], gy + e);
+                    cp_async_elem<sizeof(T)>(&ys[e + (pad ? fdiv(e, rdiv) : 0u)], src + u * THREADS);
                 }
             }
-            for (; i < nel; i += THREADS) {
+            for (; i < nel; i += THREADS, src += THREADS) {
                 const uint32_t e = (uint32_t)i;
-                cp_async_elem<sizeof(T)>(&ys[e + (pad ? fdiv(e, rdiv) : 0u)], gy + e);
+                cp_async_elem<sizeof(T)>(&ys[e + (pad ? fdiv(e, rdiv) : 0u)], src);
             }
             cp_async_commit();
         }
@@ -381,8 +383,9 @@ pava_small_kernel(T *__restrict__ yg, int32_t *__restrict__ wg, long long first,
         __syncthreads();
         // coalesced store; with `update` every element takes the value of the head its mask names
         if (pairs) {
+            T *dst = gy + 2 * tid;
 #pragma unroll 2
-            for (int e2 = 2 * tid; e2 < nel; e2 += 2 * THREADS) {  // nel is even (KR is)
+            for (int e2 = 2 * tid; e2 < nel; e2 += 2 * THREADS, dst += 2 * THREADS) {  // nel is even (KR is)
                 const uint32_t e = (uint32_t)e2, r = fdiv(e, rdiv), c = e - r * KR;
                 const M m = masks[r];
                 const uint32_t h0 = (uint32_t)bit_hi((M)(m & ((((M)2) << c) - 1)));
@@ -392,7 +395,7 @@ pava_small_kernel(T *__restrict__ yg, int32_t *__restrict__ wg, long long first,
                     v0 = clip01(v0);
                     v1 = clip01(v1);
                 }
-                st_stream_v2(reinterpret_cast<double *>(gy + e2), (double)v0, (double)v1);
+                st_stream_v2(reinterpret_cast<double *>(dst), (double)v0, (double)v1);
             }
         } else {
 #pragma unroll 4
