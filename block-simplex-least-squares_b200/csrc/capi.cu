@@ -88,6 +88,16 @@ static int dev_pava(const bsls_plan *plan_, T *y, int32_t *weight, int update, i
         set_error("isotonic regression: a block of %d entries exceeds the %d-entry limit of this revision", plan->max_size, kPlanPavaLargeMax);
         return BSLS_ERR_ARG;
     }
+    const bool cold = weight == nullptr && update != 0;  // the configuration of main.py:64
+    const bool words_off = getenv("BSLS_PAVA_NO_WORDS") != nullptr;  // A/B switch for measurements
+    if (cold && !words_off && plan->uniform > kPlanPavaSmallMax && plan->uniform <= kPlanWordsMax) {
+        const int bpp = 32 / ((plan->uniform + 31) >> 5);
+        const int npacks = (plan->nb + bpp - 1) / bpp;
+        if constexpr (sizeof(T) == 8)
+            return pava_words_f64((double *)y, nullptr, nullptr, nullptr, npacks, plan->first, plan->nb, plan->uniform, clip01, stream);
+        else
+            return pava_words_f32((float *)y, nullptr, nullptr, nullptr, npacks, plan->first, plan->nb, plan->uniform, clip01, stream);
+    }
     if (plan->uniform > 0 && plan->uniform <= kPlanPavaSmallMax) {
         if constexpr (sizeof(T) == 8)
             return pava_small_f64((double *)y, weight, plan->first, plan->nb, plan->uniform, update, clip01, stream);
@@ -101,7 +111,26 @@ static int dev_pava(const bsls_plan *plan_, T *y, int32_t *weight, int update, i
         if (int rc = ensure_streams(plan)) return rc;
         BSLS_CUDA_TRY(cudaEventRecord(plan->ev_fork, stream));
         int rc = BSLS_OK;
-        if (plan->mid > 0) {
+        if (plan->mid > 0 && cold && !words_off) {
+            if (plan->mid_packs < 0) {  // pack the mid list once
+                int *d_np = nullptr, h_np = 0;
+                BSLS_CUDA_TRY(cudaMalloc(&d_np, sizeof(int)));
+                BSLS_CUDA_TRY(cudaMalloc(&plan->d_mid_pack, sizeof(int32_t) * ((size_t)plan->mid + 1)));
+                if (int rc2 = plan_pack_words(plan->d_starts, plan->d_mid_ids, plan->mid, plan->d_mid_pack, d_np, stream)) return rc2;
+                BSLS_CUDA_TRY(cudaMemcpyAsync(&h_np, d_np, sizeof(int), cudaMemcpyDeviceToHost, stream));
+                BSLS_CUDA_TRY(cudaStreamSynchronize(stream));
+                cudaFree(d_np);
+                plan->mid_packs = h_np;
+                BSLS_CUDA_TRY(cudaEventRecord(plan->ev_fork, stream));
+            }
+            BSLS_CUDA_TRY(cudaStreamWaitEvent(plan->aux[0], plan->ev_fork, 0));
+            if constexpr (sizeof(T) == 8)
+                rc = pava_words_f64((double *)y, plan->d_starts, plan->d_mid_ids, plan->d_mid_pack, plan->mid_packs, 0, plan->nb, 0, clip01, plan->aux[0]);
+            else
+                rc = pava_words_f32((float *)y, plan->d_starts, plan->d_mid_ids, plan->d_mid_pack, plan->mid_packs, 0, plan->nb, 0, clip01, plan->aux[0]);
+            if (rc) return rc;
+            BSLS_CUDA_TRY(cudaEventRecord(plan->ev_join[0], plan->aux[0]));
+        } else if (plan->mid > 0) {
             BSLS_CUDA_TRY(cudaStreamWaitEvent(plan->aux[0], plan->ev_fork, 0));
             if constexpr (sizeof(T) == 8)
                 rc = pava_mid_f64((double *)y, weight, plan->d_starts, plan->d_mid_ids, plan->mid, update, clip01, plan->aux[0]);
@@ -110,7 +139,15 @@ static int dev_pava(const bsls_plan *plan_, T *y, int32_t *weight, int update, i
             if (rc) return rc;
             BSLS_CUDA_TRY(cudaEventRecord(plan->ev_join[0], plan->aux[0]));
         }
-        if (plan->large > 0) {
+        if (plan->large > 0 && cold && !words_off) {
+            BSLS_CUDA_TRY(cudaStreamWaitEvent(plan->aux[1], plan->ev_fork, 0));
+            if constexpr (sizeof(T) == 8)
+                rc = pava_words_cta_f64((double *)y, plan->d_starts, plan->d_large_ids, plan->large, plan->max_size, clip01, plan->aux[1]);
+            else
+                rc = pava_words_cta_f32((float *)y, plan->d_starts, plan->d_large_ids, plan->large, plan->max_size, clip01, plan->aux[1]);
+            if (rc) return rc;
+            BSLS_CUDA_TRY(cudaEventRecord(plan->ev_join[1], plan->aux[1]));
+        } else if (plan->large > 0) {
             BSLS_CUDA_TRY(cudaStreamWaitEvent(plan->aux[1], plan->ev_fork, 0));
             if constexpr (sizeof(T) == 8)
                 rc = pava_f64((double *)y, weight, plan->d_starts, nullptr, 0, plan->d_large_ids, plan->large, plan->max_size, update, clip01, plan->aux[1]);
@@ -537,6 +574,7 @@ int bsls_plan_destroy(bsls_plan *plan) {
     if (plan->d_large_ids) cudaFree(plan->d_large_ids);
     if (plan->d_pava_first) cudaFree(plan->d_pava_first);
     if (plan->d_pava_large) cudaFree(plan->d_pava_large);
+    if (plan->d_mid_pack) cudaFree(plan->d_mid_pack);
     if (plan->d_slow) cudaFree(plan->d_slow);
     if (plan->d_huge) cudaFree(plan->d_huge);
     if (plan->d_huge_lock) cudaFree(plan->d_huge_lock);

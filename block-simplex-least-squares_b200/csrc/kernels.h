@@ -62,6 +62,19 @@ int pava_tile_f32(float *y, int32_t *w, const int32_t *starts, const int32_t *ti
 int pava_mid_f64(double *y, int32_t *w, const int32_t *starts, const int32_t *mid_ids, int nmid, int update, int clip01, cudaStream_t stream);
 int pava_mid_f32(float *y, int32_t *w, const int32_t *starts, const int32_t *mid_ids, int nmid, int update, int clip01, cudaStream_t stream);
 
+// blocks of 33 .. kPlanWordsMax entries, cold start: one lane per 32-entry word, packs of blocks per warp (pava_words.cuh).
+// ragged: ids / pack_first from plan_pack_words, first = 0; uniform: starts = ids = pack_first = nullptr.
+constexpr int kPlanWordsMax = 1024;
+int pava_words_f64(double *y, const int32_t *starts, const int32_t *ids, const int32_t *pack_first, int npacks, long long first, int nb,
+                   int Kuni, int clip01, cudaStream_t stream);
+int pava_words_f32(float *y, const int32_t *starts, const int32_t *ids, const int32_t *pack_first, int npacks, long long first, int nb,
+                   int Kuni, int clip01, cudaStream_t stream);
+// one CTA per block of up to kPlanPavaLargeMax entries (cold start), same engine
+int pava_words_cta_f64(double *y, const int32_t *starts, const int32_t *ids, int count, int max_block, int clip01, cudaStream_t stream);
+int pava_words_cta_f32(float *y, const int32_t *starts, const int32_t *ids, int count, int max_block, int clip01, cudaStream_t stream);
+// greedy packing of ids[0..count) into packs of at most 32 words (32 entries each); pack_first has count + 1 slots
+int plan_pack_words(const int32_t *starts, const int32_t *ids, int count, int32_t *pack_first, int *d_npacks, cudaStream_t stream);
+
 int device_ok();  // BSLS_OK when an sm_100 device is current (capi.cu)
 }  // namespace bsls
 
@@ -82,6 +95,8 @@ struct bsls_plan {
     int32_t *d_pava_large = nullptr;  // blocks longer than kPlanPavaWarpMax
     int mid = 0;
     int32_t *d_mid_ids = nullptr;     // ragged: blocks with kPlanMidMin < size <= kPlanTileMaxBlock
+    int mid_packs = -1;               // packs of the mid list for pava_words (built on first use)
+    int32_t *d_mid_pack = nullptr;    // mid_packs + 1 entries
     // fork/join inside one call: the tile, mid and large kernels own disjoint blocks and run side by side
     cudaStream_t aux[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};

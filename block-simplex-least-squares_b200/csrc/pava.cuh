@@ -47,6 +47,12 @@ __device__ __forceinline__ void cp_async_8(void *dst_smem, const void *src) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+template <int BYTES> __device__ __forceinline__ void cp_async_elem(void *dst_smem, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_addr(dst_smem)), "l"(src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <typename T> __device__ __forceinline__ T clip01(T v) {
     v = (v > T(0)) ? v : T(0);  // np.maximum(0., x)
     v = (v < T(1)) ? v : T(1);  // np.minimum(1., x)
@@ -295,12 +301,6 @@ constexpr int kPavaSmallMaxBlock = 64;  // longest block of the thread-per-block
 // (rows padded to an odd pitch so that lanes walking their own rows do not bank-conflict),
 // every thread regresses its own block(s) and leaves the head mask, then the tile is written
 // back coalesced -- every element fetches the value of the head its mask names.
-template <int BYTES> __device__ __forceinline__ void cp_async_elem(void *dst_smem, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_addr(dst_smem)), "l"(src), "n"(BYTES) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 // A ROW is what one thread regresses: G consecutive blocks of K entries (KR = G*K <= bits of M),
 // G > 1 for short blocks so that a lane has enough work to stay in step with its warp.
 // A tile is THREADS rows, staged in shared memory with rows padded to an odd pitch (lanes walking
@@ -755,6 +755,137 @@ pava_tile_kernel(T *__restrict__ yg, int32_t *__restrict__ wg, const int32_t *__
         }
         __syncthreads();
     }
+}
+
+// Cold start (no weight array, update = 1): the tile's short blocks are regressed as ROWS -- runs of
+// consecutive blocks that one thread takes as a single 32-bit mask problem with forced run starts at
+// the block boundaries (pava_block_runs, `bst`), so that a lane has 16..31 entries of work whatever
+// the block sizes are.  Rows follow from a bitmap of block starts alone, without lists or scans:
+// thread q owns the 16-entry bucket q of the tile; the blocks that START in a bucket are a sequence
+// of blocks of <= 16 entries (row A, span <= 31) followed by at most one longer block (a block of
+// more than 16 entries that starts in the bucket ends beyond it), which is row B if it has <= 32
+// entries and belongs to pava_words_kernel / pava_words_cta_kernel otherwise.
+template <typename T, bool CLIP>
+__global__ void __launch_bounds__(kPavaTileThreads)
+pava_tile_rows_kernel(T *__restrict__ yg, const int32_t *__restrict__ starts, const int32_t *__restrict__ tile_first, int ntiles) {
+    static_assert(kPavaTileThreads * 16 == kPavaTileElems, "one 16-entry bucket per thread");
+    constexpr int WIN = kPavaTileElems + kPavaTileMaxBlock;
+    constexpr int NW = WIN / 32 + 4;  // bitmap words (+ look-ahead)
+    __shared__ __align__(16) T ybuf[WIN];
+    __shared__ uint32_t sb[NW];   // bit i: a block starts at entry i of the window (and one bit at the window's end)
+    __shared__ uint32_t cov[NW];  // bit i: entry i belongs to a row (is written back from here)
+    __shared__ T rcp[kPavaThreadMax + 1];
+    const int tid = threadIdx.x;
+    for (int i = tid + 1; i <= kPavaThreadMax; i += kPavaTileThreads) rcp[i] = T(1) / (T)i;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int fb = tile_first[tile];
+        const int nblk = tile_first[tile + 1] - fb;
+        if (nblk <= 0) continue;
+        const int tile_lo = starts[fb];
+        int nel = starts[fb + nblk] - tile_lo;                        // to the end of the last block that starts in the tile
+        const int last = starts[fb + nblk - 1] - tile_lo;             // ... which may be a long one: not staged
+        if (nel - last > kPavaTileMaxBlock) nel = last;
+        for (int i = tid; i < NW; i += kPavaTileThreads) {
+            sb[i] = 0;
+            cov[i] = 0;
+        }
+        {
+            const T *src = yg + (size_t)tile_lo + tid;
+            for (int i = tid; i < nel; i += kPavaTileThreads, src += kPavaTileThreads) cp_async_elem<sizeof(T)>(&ybuf[i], src);
+            cp_async_commit();
+        }
+        __syncthreads();
+        for (int i = tid; i <= nblk; i += kPavaTileThreads) {
+            const int s = starts[fb + i] - tile_lo;
+            if (s < NW * 32) atomicOr(&sb[s >> 5], 1u << (s & 31));  // a long last block ends beyond the window: no bit needed
+        }
+        cp_async_wait<0>();
+        __syncthreads();
+        {
+            // 64 entries of the bitmap from the bucket's first position
+            const int word = tid >> 1, sh = (tid & 1) * 16;
+            const unsigned long long lo64 = ((unsigned long long)sb[word + 1] << 32) | sb[word];
+            const unsigned long long W = sh ? ((lo64 >> 16) | ((unsigned long long)sb[word + 2] << 48)) : lo64;
+            uint32_t field = (uint32_t)W & 0xffffu;  // blocks that start in this bucket
+            if (field) {
+                const int s0 = __ffs((int)field) - 1;
+                // row A: leading blocks of <= 16 entries
+                int e = s0;
+                uint32_t bst = 0;
+                int longer = -1, longer_len = 0;
+                while (field) {
+                    const int s = __ffs((int)field) - 1;
+                    field &= field - 1;
+                    const unsigned long long up = W >> (s + 1);
+                    const int len = up ? __ffsll((long long)up) : 64;  // distance to the next block start (64: none in sight)
+                    if (len <= 16) {
+                        bst |= 1u << (s - s0);
+                        e = s + len;
+                    } else {
+                        longer = s;
+                        longer_len = len;
+                        break;
+                    }
+                }
+                const int p0 = tid * 16;
+                if (e > s0) {
+                    const int len = e - s0;
+                    const uint32_t full = (1u << len) - 1u;  // len <= 31
+                    T *yb = ybuf + p0 + s0;
+                    const uint32_t heads = pava_block_runs<T, uint16_t, uint32_t, false>(yb, nullptr, len, full, bst, false, rcp, kPavaThreadMax + 1);
+                    pava_spread(yb, len, heads);
+                    const unsigned long long span = (unsigned long long)full << ((p0 + s0) & 31);
+                    atomicOr(&cov[(p0 + s0) >> 5], (uint32_t)span);
+                    if (span >> 32) atomicOr(&cov[((p0 + s0) >> 5) + 1], (uint32_t)(span >> 32));
+                }
+                if (longer >= 0 && longer_len <= kPavaThreadMax) {
+                    const int len = longer_len;
+                    const uint32_t full = len == 32 ? ~0u : ((1u << len) - 1u);
+                    T *yb = ybuf + p0 + longer;
+                    const uint32_t heads = pava_block_runs<T, uint16_t, uint32_t, false>(yb, nullptr, len, full, 1u, false, rcp, kPavaThreadMax + 1);
+                    pava_spread(yb, len, heads);
+                    const unsigned long long span = (unsigned long long)full << ((p0 + longer) & 31);
+                    atomicOr(&cov[(p0 + longer) >> 5], (uint32_t)span);
+                    if (span >> 32) atomicOr(&cov[((p0 + longer) >> 5) + 1], (uint32_t)(span >> 32));
+                }
+            }
+        }
+        __syncthreads();
+        {
+            T *dst = yg + (size_t)tile_lo + tid;
+            for (int i = tid; i < nel; i += kPavaTileThreads, dst += kPavaTileThreads) {
+                if (!((cov[i >> 5] >> (i & 31)) & 1u)) continue;
+                T v = ybuf[i];
+                if (CLIP) v = clip01(v);
+                *dst = v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T>
+int launch_pava_tile_rows(T *y, const int32_t *starts, const int32_t *tile_first, int ntiles, int clip, cudaStream_t stream) {
+    if (ntiles <= 0) return BSLS_OK;
+    static thread_local int grid_full[2] = {0, 0};
+    const int c = clip ? 1 : 0;
+    if (!grid_full[c]) {
+        int dev = 0, num_sm = kNumSM, per_sm = 1;
+        BSLS_CUDA_TRY(cudaGetDevice(&dev));
+        BSLS_CUDA_TRY(cudaDeviceGetAttribute(&num_sm, cudaDevAttrMultiProcessorCount, dev));
+        if (clip)
+            BSLS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pava_tile_rows_kernel<T, true>, kPavaTileThreads, 0));
+        else
+            BSLS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pava_tile_rows_kernel<T, false>, kPavaTileThreads, 0));
+        grid_full[c] = num_sm * (per_sm < 1 ? 1 : per_sm);
+    }
+    const int grid = ntiles < grid_full[c] ? ntiles : grid_full[c];
+    if (clip)
+        pava_tile_rows_kernel<T, true><<<grid, kPavaTileThreads, 0, stream>>>(y, starts, tile_first, ntiles);
+    else
+        pava_tile_rows_kernel<T, false><<<grid, kPavaTileThreads, 0, stream>>>(y, starts, tile_first, ntiles);
+    BSLS_LAUNCH_CHECK();
+    return BSLS_OK;
 }
 
 // Blocks of kPavaThreadMax < K <= kPavaTileMaxBlock: one WARP per block, staged in the warp's own

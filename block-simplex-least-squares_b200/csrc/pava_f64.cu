@@ -1,6 +1,7 @@
 // pava_f64.cu -- double instantiation of the segmented isotonic regression kernels.
 #include "kernels.h"
 #include "pava.cuh"
+#include "pava_words.cuh"
 
 namespace bsls {
 int pava_f64(double *y, int32_t *w, const int32_t *starts, const int32_t *win_first, int nwin, const int32_t *large_ids,
@@ -28,6 +29,7 @@ int pava_tile_f64(double *y, int32_t *w, const int32_t *starts, const int32_t *t
     fl.update = update;
     fl.clip01 = clip01;
     fl.has_weight = w != nullptr;
+    if (!w && update && !getenv("BSLS_PAVA_NO_ROWS")) return launch_pava_tile_rows<double>(y, starts, tile_first, ntiles, clip01, stream);
     return launch_pava_tile<double>(y, w, starts, tile_first, ntiles, fl, stream);
 }
 
@@ -37,5 +39,16 @@ int pava_mid_f64(double *y, int32_t *w, const int32_t *starts, const int32_t *mi
     fl.clip01 = clip01;
     fl.has_weight = w != nullptr;
     return launch_pava_mid<double>(y, w, starts, mid_ids, nmid, fl, stream);
+}
+
+int pava_words_f64(double *y, const int32_t *starts, const int32_t *ids, const int32_t *pack_first, int npacks, long long first, int nb,
+                   int Kuni, int clip01, cudaStream_t stream) {
+    static_assert(kWordsMaxBlock == kPlanWordsMax, "plan constants");
+    return launch_pava_words<double>(y, starts, ids, pack_first, npacks, first, nb, Kuni, clip01, stream);
+}
+
+int pava_words_cta_f64(double *y, const int32_t *starts, const int32_t *ids, int count, int max_block, int clip01, cudaStream_t stream) {
+    static_assert(32 * kWordsCtaThreads == kPlanPavaLargeMax, "plan constants");
+    return launch_pava_words_cta<double>(y, starts, ids, count, max_block, clip01, stream);
 }
 }  // namespace bsls

@@ -1,0 +1,383 @@
+// pava_words.cuh -- isotonic regression of blocks of 33 .. 1024 entries: one LANE per 32-entry word.
+//
+// Same replay of the reference's sweeps as pava_block_runs (pava.cuh; isotonic_regression.h:13-58),
+// with the head / run-start bit masks of a block spread over the lanes of a warp: lane j of a
+// block owns entries 32j .. 32j+31, their `alive` word (pool heads) and their `S` word (heads that
+// start a run of the current sweep).  A warp regresses a PACK of blocks that together fill at most
+// 32 words, so short and long blocks use the same kernel and no lane idles by construction.
+//
+// One sweep:
+//   A  every lane publishes its words (frozen copies A0 / St for run finding, A for the kills).
+//   B  every lane merges the runs whose HEAD lies in its word.  A run may continue into later
+//      words: followers there are found through the published words, summed in the reference's
+//      order (0 + y*w products left to right, weights = gaps between head positions, :33-39) and,
+//      when the run pools (first != last, :29), removed with atomicAnd on the owning word.
+//      Runs of one sweep are independent (the reference reads only values the sweep has not
+//      rewritten, :23-28), so all lanes work at once.  A merge marks two heads DIRTY: its own head
+//      and the head that follows the run.
+//   C  every lane re-evaluates the run-start bit of its dirty heads against the previous head
+//      (possibly in an earlier word) on the new values -- the state the next sweep starts from.
+// until a sweep merges nothing anywhere in the warp (a block that is finished has no run left
+// that pools, so idling through the others' sweeps does not change it).
+//
+// Cold start only (all weights 1, no weight array, update = 1: the configuration of main.py:64);
+// callers route the other configurations to the kernels of pava.cuh.
+#pragma once
+#include "pava.cuh"
+
+namespace bsls {
+
+constexpr int kWordsWarps = 2;             // warps per CTA
+constexpr int kWordsMaxBlock = 1024;       // 32 words
+constexpr int kWordsRcp = kPavaSmallMaxBlock + 1;
+
+template <typename T> struct WordsWarpSmem {
+    T y[1024];
+    uint32_t A0[32], A[32], St[32], D[32];
+};
+
+struct WordsWarpSync {  // the lanes of one warp
+    __device__ __forceinline__ static void sync() { __syncwarp(); }
+    __device__ __forceinline__ static bool any(bool p) { return __any_sync(0xffffffffu, p); }
+};
+struct WordsCtaSync {  // all threads of the CTA (one long block per CTA)
+    __device__ __forceinline__ static void sync() { __syncthreads(); }
+    __device__ __forceinline__ static bool any(bool p) { return __syncthreads_or(p) != 0; }
+};
+
+// y: the block, linear; A0 / A / St / D: its word arrays (LW entries each).  lane state: j = word index inside the
+// block (j < 0: the lane has no word), K = entries of the block.
+template <typename T, typename P>
+__device__ __forceinline__ void pava_words_engine(T *y, uint32_t *A0, uint32_t *A, uint32_t *St, uint32_t *D, int lane, int j, int LW, int K,
+                                                  const T *rcp) {
+    const bool have = j >= 0;
+    const int base = have ? 32 * j : 0;
+    const int nloc = have ? min(32, K - base) : 0;
+    uint32_t alive = nloc >= 32 ? ~0u : ((1u << nloc) - 1u);
+    // run-start bits of the first sweep; entries visited in a lane-rotated order so that the lanes of a
+    // warp read different banks of the linear layout
+    uint32_t S = 0;
+    if (have) {
+        int r = lane & 31;
+        T prev = (base + r > 0) ? y[base + r - 1] : T(0);
+#pragma unroll 4
+        for (int t = 0; t < 32; ++t) {
+            if (r < nloc) {
+                const T v = y[base + r];
+                const bool st = (base + r == 0) || !(v <= prev);
+                S |= (uint32_t)st << r;
+                prev = v;
+            }
+            r = (r + 1) & 31;
+            if (r == 0 && base > 0) prev = y[base - 1];
+        }
+    }
+    for (;;) {
+        if (have) {
+            A0[j] = alive;
+            A[j] = alive;
+            St[j] = S & alive;
+            D[j] = 0;
+        }
+        P::sync();
+        bool merged = false;
+        uint32_t dirty = 0;
+        if (alive) {
+            const uint32_t Sal = S & alive;
+            const uint32_t NS = alive & ~S;
+            // first follower of every run that has followers in this word: a carry started at a run start
+            // ripples through the dead positions above it and stops at the next head if that is a follower
+            uint32_t ff = ((~alive | Sal) + Sal) & NS;
+            // the run through the end of this word continues if the next non-empty word opens with a follower
+            bool tail = false;
+            int hs = 0;
+            if (Sal) {
+                hs = 31 - __clz((int)Sal);                            // highest run start of the word
+                if (!(alive & ((~1u) << hs))) {                        // ... with no follower in this word
+                    for (int jj = j + 1; jj < LW; ++jj) {
+                        const uint32_t a = A0[jj];
+                        if (a) {
+                            tail = !(St[jj] & (a & (~a + 1)));
+                            break;
+                        }
+                    }
+                }
+            }
+            uint32_t kill = 0;
+            while (ff || tail) {
+                int p;
+                if (ff) {
+                    const uint32_t fb = ff & (~ff + 1);
+                    ff ^= fb;
+                    p = 31 - __clz((int)(alive & (fb - 1)));
+                } else {
+                    p = hs;
+                    tail = false;
+                }
+                const uint32_t pb = 1u << p;
+                const uint32_t above = (~1u) << p;
+                const uint32_t Sab = Sal & above;
+                const uint32_t eb = Sab & (~Sab + 1);
+                const uint32_t fol = alive & (eb - 1) & above;
+                const T first = y[base + p];
+                T num = T(0), vprev = first;
+                int kprev = base + p;
+                uint32_t rem = fol;
+                while (rem) {
+                    const int k = base + __ffs((int)rem) - 1;
+                    rem &= rem - 1;
+                    num += vprev * small_int_to(T(0), k - kprev);  // -fmad=false: product and sum round separately
+                    kprev = k;
+                    vprev = y[k];
+                }
+                int e = K;
+                if (eb) {
+                    e = base + __ffs((int)eb) - 1;
+                } else {
+                    for (int jj = j + 1; jj < LW; ++jj) {
+                        const uint32_t a = A0[jj];
+                        if (!a) continue;
+                        const uint32_t st = St[jj];
+                        uint32_t fm = st ? (a & ((st & (~st + 1)) - 1)) : a;
+                        while (fm) {
+                            const int k = 32 * jj + __ffs((int)fm) - 1;
+                            fm &= fm - 1;
+                            num += vprev * small_int_to(T(0), k - kprev);
+                            kprev = k;
+                            vprev = y[k];
+                        }
+                        if (st) {
+                            e = 32 * jj + __ffs((int)st) - 1;
+                            break;
+                        }
+                    }
+                }
+                num += vprev * small_int_to(T(0), e - kprev);
+                if (kprev != base + p && first != vprev) {
+                    y[base + p] = div_small(num, e - (base + p), rcp, kWordsRcp);
+                    kill |= fol;
+                    dirty |= pb | eb;
+                    merged = true;
+                    if (!eb) {
+                        for (int jj = j + 1; jj < LW; ++jj) {
+                            const uint32_t a = A0[jj];
+                            if (!a) continue;
+                            const uint32_t st = St[jj];
+                            const uint32_t fm = st ? (a & ((st & (~st + 1)) - 1)) : a;
+                            if (fm) atomicAnd(&A[jj], ~fm);
+                            if (st) {
+                                atomicOr(&D[jj], st & (~st + 1));
+                                break;
+                            }
+                        }
+                    }
+                }
+            }
+            if (kill) atomicAnd(&A[j], ~kill);
+        }
+        const bool any = P::any(merged);
+        P::sync();
+        if (!any) break;
+        if (have) {
+            alive = A[j];
+            dirty = (dirty | D[j]) & alive;
+            while (dirty) {
+                const uint32_t kb = dirty & (~dirty + 1);
+                dirty ^= kb;
+                const int k = base + __ffs((int)kb) - 1;
+                const uint32_t low = alive & (kb - 1);
+                bool st = true;  // no head before it: the block opens here
+                if (low) {
+                    st = !(y[k] <= y[base + 31 - __clz((int)low)]);
+                } else {
+                    for (int jj = j - 1; jj >= 0; --jj) {
+                        const uint32_t a = A[jj];
+                        if (a) {
+                            st = !(y[k] <= y[32 * jj + 31 - __clz((int)a)]);
+                            break;
+                        }
+                    }
+                }
+                S = st ? (S | kb) : (S & ~kb);
+            }
+        }
+        P::sync();
+    }
+    if (have) A[j] = alive;
+    P::sync();
+}
+
+// A pack = consecutive entries of `ids` (ragged layouts; pack_first[] from plan_pack_words) or consecutive blocks of a
+// uniform layout (starts == nullptr: block b covers [first + b*Kuni, first + (b+1)*Kuni)).
+template <typename T, bool CLIP>
+__global__ void __launch_bounds__(kWordsWarps * 32)
+pava_words_kernel(T *__restrict__ yg, const int32_t *__restrict__ starts, const int32_t *__restrict__ ids,
+                  const int32_t *__restrict__ pack_first, int npacks, long long first, int nb, int Kuni) {
+    __shared__ __align__(16) WordsWarpSmem<T> smem[kWordsWarps];
+    __shared__ T rcp[kWordsRcp];
+    for (int i = threadIdx.x + 1; i < kWordsRcp; i += kWordsWarps * 32) rcp[i] = T(1) / (T)i;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    WordsWarpSmem<T> &sm = smem[wid];
+    const int wpb = starts ? 0 : (Kuni + 31) >> 5;   // uniform: words per block
+    const int bpp = starts ? 0 : 32 / wpb;           // uniform: blocks per pack
+    for (int pack = blockIdx.x * kWordsWarps + wid; pack < npacks; pack += gridDim.x * kWordsWarps) {
+        // lane b < cnt describes block b of the pack: global start, length, first word slot
+        int cnt, g0 = 0, Kb = 0, w0 = 0;
+        if (starts) {
+            const int pf = pack_first[pack];
+            cnt = pack_first[pack + 1] - pf;
+            if (lane < cnt) {
+                const int b = ids[pf + lane];
+                g0 = starts[b];
+                Kb = starts[b + 1] - g0;
+            }
+            const int words = (Kb + 31) >> 5;
+            int incl = words;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            w0 = incl - words;
+        } else {
+            cnt = min(bpp, nb - pack * bpp);
+            if (lane < cnt) {
+                g0 = (int)((long long)(pack * bpp + lane) * Kuni);  // relative to `first`
+                Kb = Kuni;
+                w0 = lane * wpb;
+            }
+        }
+        // which block / word this lane serves
+        const unsigned startmask = __reduce_or_sync(0xffffffffu, (lane < cnt) ? (1u << w0) : 0u);
+        const int total_words = __shfl_sync(0xffffffffu, w0 + ((Kb + 31) >> 5), cnt - 1);
+        const int myb = __popc(startmask & ((2u << lane) - 1u)) - 1;
+        const int my_w0 = __shfl_sync(0xffffffffu, w0, myb < 0 ? 0 : myb);
+        const int my_K = __shfl_sync(0xffffffffu, Kb, myb < 0 ? 0 : myb);
+        const bool have = lane < total_words;
+        const int j = have ? lane - my_w0 : -1;
+        const int LW = (my_K + 31) >> 5;
+        // fetch: block by block, coalesced
+        for (int b = 0; b < cnt; ++b) {
+            const int bg = __shfl_sync(0xffffffffu, g0, b), bK = __shfl_sync(0xffffffffu, Kb, b), bw = __shfl_sync(0xffffffffu, w0, b);
+            const T *src = yg + first + bg;
+            for (int i = lane; i < bK; i += 32) cp_async_elem<sizeof(T)>(&sm.y[32 * bw + i], src + i);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncwarp();
+        {
+            const int wb = have ? my_w0 : 0;
+            pava_words_engine<T, WordsWarpSync>(sm.y + 32 * wb, sm.A0 + wb, sm.A + wb, sm.St + wb, sm.D + wb, lane, j, LW, my_K, rcp);
+        }
+        // store: every entry takes the value of the head at or below it
+        for (int b = 0; b < cnt; ++b) {
+            const int bg = __shfl_sync(0xffffffffu, g0, b), bK = __shfl_sync(0xffffffffu, Kb, b), bw = __shfl_sync(0xffffffffu, w0, b);
+            T *dst = yg + first + bg;
+            for (int i = lane; i < bK; i += 32) {
+                int w = i >> 5;
+                uint32_t m = sm.A[bw + w] & ((2u << (i & 31)) - 1u);
+                while (m == 0) m = sm.A[bw + --w];
+                T v = sm.y[32 * (bw + w) + 31 - __clz((int)m)];
+                if (CLIP) v = clip01(v);
+                dst[i] = v;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// Blocks longer than a warp's pack: one CTA per block, one thread per word (K <= 32 * kWordsCtaThreads).
+constexpr int kWordsCtaThreads = 256;
+inline size_t pava_words_cta_smem(int K, size_t elem) {
+    const size_t words = ((size_t)K + 31) / 32;
+    return (((size_t)K * elem + 15) & ~size_t(15)) + 4 * words * sizeof(uint32_t) + kWordsRcp * elem + 32;
+}
+template <typename T, bool CLIP>
+__global__ void __launch_bounds__(kWordsCtaThreads)
+pava_words_cta_kernel(T *__restrict__ yg, const int32_t *__restrict__ starts, const int32_t *__restrict__ ids, int count, int max_block) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    const int max_words = (max_block + 31) >> 5;
+    T *y = reinterpret_cast<T *>(smem_raw);
+    uint32_t *A0 = reinterpret_cast<uint32_t *>(smem_raw + (((size_t)max_block * sizeof(T) + 15) & ~size_t(15)));
+    uint32_t *A = A0 + max_words, *St = A + max_words, *D = St + max_words;
+    T *rcp = reinterpret_cast<T *>((reinterpret_cast<uintptr_t>(D + max_words) + 15) & ~uintptr_t(15));
+    for (int i = tid + 1; i < kWordsRcp; i += kWordsCtaThreads) rcp[i] = T(1) / (T)i;
+    for (int it = blockIdx.x; it < count; it += gridDim.x) {
+        const int b = ids[it];
+        const int g0 = starts[b];
+        const int K = starts[b + 1] - g0;
+        const int LW = (K + 31) >> 5;
+        T *gy = yg + g0;
+        for (int i = tid; i < K; i += kWordsCtaThreads) cp_async_elem<sizeof(T)>(&y[i], gy + i);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        pava_words_engine<T, WordsCtaSync>(y, A0, A, St, D, tid, tid < LW ? tid : -1, LW, K, rcp);
+        for (int i = tid; i < K; i += kWordsCtaThreads) {
+            int w = i >> 5;
+            uint32_t m = A[w] & ((2u << (i & 31)) - 1u);
+            while (m == 0) m = A[--w];
+            T v = y[32 * w + 31 - __clz((int)m)];
+            if (CLIP) v = clip01(v);
+            gy[i] = v;
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T>
+int launch_pava_words_cta(T *y, const int32_t *starts, const int32_t *ids, int count, int max_block, int clip, cudaStream_t stream) {
+    if (count <= 0) return BSLS_OK;
+    if (max_block > 32 * kWordsCtaThreads) {
+        set_error("pava_words_cta: block of %d entries exceeds %d", max_block, 32 * kWordsCtaThreads);
+        return BSLS_ERR_ARG;
+    }
+    const size_t smem = pava_words_cta_smem(max_block, sizeof(T));
+    int dev = 0, num_sm = kNumSM, per_sm = 1;
+    BSLS_CUDA_TRY(cudaGetDevice(&dev));
+    BSLS_CUDA_TRY(cudaDeviceGetAttribute(&num_sm, cudaDevAttrMultiProcessorCount, dev));
+    if (clip) {
+        auto k = pava_words_cta_kernel<T, true>;
+        BSLS_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pava_words_cta_smem(32 * kWordsCtaThreads, sizeof(T))));
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kWordsCtaThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        k<<<count < per_sm * num_sm ? count : per_sm * num_sm, kWordsCtaThreads, smem, stream>>>(y, starts, ids, count, max_block);
+    } else {
+        auto k = pava_words_cta_kernel<T, false>;
+        BSLS_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pava_words_cta_smem(32 * kWordsCtaThreads, sizeof(T))));
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kWordsCtaThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        k<<<count < per_sm * num_sm ? count : per_sm * num_sm, kWordsCtaThreads, smem, stream>>>(y, starts, ids, count, max_block);
+    }
+    BSLS_LAUNCH_CHECK();
+    return BSLS_OK;
+}
+
+template <typename T>
+int launch_pava_words(T *y, const int32_t *starts, const int32_t *ids, const int32_t *pack_first, int npacks, long long first, int nb,
+                      int Kuni, int clip, cudaStream_t stream) {
+    if (npacks <= 0) return BSLS_OK;
+    static thread_local int full[2] = {0, 0};
+    auto k0 = pava_words_kernel<T, false>;
+    auto k1 = pava_words_kernel<T, true>;
+    if (!full[clip ? 1 : 0]) {
+        int dev = 0, num_sm = kNumSM, per_sm = 1;
+        BSLS_CUDA_TRY(cudaGetDevice(&dev));
+        BSLS_CUDA_TRY(cudaDeviceGetAttribute(&num_sm, cudaDevAttrMultiProcessorCount, dev));
+        if (clip)
+            BSLS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1, kWordsWarps * 32, 0));
+        else
+            BSLS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k0, kWordsWarps * 32, 0));
+        full[clip ? 1 : 0] = num_sm * (per_sm < 1 ? 1 : per_sm);
+    }
+    const int want = (npacks + kWordsWarps - 1) / kWordsWarps;
+    const int grid = want < full[clip ? 1 : 0] ? want : full[clip ? 1 : 0];
+    if (clip)
+        k1<<<grid, kWordsWarps * 32, 0, stream>>>(y, starts, ids, pack_first, npacks, first, nb, Kuni);
+    else
+        k0<<<grid, kWordsWarps * 32, 0, stream>>>(y, starts, ids, pack_first, npacks, first, nb, Kuni);
+    BSLS_LAUNCH_CHECK();
+    return BSLS_OK;
+}
+
+}  // namespace bsls

@@ -72,4 +72,29 @@ int plan_large_list(const int32_t *starts, int nb, int threshold, int32_t *ids, 
     return BSLS_OK;
 }
 
+// One thread walks the list once per layout: consecutive ids are packed while they fit 32 words / 32 blocks.
+__global__ void pack_words_kernel(const int32_t *__restrict__ starts, const int32_t *__restrict__ ids, int count,
+                                  int32_t *__restrict__ pack_first, int *npacks) {
+    if (threadIdx.x || blockIdx.x) return;
+    int acc = 0, np = 0, opened = 0;
+    for (int i = 0; i < count; ++i) {
+        const int b = ids[i];
+        const int words = (starts[b + 1] - starts[b] + 31) >> 5;
+        if (i == 0 || acc + words > 32 || i - opened >= 32) {
+            pack_first[np++] = i;
+            opened = i;
+            acc = 0;
+        }
+        acc += words;
+    }
+    pack_first[np] = count;
+    *npacks = np;
+}
+
+int plan_pack_words(const int32_t *starts, const int32_t *ids, int count, int32_t *pack_first, int *d_npacks, cudaStream_t stream) {
+    pack_words_kernel<<<1, 32, 0, stream>>>(starts, ids, count, pack_first, d_npacks);
+    BSLS_LAUNCH_CHECK();
+    return BSLS_OK;
+}
+
 }  // namespace bsls
