@@ -774,6 +774,8 @@ pava_tile_rows_kernel(T *__restrict__ yg, const int32_t *__restrict__ starts, co
     __shared__ __align__(16) T ybuf[WIN];
     __shared__ uint32_t sb[NW];   // bit i: a block starts at entry i of the window (and one bit at the window's end)
     __shared__ uint32_t cov[NW];  // bit i: entry i belongs to a row (is written back from here)
+    __shared__ uint2 rows[2 * kPavaTileThreads];  // {position | length << 16, block-start mask}
+    __shared__ int nrows;
     __shared__ T rcp[kPavaThreadMax + 1];
     const int tid = threadIdx.x;
     for (int i = tid + 1; i <= kPavaThreadMax; i += kPavaTileThreads) rcp[i] = T(1) / (T)i;
@@ -789,6 +791,7 @@ pava_tile_rows_kernel(T *__restrict__ yg, const int32_t *__restrict__ starts, co
             sb[i] = 0;
             cov[i] = 0;
         }
+        if (tid == 0) nrows = 0;
         {
             const T *src = yg + (size_t)tile_lo + tid;
             for (int i = tid; i < nel; i += kPavaTileThreads, src += kPavaTileThreads) cp_async_elem<sizeof(T)>(&ybuf[i], src);
@@ -827,28 +830,29 @@ pava_tile_rows_kernel(T *__restrict__ yg, const int32_t *__restrict__ starts, co
                         break;
                     }
                 }
+                // queue the rows: the threads then share them evenly (a bucket has 0, 1 or 2 rows)
                 const int p0 = tid * 16;
                 if (e > s0) {
-                    const int len = e - s0;
-                    const uint32_t full = (1u << len) - 1u;  // len <= 31
-                    T *yb = ybuf + p0 + s0;
-                    const uint32_t heads = pava_block_runs<T, uint16_t, uint32_t, false>(yb, nullptr, len, full, bst, false, rcp, kPavaThreadMax + 1);
-                    pava_spread(yb, len, heads);
-                    const unsigned long long span = (unsigned long long)full << ((p0 + s0) & 31);
-                    atomicOr(&cov[(p0 + s0) >> 5], (uint32_t)span);
-                    if (span >> 32) atomicOr(&cov[((p0 + s0) >> 5) + 1], (uint32_t)(span >> 32));
+                    const int slot = atomicAdd(&nrows, 1);
+                    rows[slot] = make_uint2((uint32_t)(p0 + s0) | ((uint32_t)(e - s0) << 16), bst);
                 }
                 if (longer >= 0 && longer_len <= kPavaThreadMax) {
-                    const int len = longer_len;
-                    const uint32_t full = len == 32 ? ~0u : ((1u << len) - 1u);
-                    T *yb = ybuf + p0 + longer;
-                    const uint32_t heads = pava_block_runs<T, uint16_t, uint32_t, false>(yb, nullptr, len, full, 1u, false, rcp, kPavaThreadMax + 1);
-                    pava_spread(yb, len, heads);
-                    const unsigned long long span = (unsigned long long)full << ((p0 + longer) & 31);
-                    atomicOr(&cov[(p0 + longer) >> 5], (uint32_t)span);
-                    if (span >> 32) atomicOr(&cov[((p0 + longer) >> 5) + 1], (uint32_t)(span >> 32));
+                    const int slot = atomicAdd(&nrows, 1);
+                    rows[slot] = make_uint2((uint32_t)(p0 + longer) | ((uint32_t)longer_len << 16), 1u);
                 }
             }
+        }
+        __syncthreads();
+        for (int r = tid; r < nrows; r += kPavaTileThreads) {
+            const uint2 d = rows[r];
+            const int pos = (int)(d.x & 0xffffu), len = (int)(d.x >> 16);
+            const uint32_t full = len == 32 ? ~0u : ((1u << len) - 1u);
+            T *yb = ybuf + pos;
+            const uint32_t heads = pava_block_runs<T, uint16_t, uint32_t, false>(yb, nullptr, len, full, d.y, false, rcp, kPavaThreadMax + 1);
+            pava_spread(yb, len, heads);
+            const unsigned long long span = (unsigned long long)full << (pos & 31);
+            atomicOr(&cov[pos >> 5], (uint32_t)span);
+            if (span >> 32) atomicOr(&cov[(pos >> 5) + 1], (uint32_t)(span >> 32));
         }
         __syncthreads();
         {
