@@ -94,9 +94,9 @@ static int dev_pava(const bsls_plan *plan_, T *y, int32_t *weight, int update, i
         const int bpp = 32 / ((plan->uniform + 31) >> 5);
         const int npacks = (plan->nb + bpp - 1) / bpp;
         if constexpr (sizeof(T) == 8)
-            return pava_words_f64((double *)y, nullptr, nullptr, nullptr, npacks, plan->first, plan->nb, plan->uniform, clip01, stream);
+            return pava_words_f64((double *)y, nullptr, nullptr, nullptr, npacks, plan->first, plan->nb, plan->uniform, clip01, 0, stream);
         else
-            return pava_words_f32((float *)y, nullptr, nullptr, nullptr, npacks, plan->first, plan->nb, plan->uniform, clip01, stream);
+            return pava_words_f32((float *)y, nullptr, nullptr, nullptr, npacks, plan->first, plan->nb, plan->uniform, clip01, 0, stream);
     }
     if (plan->uniform > 0 && plan->uniform <= kPlanPavaSmallMax) {
         if constexpr (sizeof(T) == 8)
@@ -111,6 +111,13 @@ static int dev_pava(const bsls_plan *plan_, T *y, int32_t *weight, int update, i
         if (int rc = ensure_streams(plan)) return rc;
         BSLS_CUDA_TRY(cudaEventRecord(plan->ev_fork, stream));
         int rc = BSLS_OK;
+        // Grids of the three cold-start kernels are capped so that all of them are resident side by side
+        // (persistent grids that each fill the GPU would run one after the other): CTAs per SM.
+        int cap_tile = 0, cap_words = 0, cap_cta = 0;
+        if (cold && !words_off) {
+            cap_tile = 0, cap_words = 0, cap_cta = 0;  // measured on C3: uncapped grids (kernels mostly back to back) beat any split tried (tools/c3_caps.py)
+            if (const char *c = getenv("BSLS_PAVA_CAPS")) sscanf(c, "%d,%d,%d", &cap_tile, &cap_words, &cap_cta);
+        }
         if (plan->mid > 0 && cold && !words_off) {
             if (plan->mid_packs < 0) {  // pack the mid list once
                 int *d_np = nullptr, h_np = 0;
@@ -125,9 +132,9 @@ static int dev_pava(const bsls_plan *plan_, T *y, int32_t *weight, int update, i
             }
             BSLS_CUDA_TRY(cudaStreamWaitEvent(plan->aux[0], plan->ev_fork, 0));
             if constexpr (sizeof(T) == 8)
-                rc = pava_words_f64((double *)y, plan->d_starts, plan->d_mid_ids, plan->d_mid_pack, plan->mid_packs, 0, plan->nb, 0, clip01, plan->aux[0]);
+                rc = pava_words_f64((double *)y, plan->d_starts, plan->d_mid_ids, plan->d_mid_pack, plan->mid_packs, 0, plan->nb, 0, clip01, cap_words, plan->aux[0]);
             else
-                rc = pava_words_f32((float *)y, plan->d_starts, plan->d_mid_ids, plan->d_mid_pack, plan->mid_packs, 0, plan->nb, 0, clip01, plan->aux[0]);
+                rc = pava_words_f32((float *)y, plan->d_starts, plan->d_mid_ids, plan->d_mid_pack, plan->mid_packs, 0, plan->nb, 0, clip01, cap_words, plan->aux[0]);
             if (rc) return rc;
             BSLS_CUDA_TRY(cudaEventRecord(plan->ev_join[0], plan->aux[0]));
         } else if (plan->mid > 0) {
@@ -142,9 +149,9 @@ static int dev_pava(const bsls_plan *plan_, T *y, int32_t *weight, int update, i
         if (plan->large > 0 && cold && !words_off) {
             BSLS_CUDA_TRY(cudaStreamWaitEvent(plan->aux[1], plan->ev_fork, 0));
             if constexpr (sizeof(T) == 8)
-                rc = pava_words_cta_f64((double *)y, plan->d_starts, plan->d_large_ids, plan->large, plan->max_size, clip01, plan->aux[1]);
+                rc = pava_words_cta_f64((double *)y, plan->d_starts, plan->d_large_ids, plan->large, plan->max_size, clip01, cap_cta, plan->aux[1]);
             else
-                rc = pava_words_cta_f32((float *)y, plan->d_starts, plan->d_large_ids, plan->large, plan->max_size, clip01, plan->aux[1]);
+                rc = pava_words_cta_f32((float *)y, plan->d_starts, plan->d_large_ids, plan->large, plan->max_size, clip01, cap_cta, plan->aux[1]);
             if (rc) return rc;
             BSLS_CUDA_TRY(cudaEventRecord(plan->ev_join[1], plan->aux[1]));
         } else if (plan->large > 0) {
@@ -157,9 +164,9 @@ static int dev_pava(const bsls_plan *plan_, T *y, int32_t *weight, int update, i
             BSLS_CUDA_TRY(cudaEventRecord(plan->ev_join[1], plan->aux[1]));
         }
         if constexpr (sizeof(T) == 8)
-            rc = pava_tile_f64((double *)y, weight, plan->d_starts, plan->d_tile_first, plan->tiles, update, clip01, stream);
+            rc = pava_tile_f64((double *)y, weight, plan->d_starts, plan->d_tile_first, plan->tiles, update, clip01, cap_tile, stream);
         else
-            rc = pava_tile_f32((float *)y, weight, plan->d_starts, plan->d_tile_first, plan->tiles, update, clip01, stream);
+            rc = pava_tile_f32((float *)y, weight, plan->d_starts, plan->d_tile_first, plan->tiles, update, clip01, cap_tile, stream);
         if (rc) return rc;
         if (plan->mid > 0) BSLS_CUDA_TRY(cudaStreamWaitEvent(stream, plan->ev_join[0], 0));
         if (plan->large > 0) BSLS_CUDA_TRY(cudaStreamWaitEvent(stream, plan->ev_join[1], 0));

@@ -23,13 +23,13 @@ int pava_small_f64(double *y, int32_t *w, long long first, int nb, int K, int up
 }
 
 int pava_tile_f64(double *y, int32_t *w, const int32_t *starts, const int32_t *tile_first, int ntiles, int update, int clip01,
-                  cudaStream_t stream) {
+                  int cap_per_sm, cudaStream_t stream) {
     static_assert(kPavaTileElems == kPlanTileElems && kPavaTileMaxBlock == kPlanTileMaxBlock && kPavaThreadMax == kPlanMidMin, "plan constants");
     PavaFlags fl;
     fl.update = update;
     fl.clip01 = clip01;
     fl.has_weight = w != nullptr;
-    if (!w && update && !getenv("BSLS_PAVA_NO_ROWS")) return launch_pava_tile_rows<double>(y, starts, tile_first, ntiles, clip01, stream);
+    if (!w && update && !getenv("BSLS_PAVA_NO_ROWS")) return launch_pava_tile_rows<double>(y, starts, tile_first, ntiles, clip01, cap_per_sm, stream);
     return launch_pava_tile<double>(y, w, starts, tile_first, ntiles, fl, stream);
 }
 
@@ -42,13 +42,13 @@ int pava_mid_f64(double *y, int32_t *w, const int32_t *starts, const int32_t *mi
 }
 
 int pava_words_f64(double *y, const int32_t *starts, const int32_t *ids, const int32_t *pack_first, int npacks, long long first, int nb,
-                   int Kuni, int clip01, cudaStream_t stream) {
+                   int Kuni, int clip01, int cap_per_sm, cudaStream_t stream) {
     static_assert(kWordsMaxBlock == kPlanWordsMax, "plan constants");
-    return launch_pava_words<double>(y, starts, ids, pack_first, npacks, first, nb, Kuni, clip01, stream);
+    return launch_pava_words<double>(y, starts, ids, pack_first, npacks, first, nb, Kuni, clip01, cap_per_sm, stream);
 }
 
-int pava_words_cta_f64(double *y, const int32_t *starts, const int32_t *ids, int count, int max_block, int clip01, cudaStream_t stream) {
+int pava_words_cta_f64(double *y, const int32_t *starts, const int32_t *ids, int count, int max_block, int clip01, int cap_per_sm, cudaStream_t stream) {
     static_assert(32 * kWordsCtaThreads == kPlanPavaLargeMax, "plan constants");
-    return launch_pava_words_cta<double>(y, starts, ids, count, max_block, clip01, stream);
+    return launch_pava_words_cta<double>(y, starts, ids, count, max_block, clip01, cap_per_sm, stream);
 }
 }  // namespace bsls

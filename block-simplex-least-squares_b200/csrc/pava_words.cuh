@@ -328,7 +328,7 @@ pava_words_cta_kernel(T *__restrict__ yg, const int32_t *__restrict__ starts, co
 }
 
 template <typename T>
-int launch_pava_words_cta(T *y, const int32_t *starts, const int32_t *ids, int count, int max_block, int clip, cudaStream_t stream) {
+int launch_pava_words_cta(T *y, const int32_t *starts, const int32_t *ids, int count, int max_block, int clip, int cap_per_sm, cudaStream_t stream) {
     if (count <= 0) return BSLS_OK;
     if (max_block > 32 * kWordsCtaThreads) {
         set_error("pava_words_cta: block of %d entries exceeds %d", max_block, 32 * kWordsCtaThreads);
@@ -342,11 +342,13 @@ int launch_pava_words_cta(T *y, const int32_t *starts, const int32_t *ids, int c
         auto k = pava_words_cta_kernel<T, true>;
         BSLS_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pava_words_cta_smem(32 * kWordsCtaThreads, sizeof(T))));
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kWordsCtaThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        if (cap_per_sm > 0 && per_sm > cap_per_sm) per_sm = cap_per_sm;
         k<<<count < per_sm * num_sm ? count : per_sm * num_sm, kWordsCtaThreads, smem, stream>>>(y, starts, ids, count, max_block);
     } else {
         auto k = pava_words_cta_kernel<T, false>;
         BSLS_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pava_words_cta_smem(32 * kWordsCtaThreads, sizeof(T))));
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kWordsCtaThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        if (cap_per_sm > 0 && per_sm > cap_per_sm) per_sm = cap_per_sm;
         k<<<count < per_sm * num_sm ? count : per_sm * num_sm, kWordsCtaThreads, smem, stream>>>(y, starts, ids, count, max_block);
     }
     BSLS_LAUNCH_CHECK();
@@ -355,7 +357,7 @@ int launch_pava_words_cta(T *y, const int32_t *starts, const int32_t *ids, int c
 
 template <typename T>
 int launch_pava_words(T *y, const int32_t *starts, const int32_t *ids, const int32_t *pack_first, int npacks, long long first, int nb,
-                      int Kuni, int clip, cudaStream_t stream) {
+                      int Kuni, int clip, int cap_per_sm, cudaStream_t stream) {
     if (npacks <= 0) return BSLS_OK;
     static thread_local int full[2] = {0, 0};
     auto k0 = pava_words_kernel<T, false>;
@@ -371,7 +373,8 @@ int launch_pava_words(T *y, const int32_t *starts, const int32_t *ids, const int
         full[clip ? 1 : 0] = num_sm * (per_sm < 1 ? 1 : per_sm);
     }
     const int want = (npacks + kWordsWarps - 1) / kWordsWarps;
-    const int grid = want < full[clip ? 1 : 0] ? want : full[clip ? 1 : 0];
+    int grid = want < full[clip ? 1 : 0] ? want : full[clip ? 1 : 0];
+    if (cap_per_sm > 0 && grid > cap_per_sm * kNumSM) grid = cap_per_sm * kNumSM;
     if (clip)
         k1<<<grid, kWordsWarps * 32, 0, stream>>>(y, starts, ids, pack_first, npacks, first, nb, Kuni);
     else
