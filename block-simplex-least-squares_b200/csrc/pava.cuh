@@ -174,20 +174,31 @@ BSLS_HD float div_small(float num, int den, const float *, int) { return num / (
 // Returns the final head mask.
 // bst: positions that always start a run -- bit 0, and the first entry of every further block when
 // one thread takes several short blocks as one row (runs then never cross a block boundary).
-template <typename T, typename W, typename M, bool WMEM>
+// KC > 0: K == KC is known at compile time (the run-start scan is unrolled).
+template <typename T, typename W, typename M, bool WMEM, int KC = 0>
 BSLS_HD M pava_block_runs(T *y, W *w, int K, M alive, M bst, bool wout, const T *rcp, int rcp_n) {
     const M one = 1;
     M S;
+    if (KC > 0) K = KC;
     if (!WMEM) {
         T prev = y[0];
 #ifdef __CUDA_ARCH__
         if (sizeof(M) == 4) {
             // compare bits shifted in from the top (one funnel shift per entry), aligned afterwards
             uint32_t acc = 0x80000000u;  // entry 0
-            for (int r = 1; r < K; ++r) {
-                const T v = y[r];
-                acc = __funnelshift_r(acc, (uint32_t)(!(v <= prev)), 1);
-                prev = v;
+            if (KC > 0) {
+#pragma unroll
+                for (int r = 1; r < (KC > 0 ? KC : 1); ++r) {
+                    const T v = y[r];
+                    acc = __funnelshift_r(acc, (uint32_t)(!(v <= prev)), 1);
+                    prev = v;
+                }
+            } else {
+                for (int r = 1; r < K; ++r) {
+                    const T v = y[r];
+                    acc = __funnelshift_r(acc, (uint32_t)(!(v <= prev)), 1);
+                    prev = v;
+                }
             }
             S = (M)(acc >> (32 - K)) | bst;
         } else
@@ -217,14 +228,7 @@ BSLS_HD M pava_block_runs(T *y, W *w, int K, M alive, M bst, bool wout, const T 
     M Snext = S;
     M NS = alive & ~S;  // followers not yet consumed by this sweep
     bool any = false;
-    for (;;) {
-        if (NS == 0) {
-            if (!any) break;
-            S = Snext;
-            NS = alive & ~S;
-            any = false;
-            if (NS == 0) break;
-        }
+    while (NS) {
         const M fb = NS & (~NS + 1);              // lowest follower
         const M low = alive & (fb - 1);           // heads below it: the highest is its run's head
         const int p = bit_hi(low);
@@ -246,7 +250,9 @@ BSLS_HD M pava_block_runs(T *y, W *w, int K, M alive, M bst, bool wout, const T 
         rem &= rem - 1;
         int wp = WMEM ? (int)w[p] : k - p;
         int den = wp;
-        T num = T(0) + first * small_int_to(T(0), wp);  // -fmad=false: product and sum round separately
+        // the reference starts from 0.0 (isotonic_regression.h:33): 0 + y*w differs from y*w only for a product of
+        // -0.0, and a run whose sum could keep that sign (all members -0.0) has first == last and does not pool
+        T num = first * small_int_to(T(0), wp);  // -fmad=false: product and sum round separately
         T vprev = y[k];
         int kprev = k;
         while (rem) {
@@ -271,6 +277,11 @@ BSLS_HD M pava_block_runs(T *y, W *w, int K, M alive, M bst, bool wout, const T 
             const bool sq = (eb & bst) || !(ynext <= val);
             Snext = sp ? (Snext | pb) : (Snext & ~pb);
             Snext = sq ? (Snext | eb) : (Snext & ~eb);
+        }
+        if (NS == 0 && any) {  // this sweep is through and pooled something: the next one starts from Snext
+            S = Snext;
+            NS = alive & ~S;
+            any = false;
         }
     }
     return alive;
@@ -311,13 +322,17 @@ constexpr int kPavaSmallMaxBlock = 64;  // longest block of the thread-per-block
 // K = 16: 0.45 ms against 0.50 ms for 10^8 values).
 // FAST = the hot configuration (cold start, no weight array, update = 1; main.py:64): the
 // loops carry no run-time flags.  CLIP is the [0,1] clamp of python/main.py:65.
-template <typename T, int THREADS, typename M, bool FAST, bool CLIP>
+// KRC > 0: the row length KR == KRC is a compile-time divisor of THREADS (K = 16, or 4 blocks of 4, ...): every
+// thread keeps its column and strides over rows, so the fetch and store loops need no index division, and the
+// run-start scan is unrolled.
+template <typename T, int THREADS, typename M, bool FAST, bool CLIP, int KRC>
 __global__ void __launch_bounds__(THREADS)  // a register cap for 20 CTAs per SM (45 registers) measured 3-6 % slower than 58 registers / 16 CTAs
 pava_small_kernel(T *__restrict__ yg, int32_t *__restrict__ wg, long long first, int nb, int K, int G, FastDiv rdiv, PavaFlags fl) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int KR = K * G;     // row length (elements)
-    const int KS = KR | 1;    // row pitch
-    const int pad = KS - KR;  // 1 for even KR: element e of the tile sits at e + row
+    static_assert(KRC == 0 || (THREADS % KRC == 0 && KRC % 2 == 0 && FAST), "compile-time rows: even length dividing the CTA");
+    const int KR = KRC ? KRC : K * G;  // row length (elements)
+    const int KS = KR | 1;             // row pitch
+    const int pad = KS - KR;           // 1 for even KR: element e of the tile sits at e + row
     constexpr int RCPN = kPavaSmallMaxBlock + 1;
     T *rcp = reinterpret_cast<T *>(smem_raw);
     M *masks = reinterpret_cast<M *>(smem_raw + ((RCPN * sizeof(T) + 15) & ~size_t(15)));
@@ -342,7 +357,21 @@ pava_small_kernel(T *__restrict__ yg, int32_t *__restrict__ wg, long long first,
         const int nel = (int)min((long long)tile_elems, ntot - e0);
         T *gy = yg + first + e0;
         int32_t *gw = wg ? wg + first + e0 : nullptr;
-        {
+        if (KRC > 0) {
+            // element tid + j*THREADS sits in row tid/KRC + j*(THREADS/KRC), column tid % KRC
+            constexpr int KRX = KRC > 0 ? KRC : 1;
+            constexpr int RPI = THREADS / KRX;
+            const T *src = gy + tid;
+            T *dst = ys + (tid / KRX) * (KRX + 1) + (tid % KRX);
+            if (nel == tile_elems) {
+#pragma unroll
+                for (int j = 0; j < KRX; ++j) cp_async_elem<sizeof(T)>(dst + j * RPI * (KRX + 1), src + j * THREADS);
+            } else {
+                for (int j = 0; j < KRX; ++j)
+                    if (tid + j * THREADS < nel) cp_async_elem<sizeof(T)>(dst + j * RPI * (KRX + 1), src + j * THREADS);
+            }
+            cp_async_commit();
+        } else {
             // thread-relative pointer + constant offsets: no 64-bit address arithmetic per element
             const T *src = gy + tid;
             int i = tid;
@@ -375,6 +404,8 @@ pava_small_kernel(T *__restrict__ yg, int32_t *__restrict__ wg, long long first,
                 if (has_weight) {
                     uint8_t *wb = wsm + (size_t)tid * KS;
                     masks[tid] = pava_block_runs<T, uint8_t, M, true>(yb, wb, len, pava_heads_from_weights<uint8_t, M>(wb, len), (M)(bst & full), true, rcp, RCPN);
+                } else if (KRC > 0 && len == KRC) {
+                    masks[tid] = pava_block_runs<T, uint8_t, M, false, KRC>(yb, nullptr, len, full, bst, false, rcp, RCPN);
                 } else {
                     masks[tid] = pava_block_runs<T, uint8_t, M, false>(yb, nullptr, len, full, (M)(bst & full), false, rcp, RCPN);
                 }
@@ -382,7 +413,43 @@ pava_small_kernel(T *__restrict__ yg, int32_t *__restrict__ wg, long long first,
         }
         __syncthreads();
         // coalesced store; with `update` every element takes the value of the head its mask names
-        if (pairs) {
+        if (KRC > 0 && pairs) {
+            // pair 2*tid + j*2*THREADS: row (2*tid)/KRC + j*(2*THREADS/KRC), columns c2 and c2 + 1 of that row
+            constexpr int KRX = KRC > 0 ? KRC : 2;
+            constexpr int RP2 = 2 * THREADS / KRX;
+            const int c2 = (2 * tid) % KRX, rr0 = (2 * tid) / KRX;
+            const M below = (((M)2) << c2) - 1;
+            T *dst = gy + 2 * tid;
+            const M *mrow = masks + rr0;
+            const T *yrow = ys + rr0 * (KRX + 1);
+            if (nel == tile_elems) {
+#pragma unroll
+                for (int j = 0; j < KRX / 2; ++j) {
+                    const M m = mrow[j * RP2];
+                    const uint32_t h0 = (uint32_t)bit_hi((M)(m & below));
+                    const uint32_t h1 = ((m >> (c2 + 1)) & 1) ? (uint32_t)(c2 + 1) : h0;
+                    T v0 = yrow[j * RP2 * (KRX + 1) + h0], v1 = yrow[j * RP2 * (KRX + 1) + h1];
+                    if (clip) {
+                        v0 = clip01(v0);
+                        v1 = clip01(v1);
+                    }
+                    st_stream_v2(reinterpret_cast<double *>(dst + j * 2 * THREADS), (double)v0, (double)v1);
+                }
+            } else {
+                for (int j = 0; j < KRX / 2; ++j) {
+                    if (2 * tid + j * 2 * THREADS >= nel) break;
+                    const M m = mrow[j * RP2];
+                    const uint32_t h0 = (uint32_t)bit_hi((M)(m & below));
+                    const uint32_t h1 = ((m >> (c2 + 1)) & 1) ? (uint32_t)(c2 + 1) : h0;
+                    T v0 = yrow[j * RP2 * (KRX + 1) + h0], v1 = yrow[j * RP2 * (KRX + 1) + h1];
+                    if (clip) {
+                        v0 = clip01(v0);
+                        v1 = clip01(v1);
+                    }
+                    st_stream_v2(reinterpret_cast<double *>(dst + j * 2 * THREADS), (double)v0, (double)v1);
+                }
+            }
+        } else if (pairs) {
             T *dst = gy + 2 * tid;
 #pragma unroll 2
             for (int e2 = 2 * tid; e2 < nel; e2 += 2 * THREADS, dst += 2 * THREADS) {  // nel is even (KR is)
@@ -413,9 +480,9 @@ pava_small_kernel(T *__restrict__ yg, int32_t *__restrict__ wg, long long first,
     }
 }
 
-template <typename T, int THREADS, typename M, bool FAST, bool CLIP>
+template <typename T, int THREADS, typename M, bool FAST, bool CLIP, int KRC = 0>
 int launch_pava_small_cfg(T *y, int32_t *w, long long first, int nb, int K, int G, PavaFlags fl, cudaStream_t stream) {
-    auto kern = pava_small_kernel<T, THREADS, M, FAST, CLIP>;
+    auto kern = pava_small_kernel<T, THREADS, M, FAST, CLIP, KRC>;
     const int KR = K * G, KS = KR | 1;
     const size_t buf_elems = ((size_t)THREADS * KS + 1) & ~size_t(1);
     const size_t smem = (((kPavaSmallMaxBlock + 1) * sizeof(T) + 15) & ~size_t(15)) + (size_t)THREADS * sizeof(M) + buf_elems * sizeof(T) +
@@ -445,6 +512,17 @@ int launch_pava_small_cfg(T *y, int32_t *w, long long first, int nb, int K, int 
 template <typename T, int THREADS, typename M>
 int launch_pava_small_flags(T *y, int32_t *w, long long first, int nb, int K, int G, PavaFlags fl, cudaStream_t stream) {
     if (!fl.has_weight && fl.update) {  // hot configuration
+        if constexpr (sizeof(M) == 4 && THREADS == 64 && sizeof(T) == 8) {
+            const int KR = K * G;
+            if (KR == 16 && !getenv("BSLS_PAVA_NO_KRC")) {
+                if (fl.clip01) return launch_pava_small_cfg<T, THREADS, M, true, true, 16>(y, w, first, nb, K, G, fl, stream);
+                return launch_pava_small_cfg<T, THREADS, M, true, false, 16>(y, w, first, nb, K, G, fl, stream);
+            }
+            if (KR == 32 && !getenv("BSLS_PAVA_NO_KRC")) {
+                if (fl.clip01) return launch_pava_small_cfg<T, THREADS, M, true, true, 32>(y, w, first, nb, K, G, fl, stream);
+                return launch_pava_small_cfg<T, THREADS, M, true, false, 32>(y, w, first, nb, K, G, fl, stream);
+            }
+        }
         if (fl.clip01) return launch_pava_small_cfg<T, THREADS, M, true, true>(y, w, first, nb, K, G, fl, stream);
         return launch_pava_small_cfg<T, THREADS, M, true, false>(y, w, first, nb, K, G, fl, stream);
     }
