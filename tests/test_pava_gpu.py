@@ -107,8 +107,11 @@ def test_uniform_blocks(api, K, kind):
         gy, gw = gpu_pava(api, y, starts, update=update)
         assert np.array_equal(gw, ww)           # pool structure (and stale entries), bit-exact
         assert np.array_equal(gy, want)         # values, bit-exact
+    # cold start without a weight array (the configuration of main.py:64): the mask-driven kernels
     want = y.copy()
     port().pava_multi(want, starts)
+    gy, _ = gpu_pava(api, y, starts, with_weight=False)
+    assert np.array_equal(gy, want)
     port().clip01(want)
     gy, _ = gpu_pava(api, y, starts, with_weight=False, clip=True)
     assert np.array_equal(gy, want)
@@ -138,6 +141,12 @@ def test_ragged_blocks(api, lo, hi, total, first):
         assert np.array_equal(gy[:first], y[:first])
         assert np.array_equal(gw, ww), kind
         assert np.array_equal(gy, want), kind
+        # cold start without a weight array: row / word-per-lane kernels
+        gy, _ = gpu_pava(api, y, starts, with_weight=False)
+        assert np.array_equal(gy, want), kind
+        port().clip01(want[first:])
+        gy, _ = gpu_pava(api, y, starts, with_weight=False, clip=True)
+        assert np.array_equal(gy[first:], want[first:]), kind
 
 
 def test_worst_case_and_warm_start(api):
@@ -167,6 +176,36 @@ def test_worst_case_and_warm_start(api):
     port().pava_multi(want, starts, weight=w_ref, update=1)
     gy, gw = gpu_pava(api, y1, starts, w0=wa)
     assert np.array_equal(gy, want) and np.array_equal(gw, w_ref)
+
+
+@pytest.mark.parametrize("K", [4, 16, 20, 64, 100, 1000])
+def test_fp32_extension(api, K):
+    """fp32 twin: values within north_star's 1e-4 of the fp64 oracle on the same (fp32-rounded) input, and isotonic."""
+    rng = np.random.RandomState(SEED + K)
+    nb = max(3, 200000 // K)
+    sizes = np.full(nb, K)
+    y = make_input(rng, sizes, "normal").astype(np.float32)
+    starts = np.arange(0, nb * K, K, dtype=np.int64)
+    want = y.astype(np.float64)
+    port().pava_multi(want, starts)
+    t = dev(y)
+    api.isotonic_regression_multi_c(t, dev(starts))
+    got = t.cpu().numpy().astype(np.float64)
+    assert np.abs(got - want).max() <= 1e-4 * max(1.0, np.abs(want).max())
+    assert (np.diff(got.reshape(nb, K), axis=1) >= 0).all()
+
+
+def test_fp32_ragged(api):
+    rng = np.random.RandomState(SEED)
+    sizes = power_law_sizes(rng, 300000, 2, 4096)
+    starts = np.concatenate(([0], np.cumsum(sizes)[:-1]))
+    y = make_input(rng, sizes, "normal").astype(np.float32)
+    want = y.astype(np.float64)
+    port().pava_multi(want, starts)
+    t = dev(y)
+    api.isotonic_regression_multi_c(t, dev(starts))
+    got = t.cpu().numpy().astype(np.float64)
+    assert np.abs(got - want).max() <= 1e-4 * max(1.0, np.abs(want).max())
 
 
 @pytest.mark.parametrize("K,nb", [(15, 10 ** 6), (63, 250000)])
