@@ -118,51 +118,62 @@ static int dev_pava(const bsls_plan *plan_, T *y, int32_t *weight, int update, i
             cap_tile = 0, cap_words = 0, cap_cta = 0;  // measured on C3: uncapped grids (kernels mostly back to back) beat any split tried (tools/c3_caps.py)
             if (const char *c = getenv("BSLS_PAVA_CAPS")) sscanf(c, "%d,%d,%d", &cap_tile, &cap_words, &cap_cta);
         }
-        if (plan->mid > 0 && cold && !words_off) {
-            if (plan->mid_packs < 0) {  // pack the mid list once
-                int *d_np = nullptr, h_np = 0;
-                BSLS_CUDA_TRY(cudaMalloc(&d_np, sizeof(int)));
-                BSLS_CUDA_TRY(cudaMalloc(&plan->d_mid_pack, sizeof(int32_t) * ((size_t)plan->mid + 1)));
-                if (int rc2 = plan_pack_words(plan->d_starts, plan->d_mid_ids, plan->mid, plan->d_mid_pack, d_np, stream)) return rc2;
-                BSLS_CUDA_TRY(cudaMemcpyAsync(&h_np, d_np, sizeof(int), cudaMemcpyDeviceToHost, stream));
-                BSLS_CUDA_TRY(cudaStreamSynchronize(stream));
-                cudaFree(d_np);
-                plan->mid_packs = h_np;
-                BSLS_CUDA_TRY(cudaEventRecord(plan->ev_fork, stream));
+        auto launch_mid = [&]() -> int {
+            int rc = BSLS_OK;
+            if (plan->mid > 0 && cold && !words_off) {
+                if (plan->mid_packs < 0) {  // pack the mid list once
+                    int *d_np = nullptr, h_np = 0;
+                    BSLS_CUDA_TRY(cudaMalloc(&d_np, sizeof(int)));
+                    BSLS_CUDA_TRY(cudaMalloc(&plan->d_mid_pack, sizeof(int32_t) * ((size_t)plan->mid + 1)));
+                    if (int rc2 = plan_pack_words(plan->d_starts, plan->d_mid_ids, plan->mid, plan->d_mid_pack, d_np, stream)) return rc2;
+                    BSLS_CUDA_TRY(cudaMemcpyAsync(&h_np, d_np, sizeof(int), cudaMemcpyDeviceToHost, stream));
+                    BSLS_CUDA_TRY(cudaStreamSynchronize(stream));
+                    cudaFree(d_np);
+                    plan->mid_packs = h_np;
+                    BSLS_CUDA_TRY(cudaEventRecord(plan->ev_fork, stream));
+                }
+                BSLS_CUDA_TRY(cudaStreamWaitEvent(plan->aux[0], plan->ev_fork, 0));
+                if constexpr (sizeof(T) == 8)
+                    rc = pava_words_f64((double *)y, plan->d_starts, plan->d_mid_ids, plan->d_mid_pack, plan->mid_packs, 0, plan->nb, 0, clip01, cap_words, plan->aux[0]);
+                else
+                    rc = pava_words_f32((float *)y, plan->d_starts, plan->d_mid_ids, plan->d_mid_pack, plan->mid_packs, 0, plan->nb, 0, clip01, cap_words, plan->aux[0]);
+                if (rc) return rc;
+                BSLS_CUDA_TRY(cudaEventRecord(plan->ev_join[0], plan->aux[0]));
+            } else if (plan->mid > 0) {
+                BSLS_CUDA_TRY(cudaStreamWaitEvent(plan->aux[0], plan->ev_fork, 0));
+                if constexpr (sizeof(T) == 8)
+                    rc = pava_mid_f64((double *)y, weight, plan->d_starts, plan->d_mid_ids, plan->mid, update, clip01, plan->aux[0]);
+                else
+                    rc = pava_mid_f32((float *)y, weight, plan->d_starts, plan->d_mid_ids, plan->mid, update, clip01, plan->aux[0]);
+                if (rc) return rc;
+                BSLS_CUDA_TRY(cudaEventRecord(plan->ev_join[0], plan->aux[0]));
             }
-            BSLS_CUDA_TRY(cudaStreamWaitEvent(plan->aux[0], plan->ev_fork, 0));
-            if constexpr (sizeof(T) == 8)
-                rc = pava_words_f64((double *)y, plan->d_starts, plan->d_mid_ids, plan->d_mid_pack, plan->mid_packs, 0, plan->nb, 0, clip01, cap_words, plan->aux[0]);
-            else
-                rc = pava_words_f32((float *)y, plan->d_starts, plan->d_mid_ids, plan->d_mid_pack, plan->mid_packs, 0, plan->nb, 0, clip01, cap_words, plan->aux[0]);
-            if (rc) return rc;
-            BSLS_CUDA_TRY(cudaEventRecord(plan->ev_join[0], plan->aux[0]));
-        } else if (plan->mid > 0) {
-            BSLS_CUDA_TRY(cudaStreamWaitEvent(plan->aux[0], plan->ev_fork, 0));
-            if constexpr (sizeof(T) == 8)
-                rc = pava_mid_f64((double *)y, weight, plan->d_starts, plan->d_mid_ids, plan->mid, update, clip01, plan->aux[0]);
-            else
-                rc = pava_mid_f32((float *)y, weight, plan->d_starts, plan->d_mid_ids, plan->mid, update, clip01, plan->aux[0]);
-            if (rc) return rc;
-            BSLS_CUDA_TRY(cudaEventRecord(plan->ev_join[0], plan->aux[0]));
-        }
-        if (plan->large > 0 && cold && !words_off) {
-            BSLS_CUDA_TRY(cudaStreamWaitEvent(plan->aux[1], plan->ev_fork, 0));
-            if constexpr (sizeof(T) == 8)
-                rc = pava_words_cta_f64((double *)y, plan->d_starts, plan->d_large_ids, plan->large, plan->max_size, clip01, cap_cta, plan->aux[1]);
-            else
-                rc = pava_words_cta_f32((float *)y, plan->d_starts, plan->d_large_ids, plan->large, plan->max_size, clip01, cap_cta, plan->aux[1]);
-            if (rc) return rc;
-            BSLS_CUDA_TRY(cudaEventRecord(plan->ev_join[1], plan->aux[1]));
-        } else if (plan->large > 0) {
-            BSLS_CUDA_TRY(cudaStreamWaitEvent(plan->aux[1], plan->ev_fork, 0));
-            if constexpr (sizeof(T) == 8)
-                rc = pava_f64((double *)y, weight, plan->d_starts, nullptr, 0, plan->d_large_ids, plan->large, plan->max_size, update, clip01, plan->aux[1]);
-            else
-                rc = pava_f32((float *)y, weight, plan->d_starts, nullptr, 0, plan->d_large_ids, plan->large, plan->max_size, update, clip01, plan->aux[1]);
-            if (rc) return rc;
-            BSLS_CUDA_TRY(cudaEventRecord(plan->ev_join[1], plan->aux[1]));
-        }
+            return rc;
+        };
+        auto launch_large = [&]() -> int {
+            int rc = BSLS_OK;
+            if (plan->large > 0 && cold && !words_off) {
+                BSLS_CUDA_TRY(cudaStreamWaitEvent(plan->aux[1], plan->ev_fork, 0));
+                if constexpr (sizeof(T) == 8)
+                    rc = pava_words_cta_f64((double *)y, plan->d_starts, plan->d_large_ids, plan->large, plan->max_size, clip01, cap_cta, plan->aux[1]);
+                else
+                    rc = pava_words_cta_f32((float *)y, plan->d_starts, plan->d_large_ids, plan->large, plan->max_size, clip01, cap_cta, plan->aux[1]);
+                if (rc) return rc;
+                BSLS_CUDA_TRY(cudaEventRecord(plan->ev_join[1], plan->aux[1]));
+            } else if (plan->large > 0) {
+                BSLS_CUDA_TRY(cudaStreamWaitEvent(plan->aux[1], plan->ev_fork, 0));
+                if constexpr (sizeof(T) == 8)
+                    rc = pava_f64((double *)y, weight, plan->d_starts, nullptr, 0, plan->d_large_ids, plan->large, plan->max_size, update, clip01, plan->aux[1]);
+                else
+                    rc = pava_f32((float *)y, weight, plan->d_starts, nullptr, 0, plan->d_large_ids, plan->large, plan->max_size, update, clip01, plan->aux[1]);
+                if (rc) return rc;
+                BSLS_CUDA_TRY(cudaEventRecord(plan->ev_join[1], plan->aux[1]));
+            }
+            return rc;
+        };
+        // the long blocks first: few CTAs with a long critical path each, the grids that fill the GPU queue behind them
+        if (int rcl = launch_large()) return rcl;
+        if (int rcm = launch_mid()) return rcm;
         if constexpr (sizeof(T) == 8)
             rc = pava_tile_f64((double *)y, weight, plan->d_starts, plan->d_tile_first, plan->tiles, update, clip01, cap_tile, stream);
         else

@@ -75,6 +75,13 @@ template <int N> __device__ __forceinline__ void bulk_wait_read() {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ---- per-element asynchronous copies global -> shared (LDGSTS) ---------------------------------
+template <int BYTES> __device__ __forceinline__ void cp_async_elem(void *dst_smem, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_addr(dst_smem)), "l"(src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ---- streaming global accesses --------------------------------------------------------------
 __device__ __forceinline__ void st_stream_v2(double *p, double a, double b) {
     asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");

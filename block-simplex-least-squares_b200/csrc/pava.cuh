@@ -47,12 +47,6 @@ __device__ __forceinline__ void cp_async_8(void *dst_smem, const void *src) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <int BYTES> __device__ __forceinline__ void cp_async_elem(void *dst_smem, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_addr(dst_smem)), "l"(src), "n"(BYTES) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 template <typename T> __device__ __forceinline__ T clip01(T v) {
     v = (v > T(0)) ? v : T(0);  // np.maximum(0., x)
     v = (v < T(1)) ? v : T(1);  // np.minimum(1., x)
@@ -847,7 +841,9 @@ template <typename T, bool CLIP>
 __global__ void __launch_bounds__(kPavaTileThreads)
 pava_tile_rows_kernel(T *__restrict__ yg, const int32_t *__restrict__ starts, const int32_t *__restrict__ tile_first, int ntiles) {
     static_assert(kPavaTileThreads * 16 == kPavaTileElems, "one 16-entry bucket per thread");
-    constexpr int WIN = kPavaTileElems + kPavaTileMaxBlock;
+    // the window holds the rows: blocks that start inside the tile and have at most kPavaThreadMax entries; the body of
+    // a longer last block beyond it is neither staged nor written back
+    constexpr int WIN = kPavaTileElems + kPavaThreadMax;
     constexpr int NW = WIN / 32 + 4;  // bitmap words (+ look-ahead)
     __shared__ __align__(16) T ybuf[WIN];
     __shared__ uint32_t sb[NW];   // bit i: a block starts at entry i of the window (and one bit at the window's end)
@@ -862,9 +858,7 @@ pava_tile_rows_kernel(T *__restrict__ yg, const int32_t *__restrict__ starts, co
         const int nblk = tile_first[tile + 1] - fb;
         if (nblk <= 0) continue;
         const int tile_lo = starts[fb];
-        int nel = starts[fb + nblk] - tile_lo;                        // to the end of the last block that starts in the tile
-        const int last = starts[fb + nblk - 1] - tile_lo;             // ... which may be a long one: not staged
-        if (nel - last > kPavaTileMaxBlock) nel = last;
+        const int nel = min(starts[fb + nblk] - tile_lo, WIN);        // to the end of the last block that starts in the tile
         for (int i = tid; i < NW; i += kPavaTileThreads) {
             sb[i] = 0;
             cov[i] = 0;

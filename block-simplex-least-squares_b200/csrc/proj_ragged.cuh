@@ -80,11 +80,16 @@ template <typename T, int E, int MODE> __device__ __forceinline__ void tiny_bloc
 // tile_first[t] = index of the first block whose start lies in tile t (tile_first[ntiles] = nb)
 // slow: queue of block ids for the LARGE kernel, count at slow[nb]
 template <typename T, int MODE>
-__global__ void __launch_bounds__(kTileThreads)
+__global__ void __launch_bounds__(kTileThreads, 5)
 proj_tile_kernel(T *__restrict__ y, const int32_t *__restrict__ starts /* nb+1, last = n */,
                  const int32_t *__restrict__ tile_first, int ntiles, int32_t *__restrict__ slow, int nb) {
     constexpr int NW = kTileThreads / 32;
-    __shared__ __align__(16) T ybuf[kTileElems + kTileMaxBlock];
+    // the window holds the blocks this kernel owns: they start inside the tile and have at most kTileThreadMax values;
+    // what lies beyond (the body of a longer last block) is neither staged nor written back
+    constexpr int WIN = kTileElems + kTileThreadMax;
+    constexpr int NCOV = WIN / 32 + 2;
+    __shared__ __align__(16) T ybuf[WIN];
+    __shared__ uint32_t cov[NCOV];                    // bit i: entry i was projected here (is written back)
     __shared__ uint16_t sstart[kTileElems + 2];       // block starts relative to the window
     __shared__ uint16_t list[kTileElems];
     __shared__ uint16_t wlist[(kTileElems + kTileMaxBlock) / 17 + 8];  // single-thread failures (17..32 values only)
@@ -93,7 +98,6 @@ proj_tile_kernel(T *__restrict__ y, const int32_t *__restrict__ starts /* nb+1, 
     T(*wcand)[kSelWarpCand] = reinterpret_cast<T(*)[kSelWarpCand]>(tcand);
     __shared__ int cnt[kNumClasses], off[kNumClasses + 1], fill[kNumClasses];
     __shared__ int s_nwarp;
-    __shared__ uint8_t skip[kTileElems + kTileMaxBlock];  // 1: element of a block another kernel owns (not written back)
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -109,22 +113,19 @@ proj_tile_kernel(T *__restrict__ y, const int32_t *__restrict__ starts /* nb+1, 
         // relative starts; a "large" last block (it ends the window) is clamped, it is never touched here
         for (int i = tid; i <= nblk; i += kTileThreads) sstart[i] = (uint16_t)min(starts[fb + i] - tile_lo, 65535);
         __syncthreads();
-        int nel = sstart[nblk];
-        if (nel - sstart[nblk - 1] > kTileMaxBlock) nel = sstart[nblk - 1];
-        for (int i = tid; i < nel; i += kTileThreads) {
-            ybuf[i] = y[(size_t)tile_lo + i];
-            skip[i] = 0;
+        const int nel = min((int)sstart[nblk], WIN);
+        {
+            const T *src = y + (size_t)tile_lo + tid;
+            for (int i = tid; i < nel; i += kTileThreads, src += kTileThreads) cp_async_elem<sizeof(T)>(&ybuf[i], src);
+            cp_async_commit();
         }
+        for (int i = tid; i < NCOV; i += kTileThreads) cov[i] = 0;
+        cp_async_wait<0>();
         __syncthreads();
         // ---- bin the blocks by size class (counting sort on shared counters) ---------------
         for (int i = tid; i < nblk; i += kTileThreads) {
             const int K = sstart[i + 1] - sstart[i];
-            if (K <= kTileThreadMax) {
-                atomicAdd(&cnt[size_class(K)], 1);
-            } else {  // a block of proj_mid_kernel / proj_large_kernel
-                const int e1 = min((int)sstart[i + 1], nel);
-                for (int e = sstart[i]; e < e1; ++e) skip[e] = 1;
-            }
+            if (K <= kTileThreadMax) atomicAdd(&cnt[size_class(K)], 1);  // longer: a block of proj_mid_kernel / proj_large_kernel
         }
         __syncthreads();
         if (tid == 0) {
@@ -151,6 +152,11 @@ proj_tile_kernel(T *__restrict__ y, const int32_t *__restrict__ starts /* nb+1, 
             const int s = sstart[b];
             const int K = sstart[b + 1] - s;
             T *blk = ybuf + s;
+            {  // mark the block for the write-back (a block the LARGE kernel ends up with goes back unchanged)
+                const unsigned long long span = (K == 32 ? 0xffffffffull : ((1ull << K) - 1ull)) << (s & 31);
+                atomicOr(&cov[s >> 5], (uint32_t)span);
+                if (span >> 32) atomicOr(&cov[(s >> 5) + 1], (uint32_t)(span >> 32));
+            }
             if (MODE == kBall && !ball_needs_projection<T>(blk, K)) {
                 for (int j = 0; j < K; ++j) blk[j] = clip_neg(blk[j]);
                 continue;
@@ -199,8 +205,11 @@ proj_tile_kernel(T *__restrict__ y, const int32_t *__restrict__ starts /* nb+1, 
         __syncthreads();
         // ---- coalesced write-back (large blocks inside the window are rewritten unchanged;
         //      the LARGE kernel runs afterwards on the same stream) ----------------------------
-        for (int i = tid; i < nel; i += kTileThreads)
-            if (!skip[i]) y[(size_t)tile_lo + i] = ybuf[i];
+        {
+            T *dst = y + (size_t)tile_lo + tid;
+            for (int i = tid; i < nel; i += kTileThreads, dst += kTileThreads)
+                if ((cov[i >> 5] >> (i & 31)) & 1u) *dst = ybuf[i];
+        }
         __syncthreads();
     }
 }
