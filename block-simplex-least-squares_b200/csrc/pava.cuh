@@ -169,13 +169,15 @@ BSLS_HD float div_small(float num, int den, const float *, int) { return num / (
 // bst: positions that always start a run -- bit 0, and the first entry of every further block when
 // one thread takes several short blocks as one row (runs then never cross a block boundary).
 // KC > 0: K == KC is known at compile time (the run-start scan is unrolled).
-template <typename T, typename W, typename M, bool WMEM, int KC = 0>
+// STRIDE: distance between consecutive entries of the block in y (1: a row; THREADS: a column of a
+// [entry][thread] array, which every lane addresses in its own bank whatever entry it reads).
+template <typename T, typename W, typename M, bool WMEM, int KC = 0, int STRIDE = 1>
 BSLS_HD M pava_block_runs(T *y, W *w, int K, M alive, M bst, bool wout, const T *rcp, int rcp_n) {
     const M one = 1;
     M S;
     if (KC > 0) K = KC;
     if (!WMEM) {
-        T prev = y[0];
+        T prev = y[(0) * STRIDE];
 #ifdef __CUDA_ARCH__
         if (sizeof(M) == 4) {
             // compare bits shifted in from the top (one funnel shift per entry), aligned afterwards
@@ -183,13 +185,13 @@ BSLS_HD M pava_block_runs(T *y, W *w, int K, M alive, M bst, bool wout, const T 
             if (KC > 0) {
 #pragma unroll
                 for (int r = 1; r < (KC > 0 ? KC : 1); ++r) {
-                    const T v = y[r];
+                    const T v = y[(r) * STRIDE];
                     acc = __funnelshift_r(acc, (uint32_t)(!(v <= prev)), 1);
                     prev = v;
                 }
             } else {
                 for (int r = 1; r < K; ++r) {
-                    const T v = y[r];
+                    const T v = y[(r) * STRIDE];
                     acc = __funnelshift_r(acc, (uint32_t)(!(v <= prev)), 1);
                     prev = v;
                 }
@@ -200,7 +202,7 @@ BSLS_HD M pava_block_runs(T *y, W *w, int K, M alive, M bst, bool wout, const T 
         {
             S = bst;
             for (int r = 1; r < K; ++r) {
-                const T v = y[r];
+                const T v = y[(r) * STRIDE];
                 S |= (M)(!(v <= prev)) << r;
                 prev = v;
             }
@@ -210,11 +212,11 @@ BSLS_HD M pava_block_runs(T *y, W *w, int K, M alive, M bst, bool wout, const T 
         int k = bit_lo(rem);
         rem &= rem - 1;
         S = (one << k) | (bst & alive);
-        T prev = y[k];
+        T prev = y[(k) * STRIDE];
         while (rem) {
             k = bit_lo(rem);
             rem &= rem - 1;
-            const T v = y[k];
+            const T v = y[(k) * STRIDE];
             if (!(v <= prev)) S |= one << k;
             prev = v;
         }
@@ -234,9 +236,9 @@ BSLS_HD M pava_block_runs(T *y, W *w, int K, M alive, M bst, bool wout, const T 
         const int e = eb ? bit_lo(eb) : K;
         const M lowp = low ^ pb;                  // heads below p
         // the two neighbours whose run-start bit a merge re-evaluates; fetched early, next to `first`
-        const T first = y[p];
-        const T yprev = y[lowp ? bit_hi(lowp) : p];
-        const T ynext = y[eb ? e : p];
+        const T first = y[(p) * STRIDE];
+        const T yprev = y[(lowp ? bit_hi(lowp) : p) * STRIDE];
+        const T ynext = y[(eb ? e : p) * STRIDE];
         NS &= ~fol;
         // first follower (always there), then the rare longer tail
         M rem = fol;
@@ -247,7 +249,7 @@ BSLS_HD M pava_block_runs(T *y, W *w, int K, M alive, M bst, bool wout, const T 
         // the reference starts from 0.0 (isotonic_regression.h:33): 0 + y*w differs from y*w only for a product of
         // -0.0, and a run whose sum could keep that sign (all members -0.0) has first == last and does not pool
         T num = first * small_int_to(T(0), wp);  // -fmad=false: product and sum round separately
-        T vprev = y[k];
+        T vprev = y[(k) * STRIDE];
         int kprev = k;
         while (rem) {
             k = bit_lo(rem);
@@ -256,14 +258,14 @@ BSLS_HD M pava_block_runs(T *y, W *w, int K, M alive, M bst, bool wout, const T 
             num += vprev * small_int_to(T(0), wp);
             den += wp;
             kprev = k;
-            vprev = y[k];
+            vprev = y[(k) * STRIDE];
         }
         wp = WMEM ? (int)w[kprev] : e - kprev;
         num += vprev * small_int_to(T(0), wp);
         den += wp;
         if (first != vprev) {
             const T val = div_small(num, den, rcp, rcp_n);
-            y[p] = val;
+            y[(p) * STRIDE] = val;
             if (WMEM || wout) w[p] = (W)den;
             alive &= ~fol;
             any = true;
