@@ -298,8 +298,9 @@ struct HostWorkspace {  // grow-only device staging owned by the calling thread
 };
 thread_local HostWorkspace g_ws;
 
-// the reference's Python-side asserts (c_extensions.pyx:33-34), checked on the host copy
-int validate_blocks(const int *blocks, int numblocks, int n) {
+// the reference's Python-side asserts (c_extensions.pyx:33-34), checked on the host copy; the same pass finds the
+// common block size.  *uniform = K when every block has K entries, else 0.
+int validate_blocks(const int *blocks, int numblocks, int n, int *uniform = nullptr) {
     if (!blocks || numblocks <= 0 || n <= 0) {
         set_error("need numblocks > 0 and n > 0");
         return BSLS_ERR_ARG;
@@ -308,23 +309,21 @@ int validate_blocks(const int *blocks, int numblocks, int n) {
         set_error("block starts out of range");
         return BSLS_ERR_ARG;
     }
-    int bad = 0;  // branch-free scan (vectorised); the position is looked up only on failure
-    for (int i = 1; i < numblocks; ++i) bad |= (blocks[i] <= blocks[i - 1]);
+    const int K = (numblocks > 1 ? blocks[1] : n) - blocks[0];
+    int bad = 0, diff = 0;  // branch-free scan (vectorised); the position is looked up only on failure
+    for (int i = 1; i < numblocks; ++i) {
+        const int d = blocks[i] - blocks[i - 1];
+        bad |= (d <= 0);
+        diff |= d ^ K;
+    }
     if (bad) {
         int i = 1;
         while (i < numblocks && blocks[i] > blocks[i - 1]) ++i;
         set_error("block starts not strictly increasing at %d", i);
         return BSLS_ERR_ARG;
     }
+    if (uniform) *uniform = (diff == 0 && n - blocks[numblocks - 1] == K) ? K : 0;
     return BSLS_OK;
-}
-
-// common block size of a layout, or 0 (host side)
-int uniform_size(const int *blocks, int numblocks, int n) {
-    const int K = (numblocks > 1 ? blocks[1] : n) - blocks[0];
-    int diff = 0;  // branch-free so that the compiler vectorises the scan
-    for (int i = 1; i < numblocks; ++i) diff |= (blocks[i] - blocks[i - 1]) ^ K;
-    return (diff == 0 && n - blocks[numblocks - 1] == K) ? K : 0;
 }
 
 // Uniform layouts need no plan, which lets the host entry points pipeline: the span is cut into
@@ -356,7 +355,20 @@ struct HostPipeline {
 thread_local HostPipeline g_pipe;
 
 size_t pipeline_chunk_blocks(int K, int numblocks) {
-    size_t cb = ((size_t)8 << 20) / ((size_t)K * sizeof(double));  // ~8 MB of values per chunk: short fill / drain
+    // chunk size: 1/16 of the span, between 8 MB (short fill / drain for small arrays) and 32 MB (long transfers keep
+    // both copy engines nearer the link rate: 512 MB each way took 14.0 ms in 8 MB chunks, 12.4 ms in 32 MB chunks);
+    // BSLS_PIPE_MB overrides, for tuning
+    static const size_t forced_mb = [] {
+        const char *e = getenv("BSLS_PIPE_MB");
+        const int v = e ? atoi(e) : 0;
+        return (size_t)(v > 0 ? v : 0);
+    }();
+    const size_t span_bytes = (size_t)numblocks * K * sizeof(double);
+    size_t bytes = span_bytes / 16;
+    if (bytes < ((size_t)8 << 20)) bytes = (size_t)8 << 20;
+    if (bytes > ((size_t)32 << 20)) bytes = (size_t)32 << 20;
+    if (forced_mb) bytes = forced_mb << 20;
+    size_t cb = bytes / ((size_t)K * sizeof(double));
     if (cb < 1024) cb = 1024;
     if (cb > (size_t)numblocks) cb = (size_t)numblocks;
     return cb;
@@ -385,15 +397,16 @@ int host_project_uniform(double *y, int first, int numblocks, int K, int mode) {
 }
 
 int host_project(double *y, const int *blocks, int numblocks, int n, int mode) {
-    if (int rc = device_ok()) return rc;
     if (!y) {
         set_error("null buffer");
         return BSLS_ERR_ARG;
     }
-    if (int rc = validate_blocks(blocks, numblocks, n)) return rc;
+    int K = 0;
+    if (int rc = validate_blocks(blocks, numblocks, n, &K)) return rc;  // argument errors first, as the reference's asserts
+    if (int rc = device_ok()) return rc;
     const int first = blocks[0];
     const size_t span = (size_t)n - first;  // entries before blocks[0] never leave the host
-    if (const int K = uniform_size(blocks, numblocks, n); K > 0 && K <= 512) return host_project_uniform(y, first, numblocks, K, mode);
+    if (K > 0 && K <= 512) return host_project_uniform(y, first, numblocks, K, mode);
     if (int rc = g_ws.reserve(span, (size_t)numblocks)) return rc;
     cudaStream_t st = g_ws.stream;
     BSLS_CUDA_TRY(cudaMemcpyAsync(g_ws.d_y, y + first, span * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -413,18 +426,19 @@ int host_project(double *y, const int *blocks, int numblocks, int n, int mode) {
 
 // isotonic regression on host buffers; `weight` may be NULL (all ones in, result dropped)
 int host_pava(double *y, const int *blocks, int numblocks, int n, int *weight, int update) {
-    if (int rc = device_ok()) return rc;
     if (!y) {
         set_error("null buffer");
         return BSLS_ERR_ARG;
     }
-    if (int rc = validate_blocks(blocks, numblocks, n)) return rc;
+    int K = 0;
+    if (int rc = validate_blocks(blocks, numblocks, n, &K)) return rc;
+    if (int rc = device_ok()) return rc;
     const int first = blocks[0];
     const size_t span = (size_t)n - first;
     if (int rc = g_ws.reserve(span, (size_t)numblocks)) return rc;
     if (weight)
         if (int rc = g_ws.reserve_w(span)) return rc;
-    if (const int K = uniform_size(blocks, numblocks, n); K > 0 && K <= kPlanPavaSmallMax) {
+    if (K > 0 && K <= kPlanPavaSmallMax) {
         // pipelined like host_project_uniform: chunks of whole blocks on three streams
         const size_t cb = pipeline_chunk_blocks(K, numblocks);
         if (int rc = g_pipe.prepare(cb)) return rc;
