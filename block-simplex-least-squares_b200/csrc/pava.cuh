@@ -325,7 +325,7 @@ template <typename T, int THREADS, typename M, bool FAST, bool CLIP, int KRC>
 __global__ void __launch_bounds__(THREADS)  // a register cap for 20 CTAs per SM (45 registers) measured 3-6 % slower than 58 registers / 16 CTAs
 pava_small_kernel(T *__restrict__ yg, int32_t *__restrict__ wg, long long first, int nb, int K, int G, FastDiv rdiv, PavaFlags fl) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    static_assert(KRC == 0 || (THREADS % KRC == 0 && KRC % 2 == 0 && FAST), "compile-time rows: even length dividing the CTA");
+    static_assert(KRC == 0 || (THREADS % KRC == 0 && FAST), "compile-time rows: a length dividing the CTA");
     const int KR = KRC ? KRC : K * G;  // row length (elements)
     const int KS = KR | 1;             // row pitch
     const int pad = KS - KR;           // 1 for even KR: element e of the tile sits at e + row
@@ -356,15 +356,16 @@ pava_small_kernel(T *__restrict__ yg, int32_t *__restrict__ wg, long long first,
         if (KRC > 0) {
             // element tid + j*THREADS sits in row tid/KRC + j*(THREADS/KRC), column tid % KRC
             constexpr int KRX = KRC > 0 ? KRC : 1;
+            constexpr int KSX = KRX | 1;
             constexpr int RPI = THREADS / KRX;
             const T *src = gy + tid;
-            T *dst = ys + (tid / KRX) * (KRX + 1) + (tid % KRX);
+            T *dst = ys + (tid / KRX) * KSX + (tid % KRX);
             if (nel == tile_elems) {
 #pragma unroll
-                for (int j = 0; j < KRX; ++j) cp_async_elem<sizeof(T)>(dst + j * RPI * (KRX + 1), src + j * THREADS);
+                for (int j = 0; j < KRX; ++j) cp_async_elem<sizeof(T)>(dst + j * RPI * KSX, src + j * THREADS);
             } else {
                 for (int j = 0; j < KRX; ++j)
-                    if (tid + j * THREADS < nel) cp_async_elem<sizeof(T)>(dst + j * RPI * (KRX + 1), src + j * THREADS);
+                    if (tid + j * THREADS < nel) cp_async_elem<sizeof(T)>(dst + j * RPI * KSX, src + j * THREADS);
             }
             cp_async_commit();
         } else {
@@ -409,7 +410,34 @@ pava_small_kernel(T *__restrict__ yg, int32_t *__restrict__ wg, long long first,
         }
         __syncthreads();
         // coalesced store; with `update` every element takes the value of the head its mask names
-        if (KRC > 0 && pairs) {
+        if (KRC > 0 && (KRC % 2 != 0 || !pairs)) {
+            // element tid + j*THREADS: row tid/KRC + j*(THREADS/KRC), column tid % KRC (odd row lengths, unaligned spans)
+            constexpr int KRX = KRC > 0 ? KRC : 1;
+            constexpr int KSX = KRX | 1;
+            constexpr int RPI = THREADS / KRX;
+            const int c = tid % KRX, rr0 = tid / KRX;
+            const M below = (((M)2) << c) - 1;
+            T *dst = gy + tid;
+            const M *mrow = masks + rr0;
+            const T *yrow = ys + rr0 * KSX;
+            if (nel == tile_elems) {
+#pragma unroll
+                for (int j = 0; j < KRX; ++j) {
+                    const uint32_t h = (uint32_t)bit_hi((M)(mrow[j * RPI] & below));
+                    T v = yrow[j * RPI * KSX + h];
+                    if (clip) v = clip01(v);
+                    dst[j * THREADS] = v;
+                }
+            } else {
+                for (int j = 0; j < KRX; ++j) {
+                    if (tid + j * THREADS >= nel) break;
+                    const uint32_t h = (uint32_t)bit_hi((M)(mrow[j * RPI] & below));
+                    T v = yrow[j * RPI * KSX + h];
+                    if (clip) v = clip01(v);
+                    dst[j * THREADS] = v;
+                }
+            }
+        } else if (KRC > 0) {
             // pair 2*tid + j*2*THREADS: row (2*tid)/KRC + j*(2*THREADS/KRC), columns c2 and c2 + 1 of that row
             constexpr int KRX = KRC > 0 ? KRC : 2;
             constexpr int RP2 = 2 * THREADS / KRX;
@@ -525,10 +553,26 @@ int launch_pava_small_flags(T *y, int32_t *w, long long first, int nb, int K, in
     return launch_pava_small_cfg<T, THREADS, M, false, false>(y, w, first, nb, K, 1, fl, stream);
 }
 
+// row lengths with their own instantiation (CTA size a multiple of the row length): the z-space block sizes of the
+// named configurations (K - 1 = 15, 19; also 3 blocks of 5, 5 blocks of 3), besides the 16 / 32 handled with 64
+// threads.  (K = 20 with 120 threads measured slower than the generic path: 0.50 ms against 0.44 ms.)
+template <typename T, int THREADS, int KRC>
+int launch_pava_small_krc(T *y, int32_t *w, long long first, int nb, int K, int G, PavaFlags fl, cudaStream_t stream) {
+    if (fl.clip01) return launch_pava_small_cfg<T, THREADS, uint32_t, true, true, KRC>(y, w, first, nb, K, G, fl, stream);
+    return launch_pava_small_cfg<T, THREADS, uint32_t, true, false, KRC>(y, w, first, nb, K, G, fl, stream);
+}
+
 template <typename T> int launch_pava_small(T *y, int32_t *w, long long first, int nb, int K, PavaFlags fl, cudaStream_t stream) {
     if (nb <= 0) return BSLS_OK;
     if (K <= 32) {
         int G = K <= 8 ? 16 / K : 1;  // short blocks: several to a row (<= 16 entries)
+        if constexpr (sizeof(T) == 8) {
+            if (!fl.has_weight && fl.update && !getenv("BSLS_PAVA_NO_KRC") && !getenv("BSLS_PAVA_CFG")) {
+                const int KR = K * G;
+                if (KR == 15) return launch_pava_small_krc<T, 120, 15>(y, w, first, nb, K, G, fl, stream);
+                if (KR == 19) return launch_pava_small_krc<T, 114, 19>(y, w, first, nb, K, G, fl, stream);
+            }
+        }
         int th = 64;
         if (const char *cfg = getenv("BSLS_PAVA_CFG")) {  // tuning experiments: "<threads>,<G>"
             int g = G;
