@@ -284,6 +284,35 @@ def bench_1e8(bsls_b200, torch, dev, peak, reps=4):
                                          "frac": bytes_ / t / 1e6 / peak}
         del plan
         torch.cuda.empty_cache()
+    # the z-space projection of config 5 (python/main.py:57-65): blocks of K - 1 = 15 running sums of a simplex point,
+    # perturbed by a gradient step (here N(0, 0.05)) -- the input PAVA sees inside solve_in_z
+    K = 15
+    nb = 10 ** 8 // K
+    n = nb * K
+    plan = bsls_b200.BlockPlan(torch.arange(0, n, K, dtype=torch.int64, device=dev), n)
+
+    def make_z():
+        e = -torch.log(torch.rand(nb, K + 1, dtype=torch.float64, device=dev, generator=gen))
+        z = torch.cumsum(e / e.sum(1, keepdim=True), 1)[:, :K]
+        return (z + 0.05 * torch.randn(nb, K, dtype=torch.float64, device=dev, generator=gen)).reshape(-1)
+    ms = []
+    for r in range(reps + 1):
+        y = make_z()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        bsls_b200.isotonic_regression_multi_c(y, plan, None, 1, clip01=True)
+        e1.record()
+        torch.cuda.synchronize()
+        if r > 0:
+            ms.append(e0.elapsed_time(e1))
+        del y
+    t = float(np.mean(ms))
+    bytes_ = 16 * n + 4 * nb
+    out["pava_zspace_K15_clip"] = {"avg_ms": t, "var_per_s": n / t * 1e3, "algorithmic_bytes": bytes_, "GBs": bytes_ / t / 1e6,
+                                   "frac": bytes_ / t / 1e6 / peak,
+                                   "input": "cumulative sums of Dirichlet(1) blocks + N(0, 0.05); regression + [0,1] clamp in one launch"}
+    del plan
+    torch.cuda.empty_cache()
     return out
 
 

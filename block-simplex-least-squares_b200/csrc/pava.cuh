@@ -536,7 +536,7 @@ int launch_pava_small_cfg(T *y, int32_t *w, long long first, int nb, int K, int 
 template <typename T, int THREADS, typename M>
 int launch_pava_small_flags(T *y, int32_t *w, long long first, int nb, int K, int G, PavaFlags fl, cudaStream_t stream) {
     if (!fl.has_weight && fl.update) {  // hot configuration
-        if constexpr (sizeof(M) == 4 && THREADS == 64 && sizeof(T) == 8) {
+        if constexpr (sizeof(M) == 4 && (THREADS == 64 || THREADS == 128) && sizeof(T) == 8) {
             const int KR = K * G;
             if (KR == 16 && !getenv("BSLS_PAVA_NO_KRC")) {
                 if (fl.clip01) return launch_pava_small_cfg<T, THREADS, M, true, true, 16>(y, w, first, nb, K, G, fl, stream);
