@@ -90,7 +90,12 @@ static int dev_pava(const bsls_plan *plan_, T *y, int32_t *weight, int update, i
     }
     const bool cold = weight == nullptr && update != 0;  // the configuration of main.py:64
     const bool words_off = getenv("BSLS_PAVA_NO_WORDS") != nullptr;  // A/B switch for measurements
-    if (cold && !words_off && plan->uniform > kPlanPavaSmallMax && plan->uniform <= kPlanWordsMax) {
+    static const int words_min = [] {  // smallest uniform block size the word-per-lane kernel takes (BSLS_PAVA_WORDS_MIN: experiments)
+        const char *e = getenv("BSLS_PAVA_WORDS_MIN");
+        const int v = e ? atoi(e) : 0;
+        return v > 32 ? v : kPlanPavaSmallMax + 1;
+    }();
+    if (cold && !words_off && plan->uniform >= words_min && plan->uniform <= kPlanWordsMax) {
         const int bpp = 32 / ((plan->uniform + 31) >> 5);
         const int npacks = (plan->nb + bpp - 1) / bpp;
         if constexpr (sizeof(T) == 8)
