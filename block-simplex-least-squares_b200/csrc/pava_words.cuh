@@ -212,7 +212,7 @@ __device__ __forceinline__ void pava_words_engine(T *y, uint32_t *A0, uint32_t *
 template <typename T, bool CLIP>
 __global__ void __launch_bounds__(kWordsWarps * 32)
 pava_words_kernel(T *__restrict__ yg, const int32_t *__restrict__ starts, const int32_t *__restrict__ ids,
-                  const int32_t *__restrict__ pack_first, int npacks, long long first, int nb, int Kuni) {
+                  const int32_t *__restrict__ pack_first, int npacks, long long first, int nb, int Kuni, FastDiv kdiv) {
     __shared__ __align__(16) WordsWarpSmem<T> smem[kWordsWarps];
     __shared__ T rcp[kWordsRcp];
     for (int i = threadIdx.x + 1; i < kWordsRcp; i += kWordsWarps * 32) rcp[i] = T(1) / (T)i;
@@ -257,11 +257,25 @@ pava_words_kernel(T *__restrict__ yg, const int32_t *__restrict__ starts, const 
         const bool have = lane < total_words;
         const int j = have ? lane - my_w0 : -1;
         const int LW = (my_K + 31) >> 5;
-        // fetch: block by block, coalesced
-        for (int b = 0; b < cnt; ++b) {
-            const int bg = __shfl_sync(0xffffffffu, g0, b), bK = __shfl_sync(0xffffffffu, Kb, b), bw = __shfl_sync(0xffffffffu, w0, b);
-            const T *src = yg + first + bg;
-            for (int i = lane; i < bK; i += 32) cp_async_elem<sizeof(T)>(&sm.y[32 * bw + i], src + i);
+        if (!starts) {
+            // uniform layout: the pack is one contiguous span; entry e of it is entry e % K of block e / K
+            const int nel = cnt * Kuni;
+            const T *src = yg + first + (long long)pack * bpp * Kuni + lane;
+            if (Kuni == 32 * wpb) {  // whole words: the shared image is the span itself
+                for (int e = lane; e < nel; e += 32, src += 32) cp_async_elem<sizeof(T)>(&sm.y[e], src);
+            } else {
+                for (int e = lane; e < nel; e += 32, src += 32) {
+                    const int b = (int)fdiv((uint32_t)e, kdiv);
+                    cp_async_elem<sizeof(T)>(&sm.y[32 * wpb * b + (e - b * Kuni)], src);
+                }
+            }
+        } else {
+            // fetch: block by block, coalesced
+            for (int b = 0; b < cnt; ++b) {
+                const int bg = __shfl_sync(0xffffffffu, g0, b), bK = __shfl_sync(0xffffffffu, Kb, b), bw = __shfl_sync(0xffffffffu, w0, b);
+                const T *src = yg + first + bg;
+                for (int i = lane; i < bK; i += 32) cp_async_elem<sizeof(T)>(&sm.y[32 * bw + i], src + i);
+            }
         }
         cp_async_commit();
         cp_async_wait<0>();
@@ -271,6 +285,20 @@ pava_words_kernel(T *__restrict__ yg, const int32_t *__restrict__ starts, const 
             pava_words_engine<T, WordsWarpSync>(sm.y + 32 * wb, sm.A0 + wb, sm.A + wb, sm.St + wb, sm.D + wb, lane, j, LW, my_K, rcp);
         }
         // store: every entry takes the value of the head at or below it
+        if (!starts) {
+            const int nel = cnt * Kuni;
+            T *dst = yg + first + (long long)pack * bpp * Kuni + lane;
+            for (int e = lane; e < nel; e += 32, dst += 32) {
+                const int b = (int)fdiv((uint32_t)e, kdiv);
+                const int wbase = wpb * b, i = e - b * Kuni;
+                int w = i >> 5;
+                uint32_t m = sm.A[wbase + w] & ((2u << (i & 31)) - 1u);
+                while (m == 0) m = sm.A[wbase + --w];
+                T v = sm.y[32 * (wbase + w) + 31 - __clz((int)m)];
+                if (CLIP) v = clip01(v);
+                *dst = v;
+            }
+        } else
         for (int b = 0; b < cnt; ++b) {
             const int bg = __shfl_sync(0xffffffffu, g0, b), bK = __shfl_sync(0xffffffffu, Kb, b), bw = __shfl_sync(0xffffffffu, w0, b);
             T *dst = yg + first + bg;
@@ -376,9 +404,9 @@ int launch_pava_words(T *y, const int32_t *starts, const int32_t *ids, const int
     int grid = want < full[clip ? 1 : 0] ? want : full[clip ? 1 : 0];
     if (cap_per_sm > 0 && grid > cap_per_sm * kNumSM) grid = cap_per_sm * kNumSM;
     if (clip)
-        k1<<<grid, kWordsWarps * 32, 0, stream>>>(y, starts, ids, pack_first, npacks, first, nb, Kuni);
+        k1<<<grid, kWordsWarps * 32, 0, stream>>>(y, starts, ids, pack_first, npacks, first, nb, Kuni, make_fastdiv((uint32_t)(Kuni > 0 ? Kuni : 1)));
     else
-        k0<<<grid, kWordsWarps * 32, 0, stream>>>(y, starts, ids, pack_first, npacks, first, nb, Kuni);
+        k0<<<grid, kWordsWarps * 32, 0, stream>>>(y, starts, ids, pack_first, npacks, first, nb, Kuni, make_fastdiv((uint32_t)(Kuni > 0 ? Kuni : 1)));
     BSLS_LAUNCH_CHECK();
     return BSLS_OK;
 }
