@@ -144,6 +144,19 @@ def cpu_baseline_sample(threads=1, reps=2):
             "seconds_per_step": best}
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The result line, on the process's real stdout (see main)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -178,7 +191,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 
@@ -614,7 +627,7 @@ def run_ours(args, rank, world, local_rank):
             line[k] = v
     if "bb_c5" in line:
         line["gpu_launches"] += line["bb_c5"]["kernel_launches"]
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -631,6 +644,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on
+    # file descriptor 1 when NCCL_DEBUG is set): for the run, descriptor 1 points at stderr and the JSON line is
+    # written to the real stdout at the end.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
