@@ -180,21 +180,34 @@ proj_uniform_kernel(T *__restrict__ y, long long first, int nb, int Krt, FastDiv
             const int blk = j * GROUPS + grp;
             const bool live = blk < nblk;
             const T *blkp = buf + blk * K;
-            bool project = true;
-            if (MODE == kBall) {
-                // clip negatives; project only when the clipped block sums to more than 1
-                // (sum left to right over the kept entries, proj_simplex.h:54-62)
-                T total = T(0);
-                if (live && sub == 0)
-                    for (int k = 0; k < K; ++k) {
-                        const T x = blkp[k];
-                        if (!(x < T(0))) total += x;
-                    }
-                if (G > 1) total = __shfl_sync(0xffffffffu, total, lane & ~(G - 1));
-                project = total > T(1);
-            }
             T v[E];
             load_block_regs<T, E, G, MODE>(v, blkp, K, lane, live, vec_ok);
+            bool project = true;
+            if (MODE == kBall) {
+                // clip negatives; project only when the clipped block sums to more than 1.  The reference adds the
+                // kept entries left to right (proj_simplex.h:54-62); all terms are >= 0, so any order of summation
+                // is within (K-1) eps of the exact sum: the lanes add their registers (padding entries are -inf:
+                // skipped), and only a total within 4 K eps of 1 is re-added in the reference's order by one lane.
+                T part = T(0);
+#pragma unroll
+                for (int e = 0; e < E; ++e)
+                    if (v[e] > T(0)) part += v[e];
+#pragma unroll
+                for (int o = G / 2; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                const T margin = T(4 * K) * (sizeof(T) == 8 ? T(2.220446049250313e-16) : T(1.1920929e-07)) * (part > T(1) ? part : T(1));
+                project = part > T(1);
+                const bool unsure = !(part > T(1) + margin) && !(part < T(1) - margin);
+                if (__any_sync(0xffffffffu, unsure)) {
+                    T total = T(0);
+                    if (unsure && live && sub == 0)
+                        for (int k = 0; k < K; ++k) {
+                            const T x = blkp[k];
+                            if (!(x < T(0))) total += x;
+                        }
+                    if (G > 1) total = __shfl_sync(0xffffffffu, total, lane & ~(G - 1));
+                    if (unsure) project = total > T(1);
+                }
+            }
             sort_desc_group<T, E, G>(v, lane);
             T shift = simplex_shift_sorted<T, E, G>(v, K, lane);
             if (MODE == kBall && !project) shift = T(0);

@@ -158,6 +158,25 @@ def test_fp32_extension(api, K):
     assert np.abs(got.reshape(nb, K).sum(1) - 1).max() < 1e-5
 
 
+@pytest.mark.parametrize("K", [3, 4, 16, 20, 24])
+def test_ball_sum_near_one(api, K):
+    """l1-ball: the decision `clipped block sums to more than 1` (proj_simplex.h:54-62) on blocks whose sum is
+    within a few ulps of 1 -- the kernels add in parallel and must fall back to the reference's order there."""
+    rng = np.random.RandomState(SEED + K)
+    nb = 20000
+    x = rng.dirichlet(np.ones(K), size=nb)                      # rows sum to 1 up to rounding
+    x *= (1.0 + rng.randint(-3, 4, size=(nb, 1)) * 2.220446049250313e-16)
+    x[rng.rand(nb, K) < 0.15] *= -1.0                           # some negatives (clipped away)
+    x = x / np.maximum(np.where(x > 0, x, 0).sum(1, keepdims=True), 1e-300)  # clipped sums back to ~1
+    x *= (1.0 + rng.randint(-2, 3, size=(nb, 1)) * 2.220446049250313e-16)
+    y = x.reshape(-1).copy()
+    starts = np.arange(0, nb * K, K)
+    want = y.copy()
+    cpu_port().proj_multi_ball(want, starts)
+    got = gpu_project(api, y, starts, ball=True)
+    assert np.array_equal(got, want)
+
+
 # ------------------------------------------------------------------ size-independent properties
 @pytest.mark.parametrize("K,nb", [(4, 10 ** 6), (16, 10 ** 6), (64, 10 ** 6)])
 def test_full_size_properties(api, K, nb):
