@@ -596,6 +596,21 @@ int bsls_dev_x2z_f64(const bsls_plan *plan, const double *x, double *z, bsls_str
         set_error("x2z: blocks[0] must be 0");
         return BSLS_ERR_ARG;
     }
+    if (plan->uniform >= 2 && plan->uniform <= kX2zTileMaxK) {
+        const int K = plan->uniform;
+        const size_t smem = (size_t)kX2zTileThreads * (K | 1) * sizeof(double);
+        static thread_local size_t attr_smem = 0;
+        if (smem > attr_smem) {
+            BSLS_CUDA_TRY(cudaFuncSetAttribute(x2z_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_smem = smem;
+        }
+        const int ntiles = (plan->nb + kX2zTileThreads - 1) / kX2zTileThreads;
+        const int grid = ntiles < 8 * kNumSM ? ntiles : 8 * kNumSM;
+        x2z_tile_kernel<<<grid, kX2zTileThreads, smem, (cudaStream_t)s>>>(x, z, plan->nb, K, make_fastdiv((uint32_t)K),
+                                                                           make_fastdiv((uint32_t)(K - 1)));
+        BSLS_LAUNCH_CHECK();
+        return BSLS_OK;
+    }
     x2z_kernel<<<grid_groups(plan->nb, 1), 256, 0, (cudaStream_t)s>>>(x, z, layout_of(plan));
     BSLS_LAUNCH_CHECK();
     return BSLS_OK;
@@ -608,7 +623,12 @@ int bsls_dev_z2x_f64(const bsls_plan *plan, double *x, const double *z, bsls_str
         set_error("z2x: blocks[0] must be 0");
         return BSLS_ERR_ARG;
     }
-    z2x_kernel<<<grid_groups(plan->nb, 1), 256, 0, (cudaStream_t)s>>>(x, z, layout_of(plan));
+    {
+        // the differences are independent of each other: the element-parallel kernel of x = x0 + N z computes exactly
+        // z_l - z_{l-1} and 1 + (0 - z_last) = 1 - z_last (the same IEEE operations as the serial loop of z2x_kernel)
+        const int lanes = lanes_for(plan);
+        DISPATCH_LANES(lanes, nz_kernel, grid_groups(plan->nb, lanes), (cudaStream_t)s, x, z, 1, layout_of(plan));
+    }
     BSLS_LAUNCH_CHECK();
     return BSLS_OK;
 }

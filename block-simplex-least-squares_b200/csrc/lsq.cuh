@@ -494,20 +494,47 @@ __global__ void __launch_bounds__(256) x2z_kernel(const double *__restrict__ x, 
     }
 }
 
-// z -> x: adjacent differences, last entry 1 - z_last (c_extensions.pyx:223-248)
-__global__ void __launch_bounds__(256) z2x_kernel(double *__restrict__ x, const double *__restrict__ z, BlockLayout lay) {
-    for (int64_t b = (int64_t)blockIdx.x * 256 + threadIdx.x; b < lay.nb; b += (int64_t)gridDim.x * 256) {
-        int s, e;
-        lay.range((int)b, s, e);
-        const int64_t zoff = b + lay.first;
-        double before = 0.0;
-        for (int i = s; i < e - 1; ++i) {
-            const double zi = z[i - zoff];
-            x[i] = zi - before;
-            before = zi;
+// x -> z for uniform layouts with short blocks: a CTA stages THREADS whole blocks in shared memory (coalesced
+// cp.async into rows of odd pitch), every thread sums ITS block left to right in place (the reference's order, so the
+// result is bit-identical), and the K - 1 running sums of every block go out coalesced.  The thread-per-block kernel
+// above reads and writes with a stride of one block per lane and stops near 30 % of the HBM peak.
+constexpr int kX2zTileThreads = 128;
+constexpr int kX2zTileMaxK = 64;
+__global__ void __launch_bounds__(kX2zTileThreads)
+x2z_tile_kernel(const double *__restrict__ x, double *__restrict__ z, int nb, int K, FastDiv kdiv, FastDiv kdiv1) {
+    extern __shared__ __align__(16) double x2z_rows[];
+    const int KS = K | 1, K1 = K - 1, tid = threadIdx.x;
+    const int ntiles = (nb + kX2zTileThreads - 1) / kX2zTileThreads;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int nblk = min(kX2zTileThreads, nb - tile * kX2zTileThreads);
+        const double *gx = x + (size_t)tile * kX2zTileThreads * K;
+        double *gz = z + (size_t)tile * kX2zTileThreads * K1;
+        const int nel = nblk * K;
+        for (int e = tid; e < nel; e += kX2zTileThreads) {
+            const uint32_t r = fdiv((uint32_t)e, kdiv);
+            cp_async_elem<8>(&x2z_rows[r * KS + (e - r * K)], gx + e);
         }
-        x[e - 1] = 1.0 - before;
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        if (tid < nblk) {
+            double *row = x2z_rows + tid * KS;
+            double run = 0.0;
+            for (int c = 0; c < K1; ++c) {
+                run += row[c];
+                row[c] = run;
+            }
+        }
+        __syncthreads();
+        const int nz = nblk * K1;
+        for (int i = tid; i < nz; i += kX2zTileThreads) {
+            const uint32_t r = fdiv((uint32_t)i, kdiv1);
+            gz[i] = x2z_rows[r * KS + (i - r * K1)];
+        }
+        __syncthreads();
     }
 }
+
+// z -> x (adjacent differences, last entry 1 - z_last; c_extensions.pyx:223-248) is nz_kernel with add_x0 = 1.
 
 }  // namespace bsls

@@ -93,7 +93,7 @@ def make_input(rng, sizes, kind):
     raise ValueError(kind)
 
 
-@pytest.mark.parametrize("K", [1, 2, 3, 4, 15, 16, 19, 32, 33, 63, 64, 65, 96, 100, 255, 256, 257, 513, 1000, 1024, 1025, 4096, 8192])
+@pytest.mark.parametrize("K", [1, 2, 3, 4, 5, 7, 8, 15, 16, 19, 20, 31, 32, 33, 63, 64, 65, 96, 100, 255, 256, 257, 513, 1000, 1024, 1025, 4096, 8192])
 @pytest.mark.parametrize("kind", ["ref", "normal", "ints", "decreasing", "zspace"])
 def test_uniform_blocks(api, K, kind):
     rng = np.random.RandomState(SEED + K)

@@ -199,6 +199,25 @@ def test_x2z_z2x_golden(B, golden_dir):
     with pytest.raises(AssertionError):
         B.x2z_c(dev(np.ones(4)), torch.empty(2, dtype=torch.float64, device="cuda"), np.array([0, 2, 2]))
 
+@pytest.mark.parametrize("K", [2, 3, 5, 16, 20, 64, 65, 100])
+def test_x2z_z2x_uniform_against_oracle(B, K):
+    """x2z / z2x on uniform layouts (tiled kernel for K <= 64, thread-per-block beyond) bit for bit against the oracle
+    (c_extensions.pyx:195-248): running sums left to right, adjacent differences, last entry 1 - z_last."""
+    from oracle import cpu
+    port = cpu.port()
+    rng = np.random.RandomState(100 + K)
+    nb = 1000 + 131 * (K % 7)          # not a multiple of the tile height
+    x = rng.dirichlet(np.ones(K), size=nb).reshape(-1) + 1e-3 * rng.randn(nb * K)
+    starts = np.arange(0, nb * K, K)
+    z = port.x2z(x.copy(), np.zeros(nb * (K - 1)), starts)
+    zd = torch.empty(nb * (K - 1), dtype=torch.float64, device="cuda")
+    B.x2z_c(dev(x), zd, starts)
+    assert np.array_equal(host(zd), z)
+    xb = port.z2x(np.zeros(nb * K), z.copy(), starts)
+    xd = torch.empty(nb * K, dtype=torch.float64, device="cuda")
+    B.z2x_c(xd, dev(z), starts)
+    assert np.array_equal(host(xd), xb)
+
 
 def test_x2z_matches_oracle_ragged(B):
     from oracle import cpu
