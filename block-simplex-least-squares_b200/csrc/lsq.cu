@@ -556,7 +556,23 @@ int bsls_dev_md_update_f64(bsls_ws *q, const bsls_plan *plan, double *x_new, con
     cudaStream_t st = (cudaStream_t)s;
     const int lanes = lanes_for(plan);
     const int grid = grid_groups(plan->nb, lanes);
-    DISPATCH_LANES(lanes, md_update_kernel, grid, st, x_new, x, g, step, per_block_log, layout_of(plan), q->red);
+    if (plan->max_size <= 2 * lanes) {  // every block fits the registers of its lanes: one pass, one resident wave
+#define MD_REG(G)                                                                                                     \
+    {                                                                                                                 \
+        static thread_local int full = 0;                                                                             \
+        if (!full) full = resident_grid(md_update_reg_kernel<G, 2>, 256);                                             \
+        md_update_reg_kernel<G, 2><<<grid < full ? grid : full, 256, 0, st>>>(x_new, x, g, step, per_block_log, layout_of(plan), q->red); \
+    }
+        switch (lanes) {
+            case 4: MD_REG(4) break;
+            case 8: MD_REG(8) break;
+            case 16: MD_REG(16) break;
+            default: MD_REG(32) break;
+        }
+#undef MD_REG
+    } else {
+        DISPATCH_LANES(lanes, md_update_kernel, grid, st, x_new, x, g, step, per_block_log, layout_of(plan), q->red);
+    }
     BSLS_LAUNCH_CHECK();
     q->launches++;
     return allreduce(q, q->d_scal + kScalMax0, 1, kNcclMax, st);

@@ -309,7 +309,31 @@ struct DotArgs {
 };
 __global__ void __launch_bounds__(256) dots_kernel(DotArgs a, int64_t n, RedCtx red) {
     double acc[5] = {0, 0, 0, 0, 0};
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    // two elements per trip: twice the loads in flight (each accumulator still adds its terms in index order)
+    for (; i + stride < n; i += 2 * stride) {
+        double xa[4], ya[4], xb[4], yb[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (k < a.count) {
+                xa[k] = a.x[k][i];
+                ya[k] = a.y[k][i];
+                xb[k] = a.x[k][i + stride];
+                yb[k] = a.y[k][i + stride];
+            }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (k < a.count) {
+                acc[k] += xa[k] * ya[k];
+                acc[k] += xb[k] * yb[k];
+            }
+        if (a.want_max) {
+            acc[4] = fmax(acc[4], fabs(xa[0] - ya[0]));
+            acc[4] = fmax(acc[4], fabs(xb[0] - yb[0]));
+        }
+    }
+    for (; i < n; i += stride) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
             if (k < a.count) acc[k] += a.x[k][i] * a.y[k][i];
@@ -425,6 +449,53 @@ __global__ void __launch_bounds__(256) md_update_kernel(double *__restrict__ xn,
             const double w = xn[i] / sum;
             xn[i] = w;
             acc[0] = fmax(acc[0], fabs(w - x[i]));
+        }
+    }
+    grid_reduce<0, 1, 256, FinMax>(acc, red);
+}
+
+// The same update with every block held in the registers of its G lanes (blocks of at most R*G entries): x and g are
+// read once, x_new is written once (24 n bytes; the two-pass kernel above re-reads what it wrote).  Same order of
+// additions as md_update_kernel (per lane in steps of G, then the xor tree), so both give the same bits.
+template <int G, int R>
+__global__ void __launch_bounds__(256) md_update_reg_kernel(double *__restrict__ xn, const double *__restrict__ x, const double *__restrict__ g,
+                                                             double step, int per_block_log, BlockLayout lay, RedCtx red) {
+    const int sub = threadIdx.x & (G - 1);
+    const int64_t group = ((int64_t)blockIdx.x * 256 + threadIdx.x) / G;
+    const int64_t ngroups = (int64_t)gridDim.x * 256 / G;
+    const int64_t rounds = (lay.nb + ngroups - 1) / ngroups;
+    double acc[1] = {0};
+    for (int64_t it = 0; it < rounds; ++it) {
+        const int64_t b = it * ngroups + group;
+        const bool valid = b < lay.nb;
+        int s = 0, e = 0;
+        if (valid) lay.range((int)b, s, e);
+        double t = step;
+        if (per_block_log) t = sqrt(2.0 * log((double)(e - s > 0 ? e - s : 1))) / step;
+        double xv[R], w[R];
+        double sum = 0.0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = s + sub + r * G;
+            xv[r] = 0.0;
+            w[r] = 0.0;
+            if (i < e) {
+                xv[r] = x[i];
+                const double up = per_block_log ? g[i] * t : -t * g[i];
+                w[r] = xv[r] * exp(per_block_log ? -up : up);
+                sum += w[r];
+            }
+        }
+#pragma unroll
+        for (int o = G / 2; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = s + sub + r * G;
+            if (i < e) {
+                const double q = w[r] / sum;
+                xn[i] = q;
+                acc[0] = fmax(acc[0], fabs(q - xv[r]));
+            }
         }
     }
     grid_reduce<0, 1, 256, FinMax>(acc, red);
