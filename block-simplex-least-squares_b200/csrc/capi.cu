@@ -95,13 +95,13 @@ static int dev_pava(const bsls_plan *plan_, T *y, int32_t *weight, int update, i
         const int v = e ? atoi(e) : 0;
         return v > 32 ? v : kPlanPavaSmallMax + 1;
     }();
-    if (cold && !words_off && plan->uniform >= words_min && plan->uniform <= kPlanWordsMax) {
+    if (!words_off && plan->uniform >= words_min && plan->uniform <= kPlanWordsMax) {
         const int bpp = 32 / ((plan->uniform + 31) >> 5);
         const int npacks = (plan->nb + bpp - 1) / bpp;
         if constexpr (sizeof(T) == 8)
-            return pava_words_f64((double *)y, nullptr, nullptr, nullptr, npacks, plan->first, plan->nb, plan->uniform, clip01, 0, stream);
+            return pava_words_f64((double *)y, weight, nullptr, nullptr, nullptr, npacks, plan->first, plan->nb, plan->uniform, update, clip01, 0, stream);
         else
-            return pava_words_f32((float *)y, nullptr, nullptr, nullptr, npacks, plan->first, plan->nb, plan->uniform, clip01, 0, stream);
+            return pava_words_f32((float *)y, weight, nullptr, nullptr, nullptr, npacks, plan->first, plan->nb, plan->uniform, update, clip01, 0, stream);
     }
     if (plan->uniform > 0 && plan->uniform <= kPlanPavaSmallMax) {
         if constexpr (sizeof(T) == 8)
@@ -125,7 +125,7 @@ static int dev_pava(const bsls_plan *plan_, T *y, int32_t *weight, int update, i
         }
         auto launch_mid = [&]() -> int {
             int rc = BSLS_OK;
-            if (plan->mid > 0 && cold && !words_off) {
+            if (plan->mid > 0 && !words_off) {
                 if (plan->mid_packs < 0) {  // pack the mid list once
                     int *d_np = nullptr, h_np = 0;
                     BSLS_CUDA_TRY(cudaMalloc(&d_np, sizeof(int)));
@@ -139,9 +139,9 @@ static int dev_pava(const bsls_plan *plan_, T *y, int32_t *weight, int update, i
                 }
                 BSLS_CUDA_TRY(cudaStreamWaitEvent(plan->aux[0], plan->ev_fork, 0));
                 if constexpr (sizeof(T) == 8)
-                    rc = pava_words_f64((double *)y, plan->d_starts, plan->d_mid_ids, plan->d_mid_pack, plan->mid_packs, 0, plan->nb, 0, clip01, cap_words, plan->aux[0]);
+                    rc = pava_words_f64((double *)y, weight, plan->d_starts, plan->d_mid_ids, plan->d_mid_pack, plan->mid_packs, 0, plan->nb, 0, update, clip01, cap_words, plan->aux[0]);
                 else
-                    rc = pava_words_f32((float *)y, plan->d_starts, plan->d_mid_ids, plan->d_mid_pack, plan->mid_packs, 0, plan->nb, 0, clip01, cap_words, plan->aux[0]);
+                    rc = pava_words_f32((float *)y, weight, plan->d_starts, plan->d_mid_ids, plan->d_mid_pack, plan->mid_packs, 0, plan->nb, 0, update, clip01, cap_words, plan->aux[0]);
                 if (rc) return rc;
                 BSLS_CUDA_TRY(cudaEventRecord(plan->ev_join[0], plan->aux[0]));
             } else if (plan->mid > 0) {
@@ -157,12 +157,12 @@ static int dev_pava(const bsls_plan *plan_, T *y, int32_t *weight, int update, i
         };
         auto launch_large = [&]() -> int {
             int rc = BSLS_OK;
-            if (plan->large > 0 && cold && !words_off) {
+            if (plan->large > 0 && !words_off) {
                 BSLS_CUDA_TRY(cudaStreamWaitEvent(plan->aux[1], plan->ev_fork, 0));
                 if constexpr (sizeof(T) == 8)
-                    rc = pava_words_cta_f64((double *)y, plan->d_starts, plan->d_large_ids, plan->large, plan->max_size, clip01, cap_cta, plan->aux[1]);
+                    rc = pava_words_cta_f64((double *)y, weight, plan->d_starts, plan->d_large_ids, plan->large, plan->max_size, update, clip01, cap_cta, plan->aux[1]);
                 else
-                    rc = pava_words_cta_f32((float *)y, plan->d_starts, plan->d_large_ids, plan->large, plan->max_size, clip01, cap_cta, plan->aux[1]);
+                    rc = pava_words_cta_f32((float *)y, weight, plan->d_starts, plan->d_large_ids, plan->large, plan->max_size, update, clip01, cap_cta, plan->aux[1]);
                 if (rc) return rc;
                 BSLS_CUDA_TRY(cudaEventRecord(plan->ev_join[1], plan->aux[1]));
             } else if (plan->large > 0) {

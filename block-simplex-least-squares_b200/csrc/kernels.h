@@ -66,13 +66,16 @@ int pava_mid_f32(float *y, int32_t *w, const int32_t *starts, const int32_t *mid
 // ragged: ids / pack_first from plan_pack_words, first = 0; uniform: starts = ids = pack_first = nullptr.
 constexpr int kPlanWordsMax = 1024;
 // cap_per_sm > 0 limits the grid to that many CTAs per SM (kernels meant to be co-resident with others)
-int pava_words_f64(double *y, const int32_t *starts, const int32_t *ids, const int32_t *pack_first, int npacks, long long first, int nb,
-                   int Kuni, int clip01, int cap_per_sm, cudaStream_t stream);
-int pava_words_f32(float *y, const int32_t *starts, const int32_t *ids, const int32_t *pack_first, int npacks, long long first, int nb,
-                   int Kuni, int clip01, int cap_per_sm, cudaStream_t stream);
+// w: weight array (in / out, warm start) or nullptr (cold start)
+int pava_words_f64(double *y, int32_t *w, const int32_t *starts, const int32_t *ids, const int32_t *pack_first, int npacks, long long first, int nb,
+                   int Kuni, int update, int clip01, int cap_per_sm, cudaStream_t stream);
+int pava_words_f32(float *y, int32_t *w, const int32_t *starts, const int32_t *ids, const int32_t *pack_first, int npacks, long long first, int nb,
+                   int Kuni, int update, int clip01, int cap_per_sm, cudaStream_t stream);
 // one CTA per block of up to kPlanPavaLargeMax entries (cold start), same engine
-int pava_words_cta_f64(double *y, const int32_t *starts, const int32_t *ids, int count, int max_block, int clip01, int cap_per_sm, cudaStream_t stream);
-int pava_words_cta_f32(float *y, const int32_t *starts, const int32_t *ids, int count, int max_block, int clip01, int cap_per_sm, cudaStream_t stream);
+int pava_words_cta_f64(double *y, int32_t *w, const int32_t *starts, const int32_t *ids, int count, int max_block, int update, int clip01,
+                       int cap_per_sm, cudaStream_t stream);
+int pava_words_cta_f32(float *y, int32_t *w, const int32_t *starts, const int32_t *ids, int count, int max_block, int update, int clip01,
+                       int cap_per_sm, cudaStream_t stream);
 // greedy packing of ids[0..count) into packs of at most 32 words (32 entries each); pack_first has count + 1 slots
 int plan_pack_words(const int32_t *starts, const int32_t *ids, int count, int32_t *pack_first, int *d_npacks, cudaStream_t stream);
 

@@ -883,9 +883,12 @@ pava_tile_kernel(T *__restrict__ yg, int32_t *__restrict__ wg, const int32_t *__
 // of blocks of <= 16 entries (row A, span <= 31) followed by at most one longer block (a block of
 // more than 16 entries that starts in the bucket ends beyond it), which is row B if it has <= 32
 // entries and belongs to pava_words_kernel / pava_words_cta_kernel otherwise.
-template <typename T, bool CLIP>
+// WMEM: a weight array is given (in / out): heads follow the chain i += weight[i] inside every block of a row, weights
+// are read and written as the reference does (isotonic_regression.h:22,37-42).
+template <typename T, bool CLIP, bool WMEM>
 __global__ void __launch_bounds__(kPavaTileThreads)
-pava_tile_rows_kernel(T *__restrict__ yg, const int32_t *__restrict__ starts, const int32_t *__restrict__ tile_first, int ntiles) {
+pava_tile_rows_kernel(T *__restrict__ yg, int32_t *__restrict__ wg, const int32_t *__restrict__ starts, const int32_t *__restrict__ tile_first,
+                      int ntiles, int update) {
     static_assert(kPavaTileThreads * 16 == kPavaTileElems, "one 16-entry bucket per thread");
     // the window holds the rows: blocks that start inside the tile and have at most kPavaThreadMax entries; the body of
     // a longer last block beyond it is neither staged nor written back
@@ -896,6 +899,7 @@ pava_tile_rows_kernel(T *__restrict__ yg, const int32_t *__restrict__ starts, co
     __shared__ uint32_t cov[NW];  // bit i: entry i belongs to a row (is written back from here)
     __shared__ uint2 rows[2 * kPavaTileThreads];  // {position | length << 16, block-start mask}
     __shared__ int nrows;
+    __shared__ uint16_t wbuf[WMEM ? WIN : 2];
     __shared__ T rcp[kPavaThreadMax + 1];
     const int tid = threadIdx.x;
     for (int i = tid + 1; i <= kPavaThreadMax; i += kPavaTileThreads) rcp[i] = T(1) / (T)i;
@@ -914,6 +918,8 @@ pava_tile_rows_kernel(T *__restrict__ yg, const int32_t *__restrict__ starts, co
             const T *src = yg + (size_t)tile_lo + tid;
             for (int i = tid; i < nel; i += kPavaTileThreads, src += kPavaTileThreads) cp_async_elem<sizeof(T)>(&ybuf[i], src);
             cp_async_commit();
+            if (WMEM)
+                for (int i = tid; i < nel; i += kPavaTileThreads) wbuf[i] = (uint16_t)min(max(wg[(size_t)tile_lo + i], 0), 65535);
         }
         __syncthreads();
         for (int i = tid; i <= nblk; i += kPavaTileThreads) {
@@ -966,8 +972,22 @@ pava_tile_rows_kernel(T *__restrict__ yg, const int32_t *__restrict__ starts, co
             const int pos = (int)(d.x & 0xffffu), len = (int)(d.x >> 16);
             const uint32_t full = len == 32 ? ~0u : ((1u << len) - 1u);
             T *yb = ybuf + pos;
-            const uint32_t heads = pava_block_runs<T, uint16_t, uint32_t, false>(yb, nullptr, len, full, d.y, false, rcp, kPavaThreadMax + 1);
-            pava_spread(yb, len, heads);
+            uint32_t heads;
+            if (WMEM) {
+                uint16_t *wb = wbuf + pos;
+                uint32_t alive = 0;  // the chain of every block of the row
+                uint32_t bs = d.y;
+                while (bs) {
+                    const int s0 = __ffs((int)bs) - 1;
+                    bs &= bs - 1;
+                    const int e0 = bs ? __ffs((int)bs) - 1 : len;
+                    for (int i = s0; i < e0; i += max(1, (int)wb[i])) alive |= 1u << i;
+                }
+                heads = pava_block_runs<T, uint16_t, uint32_t, true>(yb, wb, len, alive, d.y, true, rcp, kPavaThreadMax + 1);
+            } else {
+                heads = pava_block_runs<T, uint16_t, uint32_t, false>(yb, nullptr, len, full, d.y, false, rcp, kPavaThreadMax + 1);
+            }
+            if (update) pava_spread(yb, len, heads);
             const unsigned long long span = (unsigned long long)full << (pos & 31);
             atomicOr(&cov[pos >> 5], (uint32_t)span);
             if (span >> 32) atomicOr(&cov[(pos >> 5) + 1], (uint32_t)(span >> 32));
@@ -980,35 +1000,42 @@ pava_tile_rows_kernel(T *__restrict__ yg, const int32_t *__restrict__ starts, co
                 T v = ybuf[i];
                 if (CLIP) v = clip01(v);
                 *dst = v;
+                if (WMEM) wg[(size_t)tile_lo + i] = (int32_t)wbuf[i];
             }
         }
         __syncthreads();
     }
 }
 
-template <typename T>
-int launch_pava_tile_rows(T *y, const int32_t *starts, const int32_t *tile_first, int ntiles, int clip, int cap_per_sm, cudaStream_t stream) {
-    if (ntiles <= 0) return BSLS_OK;
-    static thread_local int grid_full[2] = {0, 0};
-    const int c = clip ? 1 : 0;
-    if (!grid_full[c]) {
+template <typename T, bool CLIP, bool WMEM>
+int launch_pava_tile_rows_cfg(T *y, int32_t *w, const int32_t *starts, const int32_t *tile_first, int ntiles, int update, int cap_per_sm,
+                              cudaStream_t stream) {
+    auto k = pava_tile_rows_kernel<T, CLIP, WMEM>;
+    static thread_local int grid_full = 0;
+    if (!grid_full) {
         int dev = 0, num_sm = kNumSM, per_sm = 1;
         BSLS_CUDA_TRY(cudaGetDevice(&dev));
         BSLS_CUDA_TRY(cudaDeviceGetAttribute(&num_sm, cudaDevAttrMultiProcessorCount, dev));
-        if (clip)
-            BSLS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pava_tile_rows_kernel<T, true>, kPavaTileThreads, 0));
-        else
-            BSLS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pava_tile_rows_kernel<T, false>, kPavaTileThreads, 0));
-        grid_full[c] = num_sm * (per_sm < 1 ? 1 : per_sm);
+        BSLS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kPavaTileThreads, 0));
+        grid_full = num_sm * (per_sm < 1 ? 1 : per_sm);
     }
-    int grid = ntiles < grid_full[c] ? ntiles : grid_full[c];
+    int grid = ntiles < grid_full ? ntiles : grid_full;
     if (cap_per_sm > 0 && grid > cap_per_sm * kNumSM) grid = cap_per_sm * kNumSM;
-    if (clip)
-        pava_tile_rows_kernel<T, true><<<grid, kPavaTileThreads, 0, stream>>>(y, starts, tile_first, ntiles);
-    else
-        pava_tile_rows_kernel<T, false><<<grid, kPavaTileThreads, 0, stream>>>(y, starts, tile_first, ntiles);
+    k<<<grid, kPavaTileThreads, 0, stream>>>(y, w, starts, tile_first, ntiles, update);
     BSLS_LAUNCH_CHECK();
     return BSLS_OK;
+}
+
+template <typename T>
+int launch_pava_tile_rows(T *y, int32_t *w, const int32_t *starts, const int32_t *tile_first, int ntiles, int update, int clip, int cap_per_sm,
+                          cudaStream_t stream) {
+    if (ntiles <= 0) return BSLS_OK;
+    if (w) {
+        if (clip) return launch_pava_tile_rows_cfg<T, true, true>(y, w, starts, tile_first, ntiles, update, cap_per_sm, stream);
+        return launch_pava_tile_rows_cfg<T, false, true>(y, w, starts, tile_first, ntiles, update, cap_per_sm, stream);
+    }
+    if (clip) return launch_pava_tile_rows_cfg<T, true, false>(y, w, starts, tile_first, ntiles, update, cap_per_sm, stream);
+    return launch_pava_tile_rows_cfg<T, false, false>(y, w, starts, tile_first, ntiles, update, cap_per_sm, stream);
 }
 
 // Blocks of kPavaThreadMax < K <= kPavaTileMaxBlock: one WARP per block, staged in the warp's own

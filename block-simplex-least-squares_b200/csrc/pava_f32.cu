@@ -29,7 +29,7 @@ int pava_tile_f32(float *y, int32_t *w, const int32_t *starts, const int32_t *ti
     fl.update = update;
     fl.clip01 = clip01;
     fl.has_weight = w != nullptr;
-    if (!w && update && !getenv("BSLS_PAVA_NO_ROWS")) return launch_pava_tile_rows<float>(y, starts, tile_first, ntiles, clip01, cap_per_sm, stream);
+    if (!getenv("BSLS_PAVA_NO_ROWS")) return launch_pava_tile_rows<float>(y, w, starts, tile_first, ntiles, update, clip01, cap_per_sm, stream);
     return launch_pava_tile<float>(y, w, starts, tile_first, ntiles, fl, stream);
 }
 
@@ -41,14 +41,15 @@ int pava_mid_f32(float *y, int32_t *w, const int32_t *starts, const int32_t *mid
     return launch_pava_mid<float>(y, w, starts, mid_ids, nmid, fl, stream);
 }
 
-int pava_words_f32(float *y, const int32_t *starts, const int32_t *ids, const int32_t *pack_first, int npacks, long long first, int nb,
-                   int Kuni, int clip01, int cap_per_sm, cudaStream_t stream) {
+int pava_words_f32(float *y, int32_t *w, const int32_t *starts, const int32_t *ids, const int32_t *pack_first, int npacks, long long first, int nb,
+                   int Kuni, int update, int clip01, int cap_per_sm, cudaStream_t stream) {
     static_assert(kWordsMaxBlock == kPlanWordsMax, "plan constants");
-    return launch_pava_words<float>(y, starts, ids, pack_first, npacks, first, nb, Kuni, clip01, cap_per_sm, stream);
+    return launch_pava_words<float>(y, w, starts, ids, pack_first, npacks, first, nb, Kuni, update, clip01, cap_per_sm, stream);
 }
 
-int pava_words_cta_f32(float *y, const int32_t *starts, const int32_t *ids, int count, int max_block, int clip01, int cap_per_sm, cudaStream_t stream) {
+int pava_words_cta_f32(float *y, int32_t *w, const int32_t *starts, const int32_t *ids, int count, int max_block, int update, int clip01, int cap_per_sm,
+                       cudaStream_t stream) {
     static_assert(32 * kWordsCtaThreads == kPlanPavaLargeMax, "plan constants");
-    return launch_pava_words_cta<float>(y, starts, ids, count, max_block, clip01, cap_per_sm, stream);
+    return launch_pava_words_cta<float>(y, w, starts, ids, count, max_block, update, clip01, cap_per_sm, stream);
 }
 }  // namespace bsls
