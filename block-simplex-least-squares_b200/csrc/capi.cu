@@ -49,31 +49,6 @@ int device_ok() {
 using namespace bsls;
 
 
-// Window / long-block lists for the isotonic-regression kernels; built once, on first use.
-static int plan_ensure_pava(bsls_plan *p, cudaStream_t stream) {
-    if (p->pava_ready) return BSLS_OK;
-    p->pava_windows = (int)(((long long)p->n - p->first + kPlanPavaPitch - 1) / kPlanPavaPitch);
-    BSLS_CUDA_TRY(cudaMalloc(&p->d_pava_first, sizeof(int32_t) * ((size_t)p->pava_windows + 1)));
-    if (int rc = plan_tile_first(p->d_starts, p->nb, p->first, kPlanPavaPitch, p->d_pava_first, p->pava_windows, stream)) return rc;
-    if (p->max_size > kPlanPavaWarpMax) {
-        int *d_count = nullptr;
-        int h_count = 0;
-        BSLS_CUDA_TRY(cudaMalloc(&d_count, sizeof(int)));
-        BSLS_CUDA_TRY(cudaMemsetAsync(d_count, 0, sizeof(int), stream));
-        if (int rc = plan_large_list(p->d_starts, p->nb, kPlanPavaWarpMax, nullptr, d_count, stream)) return rc;
-        BSLS_CUDA_TRY(cudaMemcpyAsync(&h_count, d_count, sizeof(int), cudaMemcpyDeviceToHost, stream));
-        BSLS_CUDA_TRY(cudaStreamSynchronize(stream));
-        BSLS_CUDA_TRY(cudaMalloc(&p->d_pava_large, sizeof(int32_t) * (size_t)h_count));
-        BSLS_CUDA_TRY(cudaMemsetAsync(d_count, 0, sizeof(int), stream));
-        if (int rc = plan_large_list(p->d_starts, p->nb, kPlanPavaWarpMax, p->d_pava_large, d_count, stream)) return rc;
-        BSLS_CUDA_TRY(cudaStreamSynchronize(stream));
-        cudaFree(d_count);
-        p->pava_large = h_count;
-    }
-    p->pava_ready = true;
-    return BSLS_OK;
-}
-
 static int ensure_streams(bsls_plan *plan);
 
 template <typename T>
@@ -88,14 +63,12 @@ static int dev_pava(const bsls_plan *plan_, T *y, int32_t *weight, int update, i
         set_error("isotonic regression: a block of %d entries exceeds the %d-entry limit of this revision", plan->max_size, kPlanPavaLargeMax);
         return BSLS_ERR_ARG;
     }
-    const bool cold = weight == nullptr && update != 0;  // the configuration of main.py:64
-    const bool words_off = getenv("BSLS_PAVA_NO_WORDS") != nullptr;  // A/B switch for measurements
     static const int words_min = [] {  // smallest uniform block size the word-per-lane kernel takes (BSLS_PAVA_WORDS_MIN: experiments)
         const char *e = getenv("BSLS_PAVA_WORDS_MIN");
         const int v = e ? atoi(e) : 0;
         return v > 32 ? v : kPlanPavaSmallMax + 1;
     }();
-    if (!words_off && plan->uniform >= words_min && plan->uniform <= kPlanWordsMax) {
+    if (plan->uniform >= words_min && plan->uniform <= kPlanWordsMax) {  // packs of blocks per warp
         const int bpp = 32 / ((plan->uniform + 31) >> 5);
         const int npacks = (plan->nb + bpp - 1) / bpp;
         if constexpr (sizeof(T) == 8)
@@ -103,98 +76,66 @@ static int dev_pava(const bsls_plan *plan_, T *y, int32_t *weight, int update, i
         else
             return pava_words_f32((float *)y, weight, nullptr, nullptr, nullptr, npacks, plan->first, plan->nb, plan->uniform, update, clip01, 0, stream);
     }
+    if (plan->uniform > kPlanWordsMax) {  // one CTA per block
+        if constexpr (sizeof(T) == 8)
+            return pava_words_cta_f64((double *)y, weight, plan->d_starts, nullptr, plan->nb, plan->max_size, update, clip01, 0, stream);
+        else
+            return pava_words_cta_f32((float *)y, weight, plan->d_starts, nullptr, plan->nb, plan->max_size, update, clip01, 0, stream);
+    }
     if (plan->uniform > 0 && plan->uniform <= kPlanPavaSmallMax) {
         if constexpr (sizeof(T) == 8)
             return pava_small_f64((double *)y, weight, plan->first, plan->nb, plan->uniform, update, clip01, stream);
         else
             return pava_small_f32((float *)y, weight, plan->first, plan->nb, plan->uniform, update, clip01, stream);
     }
-    if (plan->ragged) {
-        // tile grid of the projection: blocks of at most kPlanMidMin values by one thread each inside
-        // tiles, up to kPlanTileMaxBlock by one warp each (d_mid_ids), longer ones by one CTA each
-        // (d_large_ids).  The three kernels own disjoint blocks: fork onto two auxiliary streams, join.
-        if (int rc = ensure_streams(plan)) return rc;
-        BSLS_CUDA_TRY(cudaEventRecord(plan->ev_fork, stream));
-        int rc = BSLS_OK;
-        // Grids of the three cold-start kernels are capped so that all of them are resident side by side
-        // (persistent grids that each fill the GPU would run one after the other): CTAs per SM.
-        int cap_tile = 0, cap_words = 0, cap_cta = 0;
-        if (cold && !words_off) {
-            cap_tile = 0, cap_words = 0, cap_cta = 0;  // measured on C3: uncapped grids (kernels mostly back to back) beat any split tried (tools/c3_caps.py)
-            if (const char *c = getenv("BSLS_PAVA_CAPS")) sscanf(c, "%d,%d,%d", &cap_tile, &cap_words, &cap_cta);
-        }
-        auto launch_mid = [&]() -> int {
-            int rc = BSLS_OK;
-            if (plan->mid > 0 && !words_off) {
-                if (plan->mid_packs < 0) {  // pack the mid list once
-                    int *d_np = nullptr, h_np = 0;
-                    BSLS_CUDA_TRY(cudaMalloc(&d_np, sizeof(int)));
-                    BSLS_CUDA_TRY(cudaMalloc(&plan->d_mid_pack, sizeof(int32_t) * ((size_t)plan->mid + 1)));
-                    if (int rc2 = plan_pack_words(plan->d_starts, plan->d_mid_ids, plan->mid, plan->d_mid_pack, d_np, stream)) return rc2;
-                    BSLS_CUDA_TRY(cudaMemcpyAsync(&h_np, d_np, sizeof(int), cudaMemcpyDeviceToHost, stream));
-                    BSLS_CUDA_TRY(cudaStreamSynchronize(stream));
-                    cudaFree(d_np);
-                    plan->mid_packs = h_np;
-                    BSLS_CUDA_TRY(cudaEventRecord(plan->ev_fork, stream));
-                }
-                BSLS_CUDA_TRY(cudaStreamWaitEvent(plan->aux[0], plan->ev_fork, 0));
-                if constexpr (sizeof(T) == 8)
-                    rc = pava_words_f64((double *)y, weight, plan->d_starts, plan->d_mid_ids, plan->d_mid_pack, plan->mid_packs, 0, plan->nb, 0, update, clip01, cap_words, plan->aux[0]);
-                else
-                    rc = pava_words_f32((float *)y, weight, plan->d_starts, plan->d_mid_ids, plan->d_mid_pack, plan->mid_packs, 0, plan->nb, 0, update, clip01, cap_words, plan->aux[0]);
-                if (rc) return rc;
-                BSLS_CUDA_TRY(cudaEventRecord(plan->ev_join[0], plan->aux[0]));
-            } else if (plan->mid > 0) {
-                BSLS_CUDA_TRY(cudaStreamWaitEvent(plan->aux[0], plan->ev_fork, 0));
-                if constexpr (sizeof(T) == 8)
-                    rc = pava_mid_f64((double *)y, weight, plan->d_starts, plan->d_mid_ids, plan->mid, update, clip01, plan->aux[0]);
-                else
-                    rc = pava_mid_f32((float *)y, weight, plan->d_starts, plan->d_mid_ids, plan->mid, update, clip01, plan->aux[0]);
-                if (rc) return rc;
-                BSLS_CUDA_TRY(cudaEventRecord(plan->ev_join[0], plan->aux[0]));
-            }
-            return rc;
-        };
-        auto launch_large = [&]() -> int {
-            int rc = BSLS_OK;
-            if (plan->large > 0 && !words_off) {
-                BSLS_CUDA_TRY(cudaStreamWaitEvent(plan->aux[1], plan->ev_fork, 0));
-                if constexpr (sizeof(T) == 8)
-                    rc = pava_words_cta_f64((double *)y, weight, plan->d_starts, plan->d_large_ids, plan->large, plan->max_size, update, clip01, cap_cta, plan->aux[1]);
-                else
-                    rc = pava_words_cta_f32((float *)y, weight, plan->d_starts, plan->d_large_ids, plan->large, plan->max_size, update, clip01, cap_cta, plan->aux[1]);
-                if (rc) return rc;
-                BSLS_CUDA_TRY(cudaEventRecord(plan->ev_join[1], plan->aux[1]));
-            } else if (plan->large > 0) {
-                BSLS_CUDA_TRY(cudaStreamWaitEvent(plan->aux[1], plan->ev_fork, 0));
-                if constexpr (sizeof(T) == 8)
-                    rc = pava_f64((double *)y, weight, plan->d_starts, nullptr, 0, plan->d_large_ids, plan->large, plan->max_size, update, clip01, plan->aux[1]);
-                else
-                    rc = pava_f32((float *)y, weight, plan->d_starts, nullptr, 0, plan->d_large_ids, plan->large, plan->max_size, update, clip01, plan->aux[1]);
-                if (rc) return rc;
-                BSLS_CUDA_TRY(cudaEventRecord(plan->ev_join[1], plan->aux[1]));
-            }
-            return rc;
-        };
-        // the long blocks first: few CTAs with a long critical path each, the grids that fill the GPU queue behind them
-        if (int rcl = launch_large()) return rcl;
-        if (int rcm = launch_mid()) return rcm;
-        if constexpr (sizeof(T) == 8)
-            rc = pava_tile_f64((double *)y, weight, plan->d_starts, plan->d_tile_first, plan->tiles, update, clip01, cap_tile, stream);
-        else
-            rc = pava_tile_f32((float *)y, weight, plan->d_starts, plan->d_tile_first, plan->tiles, update, clip01, cap_tile, stream);
-        if (rc) return rc;
-        if (plan->mid > 0) BSLS_CUDA_TRY(cudaStreamWaitEvent(stream, plan->ev_join[0], 0));
-        if (plan->large > 0) BSLS_CUDA_TRY(cudaStreamWaitEvent(stream, plan->ev_join[1], 0));
-        return BSLS_OK;
+    // Ragged layout, on the tile grid of the projection: blocks of at most kPlanMidMin entries as rows inside tiles
+    // (pava_tile_rows_kernel), up to kPlanTileMaxBlock in packs per warp (d_mid_ids -> pava_words_kernel), longer ones
+    // by one CTA each (d_large_ids -> pava_words_cta_kernel).  The three kernels own disjoint blocks: fork onto two
+    // auxiliary streams, join.
+    if (int rc = ensure_streams(plan)) return rc;
+    if (plan->mid > 0 && plan->mid_packs < 0) {  // pack the mid list once per layout
+        int *d_np = nullptr, h_np = 0;
+        BSLS_CUDA_TRY(cudaMalloc(&d_np, sizeof(int)));
+        BSLS_CUDA_TRY(cudaMalloc(&plan->d_mid_pack, sizeof(int32_t) * ((size_t)plan->mid + 1)));
+        if (int rc = plan_pack_words(plan->d_starts, plan->d_mid_ids, plan->mid, plan->d_mid_pack, d_np, stream)) return rc;
+        BSLS_CUDA_TRY(cudaMemcpyAsync(&h_np, d_np, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        BSLS_CUDA_TRY(cudaStreamSynchronize(stream));
+        cudaFree(d_np);
+        plan->mid_packs = h_np;
     }
-    if (int rc = plan_ensure_pava(plan, stream)) return rc;
+    BSLS_CUDA_TRY(cudaEventRecord(plan->ev_fork, stream));
+    // CTAs per SM of the (tile, words, cta) grids: 0 = as many as fit.  Capping them so that the three kernels are
+    // resident side by side measured slower on C3 than letting each fill the GPU (tools/c3_caps.py); BSLS_PAVA_CAPS
+    // is kept for that experiment.
+    int cap_tile = 0, cap_words = 0, cap_cta = 0;
+    if (const char *e = getenv("BSLS_PAVA_CAPS")) sscanf(e, "%d,%d,%d", &cap_tile, &cap_words, &cap_cta);
+    int rc = BSLS_OK;
+    if (plan->large > 0) {  // the long blocks first: few CTAs with a long critical path each
+        BSLS_CUDA_TRY(cudaStreamWaitEvent(plan->aux[1], plan->ev_fork, 0));
+        if constexpr (sizeof(T) == 8)
+            rc = pava_words_cta_f64((double *)y, weight, plan->d_starts, plan->d_large_ids, plan->large, plan->max_size, update, clip01, cap_cta, plan->aux[1]);
+        else
+            rc = pava_words_cta_f32((float *)y, weight, plan->d_starts, plan->d_large_ids, plan->large, plan->max_size, update, clip01, cap_cta, plan->aux[1]);
+        if (rc) return rc;
+        BSLS_CUDA_TRY(cudaEventRecord(plan->ev_join[1], plan->aux[1]));
+    }
+    if (plan->mid > 0) {
+        BSLS_CUDA_TRY(cudaStreamWaitEvent(plan->aux[0], plan->ev_fork, 0));
+        if constexpr (sizeof(T) == 8)
+            rc = pava_words_f64((double *)y, weight, plan->d_starts, plan->d_mid_ids, plan->d_mid_pack, plan->mid_packs, 0, plan->nb, 0, update, clip01, cap_words, plan->aux[0]);
+        else
+            rc = pava_words_f32((float *)y, weight, plan->d_starts, plan->d_mid_ids, plan->d_mid_pack, plan->mid_packs, 0, plan->nb, 0, update, clip01, cap_words, plan->aux[0]);
+        if (rc) return rc;
+        BSLS_CUDA_TRY(cudaEventRecord(plan->ev_join[0], plan->aux[0]));
+    }
     if constexpr (sizeof(T) == 8)
-        return pava_f64((double *)y, weight, plan->d_starts, plan->d_pava_first, plan->pava_windows, plan->d_pava_large,
-                        plan->pava_large, plan->max_size, update, clip01, stream);
+        rc = pava_tile_f64((double *)y, weight, plan->d_starts, plan->d_tile_first, plan->tiles, update, clip01, cap_tile, stream);
     else
-        return pava_f32((float *)y, weight, plan->d_starts, plan->d_pava_first, plan->pava_windows, plan->d_pava_large,
-                        plan->pava_large, plan->max_size, update, clip01, stream);
+        rc = pava_tile_f32((float *)y, weight, plan->d_starts, plan->d_tile_first, plan->tiles, update, clip01, cap_tile, stream);
+    if (rc) return rc;
+    if (plan->mid > 0) BSLS_CUDA_TRY(cudaStreamWaitEvent(stream, plan->ev_join[0], 0));
+    if (plan->large > 0) BSLS_CUDA_TRY(cudaStreamWaitEvent(stream, plan->ev_join[1], 0));
+    return BSLS_OK;
 }
 
 // ------------------------------------------------------------------------------------
@@ -609,8 +550,6 @@ int bsls_plan_destroy(bsls_plan *plan) {
     if (plan->d_starts) cudaFree(plan->d_starts);
     if (plan->d_tile_first) cudaFree(plan->d_tile_first);
     if (plan->d_large_ids) cudaFree(plan->d_large_ids);
-    if (plan->d_pava_first) cudaFree(plan->d_pava_first);
-    if (plan->d_pava_large) cudaFree(plan->d_pava_large);
     if (plan->d_mid_pack) cudaFree(plan->d_mid_pack);
     if (plan->d_slow) cudaFree(plan->d_slow);
     if (plan->d_huge) cudaFree(plan->d_huge);

@@ -39,29 +39,18 @@ constexpr int kPlanMidMin = 32;           // ragged layouts: blocks of kPlanMidM
 constexpr int kPlanTileElems = 2048;      // == kTileElems (proj_ragged.cuh)
 constexpr int kPlanTileMaxBlock = 512;    // == kTileMaxBlock
 constexpr int kPlanLargeMaxBlock = 8192;  // == kLargeMaxBlock
-constexpr int kPlanPavaPitch = 256;       // == kPavaPitch (pava.cuh)
-constexpr int kPlanPavaWarpMax = 256;     // == kPavaWarpMaxBlock
-constexpr int kPlanPavaLargeMax = 8192;   // == kPavaLargeMaxBlock
+constexpr int kPlanPavaLargeMax = 8192;   // == kPavaLargeMaxBlock: longest block the isotonic regression takes
 
-// pava_f64.cu / pava_f32.cu: segmented isotonic regression (pava.cuh)
-int pava_f64(double *y, int32_t *w, const int32_t *starts, const int32_t *win_first, int nwin, const int32_t *large_ids,
-             int nlarge, int max_large, int update, int clip01, cudaStream_t stream);
-// uniform layouts with K <= kPlanPavaSmallMax: one thread per block
+// pava_f64.cu / pava_f32.cu: segmented isotonic regression (pava.cuh, pava_words.cuh).  w: weight array (in / out) or nullptr.
+// uniform layouts with K <= kPlanPavaSmallMax: one thread per row of blocks
 constexpr int kPlanPavaSmallMax = 64;
 int pava_small_f64(double *y, int32_t *w, long long first, int nb, int K, int update, int clip01, cudaStream_t stream);
 int pava_small_f32(float *y, int32_t *w, long long first, int nb, int K, int update, int clip01, cudaStream_t stream);
-int pava_f32(float *y, int32_t *w, const int32_t *starts, const int32_t *win_first, int nwin, const int32_t *large_ids,
-             int nlarge, int max_large, int update, int clip01, cudaStream_t stream);
-
-// ragged layouts: tiles of whole blocks (thread / warp per block); longer blocks go to pava_f64 with nwin = 0
+// ragged layouts: tiles of whole blocks of at most kPlanMidMin entries; longer ones go to the two kernels below
 int pava_tile_f64(double *y, int32_t *w, const int32_t *starts, const int32_t *tile_first, int ntiles, int update, int clip01,
                   int cap_per_sm, cudaStream_t stream);
 int pava_tile_f32(float *y, int32_t *w, const int32_t *starts, const int32_t *tile_first, int ntiles, int update, int clip01,
                   int cap_per_sm, cudaStream_t stream);
-// blocks of kPlanMidMin < size <= kPlanTileMaxBlock: one warp each
-int pava_mid_f64(double *y, int32_t *w, const int32_t *starts, const int32_t *mid_ids, int nmid, int update, int clip01, cudaStream_t stream);
-int pava_mid_f32(float *y, int32_t *w, const int32_t *starts, const int32_t *mid_ids, int nmid, int update, int clip01, cudaStream_t stream);
-
 // blocks of 33 .. kPlanWordsMax entries, cold start: one lane per 32-entry word, packs of blocks per warp (pava_words.cuh).
 // ragged: ids / pack_first from plan_pack_words, first = 0; uniform: starts = ids = pack_first = nullptr.
 constexpr int kPlanWordsMax = 1024;
@@ -92,11 +81,6 @@ struct bsls_plan {
     int32_t *d_tile_first = nullptr;  // tiles + 1 entries
     int32_t *d_large_ids = nullptr;   // `large` block indices (size > kPlanTileMaxBlock)
     bool ragged = false;
-    // isotonic-regression windows (built on first use, any layout)
-    bool pava_ready = false;
-    int pava_windows = 0, pava_large = 0;
-    int32_t *d_pava_first = nullptr;  // pava_windows + 1 entries
-    int32_t *d_pava_large = nullptr;  // blocks longer than kPlanPavaWarpMax
     int mid = 0;
     int32_t *d_mid_ids = nullptr;     // ragged: blocks with kPlanMidMin < size <= kPlanTileMaxBlock
     int mid_packs = -1;               // packs of the mid list for pava_words (built on first use)

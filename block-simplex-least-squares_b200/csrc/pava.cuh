@@ -4,21 +4,21 @@
 // hot path binds (python/c_extensions/isotonic_regression.h:13-58,85-92; called from
 // python/main.py:64 and through python/c_extensions/c_extensions.pyx:63-89).
 //
-// The reference sweeps each block until nothing pools.  In one sweep it walks the pool
-// heads, groups them into maximal runs in which each head is <= its predecessor, and
-// replaces a run whose first and last value differ by the size-weighted mean, summed left
-// to right (:23-44).  Decisions inside a sweep only read values that the sweep has not
-// touched yet, so ALL runs of a sweep -- and all blocks -- can be processed at once:
-//   A  flag run starts   (head j starts a run if it opens a block or y[j] > y[j-1])
-//   B  every run start walks its run and merges it exactly as the reference does
-//      (same products, same left-to-right sum, same division)
-//   C  compact the list of surviving heads (ballot + popc)
-// until a sweep merges nothing.  The arrays y[] and weight[] are the reference's own
-// representation (value / pool size stored at the head, stale entries elsewhere), so the
-// result -- values, pool sizes and even the stale interior entries -- is bit-identical.
+// The reference sweeps each block until nothing pools.  In one sweep it walks the pool heads,
+// groups them into maximal runs in which each head is <= its predecessor, and replaces a run
+// whose first and last value differ by the size-weighted mean, summed left to right (:23-44).
+// Decisions inside a sweep only read values the sweep has not touched yet, so the runs of a
+// sweep are independent, and only runs with followers ever change anything.  The kernels keep
+// the pool heads and the run-start decisions of a block as BIT MASKS and replay exactly those
+// runs (pava_block_runs below; pava_words.cuh spreads the masks over lanes for long blocks).
+// The arrays y[] and weight[] are the reference's own representation (value / pool size
+// stored at the head, stale entries elsewhere), so the result -- values, pool sizes and even
+// the stale interior entries -- is bit-identical.
 //
-// Small blocks (<= kPavaWarpMaxBlock): one WARP owns a window of whole blocks in shared
-// memory and needs no block-wide barrier.  Longer blocks: one CTA per block.
+//   uniform layouts, K <= 64      pava_small_kernel        one thread per row of 1..16 blocks
+//   ragged layouts, blocks <= 32  pava_tile_rows_kernel    rows found from a block-start bitmap
+//   blocks of 33 .. 1024          pava_words_kernel        one lane per 32-entry word, packs per warp
+//   blocks up to 8192             pava_words_cta_kernel    one CTA per block
 #pragma once
 #include <math.h>
 #include <stdio.h>
@@ -29,12 +29,7 @@
 
 namespace bsls {
 
-constexpr int kPavaPitch = 256;          // warp-window pitch (elements)
-constexpr int kPavaWarpMaxBlock = 256;   // longest block a warp window takes
-constexpr int kPavaWindow = kPavaPitch + kPavaWarpMaxBlock;
-constexpr int kPavaWarpsPerCta = 4;     // 4 x 7.5 KB of static shared memory per CTA
-constexpr int kPavaLargeMaxBlock = 8192; // longest block the one-CTA kernel takes
-constexpr int kPavaLargeThreads = 512;
+constexpr int kPavaLargeMaxBlock = 8192; // longest block (one CTA, pava_words.cuh)
 
 struct PavaFlags {
     int update;      // copy the head value over its pool at the end (reference `update`)
@@ -42,43 +37,11 @@ struct PavaFlags {
     int has_weight;  // weight array given (in/out); otherwise all ones in, result dropped
 };
 
-__device__ __forceinline__ void cp_async_8(void *dst_smem, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 template <typename T> __device__ __forceinline__ T clip01(T v) {
     v = (v > T(0)) ? v : T(0);  // np.maximum(0., x)
     v = (v < T(1)) ? v : T(1);  // np.minimum(1., x)
     return v;
-}
-
-// One run start: walk the run, merge it if first != last (isotonic_regression.h:23-44).
-// Returns true when it merged.  F[q] == 0 marks followers; merged followers get F = 2.
-template <typename T, typename W>
-__device__ __forceinline__ bool pava_merge_run(T *y, W *w, const uint16_t *A, uint8_t *F, int j, int P) {
-    const int p0 = A[j] & 0x7fff;
-    const T first = y[p0];
-    int den = (int)w[p0];
-    T num = T(0) + first * (T)den;
-    T last = first;
-    int q = j + 1;
-    while (q < P && F[q] == 0) {
-        const int pq = A[q] & 0x7fff;
-        const T vq = y[pq];
-        const int wq = (int)w[pq];
-        num += vq * (T)wq;  // -fmad=false: product and sum round separately, as on the host
-        den += wq;
-        last = vq;
-        ++q;
-    }
-    if (q > j + 1 && first != last) {
-        y[p0] = num / (T)den;
-        w[p0] = (W)den;
-        for (int r = j + 1; r < q; ++r) F[r] = 2;
-        return true;
-    }
-    return false;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -587,133 +550,6 @@ template <typename T> int launch_pava_small(T *y, int32_t *w, long long first, i
 }
 
 // ---------------------------------------------------------------------------------------------
-// warp windows
-// ---------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(kPavaWarpsPerCta * 32)
-pava_warp_kernel(T *__restrict__ yg, int32_t *__restrict__ wg, const int32_t *__restrict__ starts /* nb+1 */,
-                 const int32_t *__restrict__ win_first /* nwin+1 */, int nwin, PavaFlags fl) {
-    __shared__ __align__(16) T ys[kPavaWarpsPerCta][kPavaWindow];
-    __shared__ uint16_t ws[kPavaWarpsPerCta][kPavaWindow];
-    __shared__ uint16_t la[kPavaWarpsPerCta][kPavaWindow];
-    __shared__ uint16_t lb[kPavaWarpsPerCta][kPavaWindow];
-    __shared__ uint8_t fs[kPavaWarpsPerCta][kPavaWindow];
-
-    const int lane = threadIdx.x & 31;
-    const int wid = threadIdx.x >> 5;
-    T *y = ys[wid];
-    uint16_t *w = ws[wid];
-    uint8_t *F = fs[wid];
-    const unsigned lt_mask = (1u << lane) - 1u;
-
-    for (int win = blockIdx.x * kPavaWarpsPerCta + wid; win < nwin; win += gridDim.x * kPavaWarpsPerCta) {
-        const int fb = win_first[win];
-        const int nblk = win_first[win + 1] - fb;
-        if (nblk <= 0) continue;
-        const int lo = starts[fb];
-        int hi = starts[fb + nblk];
-        int nsmall = nblk;
-        if (hi - starts[fb + nblk - 1] > kPavaWarpMaxBlock) {  // a long block can only be the last one
-            hi = starts[fb + nblk - 1];
-            nsmall = nblk - 1;
-        }
-        const int nel = hi - lo;
-        if (nel <= 0) continue;
-        uint16_t *A = la[wid], *B = lb[wid];
-        // ---- load the window: values (async copies), weights, head list ---------------------
-        for (int i = lane; i < nel; i += 32) {
-            cp_async_8(&y[i], yg + (size_t)lo + i);
-            w[i] = fl.has_weight ? (uint16_t)wg[(size_t)lo + i] : (uint16_t)1;
-            A[i] = (uint16_t)i;
-        }
-        __syncwarp();
-        for (int b = lane; b < nsmall; b += 32) A[starts[fb + b] - lo] |= 0x8000;  // block openers
-        cp_async_wait_all();
-        __syncwarp();
-        int P = nel;
-        if (fl.has_weight) {
-            // warm start: the heads are the entries reached by i += weight[i] (isotonic_regression.h:22)
-            // -> rebuild the list serially per block (rare path)
-            for (int i = lane; i < nel; i += 32) F[i] = 0;
-            __syncwarp();
-            for (int b = lane; b < nsmall; b += 32) {
-                const int s = starts[fb + b] - lo, e = starts[fb + b + 1] - lo;
-                for (int i = s; i < e; i += max(1, (int)w[i])) F[i] = 1;
-            }
-            __syncwarp();
-            int np = 0;
-            for (int base = 0; base < nel; base += 32) {
-                const int i = base + lane;
-                const bool head = i < nel && F[i];
-                const unsigned m = __ballot_sync(0xffffffffu, head);
-                if (head) B[np + __popc(m & lt_mask)] = A[i];
-                np += __popc(m);
-            }
-            __syncwarp();
-            uint16_t *t = A;
-            A = B;
-            B = t;
-            P = np;
-        }
-        // ---- sweeps -------------------------------------------------------------------------------
-        for (;;) {
-            for (int base = 0; base < P; base += 32) {  // A: run starts
-                const int j = base + lane;
-                if (j < P) {
-                    const int e = A[j];
-                    bool st = (e & 0x8000) || j == 0;
-                    if (!st) st = y[e & 0x7fff] > y[A[j - 1] & 0x7fff];
-                    F[j] = st ? 1 : 0;
-                }
-            }
-            __syncwarp();
-            bool merged = false;
-            for (int base = 0; base < P; base += 32) {  // B: merge runs
-                const int j = base + lane;
-                if (j < P && F[j] == 1) merged |= pava_merge_run<T, uint16_t>(y, w, A, F, j, P);
-            }
-            merged = __any_sync(0xffffffffu, merged);
-            __syncwarp();
-            if (!merged) break;
-            int np = 0;
-            for (int base = 0; base < P; base += 32) {  // C: compact the survivors
-                const int j = base + lane;
-                const bool alive = j < P && F[j] != 2;
-                const unsigned m = __ballot_sync(0xffffffffu, alive);
-                if (alive) B[np + __popc(m & lt_mask)] = A[j];
-                np += __popc(m);
-            }
-            __syncwarp();
-            uint16_t *t = A;
-            A = B;
-            B = t;
-            P = np;
-        }
-        // ---- spread head values over their pools (isotonic_regression.h:50-57) -----------------
-        if (fl.update) {
-            for (int base = 0; base < P; base += 32) {
-                const int j = base + lane;
-                if (j < P) {
-                    const int p = A[j] & 0x7fff;
-                    const T v = y[p];
-                    const int stop = p + (int)w[p];
-                    for (int r = p + 1; r < stop; ++r) y[r] = v;
-                }
-            }
-            __syncwarp();
-        }
-        // ---- store ----------------------------------------------------------------------------------
-        for (int i = lane; i < nel; i += 32) {
-            T v = y[i];
-            if (fl.clip01) v = clip01(v);
-            yg[(size_t)lo + i] = v;
-            if (fl.has_weight) wg[(size_t)lo + i] = (int32_t)w[i];
-        }
-        __syncwarp();
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
 // ragged layouts: tiles of whole blocks (the projection's tile grid, plan.cu)
 // ---------------------------------------------------------------------------------------------
 constexpr int kPavaTileElems = 2048;     // == kPlanTileElems
@@ -721,161 +557,7 @@ constexpr int kPavaTileMaxBlock = 512;   // == kPlanTileMaxBlock
 constexpr int kPavaTileThreads = 128;
 constexpr int kPavaThreadMax = 32;       // longest block one thread takes in a tile (== kPlanMidMin)
 
-// One WARP regresses one block of K <= kPavaTileMaxBlock values held in shared memory: the
-// parallel replay of the reference's sweeps (flag run starts, merge runs, compact heads).
-// A / B: head lists (K entries each), F: flags (K entries) -- scratch owned by the warp.
-template <typename T>
-__device__ __forceinline__ void pava_warp_block(T *y, uint16_t *w, int K, int lane, uint16_t *A, uint16_t *B, uint8_t *F,
-                                                bool warm, int update) {
-    const unsigned lt_mask = (1u << lane) - 1u;
-    int P = K;
-    if (!warm) {
-        for (int i = lane; i < K; i += 32) A[i] = (uint16_t)i;
-        __syncwarp();
-    } else {  // heads are reached by i += weight[i] (isotonic_regression.h:22): serial, rare
-        if (lane == 0) {
-            int np = 0;
-            for (int i = 0; i < K; i += max(1, (int)w[i])) A[np++] = (uint16_t)i;
-            B[0] = (uint16_t)np;
-        }
-        __syncwarp();
-        P = B[0];
-        __syncwarp();
-    }
-    for (;;) {
-        for (int base = 0; base < P; base += 32) {  // run starts
-            const int j = base + lane;
-            if (j < P) F[j] = (j == 0 || y[A[j]] > y[A[j - 1]]) ? 1 : 0;
-        }
-        __syncwarp();
-        bool merged = false;
-        for (int base = 0; base < P; base += 32) {  // merge runs
-            const int j = base + lane;
-            if (j < P && F[j] == 1) merged |= pava_merge_run<T, uint16_t>(y, w, A, F, j, P);
-        }
-        merged = __any_sync(0xffffffffu, merged);
-        __syncwarp();
-        if (!merged) break;
-        int np = 0;
-        for (int base = 0; base < P; base += 32) {  // compact the survivors
-            const int j = base + lane;
-            const bool alive = j < P && F[j] != 2;
-            const unsigned m = __ballot_sync(0xffffffffu, alive);
-            if (alive) B[np + __popc(m & lt_mask)] = A[j];
-            np += __popc(m);
-        }
-        __syncwarp();
-        uint16_t *t = A;
-        A = B;
-        B = t;
-        P = np;
-    }
-    if (update) {
-        for (int base = 0; base < P; base += 32) {
-            const int j = base + lane;
-            if (j < P) {
-                const int p = A[j];
-                const T v = y[p];
-                const int stop = p + (int)w[p];
-                for (int r = p + 1; r < stop; ++r) y[r] = v;
-            }
-        }
-    }
-    __syncwarp();
-}
-
-// tile_first[t] = index of the first block whose start lies in tile t (tile_first[ntiles] = nb).
-// Blocks longer than kPavaTileMaxBlock are left to pava_large_kernel.
-template <typename T>
-__global__ void __launch_bounds__(kPavaTileThreads)
-pava_tile_kernel(T *__restrict__ yg, int32_t *__restrict__ wg, const int32_t *__restrict__ starts,
-                 const int32_t *__restrict__ tile_first, int ntiles, PavaFlags fl) {
-    constexpr int WIN = kPavaTileElems + kPavaTileMaxBlock;
-    __shared__ __align__(16) T ybuf[WIN];
-    __shared__ uint16_t wbuf[WIN];
-    __shared__ uint16_t sstart[kPavaTileElems + 2];
-    __shared__ uint16_t list[kPavaTileElems];
-    __shared__ uint8_t skip[WIN];  // 1: element of a block another kernel owns (not written back)
-    constexpr int NC = 6;  // size classes of the thread path: <=1, 2, <=4, <=8, <=16, <=32
-    __shared__ int cnt[NC], off[NC + 1], fill[NC];
-    __shared__ T rcp[kPavaThreadMax + 1];
-    for (int i = threadIdx.x + 1; i <= kPavaThreadMax; i += kPavaTileThreads) rcp[i] = T(1) / (T)i;
-    auto cls = [](int K) { return K <= 1 ? 0 : 32 - __clz(K - 1); };  // ceil(log2 K) + (K > 1)
-
-    const int tid = threadIdx.x;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int fb = tile_first[tile];
-        const int nblk = tile_first[tile + 1] - fb;
-        if (nblk <= 0) continue;
-        if (tid < NC) {
-            cnt[tid] = 0;
-            fill[tid] = 0;
-        }
-        const int tile_lo = starts[fb];
-        for (int i = tid; i <= nblk; i += kPavaTileThreads) sstart[i] = (uint16_t)min(starts[fb + i] - tile_lo, 65535);
-        __syncthreads();
-        int nel = sstart[nblk];
-        if (nel - sstart[nblk - 1] > kPavaTileMaxBlock) nel = sstart[nblk - 1];
-        for (int i = tid; i < nel; i += kPavaTileThreads) {
-            ybuf[i] = yg[(size_t)tile_lo + i];
-            wbuf[i] = fl.has_weight ? (uint16_t)wg[(size_t)tile_lo + i] : (uint16_t)1;
-            skip[i] = 0;
-        }
-        __syncthreads();
-        // work lists: short blocks binned by size class (lanes of a warp then do similar work) from the
-        // front of list[], longer ones from its back
-        for (int i = tid; i < nblk; i += kPavaTileThreads) {
-            const int K = sstart[i + 1] - sstart[i];
-            if (K <= kPavaThreadMax) atomicAdd(&cnt[cls(K)], 1);
-        }
-        __syncthreads();
-        if (tid == 0) {
-            int acc = 0;
-            for (int c = 0; c < NC; ++c) {
-                off[c] = acc;
-                acc += cnt[c];
-            }
-            off[NC] = acc;
-        }
-        __syncthreads();
-        for (int i = tid; i < nblk; i += kPavaTileThreads) {
-            const int K = sstart[i + 1] - sstart[i];
-            if (K <= kPavaThreadMax) {
-                const int c = cls(K);
-                list[off[c] + atomicAdd(&fill[c], 1)] = (uint16_t)i;
-            } else {  // a block of pava_mid_kernel / pava_large_kernel: never written back from here
-                const int e1 = min((int)sstart[i + 1], nel);
-                for (int e = sstart[i]; e < e1; ++e) skip[e] = 1;
-            }
-        }
-        __syncthreads();
-        const int nthread = off[NC];
-        for (int p = tid; p < nthread; p += kPavaTileThreads) {
-            const int b = list[p];
-            const int s0 = sstart[b];
-            const int Kb = sstart[b + 1] - s0;
-            uint32_t heads;
-            if (fl.has_weight)
-                heads = pava_block_runs<T, uint16_t, uint32_t, true>(ybuf + s0, wbuf + s0, Kb, pava_heads_from_weights<uint16_t, uint32_t>(wbuf + s0, Kb),
-                                                                     1u, true, rcp, kPavaThreadMax + 1);
-            else
-                heads = pava_block_runs<T, uint16_t, uint32_t, false>(ybuf + s0, nullptr, Kb, Kb == 32 ? ~0u : ((1u << Kb) - 1u), 1u, false, rcp,
-                                                                      kPavaThreadMax + 1);
-            if (fl.update) pava_spread(ybuf + s0, Kb, heads);
-        }
-        __syncthreads();
-        for (int i = tid; i < nel; i += kPavaTileThreads) {
-            if (skip[i]) continue;
-            T v = ybuf[i];
-            if (fl.clip01) v = clip01(v);
-            yg[(size_t)tile_lo + i] = v;
-            if (fl.has_weight) wg[(size_t)tile_lo + i] = (int32_t)wbuf[i];
-        }
-        __syncthreads();
-    }
-}
-
-// Cold start (no weight array, update = 1): the tile's short blocks are regressed as ROWS -- runs of
+// The tile's short blocks are regressed as ROWS -- runs of
 // consecutive blocks that one thread takes as a single 32-bit mask problem with forced run starts at
 // the block boundaries (pava_block_runs, `bst`), so that a lane has 16..31 entries of work whatever
 // the block sizes are.  Rows follow from a bitmap of block starts alone, without lists or scans:
@@ -1036,225 +718,6 @@ int launch_pava_tile_rows(T *y, int32_t *w, const int32_t *starts, const int32_t
     }
     if (clip) return launch_pava_tile_rows_cfg<T, true, false>(y, w, starts, tile_first, ntiles, update, cap_per_sm, stream);
     return launch_pava_tile_rows_cfg<T, false, false>(y, w, starts, tile_first, ntiles, update, cap_per_sm, stream);
-}
-
-// Blocks of kPavaThreadMax < K <= kPavaTileMaxBlock: one WARP per block, staged in the warp's own
-// slice of shared memory.  A separate launch (instead of a phase of the tile kernel) puts every
-// such block in flight at once; inside a tile only a handful exist and the other warps would idle.
-constexpr int kPavaMidWarps = 4;
-template <typename T>
-__global__ void __launch_bounds__(kPavaMidWarps * 32)
-pava_mid_kernel(T *__restrict__ yg, int32_t *__restrict__ wg, const int32_t *__restrict__ starts, const int32_t *__restrict__ ids,
-                int count, PavaFlags fl) {
-    __shared__ __align__(16) T ys[kPavaMidWarps][kPavaTileMaxBlock];
-    __shared__ uint16_t ws[kPavaMidWarps][kPavaTileMaxBlock];
-    __shared__ uint16_t la[kPavaMidWarps][kPavaTileMaxBlock], lb[kPavaMidWarps][kPavaTileMaxBlock];
-    __shared__ uint8_t lf[kPavaMidWarps][kPavaTileMaxBlock];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int it = blockIdx.x * kPavaMidWarps + wid; it < count; it += gridDim.x * kPavaMidWarps) {
-        const int b = ids[it];
-        const int lo = starts[b];
-        const int K = starts[b + 1] - lo;
-        T *gy = yg + (size_t)lo;
-        int32_t *gw = wg ? wg + (size_t)lo : nullptr;
-        for (int i = lane; i < K; i += 32) {
-            ys[wid][i] = gy[i];
-            ws[wid][i] = fl.has_weight ? (uint16_t)gw[i] : (uint16_t)1;
-        }
-        __syncwarp();
-        pava_warp_block<T>(ys[wid], ws[wid], K, lane, la[wid], lb[wid], lf[wid], fl.has_weight != 0, fl.update);
-        for (int i = lane; i < K; i += 32) {
-            T v = ys[wid][i];
-            if (fl.clip01) v = clip01(v);
-            gy[i] = v;
-            if (fl.has_weight) gw[i] = (int32_t)ws[wid][i];
-        }
-        __syncwarp();
-    }
-}
-
-template <typename T>
-int launch_pava_mid(T *y, int32_t *w, const int32_t *starts, const int32_t *mid_ids, int nmid, PavaFlags fl, cudaStream_t stream) {
-    if (nmid > 0) {
-        auto mid = pava_mid_kernel<T>;
-        static thread_local int mid_full = 0;
-        if (!mid_full) {
-            int dev = 0, num_sm = kNumSM, per_sm = 1;
-            BSLS_CUDA_TRY(cudaGetDevice(&dev));
-            BSLS_CUDA_TRY(cudaDeviceGetAttribute(&num_sm, cudaDevAttrMultiProcessorCount, dev));
-            BSLS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mid, kPavaMidWarps * 32, 0));
-            mid_full = num_sm * (per_sm < 1 ? 1 : per_sm);
-        }
-        const int want = (nmid + kPavaMidWarps - 1) / kPavaMidWarps;
-        mid<<<want < mid_full ? want : mid_full, kPavaMidWarps * 32, 0, stream>>>(y, w, starts, mid_ids, nmid, fl);
-        BSLS_LAUNCH_CHECK();
-    }
-    return BSLS_OK;
-}
-
-template <typename T>
-int launch_pava_tile(T *y, int32_t *w, const int32_t *starts, const int32_t *tile_first, int ntiles, PavaFlags fl, cudaStream_t stream) {
-    if (ntiles <= 0) return BSLS_OK;
-    auto kern = pava_tile_kernel<T>;
-    static thread_local int grid_full = 0;
-    if (!grid_full) {
-        int dev = 0, num_sm = kNumSM, per_sm = 1;
-        BSLS_CUDA_TRY(cudaGetDevice(&dev));
-        BSLS_CUDA_TRY(cudaDeviceGetAttribute(&num_sm, cudaDevAttrMultiProcessorCount, dev));
-        BSLS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPavaTileThreads, 0));
-        grid_full = num_sm * (per_sm < 1 ? 1 : per_sm);
-    }
-    kern<<<ntiles < grid_full ? ntiles : grid_full, kPavaTileThreads, 0, stream>>>(y, w, starts, tile_first, ntiles, fl);
-    BSLS_LAUNCH_CHECK();
-    return BSLS_OK;
-}
-
-// ---------------------------------------------------------------------------------------------
-// one CTA per long block
-// ---------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(kPavaLargeThreads)
-pava_large_kernel(T *__restrict__ yg, int32_t *__restrict__ wg, const int32_t *__restrict__ starts,
-                  const int32_t *__restrict__ ids, int count, PavaFlags fl) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int s_cnt[kPavaLargeThreads / 32 + 1];
-    __shared__ int s_merged;
-    constexpr int NW = kPavaLargeThreads / 32;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const unsigned lt_mask = (1u << lane) - 1u;
-
-    for (int it = blockIdx.x; it < count; it += gridDim.x) {
-        const int b = ids ? ids[it] : it;
-        const int lo = starts[b];
-        const int K = starts[b + 1] - lo;
-        T *y = reinterpret_cast<T *>(smem_raw);
-        int32_t *w = reinterpret_cast<int32_t *>(y + K + (K & 1));
-        uint16_t *A = reinterpret_cast<uint16_t *>(w + K);
-        uint16_t *B = A + K + (K & 1);
-        uint8_t *F = reinterpret_cast<uint8_t *>(B + K + (K & 1));
-        T *gy = yg + (size_t)lo;
-        int32_t *gw = wg ? wg + (size_t)lo : nullptr;
-        for (int i = tid; i < K; i += kPavaLargeThreads) {
-            y[i] = gy[i];
-            w[i] = fl.has_weight ? gw[i] : 1;
-            A[i] = (uint16_t)i;
-            F[i] = 0;
-        }
-        __syncthreads();
-        int P = K;
-        if (fl.has_weight) {  // warm start: heads are reached by i += weight[i]; serial, rare
-            if (tid == 0) {
-                int np = 0;
-                for (int i = 0; i < K; i += max(1, w[i])) B[np++] = (uint16_t)i;
-                s_cnt[NW] = np;
-            }
-            __syncthreads();
-            P = s_cnt[NW];
-            uint16_t *t = A;
-            A = B;
-            B = t;
-            __syncthreads();
-        }
-        for (;;) {
-            if (tid == 0) s_merged = 0;
-            for (int j = tid; j < P; j += kPavaLargeThreads) {
-                bool st = (j == 0);
-                if (!st) st = y[A[j]] > y[A[j - 1]];
-                F[j] = st ? 1 : 0;
-            }
-            __syncthreads();
-            bool merged = false;
-            for (int j = tid; j < P; j += kPavaLargeThreads)
-                if (F[j] == 1) merged |= pava_merge_run<T, int32_t>(y, w, A, F, j, P);
-            if (merged) s_merged = 1;
-            __syncthreads();
-            if (!s_merged) break;
-            // compaction: each warp owns a contiguous slice of the list
-            const int slice = ((P + NW - 1) / NW + 31) & ~31;
-            const int s0 = wid * slice, s1 = min(P, s0 + slice);
-            int cnt = 0;
-            for (int base = s0; base < s1; base += 32) {
-                const int j = base + lane;
-                cnt += __popc(__ballot_sync(0xffffffffu, j < s1 && F[j] != 2));
-            }
-            if (lane == 0) s_cnt[wid] = cnt;
-            __syncthreads();
-            int off = 0, total = 0;
-            for (int k = 0; k < NW; ++k) {
-                const int c = s_cnt[k];
-                if (k < wid) off += c;
-                total += c;
-            }
-            for (int base = s0; base < s1; base += 32) {
-                const int j = base + lane;
-                const bool alive = j < s1 && F[j] != 2;
-                const unsigned m = __ballot_sync(0xffffffffu, alive);
-                if (alive) B[off + __popc(m & lt_mask)] = A[j];
-                off += __popc(m);
-            }
-            __syncthreads();
-            uint16_t *t = A;
-            A = B;
-            B = t;
-            P = total;
-        }
-        if (fl.update) {
-            for (int j = tid; j < P; j += kPavaLargeThreads) {
-                const int p = A[j];
-                const T v = y[p];
-                const int stop = p + w[p];
-                for (int r = p + 1; r < stop; ++r) y[r] = v;
-            }
-            __syncthreads();
-        }
-        for (int i = tid; i < K; i += kPavaLargeThreads) {
-            T v = y[i];
-            if (fl.clip01) v = clip01(v);
-            gy[i] = v;
-            if (fl.has_weight) gw[i] = w[i];
-        }
-        __syncthreads();
-    }
-}
-
-inline size_t pava_large_smem(int K, size_t elem) {
-    const size_t kp = (size_t)K + (K & 1);
-    return kp * elem + (size_t)K * 4 + 2 * kp * 2 + (size_t)K + 64;
-}
-
-template <typename T>
-int launch_pava(T *y, int32_t *w, const int32_t *starts, const int32_t *win_first, int nwin, const int32_t *large_ids,
-                int nlarge, int max_large, PavaFlags fl, cudaStream_t stream) {
-    int dev = 0, num_sm = kNumSM;
-    BSLS_CUDA_TRY(cudaGetDevice(&dev));
-    BSLS_CUDA_TRY(cudaDeviceGetAttribute(&num_sm, cudaDevAttrMultiProcessorCount, dev));
-    if (nwin > 0) {
-        auto kern = pava_warp_kernel<T>;
-        static thread_local int per_sm = 0;
-        if (!per_sm) {
-            BSLS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPavaWarpsPerCta * 32, 0));
-            if (per_sm < 1) per_sm = 1;
-        }
-        const int want = (nwin + kPavaWarpsPerCta - 1) / kPavaWarpsPerCta;
-        const int grid = want < num_sm * per_sm ? want : num_sm * per_sm;
-        kern<<<grid, kPavaWarpsPerCta * 32, 0, stream>>>(y, w, starts, win_first, nwin, fl);
-        BSLS_LAUNCH_CHECK();
-    }
-    if (nlarge > 0) {
-        auto kern = pava_large_kernel<T>;
-        static thread_local bool attr_set = false;
-        if (!attr_set) {
-            BSLS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)pava_large_smem(kPavaLargeMaxBlock, sizeof(T))));
-            attr_set = true;
-        }
-        int per = 1;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, kPavaLargeThreads, pava_large_smem(max_large, sizeof(T))) != cudaSuccess || per < 1) per = 1;
-        const int grid = nlarge < per * num_sm ? nlarge : per * num_sm;
-        kern<<<grid, kPavaLargeThreads, pava_large_smem(max_large, sizeof(T)), stream>>>(y, w, starts, large_ids, nlarge, fl);
-        BSLS_LAUNCH_CHECK();
-    }
-    return BSLS_OK;
 }
 
 }  // namespace bsls

@@ -4,16 +4,6 @@
 #include "pava_words.cuh"
 
 namespace bsls {
-int pava_f32(float *y, int32_t *w, const int32_t *starts, const int32_t *win_first, int nwin, const int32_t *large_ids,
-             int nlarge, int max_large, int update, int clip01, cudaStream_t stream) {
-    static_assert(kPavaPitch == kPlanPavaPitch && kPavaWarpMaxBlock == kPlanPavaWarpMax && kPavaLargeMaxBlock == kPlanPavaLargeMax, "plan constants");
-    PavaFlags fl;
-    fl.update = update;
-    fl.clip01 = clip01;
-    fl.has_weight = w != nullptr;
-    return launch_pava<float>(y, w, starts, win_first, nwin, large_ids, nlarge, max_large, fl, stream);
-}
-
 int pava_small_f32(float *y, int32_t *w, long long first, int nb, int K, int update, int clip01, cudaStream_t stream) {
     PavaFlags fl;
     fl.update = update;
@@ -25,20 +15,7 @@ int pava_small_f32(float *y, int32_t *w, long long first, int nb, int K, int upd
 int pava_tile_f32(float *y, int32_t *w, const int32_t *starts, const int32_t *tile_first, int ntiles, int update, int clip01,
                   int cap_per_sm, cudaStream_t stream) {
     static_assert(kPavaTileElems == kPlanTileElems && kPavaTileMaxBlock == kPlanTileMaxBlock && kPavaThreadMax == kPlanMidMin, "plan constants");
-    PavaFlags fl;
-    fl.update = update;
-    fl.clip01 = clip01;
-    fl.has_weight = w != nullptr;
-    if (!getenv("BSLS_PAVA_NO_ROWS")) return launch_pava_tile_rows<float>(y, w, starts, tile_first, ntiles, update, clip01, cap_per_sm, stream);
-    return launch_pava_tile<float>(y, w, starts, tile_first, ntiles, fl, stream);
-}
-
-int pava_mid_f32(float *y, int32_t *w, const int32_t *starts, const int32_t *mid_ids, int nmid, int update, int clip01, cudaStream_t stream) {
-    PavaFlags fl;
-    fl.update = update;
-    fl.clip01 = clip01;
-    fl.has_weight = w != nullptr;
-    return launch_pava_mid<float>(y, w, starts, mid_ids, nmid, fl, stream);
+    return launch_pava_tile_rows<float>(y, w, starts, tile_first, ntiles, update, clip01, cap_per_sm, stream);
 }
 
 int pava_words_f32(float *y, int32_t *w, const int32_t *starts, const int32_t *ids, const int32_t *pack_first, int npacks, long long first, int nb,

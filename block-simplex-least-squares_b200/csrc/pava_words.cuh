@@ -423,7 +423,7 @@ pava_words_cta_kernel(T *__restrict__ yg, int32_t *__restrict__ wg, const int32_
     uint16_t *wsm = reinterpret_cast<uint16_t *>(rcp + kWordsRcp);  // max_block entries (with a weight array)
     for (int i = tid + 1; i < kWordsRcp; i += kWordsCtaThreads) rcp[i] = T(1) / (T)i;
     for (int it = blockIdx.x; it < count; it += gridDim.x) {
-        const int b = ids[it];
+        const int b = ids ? ids[it] : it;  // ids == nullptr: every block of the layout
         const int g0 = starts[b];
         const int K = starts[b + 1] - g0;
         const int LW = (K + 31) >> 5;
