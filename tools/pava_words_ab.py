@@ -1,4 +1,5 @@
-"""A/B of the word-per-lane PAVA kernel against the warp-window / CTA kernels on uniform layouts (set BSLS_PAVA_NO_WORDS=1 for B)."""
+"""Word-per-lane PAVA kernel on uniform layouts of 100..1000 entries per block, 2*10^7 values.  (The warp-window /
+CTA-per-block sweep kernels it replaced measured 0.51 / 0.50 / 1.64 / 1.12 ms on the reference generator.)"""
 import json, sys
 sys.path.insert(0, "."); sys.path.insert(0, "tools")
 import microbench as mb
