@@ -26,3 +26,17 @@ def test_pava_block_runs_on_host(tmp_path):
     run = subprocess.run([exe, "1500"], capture_output=True, text=True, timeout=300)
     assert run.returncode == 0, run.stdout[-500:] + run.stderr[-2000:]
     assert run.stdout.startswith("ok ")
+
+
+def test_small_integer_division_is_correctly_rounded(tmp_path):
+    """div_small (reciprocal table + two FMA corrections) == num / den bit for bit on 3*10^7 quotients
+    (tools/divtest.c; the full 10^9-case run takes 15 s)."""
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not found")
+    exe = str(tmp_path / "divtest")
+    res = subprocess.run([gcc, "-O2", "-mfma", "-ffp-contract=off", "-o", exe, os.path.join(ROOT, "tools", "divtest.c"), "-lm"],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-2000:]
+    run = subprocess.run([exe, "20000000"], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0 and "bad(two-step)=0" in run.stdout, run.stdout + run.stderr
