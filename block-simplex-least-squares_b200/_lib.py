@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbsls_b200.so")
 
-OK, ERR_ARG, ERR_CUDA, ERR_NO_DEVICE, ERR_ALLOC = 0, 1, 2, 3, 4
+OK, ERR_ARG, ERR_CUDA, ERR_NO_DEVICE, ERR_ALLOC, ERR_UNSUPPORTED = 0, 1, 2, 3, 4, 5
 
 _lib = None
 
@@ -53,6 +53,8 @@ def lib():
         L.bsls_isotonic_regression_multi_2.argtypes = [c_void_p, c_void_p, c_int, c_int]
         for name in ("bsls_dev_isotonic_regression_multi_f64", "bsls_dev_isotonic_regression_multi_f32"):
             getattr(L, name).argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]
+        L.bsls_dev_isotonic_regression_multi_2_f64.argtypes = [c_void_p, c_void_p, c_void_p]
+        L.bsls_dev_isotonic_regression_multi_3_f64.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p]
         L.bsls_host_alloc.argtypes = [ctypes.POINTER(c_void_p), c_i64]
         L.bsls_host_free.argtypes = [c_void_p]
         L.bsls_plan_create.argtypes = [c_void_p, c_int, c_int, c_void_p, ctypes.POINTER(c_void_p)]
@@ -120,4 +122,6 @@ def check(rc, what=""):
     msg = "%s: %s" % (what, last_error()) if what else last_error()
     if rc == ERR_ARG:
         raise AssertionError(msg)
+    if rc == ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
     raise BslsError("libbsls_b200 status %d: %s" % (rc, msg))

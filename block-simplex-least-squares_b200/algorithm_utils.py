@@ -19,6 +19,7 @@ from .plan import BlockPlan, plan_for
 from .sparse import LsqProblem, axpby, copy_, default_workspace
 
 __all__ = ["get_solver_parts", "sparse_least_squares_obj", "quad_obj_np", "decreasing_step_size", "line_search_np",
+           "line_search_exact_quad_obj",
            "stopping", "normalization", "proj_simplex", "proj_multi_simplex"]
 
 
@@ -122,6 +123,26 @@ def line_search_np(x, f, g, x_new, f_new, g_new, obj):
         f_new = obj(x_new, g_new)
         upper_line = f + suffDec * g_dot_step()
     return f_new
+
+
+def line_search_exact_quad_obj(x, f, g, x_new, f_new, g_new, Q, c):
+    """Exact line search for a quadratic objective 0.5 x'Qx + c'x (algorithm_utils.py:140-155): minimises along
+    d = x_new - x, overwrites x_new with x + t d and g_new with the gradient there, returns the new objective.
+    ``Q`` may be a prepared :class:`_DenseQuadratic` (then ``c`` is ignored)."""
+    quad = Q if isinstance(Q, _DenseQuadratic) else _DenseQuadratic(Q, c, x.device)
+    ws = quad.problem.ws
+    progTol = 1e-8
+    d = axpby(torch.empty_like(x), 1.0, x_new, -1.0, x)
+    # Check whether step has become too small
+    if ws.max_abs_diff(x_new, x) < progTol:
+        copy_(g_new, g)
+        copy_(x_new, x)
+        return f
+    tmp = quad.problem.matvec(d)                                   # Q.dot(d)
+    xt, dc, dt = ws.dots([(x, tmp), (d, quad.c), (d, tmp)])
+    t = -(xt + dc) / dt
+    axpby(x_new, 1.0, x, t, d)                                     # x + t*d
+    return quad_obj_np(x_new, quad, None, g_new)
 
 
 def stopping(i, max_iter, f, f_old, opt_tol, prog_tol, f_min=None):

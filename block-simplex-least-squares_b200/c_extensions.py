@@ -39,6 +39,18 @@ def _check_dev_vector(y, name="y"):
         raise ValueError("Buffer dtype mismatch: expected float64 (or float32), got %s" % y.dtype)
 
 
+def _check_f64_vectors(*pairs):
+    """x2z / z2x / N / N^T / block_scale exist in fp64 only: an fp32 buffer would be read as 8-byte
+    elements.  Same error as the reference's Cython layer for a wrong dtype."""
+    for t, name in pairs:
+        _check_dev_vector(t, name)
+        if t.dtype != torch.float64:
+            raise ValueError("Buffer dtype mismatch, expected 'double' but got %s for %s" % (t.dtype, name))
+    dev = pairs[0][0].device
+    for t, name in pairs[1:]:
+        assert t.device == dev, "%s is on %s, expected %s" % (name, t.device, dev)
+
+
 def _check_host_vector(y, name="y"):
     if y.dtype != np.float64:
         raise ValueError("Buffer dtype mismatch, expected 'double' but got %s" % y.dtype)
@@ -153,6 +165,21 @@ def _pava_multi(y, blocks, weight, update, clip01=False, variant=1):
             "weight must be a contiguous int32 CUDA tensor"
         assert weight.shape[0] == n
         wptr = weight.data_ptr()
+    if variant != 1:
+        # variants 2 / 3: the reference's routines as written (values and weights bit-identical), fp64 only
+        if y.dtype != torch.float64:
+            raise ValueError("Buffer dtype mismatch, expected 'double' but got %s" % y.dtype)
+        with torch.cuda.device(y.device):
+            if variant == 2:
+                _lib.check(L.bsls_dev_isotonic_regression_multi_2_f64(plan.handle, y.data_ptr(), _stream(y)), "isotonic_regression_multi_2")
+            else:
+                if wptr is None:  # weight=None: ones in, result dropped (c_extensions.pyx:118-119)
+                    weight = torch.ones(n, dtype=torch.int32, device=y.device)
+                    wptr = weight.data_ptr()
+                _lib.check(L.bsls_dev_isotonic_regression_multi_3_f64(plan.handle, y.data_ptr(), wptr, int(update), _stream(y)),
+                           "isotonic_regression_multi_3")
+        assert not clip01, "the fused clamp exists for variant 1 only"
+        return None
     fn = L.bsls_dev_isotonic_regression_multi_f64 if y.dtype == torch.float64 else L.bsls_dev_isotonic_regression_multi_f32
     with torch.cuda.device(y.device):
         _lib.check(fn(plan.handle, y.data_ptr(), wptr, int(update), int(bool(clip01)), _stream(y)), fn.__name__)
@@ -192,7 +219,7 @@ def isotonic_regression_multi_c(y, blocks, weight=None, update=1, clip01=False):
 
 
 def isotonic_regression_c_2(y, start, end):
-    """Variant 2 of the reference (c_extensions.pyx:92-98): same regression, no weight array."""
+    """Variant 2 of the reference (c_extensions.pyx:92-98): weight-free sweeps, bit-identical values."""
     return _pava_single(y, start, end, None, 1, 2)
 
 
@@ -201,8 +228,8 @@ def isotonic_regression_multi_c_2(y, blocks):
 
 
 def isotonic_regression_c_3(y, start, end, weight=None, update=1):
-    """Variant 3 of the reference (c_extensions.pyx:112-122): same regression; the weight array
-    returned here is variant 1's (pool size at each head)."""
+    """Variant 3 of the reference (c_extensions.pyx:112-122): one pass with back-tracking; values and the
+    weight array (pool sizes at the heads, tail markers ``w[k-1]``) are the reference's, bit for bit."""
     return _pava_single(y, start, end, weight, update, 3)
 
 
@@ -239,8 +266,7 @@ def x2z_c(x, z, blocks):
         x2z_c(xd, zd, np.asarray(blocks))
         z[:] = zd.cpu().numpy()
         return z
-    _check_dev_vector(x, "x")
-    _check_dev_vector(z, "z")
+    _check_f64_vectors((x, "x"), (z, "z"))
     plan = _z_plan(x, blocks)
     assert z.shape[0] == x.shape[0] - plan.numblocks, "z must have n - numblocks entries"
     with torch.cuda.device(x.device):
@@ -257,8 +283,7 @@ def z2x_c(x, z, blocks):
         z2x_c(xd, zd, np.asarray(blocks))
         x[:] = xd.cpu().numpy()
         return x
-    _check_dev_vector(x, "x")
-    _check_dev_vector(z, "z")
+    _check_f64_vectors((x, "x"), (z, "z"))
     plan = _z_plan(x, blocks)
     assert z.shape[0] == x.shape[0] - plan.numblocks, "z must have n - numblocks entries"
     with torch.cuda.device(x.device):
@@ -269,8 +294,7 @@ def z2x_c(x, z, blocks):
 def n_dot(x, z, blocks, add_x0=False):
     """x <- N z (+ x0): the change of variables of python/bsls_utils.py:139-162,327-328 as an
     operator (x_l = z_l - z_{l-1} inside a block)."""
-    _check_dev_vector(x, "x")
-    _check_dev_vector(z, "z")
+    _check_f64_vectors((x, "x"), (z, "z"))
     plan = _z_plan(x, blocks)
     assert z.shape[0] == x.shape[0] - plan.numblocks
     with torch.cuda.device(x.device):
@@ -280,8 +304,7 @@ def n_dot(x, z, blocks, add_x0=False):
 
 def nt_dot(zg, v, blocks):
     """zg <- N^T v ((N^T v)_l = v_l - v_{l+1})."""
-    _check_dev_vector(zg, "zg")
-    _check_dev_vector(v, "v")
+    _check_f64_vectors((v, "v"), (zg, "zg"))
     plan = _z_plan(v, blocks)
     assert zg.shape[0] == v.shape[0] - plan.numblocks
     with torch.cuda.device(v.device):
@@ -292,7 +315,7 @@ def nt_dot(zg, v, blocks):
 def block_scale(y, blocks, f, divide=False):
     """y[block k] *= f[k] (or /= f[k]), in place: the per-block (de)normalisation that
     get_solver_parts wraps around the projection when ``f`` is given (algorithm_utils.py:232-265)."""
-    _check_dev_vector(y, "y")
+    _check_f64_vectors((y, "y"))
     plan = plan_for(blocks, y.shape[0], y.device)
     assert torch.is_tensor(f) and f.is_cuda and f.dtype == torch.float64 and f.is_contiguous() and f.shape[0] == plan.numblocks
     with torch.cuda.device(y.device):

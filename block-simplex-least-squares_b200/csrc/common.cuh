@@ -7,7 +7,27 @@
 
 namespace bsls {
 
-constexpr int kNumSM = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+// ---- per-device host state ---------------------------------------------------------------
+// Launch parameters (resident grids, shared-memory opt-ins) are properties of a DEVICE: cudaFuncSetAttribute and the
+// occupancy queries apply to the current device only.  Caches are therefore indexed by the current device.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+    int d = 0;
+    return (cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < kMaxDevices) ? d : 0;
+}
+int num_sms();  // SM count of the current device (B200: 148 = 2 dies x 74); grids are sized in multiples of it (capi.cu)
+template <typename V> struct PerDevice {
+    V v[kMaxDevices];
+    bool seen[kMaxDevices] = {};
+    V &get(V initial = V()) {
+        const int d = current_device();
+        if (!seen[d]) {
+            v[d] = initial;
+            seen[d] = true;
+        }
+        return v[d];
+    }
+};
 
 // ---- error plumbing (host) ---------------------------------------------------------
 void set_error(const char *fmt, ...);
@@ -20,6 +40,12 @@ void set_error(const char *fmt, ...);
         }                                                                                \
     } while (0)
 #define BSLS_LAUNCH_CHECK() BSLS_CUDA_TRY(cudaGetLastError())
+
+// device-resident solver loop: where a kernel finds the step of the trial point and the "solver has stopped" flag
+struct StepCtl {
+    const double *t;
+    const int *done;
+};
 
 // ---- small numeric traits -------------------------------------------------------------
 template <typename T> struct Num;

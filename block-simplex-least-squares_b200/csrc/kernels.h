@@ -10,8 +10,9 @@ int proj_uniform_f64(double *y, long long first, int nb, int K, int mode, int32_
 int proj_uniform_f32(float *y, long long first, int nb, int K, int mode, int32_t *slow, cudaStream_t stream);
 // fused projected-gradient step x_new = proj(x - t g), uniform layouts whose K the sorting kernels take
 bool proj_step_fuses(int K);
+// ctl (device memory, may be null): the step is read from *ctl->t instead of `t`, and the kernel exits when *ctl->done
 int proj_step_uniform_f64(const double *x, const double *g, double t, double *x_new, long long first, int nb, int K, int mode,
-                          cudaStream_t stream);
+                          cudaStream_t stream, const StepCtl *ctl = nullptr);
 
 
 // fork/join inside one call: the tile, mid and large kernels own disjoint blocks and run side by side
@@ -65,6 +66,12 @@ int pava_words_cta_f64(double *y, int32_t *w, const int32_t *starts, const int32
                        int cap_per_sm, cudaStream_t stream);
 int pava_words_cta_f32(float *y, int32_t *w, const int32_t *starts, const int32_t *ids, int count, int max_block, int update, int clip01,
                        int cap_per_sm, cudaStream_t stream);
+// pava_seq.cuh: the reference's routines (variant 1, 2 or 3) as written, one thread per block; only blocks longer than
+// min_size entries; cold != 0: w is scratch, set to ones first
+int pava_seq_f64(int variant, double *y, int32_t *w, const int32_t *starts, const int32_t *ids, int count, int min_size, int update, int cold,
+                 int clip, cudaStream_t stream);
+int pava_seq_f32(int variant, float *y, int32_t *w, const int32_t *starts, const int32_t *ids, int count, int min_size, int update, int cold,
+                 int clip, cudaStream_t stream);
 // greedy packing of ids[0..count) into packs of at most 32 words (32 entries each); pack_first has count + 1 slots
 int plan_pack_words(const int32_t *starts, const int32_t *ids, int count, int32_t *pack_first, int *d_npacks, cudaStream_t stream);
 
@@ -83,7 +90,7 @@ struct bsls_plan {
     bool ragged = false;
     int mid = 0;
     int32_t *d_mid_ids = nullptr;     // ragged: blocks with kPlanMidMin < size <= kPlanTileMaxBlock
-    int mid_packs = -1;               // packs of the mid list for pava_words (built on first use)
+    int mid_packs = 0;                // packs of the mid list for pava_words
     int32_t *d_mid_pack = nullptr;    // mid_packs + 1 entries
     // fork/join inside one call: the tile, mid and large kernels own disjoint blocks and run side by side
     cudaStream_t aux[2] = {nullptr, nullptr};
@@ -92,6 +99,7 @@ struct bsls_plan {
     int huge_cap = 0;
     int *d_huge_lock = nullptr;
     int32_t *d_slow = nullptr;        // nb + 1: queue of dense blocks between the selection kernel and the sorter
+    int32_t *d_seq_w = nullptr;       // n: weight scratch of the sequential isotonic regression (layouts with blocks > kPlanPavaLargeMax)
 };
 
 namespace bsls {
@@ -99,6 +107,7 @@ namespace bsls {
 int project_f64(const bsls_plan *plan, double *y, int mode, cudaStream_t stream);
 int pava_clip_f64(const bsls_plan *plan, double *y, int32_t *weight, int update, int clip01, cudaStream_t stream);
 // x_new = proj(x - t g): one fused kernel where the layout allows it, else returns 1 ("not fused") and does nothing
-int project_step_f64(const bsls_plan *plan, const double *x, const double *g, double t, double *x_new, int mode, cudaStream_t stream, bool *fused);
+int project_step_f64(const bsls_plan *plan, const double *x, const double *g, double t, double *x_new, int mode, cudaStream_t stream, bool *fused,
+                     const StepCtl *ctl = nullptr);
 }  // namespace bsls
 

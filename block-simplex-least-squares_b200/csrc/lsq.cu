@@ -25,6 +25,7 @@ struct NcclApi {
     int (*GetUniqueId)(void *) = nullptr;
     int (*CommInitRank)(void **, int, Id128, int) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
     int (*CommDestroy)(void *) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
 };
@@ -47,9 +48,10 @@ int nccl_load(const char *path) {
     g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(h, "ncclGetUniqueId");
     g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(h, "ncclCommInitRank");
     g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(h, "ncclAllReduce");
+    g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(h, "ncclAllGather");
     g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
     g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
-    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.AllGather || !g_nccl.CommDestroy) {
         set_error("NCCL library lacks the expected symbols");
         return BSLS_ERR_ARG;
     }
@@ -78,6 +80,13 @@ struct bsls_ws {
     double *d_scal = nullptr, *h_scal = nullptr;  // kScalCount each (h_scal pinned)
     bsls_comm *comm = nullptr;
     int launches = 0;
+    // device-resident solver loop
+    DevState *d_state = nullptr, *h_state = nullptr;  // h_state: 2 pinned copies (one per iteration in flight)
+    cudaEvent_t ev_state[2] = {nullptr, nullptr};
+    double *d_gather = nullptr;                        // nranks * 5 doubles (all-gather of the per-rank step scalars)
+    int gather_cap = 0;
+    double *d_prog = nullptr;                          // 2 * prog_cap doubles: objective and device time stamp per iteration
+    int prog_cap = 0;
 };
 
 struct bsls_lsq {
@@ -96,12 +105,36 @@ struct bsls_lsq {
     double *partial = nullptr;                    // panels * m (owned)
     int p_mode = 0;
     double *r = nullptr;                          // m
+    double *r2 = nullptr;                         // m: residual of the trial point (solver loop; allocated with the workspace)
+    int t_ell = 0, a_ell = 0;                     // common row length of A^T / A when every row has the same (1..16 supported), else 0
+    cudaTextureObject_t tex_r[2] = {0, 0};        // texture views of r / r2 (experiment: BSLS_ELL_TEX)
     double *wg = nullptr, *wxn = nullptr, *wgn = nullptr;  // n each, solver workspace
     bsls_ws *ws = nullptr;                        // owned
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 
 namespace {
+
+// ptr[i] == i * L for all rows?  (one reduction over the pointer array, at handle creation)
+__global__ void uniform_rows_kernel(const int64_t *__restrict__ ptr, int64_t rows, int64_t L, int *bad) {
+    int b = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= rows; i += (int64_t)gridDim.x * blockDim.x)
+        if (ptr[i] != i * L) b = 1;
+    if (__any_sync(0xffffffffu, b) && (threadIdx.x & 31) == 0) atomicOr(bad, 1);
+}
+int uniform_row_length(const int64_t *d_ptr, int64_t rows, int64_t nnz) {
+    if (rows <= 0 || nnz <= 0 || nnz % rows) return 0;
+    const int64_t L = nnz / rows;
+    if (L < 1 || L > 64) return 0;
+    int *d_bad = nullptr, h_bad = 1;
+    if (cudaMalloc(&d_bad, sizeof(int)) != cudaSuccess) return 0;
+    cudaMemset(d_bad, 0, sizeof(int));
+    int64_t want = (rows + 1 + 255) / 256;
+    uniform_rows_kernel<<<(int)(want < 1184 ? want : 1184), 256>>>(d_ptr, rows, L, d_bad);
+    if (cudaMemcpy(&h_bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) h_bad = 1;
+    cudaFree(d_bad);
+    return h_bad ? 0 : (int)L;
+}
 
 int pick_mode(int64_t nnz, int64_t rows) {
     const double avg = rows > 0 ? (double)nnz / (double)rows : 0.0;
@@ -120,7 +153,7 @@ int grid_elems(int64_t n) {
 // Grid of a persistent kernel: every CTA resident at once (one wave), never more than the
 // reduction scratch holds.
 template <class K> int resident_grid(K kern, int threads) {
-    int dev = 0, sms = kNumSM, per = 1;
+    int dev = 0, sms = num_sms(), per = 1;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, threads, 0) != cudaSuccess || per < 1) per = 1;
     const int g = sms * per;
@@ -129,33 +162,67 @@ template <class K> int resident_grid(K kern, int threads) {
 
 template <class Epi, int LANES>
 int launch_vector(bsls_ws *w, int64_t rows, const int64_t *ptr, const int32_t *idx, const double *val, const double *v,
-                  const Epi &epi, cudaStream_t st) {
+                  const Epi &epi, cudaStream_t st, const int *skip) {
     constexpr int T = 256;
-    static thread_local int full = 0;
+    static thread_local PerDevice<int> full_pd;
+    int &full = full_pd.get(0);
     if (!full) full = resident_grid(spmv_vector_kernel<Epi, T, LANES>, T);
     int64_t want = (rows * LANES + T - 1) / T;
     const int grid = (int)(want < full ? (want < 1 ? 1 : want) : full);
-    spmv_vector_kernel<Epi, T, LANES><<<grid, T, 0, st>>>(rows, ptr, idx, val, v, epi, w->red);
+    spmv_vector_kernel<Epi, T, LANES><<<grid, T, 0, st>>>(rows, ptr, idx, val, v, epi, w->red, skip);
     return 0;
 }
 
+// rows of exactly L entries: no pointers, no staging (spmv_ell_kernel)
+template <class Epi, int L>
+int launch_ell(bsls_ws *w, int64_t rows, const int32_t *idx, const double *val, const double *v, cudaTextureObject_t tex, const Epi &epi,
+               cudaStream_t st, const int *skip) {
+    constexpr int T = 256;
+#define ELL_GO(HV, TX)                                                                                             \
+    {                                                                                                              \
+        static thread_local PerDevice<int> full_pd;                                                                \
+        int &full = full_pd.get(0);                                                                                \
+        if (!full) full = resident_grid(spmv_ell_kernel<Epi, T, L, HV, TX>, T);                                    \
+        const int64_t want = (rows + T - 1) / T;                                                                   \
+        spmv_ell_kernel<Epi, T, L, HV, TX><<<(int)(want < full ? want : full), T, 0, st>>>(rows, idx, val, v, tex, epi, w->red, skip); \
+    }
+    if (val) ELL_GO(true, 0)
+    else if (tex) ELL_GO(false, 1)
+    else ELL_GO(false, 0)
+#undef ELL_GO
+    return 0;
+}
+
+inline bool ell_supported(int L) { return L == 4 || L == 6 || L == 8 || L == 10 || L == 12 || L == 16; }
+
+// mode: 1 = stream, 2 = ELL (ell = common row length), 4/8/16/32 = lanes per row
 template <class Epi>
 int launch_spmv(bsls_ws *w, int mode, int64_t rows, const int64_t *ptr, const int32_t *idx, const double *val, const double *v,
-                const Epi &epi, cudaStream_t st) {
+                const Epi &epi, cudaStream_t st, const int *skip = nullptr, int ell = 0, cudaTextureObject_t tex = 0) {
     constexpr int T = 256;
     if (rows <= 0) return BSLS_OK;
-    if (mode == 1) {
-        static thread_local int full = 0;
+    if (mode == 2 && ell_supported(ell)) {
+        switch (ell) {
+            case 4: launch_ell<Epi, 4>(w, rows, idx, val, v, tex, epi, st, skip); break;
+            case 6: launch_ell<Epi, 6>(w, rows, idx, val, v, tex, epi, st, skip); break;
+            case 8: launch_ell<Epi, 8>(w, rows, idx, val, v, tex, epi, st, skip); break;
+            case 10: launch_ell<Epi, 10>(w, rows, idx, val, v, tex, epi, st, skip); break;
+            case 12: launch_ell<Epi, 12>(w, rows, idx, val, v, tex, epi, st, skip); break;
+            default: launch_ell<Epi, 16>(w, rows, idx, val, v, tex, epi, st, skip); break;
+        }
+    } else if (mode == 1 || mode == 2) {
+        static thread_local PerDevice<int> full_pd;
+        int &full = full_pd.get(0);
         if (!full) full = resident_grid(spmv_stream_kernel<Epi, T, 2048>, T);
         const int64_t tiles = (rows + T - 1) / T;
         const int grid = (int)(tiles < full ? tiles : full);
-        spmv_stream_kernel<Epi, T, 2048><<<grid, T, 0, st>>>(rows, ptr, idx, val, v, epi, w->red);
+        spmv_stream_kernel<Epi, T, 2048><<<grid, T, 0, st>>>(rows, ptr, idx, val, v, epi, w->red, skip);
     } else {
         switch (mode) {
-            case 4: launch_vector<Epi, 4>(w, rows, ptr, idx, val, v, epi, st); break;
-            case 8: launch_vector<Epi, 8>(w, rows, ptr, idx, val, v, epi, st); break;
-            case 16: launch_vector<Epi, 16>(w, rows, ptr, idx, val, v, epi, st); break;
-            default: launch_vector<Epi, 32>(w, rows, ptr, idx, val, v, epi, st); break;
+            case 4: launch_vector<Epi, 4>(w, rows, ptr, idx, val, v, epi, st, skip); break;
+            case 8: launch_vector<Epi, 8>(w, rows, ptr, idx, val, v, epi, st, skip); break;
+            case 16: launch_vector<Epi, 16>(w, rows, ptr, idx, val, v, epi, st, skip); break;
+            default: launch_vector<Epi, 32>(w, rows, ptr, idx, val, v, epi, st, skip); break;
         }
     }
     BSLS_LAUNCH_CHECK();
@@ -169,28 +236,38 @@ int allreduce(bsls_ws *w, double *buf, int64_t count, int op, cudaStream_t st) {
     return BSLS_OK;
 }
 
-// r = A x - b (summed over ranks), scalar F = 0.5 <r, r>
-int residual(bsls_lsq *q, const double *x, double *r, const double *b, cudaStream_t st) {
+// A^T w with an epilogue, on whichever kernel the side was given
+template <class Epi> int launch_at(bsls_lsq *q, const double *w, const Epi &epi, cudaStream_t st, const int *skip = nullptr) {
+    cudaTextureObject_t tex = 0;
+    if (w == q->r) tex = q->tex_r[0];
+    if (w == q->r2) tex = q->tex_r[1];
+    return launch_spmv(q->ws, q->t_mode, q->n, q->t_ptr, q->t_idx, q->t_val, w, epi, st, skip, q->t_ell, tex);
+}
+
+// r = A x - b (summed over ranks), scalar F = 0.5 <r, r>; with r_old also <r_old, r - r_old> and |r - r_old|^2
+int residual(bsls_lsq *q, const double *x, double *r, const double *b, cudaStream_t st, const double *r_old = nullptr,
+             const int *skip = nullptr) {
     bsls_ws *w = q->ws;
     const bool dist = w->comm && w->comm->nranks > 1;
     if (q->panels > 1) {
         // one launch per panel: the kernel boundary keeps all CTAs inside the same slice of x, which
         // therefore stays L2-resident (a single launch lets CTAs drift several panels apart)
         for (int p = 0; p < q->panels; ++p) {
-            EpiResidual epi{q->partial + (size_t)p * q->m, nullptr};
-            if (int rc = launch_spmv(w, q->p_mode, q->m, q->p_ptr + (size_t)p * q->m, q->p_idx, q->p_val, x, epi, st)) return rc;
+            EpiResidual epi{q->partial + (size_t)p * q->m, nullptr, nullptr};
+            if (int rc = launch_spmv(w, q->p_mode, q->m, q->p_ptr + (size_t)p * q->m, q->p_idx, q->p_val, x, epi, st, skip)) return rc;
         }
-        panel_reduce_kernel<<<grid_elems(q->m), 256, 0, st>>>(r, q->partial, dist ? nullptr : b, q->m, q->panels, w->red);
+        panel_reduce_kernel<<<grid_elems(q->m), 256, 0, st>>>(r, q->partial, dist ? nullptr : b, r_old, q->m, q->panels, w->red, skip);
         BSLS_LAUNCH_CHECK();
         w->launches++;
     } else {
-        EpiResidual epi{r, (dist || !b) ? nullptr : b};
-        if (int rc = launch_spmv(w, q->a_mode, q->m, q->a_ptr, q->a_idx, q->a_val, x, epi, st)) return rc;
+        const bool fin = !dist && b;
+        EpiResidual epi{r, fin ? b : nullptr, fin ? r_old : nullptr};
+        if (int rc = launch_spmv(w, q->a_mode, q->m, q->a_ptr, q->a_idx, q->a_val, x, epi, st, skip, q->a_ell)) return rc;
     }
     if (dist) {
         if (int rc = allreduce(w, r, q->m, kNcclSum, st)) return rc;
         if (b) {
-            residual_finish_kernel<<<grid_elems(q->m), 256, 0, st>>>(r, b, q->m, w->red);
+            residual_finish_kernel<<<grid_elems(q->m), 256, 0, st>>>(r, b, r_old, q->m, w->red, skip);
             BSLS_LAUNCH_CHECK();
             w->launches++;
         }
@@ -198,8 +275,28 @@ int residual(bsls_lsq *q, const double *x, double *r, const double *b, cudaStrea
     return BSLS_OK;
 }
 
+// texture view of an m-vector of doubles (as int2 texels), for the BSLS_ELL_TEX experiment
+int make_tex(const double *p, int64_t m, cudaTextureObject_t *out) {
+    static const bool on = [] {
+        const char *e = getenv("BSLS_ELL_TEX");
+        return e && atoi(e) != 0;
+    }();
+    if (!on || *out) return BSLS_OK;
+    cudaResourceDesc rd{};
+    rd.resType = cudaResourceTypeLinear;
+    rd.res.linear.devPtr = const_cast<double *>(p);
+    rd.res.linear.desc = cudaCreateChannelDesc<int2>();
+    rd.res.linear.sizeInBytes = (size_t)m * sizeof(double);
+    cudaTextureDesc td{};
+    td.readMode = cudaReadModeElementType;
+    BSLS_CUDA_TRY(cudaCreateTextureObject(out, &rd, &td, nullptr));
+    return BSLS_OK;
+}
+
 int ensure_workspace(bsls_lsq *q) {
     if (q->wg) return BSLS_OK;
+    BSLS_CUDA_TRY(cudaMalloc(&q->r2, sizeof(double) * (size_t)q->m));
+    if (int rc = make_tex(q->r2, q->m, &q->tex_r[1])) return rc;
     BSLS_CUDA_TRY(cudaMalloc(&q->wg, sizeof(double) * (size_t)q->n));
     BSLS_CUDA_TRY(cudaMalloc(&q->wxn, sizeof(double) * (size_t)q->n));
     BSLS_CUDA_TRY(cudaMalloc(&q->wgn, sizeof(double) * (size_t)q->n));
@@ -242,6 +339,35 @@ int grid_groups(int nb, int lanes) {
         case 16: KERNEL<16><<<grid, 256, 0, st>>>(__VA_ARGS__); break;       \
         default: KERNEL<32><<<grid, 256, 0, st>>>(__VA_ARGS__); break;       \
     }
+
+
+// x_new = x * exp(-t g), blocks normalised (lsq.cuh); dst != null: step and stop flag from the solver state
+int md_update(bsls_ws *q, const bsls_plan *plan, double *x_new, const double *x, const double *g, double step, int per_block_log,
+              cudaStream_t st, const DevState *dst) {
+    const int lanes = lanes_for(plan);
+    const int grid = grid_groups(plan->nb, lanes);
+    if (plan->max_size <= 2 * lanes) {  // every block fits the registers of its lanes: one pass, one resident wave
+#define MD_REG(G)                                                                                                     \
+    {                                                                                                                 \
+        static thread_local PerDevice<int> full_pd;                                                                   \
+        int &full = full_pd.get(0);                                                                                   \
+        if (!full) full = resident_grid(md_update_reg_kernel<G, 2>, 256);                                             \
+        md_update_reg_kernel<G, 2><<<grid < full ? grid : full, 256, 0, st>>>(x_new, x, g, step, per_block_log, layout_of(plan), q->red, dst); \
+    }
+        switch (lanes) {
+            case 4: MD_REG(4) break;
+            case 8: MD_REG(8) break;
+            case 16: MD_REG(16) break;
+            default: MD_REG(32) break;
+        }
+#undef MD_REG
+    } else {
+        DISPATCH_LANES(lanes, md_update_kernel, grid, st, x_new, x, g, step, per_block_log, layout_of(plan), q->red, dst);
+    }
+    BSLS_LAUNCH_CHECK();
+    q->launches++;
+    return BSLS_OK;
+}
 
 }  // namespace
 
@@ -317,6 +443,10 @@ int bsls_ws_create(bsls_ws **out) {
     TRY_OR_FAIL(cudaMemset(w->red.ticket, 0, sizeof(unsigned)));
     TRY_OR_FAIL(cudaMemset(w->d_scal, 0, sizeof(double) * kScalCount));
     TRY_OR_FAIL(cudaHostAlloc(&w->h_scal, sizeof(double) * kScalCount, cudaHostAllocDefault));
+    TRY_OR_FAIL(cudaMalloc(&w->d_state, sizeof(DevState)));
+    TRY_OR_FAIL(cudaMemset(w->d_state, 0, sizeof(DevState)));
+    TRY_OR_FAIL(cudaHostAlloc(&w->h_state, 2 * sizeof(DevState), cudaHostAllocDefault));
+    for (int k = 0; k < 2; ++k) TRY_OR_FAIL(cudaEventCreateWithFlags(&w->ev_state[k], cudaEventDisableTiming));
 #undef TRY_OR_FAIL
     w->red.out = w->d_scal;
     *out = w;
@@ -329,6 +459,12 @@ int bsls_ws_destroy(bsls_ws *w) {
     if (w->red.ticket) cudaFree(w->red.ticket);
     if (w->d_scal) cudaFree(w->d_scal);
     if (w->h_scal) cudaFreeHost(w->h_scal);
+    if (w->d_state) cudaFree(w->d_state);
+    if (w->h_state) cudaFreeHost(w->h_state);
+    for (int k = 0; k < 2; ++k)
+        if (w->ev_state[k]) cudaEventDestroy(w->ev_state[k]);
+    if (w->d_gather) cudaFree(w->d_gather);
+    if (w->d_prog) cudaFree(w->d_prog);
     delete w;
     return BSLS_OK;
 }
@@ -377,6 +513,11 @@ int bsls_lsq_create(int64_t m, int64_t n, int64_t nnz, const int64_t *a_ptr, con
     q->b = b;
     q->a_mode = pick_mode(nnz, m);
     q->t_mode = pick_mode(nnz, n);
+    // rows of one common length (every route traverses L links): the pointer-free ELL kernel
+    q->t_ell = uniform_row_length(at_ptr, n, nnz);
+    q->a_ell = uniform_row_length(a_ptr, m, nnz);
+    if (ell_supported(q->t_ell)) q->t_mode = 2;
+    if (ell_supported(q->a_ell) && q->a_ell <= 16) q->a_mode = 2;
     if (const char *e = getenv("BSLS_SPMV_A")) q->a_mode = atoi(e);
     if (const char *e = getenv("BSLS_SPMV_AT")) q->t_mode = atoi(e);
     auto fail = [&](int rc) {
@@ -392,6 +533,7 @@ int bsls_lsq_create(int64_t m, int64_t n, int64_t nnz, const int64_t *a_ptr, con
         }                                                                                    \
     } while (0)
     TRY_OR_FAIL(cudaMalloc(&q->r, sizeof(double) * (size_t)m));
+    if (int rc = make_tex(q->r, m, &q->tex_r[0])) return fail(rc);
     TRY_OR_FAIL(cudaEventCreate(&q->ev0));
     TRY_OR_FAIL(cudaEventCreate(&q->ev1));
 #undef TRY_OR_FAIL
@@ -403,6 +545,9 @@ int bsls_lsq_create(int64_t m, int64_t n, int64_t nnz, const int64_t *a_ptr, con
 int bsls_lsq_destroy(bsls_lsq *q) {
     if (!q) return BSLS_OK;
     if (q->r) cudaFree(q->r);
+    if (q->r2) cudaFree(q->r2);
+    for (int k = 0; k < 2; ++k)
+        if (q->tex_r[k]) cudaDestroyTextureObject(q->tex_r[k]);
     if (q->partial) cudaFree(q->partial);
     if (q->wg) cudaFree(q->wg);
     if (q->wxn) cudaFree(q->wxn);
@@ -430,13 +575,13 @@ int bsls_lsq_set_b(bsls_lsq *q, const double *b) {
 
 int bsls_lsq_set_modes(bsls_lsq *q, int a_mode, int at_mode) {
     if (!q) return BSLS_ERR_ARG;
-    auto ok = [](int v) { return v == 0 || v == 1 || v == 4 || v == 8 || v == 16 || v == 32; };
+    auto ok = [](int v) { return v == 0 || v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32; };
     if (!ok(a_mode) || !ok(at_mode)) {
-        set_error("lsq_set_modes: mode must be 0, 1, 4, 8, 16 or 32");
+        set_error("lsq_set_modes: mode must be 0, 1, 2, 4, 8, 16 or 32");
         return BSLS_ERR_ARG;
     }
-    q->a_mode = a_mode ? a_mode : pick_mode(q->nnz, q->m);
-    q->t_mode = at_mode ? at_mode : pick_mode(q->nnz, q->n);
+    q->a_mode = a_mode ? a_mode : (ell_supported(q->a_ell) ? 2 : pick_mode(q->nnz, q->m));
+    q->t_mode = at_mode ? at_mode : (ell_supported(q->t_ell) ? 2 : pick_mode(q->nnz, q->n));
     return BSLS_OK;
 }
 
@@ -474,7 +619,7 @@ int bsls_dev_lsq_residual_f64(bsls_lsq *q, const double *x, bsls_stream_t s) {
 int bsls_dev_lsq_gradient_f64(bsls_lsq *q, double *g, bsls_stream_t s) {
     if (!q || !g) return BSLS_ERR_ARG;
     EpiPlain epi{g};
-    return launch_spmv(q->ws, q->t_mode, q->n, q->t_ptr, q->t_idx, q->t_val, q->r, epi, (cudaStream_t)s);
+    return launch_at(q, q->r, epi, (cudaStream_t)s);
 }
 
 int bsls_dev_lsq_matvec_f64(bsls_lsq *q, const double *v, double *out, bsls_stream_t s) {
@@ -485,7 +630,7 @@ int bsls_dev_lsq_matvec_f64(bsls_lsq *q, const double *v, double *out, bsls_stre
 int bsls_dev_lsq_rmatvec_f64(bsls_lsq *q, const double *w, double *out, bsls_stream_t s) {
     if (!q || !w || !out) return BSLS_ERR_ARG;
     EpiPlain epi{out};
-    return launch_spmv(q->ws, q->t_mode, q->n, q->t_ptr, q->t_idx, q->t_val, w, epi, (cudaStream_t)s);
+    return launch_at(q, w, epi, (cudaStream_t)s);
 }
 
 int bsls_lsq_scalars(bsls_lsq *q, double out[16], bsls_stream_t s) { return q ? bsls_ws_scalars(q->ws, out, s) : BSLS_ERR_ARG; }
@@ -553,29 +698,8 @@ int bsls_dev_axpy_dot_f64(bsls_ws *q, double *d, double scale, const double *c0,
 int bsls_dev_md_update_f64(bsls_ws *q, const bsls_plan *plan, double *x_new, const double *x, const double *g, double step,
                            int per_block_log, bsls_stream_t s) {
     if (!q || !plan || !x_new || !x || !g) return BSLS_ERR_ARG;
-    cudaStream_t st = (cudaStream_t)s;
-    const int lanes = lanes_for(plan);
-    const int grid = grid_groups(plan->nb, lanes);
-    if (plan->max_size <= 2 * lanes) {  // every block fits the registers of its lanes: one pass, one resident wave
-#define MD_REG(G)                                                                                                     \
-    {                                                                                                                 \
-        static thread_local int full = 0;                                                                             \
-        if (!full) full = resident_grid(md_update_reg_kernel<G, 2>, 256);                                             \
-        md_update_reg_kernel<G, 2><<<grid < full ? grid : full, 256, 0, st>>>(x_new, x, g, step, per_block_log, layout_of(plan), q->red); \
-    }
-        switch (lanes) {
-            case 4: MD_REG(4) break;
-            case 8: MD_REG(8) break;
-            case 16: MD_REG(16) break;
-            default: MD_REG(32) break;
-        }
-#undef MD_REG
-    } else {
-        DISPATCH_LANES(lanes, md_update_kernel, grid, st, x_new, x, g, step, per_block_log, layout_of(plan), q->red);
-    }
-    BSLS_LAUNCH_CHECK();
-    q->launches++;
-    return allreduce(q, q->d_scal + kScalMax0, 1, kNcclMax, st);
+    if (int rc = md_update(q, plan, x_new, x, g, step, per_block_log, (cudaStream_t)s, nullptr)) return rc;
+    return allreduce(q, q->d_scal + kScalMax0, 1, kNcclMax, (cudaStream_t)s);
 }
 
 int bsls_dev_block_scale_f64(const bsls_plan *plan, double *y, const double *f, int divide, bsls_stream_t s) {
@@ -615,13 +739,14 @@ int bsls_dev_x2z_f64(const bsls_plan *plan, const double *x, double *z, bsls_str
     if (plan->uniform >= 2 && plan->uniform <= kX2zTileMaxK) {
         const int K = plan->uniform;
         const size_t smem = (size_t)kX2zTileThreads * (K | 1) * sizeof(double);
-        static thread_local size_t attr_smem = 0;
+        static thread_local PerDevice<size_t> attr_smem_pd;
+        size_t &attr_smem = attr_smem_pd.get(0);
         if (smem > attr_smem) {
             BSLS_CUDA_TRY(cudaFuncSetAttribute(x2z_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_smem = smem;
         }
         const int ntiles = (plan->nb + kX2zTileThreads - 1) / kX2zTileThreads;
-        const int grid = ntiles < 8 * kNumSM ? ntiles : 8 * kNumSM;
+        const int grid = ntiles < 8 * num_sms() ? ntiles : 8 * num_sms();
         x2z_tile_kernel<<<grid, kX2zTileThreads, smem, (cudaStream_t)s>>>(x, z, plan->nb, K, make_fastdiv((uint32_t)K),
                                                                            make_fastdiv((uint32_t)(K - 1)));
         BSLS_LAUNCH_CHECK();
@@ -659,23 +784,17 @@ int bsls_dev_z2x_f64(const bsls_plan *plan, double *x, const double *z, bsls_str
 static int eval_new(bsls_lsq *q, const double *x, const double *g, const double *x_new, double *g_new, cudaStream_t st) {
     if (int rc = residual(q, x_new, q->r, q->b, st)) return rc;
     EpiGradBB epi{g_new, g, x, x_new};
-    if (int rc = launch_spmv(q->ws, q->t_mode, q->n, q->t_ptr, q->t_idx, q->t_val, q->r, epi, st)) return rc;
+    if (int rc = launch_at(q, q->r, epi, st)) return rc;
     if (int rc = allreduce(q->ws, q->ws->d_scal + kScalSxy, 4, kNcclSum, st)) return rc;
     if (int rc = allreduce(q->ws, q->ws->d_scal + kScalStep, 1, kNcclMax, st)) return rc;
     return fetch_scalars(q->ws, st);
 }
 
-int bsls_batch_solve_f64(bsls_lsq *q, const bsls_plan *plan, double *x, const bsls_batch_opts *o, bsls_batch_result *res,
-                         double *progress_f, double *progress_t, int progress_cap, bsls_stream_t s) {
-    if (!q || !plan || !x || !o || !res || !q->b) {
-        set_error("batch_solve: null argument");
-        return BSLS_ERR_ARG;
-    }
-    if (plan->n != q->n) {
-        set_error("batch_solve: plan covers %d variables, A has %lld columns", plan->n, (long long)q->n);
-        return BSLS_ERR_ARG;
-    }
-    if (o->method < 0 || o->method > 2) return BSLS_ERR_ARG;
+// The round-1 loop: host-side step logic, one 128-byte read-back and one stream synchronisation per objective
+// evaluation, a back-track re-evaluates the objective with two more products.  Kept behind BSLS_BATCH_LEGACY=1 as the
+// A/B reference of the device-resident loop below.
+static int batch_solve_legacy(bsls_lsq *q, const bsls_plan *plan, double *x, const bsls_batch_opts *o, bsls_batch_result *res,
+                              double *progress_f, double *progress_t, int progress_cap, bsls_stream_t s) {
     cudaStream_t st = (cudaStream_t)s;
     if (int rc = ensure_workspace(q)) return rc;
     const int64_t n = q->n;
@@ -800,6 +919,189 @@ int bsls_batch_solve_f64(bsls_lsq *q, const bsls_plan *plan, double *x, const bs
     res->obj_evals = evals;
     res->backtracks = backtracks;
     res->kernel_launches = (q->ws->launches - launches0) + extra_launches;
+    res->device_ms = ms;
+    return BSLS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device-resident loop
+// ---------------------------------------------------------------------------------------------
+// Buffers come in two sets (x, g, r)[0..1]; iteration k reads set k & 1 (the iterate) and writes set (k + 1) & 1 (the
+// trial point).  The trial point always becomes the next iterate -- directly, or pulled back along the segment by
+// commit_kernel after a back-tracked line search -- so the roles alternate by iteration number and no kernel argument
+// depends on a decision taken on the device.  The host therefore enqueues iteration k + 1 BEFORE it learns how
+// iteration k ended (one iteration of slack: the GPU never waits for the host), reads the 80-byte solver state of
+// iteration k from pinned memory when its event fires, and stops enqueuing once `done` is set.  An iteration enqueued
+// past the stop exits in every kernel's first instructions and touches only buffers that do not hold the result.
+namespace {
+struct LoopBuffers {
+    double *x[2], *g[2], *r[2];
+};
+
+int ensure_loop_scratch(bsls_ws *w, int prog_cap) {
+    const int nr = (w->comm && w->comm->nranks > 1) ? w->comm->nranks : 0;
+    if (nr > w->gather_cap) {
+        if (w->d_gather) cudaFree(w->d_gather);
+        w->d_gather = nullptr;
+        BSLS_CUDA_TRY(cudaMalloc(&w->d_gather, sizeof(double) * 5 * (size_t)nr));
+        w->gather_cap = nr;
+    }
+    if (prog_cap > w->prog_cap) {
+        if (w->d_prog) cudaFree(w->d_prog);
+        w->d_prog = nullptr;
+        BSLS_CUDA_TRY(cudaMalloc(&w->d_prog, sizeof(double) * 2 * (size_t)prog_cap));
+        w->prog_cap = prog_cap;
+    }
+    return BSLS_OK;
+}
+
+// one iteration of BATCH.solve / solve_BB / solve_MD on the device: trial point, objective + gradient there, decision
+int enqueue_iteration(bsls_lsq *q, const bsls_plan *plan, const LoopBuffers &B, int cur, const DevOpts &d, int proj_mode, cudaStream_t st,
+                      int *extra_launches) {
+    bsls_ws *w = q->ws;
+    const int nxt = cur ^ 1;
+    const int64_t n = q->n;
+    DevState *S = w->d_state;
+    const int *done = &S->done;
+    const bool dist = w->comm && w->comm->nranks > 1;
+    // ---- trial point --------------------------------------------------------------------------
+    if (d.method == 2) {
+        if (int rc = md_update(w, plan, B.x[nxt], B.x[cur], B.g[cur], 0.0, 0, st, S)) return rc;
+    } else {
+        bool fused = false;
+        const StepCtl ctl{&S->t, done};
+        if (proj_mode != 2)  // x_new = proj(x - t g) in ONE kernel where the layout allows it
+            if (int rc = project_step_f64(plan, B.x[cur], B.g[cur], 0.0, B.x[nxt], proj_mode, st, &fused, &ctl)) return rc;
+        if (!fused) {
+            step_axpy_kernel<<<grid_elems(n), 256, 0, st>>>(B.x[nxt], B.x[cur], B.g[cur], S, n);
+            BSLS_LAUNCH_CHECK();
+            ++*extra_launches;
+            if (proj_mode == 2) {  // z-space: isotonic regression + clip to [0,1] (algorithm_utils.py:219-224)
+                if (int rc = pava_clip_f64(plan, B.x[nxt], nullptr, 1, 1, st)) return rc;
+            } else {
+                if (int rc = project_f64(plan, B.x[nxt], proj_mode, st)) return rc;
+            }
+        }
+        ++*extra_launches;
+    }
+    // ---- objective and gradient at the trial point ------------------------------------------------
+    if (int rc = residual(q, B.x[nxt], B.r[nxt], q->b, st, B.r[cur], done)) return rc;
+    const bool need_dots = d.method == 1 || d.search;
+    if (need_dots) {
+        EpiGradBB epi{B.g[nxt], B.g[cur], B.x[cur], B.x[nxt]};
+        if (int rc = launch_at(q, B.r[nxt], epi, st, done)) return rc;
+        if (dist)  // every rank needs every rank's share of the step scalars: one small all-gather (slots 1..5)
+            BSLS_NCCL_TRY(g_nccl.AllGather(w->d_scal + kScalSxy, w->d_gather, 5, kNcclFloat64, w->comm->comm, st));
+    } else {
+        EpiPlain epi{B.g[nxt]};
+        if (int rc = launch_at(q, B.r[nxt], epi, st, done)) return rc;
+    }
+    // ---- decision, and the pull-back of a back-tracked trial point ----------------------------------
+    decide_kernel<<<1, 32, 0, st>>>(S, w->d_scal, (need_dots && dist) ? w->d_gather : nullptr, d, w->d_prog,
+                                    w->d_prog ? w->d_prog + w->prog_cap : nullptr, 0);
+    BSLS_LAUNCH_CHECK();
+    ++*extra_launches;
+    if (d.search) {
+        const int64_t big = n > q->m ? n : q->m;
+        commit_kernel<<<grid_elems(big), 256, 0, st>>>(S, B.x[nxt], B.x[cur], B.g[nxt], B.g[cur], n, B.r[nxt], B.r[cur], q->m);
+        BSLS_LAUNCH_CHECK();
+        ++*extra_launches;
+    }
+    return BSLS_OK;
+}
+}  // namespace
+
+int bsls_batch_solve_f64(bsls_lsq *q, const bsls_plan *plan, double *x, const bsls_batch_opts *o, bsls_batch_result *res,
+                         double *progress_f, double *progress_t, int progress_cap, bsls_stream_t s) {
+    if (!q || !plan || !x || !o || !res || !q->b) {
+        set_error("batch_solve: null argument");
+        return BSLS_ERR_ARG;
+    }
+    if (plan->n != q->n) {
+        set_error("batch_solve: plan covers %d variables, A has %lld columns", plan->n, (long long)q->n);
+        return BSLS_ERR_ARG;
+    }
+    if (o->method < 0 || o->method > 2) return BSLS_ERR_ARG;
+    if (int rc = ensure_workspace(q)) return rc;
+    static const bool legacy = [] {
+        const char *e = getenv("BSLS_BATCH_LEGACY");
+        return e && atoi(e) != 0;
+    }();
+    if (legacy) return batch_solve_legacy(q, plan, x, o, res, progress_f, progress_t, progress_cap, s);
+
+    cudaStream_t st = (cudaStream_t)s;
+    bsls_ws *w = q->ws;
+    const int cap = (progress_f && progress_cap > 0) ? progress_cap : 0;
+    if (int rc = ensure_loop_scratch(w, cap)) return rc;
+    DevOpts d{};
+    d.method = o->method;
+    d.search = (o->method == 1) || (o->method == 0 && o->use_line_search);
+    d.has_f_min = o->has_f_min;
+    d.max_iter = o->max_iter;
+    d.f_min = o->f_min;
+    d.opt_tol = o->opt_tol;
+    d.prog_tol = o->prog_tol;
+    d.min_eig = o->min_eig;
+    d.nranks = (w->comm && w->comm->nranks > 1) ? w->comm->nranks : 1;
+    d.progress_cap = cap;
+    LoopBuffers B{{x, q->wxn}, {q->wg, q->wgn}, {q->r, q->r2}};
+    const int launches0 = w->launches;
+    int extra = 0;
+
+    BSLS_CUDA_TRY(cudaEventRecord(q->ev0, st));
+    BSLS_CUDA_TRY(cudaMemsetAsync(w->d_state, 0, sizeof(DevState), st));
+    // f = obj(x, g) at the starting point
+    if (int rc = residual(q, B.x[0], B.r[0], q->b, st)) return rc;
+    {
+        EpiPlain epi{B.g[0]};
+        if (int rc = launch_at(q, B.r[0], epi, st)) return rc;
+    }
+    decide_kernel<<<1, 32, 0, st>>>(w->d_state, w->d_scal, nullptr, d, w->d_prog, w->d_prog ? w->d_prog + w->prog_cap : nullptr, 1);
+    BSLS_LAUNCH_CHECK();
+    ++extra;
+    BSLS_CUDA_TRY(cudaMemcpyAsync(&w->h_state[1], w->d_state, sizeof(DevState), cudaMemcpyDeviceToHost, st));
+    BSLS_CUDA_TRY(cudaEventRecord(w->ev_state[1], st));
+
+    // iteration k may run only if the state after iteration k - 1 is not `done`; the host learns that one iteration late
+    const int max_body = o->max_iter > 1 ? o->max_iter - 1 : 0;  // the reference stops at i == max_iter, i starting at 1
+    int k = 0;
+    for (; k < max_body; ++k) {
+        if (int rc = enqueue_iteration(q, plan, B, k & 1, d, o->proj_mode, st, &extra)) return rc;
+        BSLS_CUDA_TRY(cudaMemcpyAsync(&w->h_state[k & 1], w->d_state, sizeof(DevState), cudaMemcpyDeviceToHost, st));
+        BSLS_CUDA_TRY(cudaEventRecord(w->ev_state[k & 1], st));
+        // the state BEFORE this iteration (after iteration k - 1, or after the initial evaluation)
+        BSLS_CUDA_TRY(cudaEventSynchronize(w->ev_state[(k + 1) & 1]));
+        if (w->h_state[(k + 1) & 1].done) break;
+    }
+    BSLS_CUDA_TRY(cudaStreamSynchronize(st));
+    DevState fin;
+    BSLS_CUDA_TRY(cudaMemcpy(&fin, w->d_state, sizeof(DevState), cudaMemcpyDeviceToHost));
+    if (!fin.done) {
+        set_error("batch_solve: the device loop ended without a stop code (i=%d)", fin.i);
+        return BSLS_ERR_CUDA;
+    }
+    if (fin.parity != 0) BSLS_CUDA_TRY(cudaMemcpyAsync(x, B.x[1], sizeof(double) * (size_t)q->n, cudaMemcpyDeviceToDevice, st));
+    if (cap > 0) {
+        const int np = fin.i < cap ? fin.i : cap;
+        BSLS_CUDA_TRY(cudaMemcpyAsync(progress_f, w->d_prog, sizeof(double) * (size_t)np, cudaMemcpyDeviceToHost, st));
+        if (progress_t) BSLS_CUDA_TRY(cudaMemcpyAsync(progress_t, w->d_prog + w->prog_cap, sizeof(double) * (size_t)np, cudaMemcpyDeviceToHost, st));
+    }
+    BSLS_CUDA_TRY(cudaEventRecord(q->ev1, st));
+    BSLS_CUDA_TRY(cudaStreamSynchronize(st));
+    if (cap > 0 && progress_t) {  // device time stamps (ns) -> seconds since the first objective value
+        const int np = fin.i < cap ? fin.i : cap;
+        const double t0 = progress_t[0];
+        for (int j = 0; j < np; ++j) progress_t[j] = (progress_t[j] - t0) * 1e-9;
+    }
+    float ms = 0.f;
+    BSLS_CUDA_TRY(cudaEventElapsedTime(&ms, q->ev0, q->ev1));
+    res->f = fin.f;
+    res->iterations = fin.i;
+    res->stop_code = fin.done;
+    res->stop_value = fin.stop_value;
+    res->obj_evals = fin.evals;
+    res->backtracks = fin.backtracks;
+    res->kernel_launches = (w->launches - launches0) + extra;
     res->device_ms = ms;
     return BSLS_OK;
 }

@@ -115,24 +115,73 @@ enum Scal {
     kScalDot0 = 6,  // generic dot products: 6..9
     kScalMax0 = 10, // generic maximum
     kScalRR = 11,   // <r, r> (not halved)
+    kScalRdr = 12,  // <r_old, r_new - r_old>      (line search along the step, see decide_kernel)
+    kScalDrdr = 13, // <r_new - r_old, r_new - r_old>
     kScalCount = 16
+};
+
+// ---- solver state on the device (device-resident step logic) ------------------------------------
+// The BATCH loops of the reference branch on scalars every iteration (python/BATCH.py:33-47,84-102,
+// python/algorithm_utils.py:113-137,158-172).  Here those scalars never leave the GPU inside the loop: the reducing
+// kernels leave them in the scalar block, decide_kernel (one thread) takes the line-search / step / stopping decisions
+// and the kernels of the next iteration read what they need (the step `t`, the `done` flag) from this struct.
+struct DevState {
+    double f, f_old;       // objective at the current / previous iterate
+    double t;              // step of the NEXT trial point (BB: <dx,dg>/<dg,dg>; else 1/(min_eig i + 1))
+    double tau;            // line-search factor of the LAST iteration: x_new = x + tau (x_trial - x); 1 = trial accepted as is
+    double sxy, syy;       // <dx, dg>, <dg, dg> of the last accepted step
+    double stop_value;
+    double change;         // mirror descent: max |x_new - x| of the last step
+    int i;                 // the reference's iteration counter
+    int done;              // 0 = running, else the stop code (1 max_iter, 2 f - f_min < opt_tol, 3 |f_old - f| < prog_tol, ...)
+    int evals, backtracks;
+    int parity;            // which buffer set holds the current iterate
+    int pad;
+};
+struct DevOpts {
+    int method;            // 0 projected gradient, 1 Barzilai-Borwein, 2 mirror descent (BATCH); 3 BB.solve, 4 mirror_descent.least_squares
+    int search;            // run line_search_np
+    int has_f_min, max_iter;
+    double f_min, opt_tol, prog_tol, min_eig;
+    double tolerance;      // method 4: stop when max |x - x_prev| < tolerance; method 3: opt_tol of solvers.stopping
+    double Lf;             // method 4
+    int nranks, progress_cap;
 };
 
 // ---- SpMV epilogues ----------------------------------------------------------------------------
 // An epilogue sees (row, dot) once per row and accumulates into acc[].
+// r_old (optional): the residual at the current iterate; then <r_old, dr> and <dr, dr> with dr = r - r_old come out too.
+// They give the objective anywhere on the segment between the iterate and the trial point without another product:
+// f(x + tau dx) = f(x) + tau <r_old, dr> + 0.5 tau^2 <dr, dr>  (the differences are formed element by element: no cancellation).
+__device__ __forceinline__ void residual_sums(double v, double ro, bool have_old, double (&acc)[3]) {
+    acc[0] += v * v;
+    if (have_old) {
+        const double d = v - ro;
+        acc[1] += ro * d;
+        acc[2] += d * d;
+    }
+}
+struct FinResidual {
+    static __device__ __forceinline__ void store(double *o, int k, double v) {
+        if (k == 0) {
+            o[kScalF] = 0.5 * v;
+            o[kScalRR] = v;
+        } else {
+            o[k == 1 ? kScalRdr : kScalDrdr] = v;
+        }
+    }
+};
 struct EpiResidual {  // r = A x - b ; f = 0.5 <r, r>       (algorithm_utils.py:91,93)
-    static constexpr int NSUM = 1, NMAX = 0;
+    static constexpr int NSUM = 3, NMAX = 0;
     double *r;
-    const double *b;  // may be null (partial product of one rank: b is subtracted after the all-reduce)
-    __device__ __forceinline__ void apply(int64_t i, double dot, double (&acc)[1]) const {
+    const double *b;      // may be null (partial product of one rank: b is subtracted after the all-reduce)
+    const double *r_old;  // may be null
+    __device__ __forceinline__ void apply(int64_t i, double dot, double (&acc)[3]) const {
         const double v = b ? dot - b[i] : dot;
         r[i] = v;
-        acc[0] += v * v;
+        residual_sums(v, r_old ? r_old[i] : 0.0, r_old != nullptr, acc);
     }
-    static __device__ __forceinline__ void store(double *out, int k, double v) {
-        out[kScalF] = 0.5 * v;
-        out[kScalRR] = v;
-    }
+    static __device__ __forceinline__ void store(double *out, int k, double v) { FinResidual::store(out, k, v); }
 };
 struct EpiPlain {  // out = M v
     static constexpr int NSUM = 1, NMAX = 0;
@@ -186,7 +235,8 @@ __device__ __forceinline__ int pad16(int k) { return k + (k >> 4); }  // one spa
 template <class Epi, int THREADS, int CHUNK>
 __global__ void __launch_bounds__(THREADS)
 spmv_stream_kernel(int64_t rows, const int64_t *__restrict__ ptr, const int32_t *__restrict__ idx,
-                   const double *__restrict__ val, const double *__restrict__ v, Epi epi, RedCtx red) {
+                   const double *__restrict__ val, const double *__restrict__ v, Epi epi, RedCtx red, const int *__restrict__ skip) {
+    if (skip && *skip) return;  // the solver has stopped: iterations enqueued ahead do nothing
     __shared__ double prod[CHUNK + CHUNK / 16 + 2];
     __shared__ int64_t s_range[2];
     constexpr int NA = Epi::NSUM + Epi::NMAX;
@@ -236,11 +286,77 @@ spmv_stream_kernel(int64_t rows, const int64_t *__restrict__ ptr, const int32_t 
     grid_reduce<Epi::NSUM, Epi::NMAX, THREADS, Epi>(acc, red);
 }
 
+// ---- ELL SpMV: every row has exactly L entries (A^T of a network whose routes all traverse L links) -----------------
+// No row pointers, no staging: a thread owns a row, fetches its L column ids with 16-byte loads (the warp reads one
+// contiguous 32 * 4L-byte span), has all L gathers in flight at once and adds them LEFT TO RIGHT (scipy's order: the
+// result is bit-identical to the stream kernel and to the reference).  The kernel is bound by the L1TEX wavefront rate
+// of the scattered gathers (~1 per clock per SM, /opt/skills/guides/B300_MICROARCH.md "L1tex wavefront queue"), so
+// everything else is kept off that path: indices and values stream with .cs / no L1 allocation.
+// TEX != 0: the operand is fetched through a texture object (tex1Dfetch<int2>) instead of LDG -- same cache, other
+// front end; kept as a measured alternative (BSLS_ELL_TEX).
+template <int L> struct EllVec {
+    static constexpr int W = (L % 4 == 0) ? 4 : ((L % 2 == 0) ? 2 : 1);
+};
+template <class Epi, int THREADS, int L, bool HAS_VAL, int TEX>
+__global__ void __launch_bounds__(THREADS)
+spmv_ell_kernel(int64_t rows, const int32_t *__restrict__ idx, const double *__restrict__ val, const double *__restrict__ v,
+                cudaTextureObject_t vtex, Epi epi, RedCtx red, const int *__restrict__ skip) {
+    if (skip && *skip) return;
+    constexpr int NA = Epi::NSUM + Epi::NMAX;
+    constexpr int W = EllVec<L>::W;
+    double acc[NA];
+#pragma unroll
+    for (int k = 0; k < NA; ++k) acc[k] = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * THREADS;
+    for (int64_t row = (int64_t)blockIdx.x * THREADS + threadIdx.x; row < rows; row += stride) {
+        int32_t j[L];
+        const int32_t *ri = idx + row * L;
+        if constexpr (W == 4) {
+#pragma unroll
+            for (int k = 0; k < L; k += 4) {
+                const int4 q = __ldcs(reinterpret_cast<const int4 *>(ri + k));
+                j[k] = q.x, j[k + 1] = q.y, j[k + 2] = q.z, j[k + 3] = q.w;
+            }
+        } else if constexpr (W == 2) {
+#pragma unroll
+            for (int k = 0; k < L; k += 2) {
+                const int2 q = __ldcs(reinterpret_cast<const int2 *>(ri + k));
+                j[k] = q.x, j[k + 1] = q.y;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < L; ++k) j[k] = __ldcs(ri + k);
+        }
+        double w[L];
+#pragma unroll
+        for (int k = 0; k < L; ++k) {
+            if constexpr (TEX) {
+                const int2 t = tex1Dfetch<int2>(vtex, j[k]);
+                w[k] = __hiloint2double(t.y, t.x);
+            } else {
+                w[k] = gather(v, j[k]);
+            }
+        }
+        double sum = 0.0;
+        if constexpr (HAS_VAL) {
+            const double *rv = val + row * L;
+#pragma unroll
+            for (int k = 0; k < L; ++k) sum += __ldcs(rv + k) * w[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < L; ++k) sum += w[k];  // 1.0 * w is exact: same bits as the multiply
+        }
+        epi.apply(row, sum, acc);
+    }
+    grid_reduce<Epi::NSUM, Epi::NMAX, THREADS, Epi>(acc, red);
+}
+
 // ---- VECTOR SpMV: LANES lanes per row ------------------------------------------------------------
 template <class Epi, int THREADS, int LANES>
 __global__ void __launch_bounds__(THREADS)
 spmv_vector_kernel(int64_t rows, const int64_t *__restrict__ ptr, const int32_t *__restrict__ idx,
-                   const double *__restrict__ val, const double *__restrict__ v, Epi epi, RedCtx red) {
+                   const double *__restrict__ val, const double *__restrict__ v, Epi epi, RedCtx red, const int *__restrict__ skip) {
+    if (skip && *skip) return;
     constexpr int NA = Epi::NSUM + Epi::NMAX;
     double acc[NA];
 #pragma unroll
@@ -366,35 +482,176 @@ __global__ void __launch_bounds__(256) axpy_dot_kernel(double *__restrict__ d, D
 }
 
 // r <- r - b ; f = 0.5 <r, r>   (after the all-reduce of the per-rank partial products)
-struct FinResidual {
-    static __device__ __forceinline__ void store(double *o, int k, double v) {
-        o[kScalF] = 0.5 * v;
-        o[kScalRR] = v;
-    }
-};
-__global__ void __launch_bounds__(256) residual_finish_kernel(double *__restrict__ r, const double *__restrict__ b, int64_t m, RedCtx red) {
-    double acc[1] = {0};
+__global__ void __launch_bounds__(256) residual_finish_kernel(double *__restrict__ r, const double *__restrict__ b, const double *__restrict__ r_old,
+                                                               int64_t m, RedCtx red, const int *__restrict__ skip) {
+    if (skip && *skip) return;
+    double acc[3] = {0, 0, 0};
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < m; i += (int64_t)gridDim.x * 256) {
         const double v = r[i] - b[i];
         r[i] = v;
-        acc[0] += v * v;
+        residual_sums(v, r_old ? r_old[i] : 0.0, r_old != nullptr, acc);
     }
-    grid_reduce<1, 0, 256, FinResidual>(acc, red);
+    grid_reduce<3, 0, 256, FinResidual>(acc, red);
 }
 
 // r_i = sum_p partial[p m + i] (- b_i), panels added in ascending order; f = 0.5 <r, r>.
 // Closes the column-panelled product A x (see bsls_lsq_set_panels).
 __global__ void __launch_bounds__(256) panel_reduce_kernel(double *__restrict__ r, const double *__restrict__ partial,
-                                                            const double *__restrict__ b, int64_t m, int panels, RedCtx red) {
-    double acc[1] = {0};
+                                                            const double *__restrict__ b, const double *__restrict__ r_old, int64_t m,
+                                                            int panels, RedCtx red, const int *__restrict__ skip) {
+    if (skip && *skip) return;
+    double acc[3] = {0, 0, 0};
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < m; i += (int64_t)gridDim.x * 256) {
         double v = partial[i];
         for (int p = 1; p < panels; ++p) v += partial[(int64_t)p * m + i];
         if (b) v -= b[i];
         r[i] = v;
-        acc[0] += v * v;
+        residual_sums(v, (b && r_old) ? r_old[i] : 0.0, b && r_old, acc);
     }
-    grid_reduce<1, 0, 256, FinResidual>(acc, red);
+    grid_reduce<3, 0, 256, FinResidual>(acc, red);
+}
+
+// ---- device-resident solver steps ----------------------------------------------------------------------------------
+// out = x - t g with t read from the solver state (np.add(x, -t*g, x_new), python/BATCH.py:38,91)
+__global__ void __launch_bounds__(256) step_axpy_kernel(double *__restrict__ out, const double *__restrict__ x, const double *__restrict__ g,
+                                                         const DevState *st, int64_t n) {
+    if (st->done) return;
+    const double nt = -st->t;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const double u = nt * g[i];
+        out[i] = x[i] + u;
+    }
+}
+
+// After a back-tracked line search (tau < 1) the trial point, its gradient and its residual are pulled back along the
+// segment: v_new <- (1 - tau) v + tau v_new for x (the reference's own update, algorithm_utils.py:133), and -- the
+// objective being quadratic -- for g and r, which the reference recomputes with two more products (:134).  tau == 0 is
+// the reference's "step too small" reset (:125-131).  Nothing to do when the trial point was accepted as is.
+__global__ void __launch_bounds__(256) commit_kernel(const DevState *st, double *__restrict__ xn, const double *__restrict__ x,
+                                                      double *__restrict__ gn, const double *__restrict__ g, int64_t n,
+                                                      double *__restrict__ rn, const double *__restrict__ r, int64_t m) {
+    const double tau = st->tau;
+    if (tau == 1.0) return;
+    const double a = 1.0 - tau;
+    const int64_t stride = (int64_t)gridDim.x * 256, i0 = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (tau == 0.0) {
+        for (int64_t i = i0; i < n; i += stride) {
+            xn[i] = x[i];
+            gn[i] = g[i];
+        }
+        for (int64_t i = i0; i < m; i += stride) rn[i] = r[i];
+        return;
+    }
+    for (int64_t i = i0; i < n; i += stride) {
+        const double u = a * x[i];
+        xn[i] = u + tau * xn[i];
+        const double w = a * g[i];
+        gn[i] = w + tau * gn[i];
+    }
+    for (int64_t i = i0; i < m; i += stride) {
+        const double u = a * r[i];
+        rn[i] = u + tau * rn[i];
+    }
+}
+
+// The scalar half of one iteration of BATCH.solve / solve_BB / solve_MD (python/BATCH.py:33-47,84-102,230-247):
+// line_search_np (python/algorithm_utils.py:113-137), the new step and `stopping` (:158-172), by one thread.
+//   scal        the scalar block the reducing kernels of this evaluation wrote (f_trial, <r,dr>, <dr,dr> replicated on
+//               every rank; slots 1..5 = this rank's share of <dx,dg>, <dg,dg>, <g,dx>, <g_new,g_new>, max|dx|)
+//   gathered    nranks x 5: slots 1..5 of every rank (all-gather); null on one GPU
+// The Armijo test of a back-tracked point needs f there: f + tau <r,dr> + 0.5 tau^2 <dr,dr> (exact for this objective),
+// so a back-track costs no product; the compounding x_new <- (1-t) x + t x_new with t = .8, .64, ... shrinks dx by
+// tau = prod t, and <g,dx>, max|dx| scale with it.
+__global__ void decide_kernel(DevState *st, const double *__restrict__ scal, const double *__restrict__ gathered, DevOpts o,
+                              double *__restrict__ progress_f, double *__restrict__ progress_t, int first) {
+    if (threadIdx.x || blockIdx.x) return;
+    if (st->done) {  // an iteration enqueued ahead of the stop: nothing to decide, nothing to commit
+        st->tau = 1.0;
+        return;
+    }
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+    if (first) {  // f = obj(x, g) of the starting point (BATCH.py:29,77,228)
+        st->f = scal[kScalF];
+        st->f_old = __longlong_as_double(0x7ff0000000000000LL);
+        st->i = 1;
+        st->evals = 1;
+        st->backtracks = 0;
+        st->tau = 1.0;
+        st->sxy = st->syy = 0.0;
+        st->parity = 0;
+        st->change = 0.0;
+        st->stop_value = 0.0;
+        if (progress_f && o.progress_cap > 0) {
+            progress_f[0] = st->f;
+            progress_t[0] = (double)now;
+        }
+    } else {
+        double sxy = scal[kScalSxy], syy = scal[kScalSyy], gd = scal[kScalGd], step = scal[kScalStep];
+        if (gathered) {
+            sxy = syy = gd = step = 0.0;
+            for (int r = 0; r < o.nranks; ++r) {  // rank order: every rank forms the same sums
+                sxy += gathered[r * 5 + 0];
+                syy += gathered[r * 5 + 1];
+                gd += gathered[r * 5 + 2];
+                step = fmax(step, gathered[r * 5 + 4]);
+            }
+        }
+        const double f = st->f;
+        double f_new = scal[kScalF];
+        double tau = 1.0;
+        int bt = 0;
+        if (o.search) {
+            const double rdr = scal[kScalRdr], drdr = scal[kScalDrdr];
+            double t = 1.0, gdt = gd, stept = step;
+            while (f_new > f + 1e-4 * gdt) {
+                t *= .8;
+                if (stept < 1e-12) {  // step too small: stay where we are
+                    tau = 0.0;
+                    f_new = f;
+                    break;
+                }
+                tau *= t;
+                gdt = tau * gd;
+                stept = tau * step;
+                const double half = 0.5 * tau;
+                f_new = f + (tau * rdr + (half * tau) * drdr);
+                ++bt;
+            }
+        }
+        st->tau = tau;
+        st->backtracks += bt;
+        st->evals += 1;
+        st->sxy = (tau * tau) * sxy;
+        st->syy = (tau * tau) * syy;
+        st->f_old = f;
+        st->f = f_new;
+        st->parity ^= 1;
+        st->i += 1;
+        if (o.method == 2) st->change = scal[kScalMax0];
+        if (progress_f && st->i - 1 < o.progress_cap) {
+            progress_f[st->i - 1] = f_new;
+            progress_t[st->i - 1] = (double)now;
+        }
+    }
+    // the step of the next trial point
+    const int i = st->i;
+    if (o.method == 1)
+        st->t = (i == 1) ? 1.0 : st->sxy / st->syy;  // BATCH.py:87-91
+    else
+        st->t = 1.0 / (o.min_eig * i + 1.0);         // decreasing_step_size(i, 1.0, min_eig), BATCH.py:38,238
+    // algorithm_utils.stopping (:158-172): later tests overwrite the reason of earlier ones
+    int code = 0;
+    if (i == o.max_iter) code = 1;
+    if (o.has_f_min && st->f - o.f_min < o.opt_tol) {
+        code = 2;
+        st->stop_value = st->f - o.f_min;
+    }
+    if (fabs(st->f_old - st->f) < o.prog_tol) {
+        code = 3;
+        st->stop_value = fabs(st->f_old - st->f);
+    }
+    st->done = code;
 }
 
 // ---- per-block kernels: G lanes per block ---------------------------------------------------------
@@ -421,9 +678,17 @@ struct BlockLayout {
 struct FinMax {
     static __device__ __forceinline__ void store(double *o, int k, double v) { o[kScalMax0] = v; }
 };
+// st != null: the step comes from the solver state on the device (step = st->t for the BATCH loop, sqrt(i) * step for
+// mirror_descent.least_squares) and the kernel does nothing once the solver has stopped
+__device__ __forceinline__ double md_step(double step, int per_block_log, const DevState *st) {
+    if (!st) return step;
+    return per_block_log ? sqrt((double)st->i) * step : st->t;
+}
 template <int G>
 __global__ void __launch_bounds__(256) md_update_kernel(double *__restrict__ xn, const double *__restrict__ x, const double *__restrict__ g,
-                                                         double step, int per_block_log, BlockLayout lay, RedCtx red) {
+                                                         double step, int per_block_log, BlockLayout lay, RedCtx red, const DevState *st) {
+    if (st && st->done) return;
+    step = md_step(step, per_block_log, st);
     const int sub = threadIdx.x & (G - 1);
     const int64_t group = ((int64_t)blockIdx.x * 256 + threadIdx.x) / G;
     const int64_t ngroups = (int64_t)gridDim.x * 256 / G;
@@ -459,7 +724,9 @@ __global__ void __launch_bounds__(256) md_update_kernel(double *__restrict__ xn,
 // additions as md_update_kernel (per lane in steps of G, then the xor tree), so both give the same bits.
 template <int G, int R>
 __global__ void __launch_bounds__(256) md_update_reg_kernel(double *__restrict__ xn, const double *__restrict__ x, const double *__restrict__ g,
-                                                             double step, int per_block_log, BlockLayout lay, RedCtx red) {
+                                                             double step, int per_block_log, BlockLayout lay, RedCtx red, const DevState *st) {
+    if (st && st->done) return;
+    step = md_step(step, per_block_log, st);
     const int sub = threadIdx.x & (G - 1);
     const int64_t group = ((int64_t)blockIdx.x * 256 + threadIdx.x) / G;
     const int64_t ngroups = (int64_t)gridDim.x * 256 / G;

@@ -474,8 +474,12 @@ int launch_pava_small_cfg(T *y, int32_t *w, long long first, int nb, int K, int 
     const size_t buf_elems = ((size_t)THREADS * KS + 1) & ~size_t(1);
     const size_t smem = (((kPavaSmallMaxBlock + 1) * sizeof(T) + 15) & ~size_t(15)) + (size_t)THREADS * sizeof(M) + buf_elems * sizeof(T) +
                         (fl.has_weight ? (size_t)THREADS * KS : 0) + 16;
-    static thread_local size_t cached_smem = 0;
-    static thread_local int per_sm = 0, num_sm = 0;
+    static thread_local PerDevice<size_t> cached_smem_pd;
+    size_t &cached_smem = cached_smem_pd.get(0);
+    static thread_local PerDevice<int> per_sm_pd;
+    int &per_sm = per_sm_pd.get(0);
+    static thread_local PerDevice<int> num_sm_pd;
+    int &num_sm = num_sm_pd.get(0);
     if (cached_smem != smem) {
         BSLS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int dev = 0;
@@ -693,16 +697,17 @@ template <typename T, bool CLIP, bool WMEM>
 int launch_pava_tile_rows_cfg(T *y, int32_t *w, const int32_t *starts, const int32_t *tile_first, int ntiles, int update, int cap_per_sm,
                               cudaStream_t stream) {
     auto k = pava_tile_rows_kernel<T, CLIP, WMEM>;
-    static thread_local int grid_full = 0;
+    static thread_local PerDevice<int> grid_full_pd;
+    int &grid_full = grid_full_pd.get(0);
     if (!grid_full) {
-        int dev = 0, num_sm = kNumSM, per_sm = 1;
+        int dev = 0, num_sm = num_sms(), per_sm = 1;
         BSLS_CUDA_TRY(cudaGetDevice(&dev));
         BSLS_CUDA_TRY(cudaDeviceGetAttribute(&num_sm, cudaDevAttrMultiProcessorCount, dev));
         BSLS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kPavaTileThreads, 0));
         grid_full = num_sm * (per_sm < 1 ? 1 : per_sm);
     }
     int grid = ntiles < grid_full ? ntiles : grid_full;
-    if (cap_per_sm > 0 && grid > cap_per_sm * kNumSM) grid = cap_per_sm * kNumSM;
+    if (cap_per_sm > 0 && grid > cap_per_sm * num_sms()) grid = cap_per_sm * num_sms();
     k<<<grid, kPavaTileThreads, 0, stream>>>(y, w, starts, tile_first, ntiles, update);
     BSLS_LAUNCH_CHECK();
     return BSLS_OK;

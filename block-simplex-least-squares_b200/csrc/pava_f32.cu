@@ -2,6 +2,7 @@
 #include "kernels.h"
 #include "pava.cuh"
 #include "pava_words.cuh"
+#include "pava_seq.cuh"
 
 namespace bsls {
 int pava_small_f32(float *y, int32_t *w, long long first, int nb, int K, int update, int clip01, cudaStream_t stream) {
@@ -28,5 +29,10 @@ int pava_words_cta_f32(float *y, int32_t *w, const int32_t *starts, const int32_
                        cudaStream_t stream) {
     static_assert(32 * kWordsCtaThreads == kPlanPavaLargeMax, "plan constants");
     return launch_pava_words_cta<float>(y, w, starts, ids, count, max_block, update, clip01, cap_per_sm, stream);
+}
+
+int pava_seq_f32(int variant, float *y, int32_t *w, const int32_t *starts, const int32_t *ids, int count, int min_size, int update, int cold,
+                 int clip, cudaStream_t stream) {
+    return launch_pava_seq<float>(variant, y, w, starts, ids, count, min_size, update, cold, clip, stream);
 }
 }  // namespace bsls

@@ -426,6 +426,7 @@ pava_words_cta_kernel(T *__restrict__ yg, int32_t *__restrict__ wg, const int32_
         const int b = ids ? ids[it] : it;  // ids == nullptr: every block of the layout
         const int g0 = starts[b];
         const int K = starts[b + 1] - g0;
+        if (K > max_block) continue;  // beyond the shared-memory window: served by pava_seq_kernel (uniform over the CTA)
         const int LW = (K + 31) >> 5;
         T *gy = yg + g0;
         for (int i = tid; i < K; i += kWordsCtaThreads) cp_async_elem<sizeof(T)>(&y[i], gy + i);
@@ -458,7 +459,7 @@ int launch_pava_words_cta_cfg(T *y, int32_t *w, const int32_t *starts, const int
                               cudaStream_t stream) {
     auto k = pava_words_cta_kernel<T, CLIP, WMEM>;
     const size_t smem = pava_words_cta_smem(max_block, sizeof(T));
-    int dev = 0, num_sm = kNumSM, per_sm = 1;
+    int dev = 0, num_sm = num_sms(), per_sm = 1;
     BSLS_CUDA_TRY(cudaGetDevice(&dev));
     BSLS_CUDA_TRY(cudaDeviceGetAttribute(&num_sm, cudaDevAttrMultiProcessorCount, dev));
     BSLS_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pava_words_cta_smem(32 * kWordsCtaThreads, sizeof(T))));
@@ -489,9 +490,10 @@ template <typename T, bool CLIP, bool WMEM>
 int launch_pava_words_cfg(T *y, int32_t *w, const int32_t *starts, const int32_t *ids, const int32_t *pack_first, int npacks, long long first, int nb,
                           int Kuni, int update, int cap_per_sm, cudaStream_t stream) {
     auto k = pava_words_kernel<T, CLIP, WMEM>;
-    static thread_local int full = 0;
+    static thread_local PerDevice<int> full_pd;
+    int &full = full_pd.get(0);
     if (!full) {
-        int dev = 0, num_sm = kNumSM, per_sm = 1;
+        int dev = 0, num_sm = num_sms(), per_sm = 1;
         BSLS_CUDA_TRY(cudaGetDevice(&dev));
         BSLS_CUDA_TRY(cudaDeviceGetAttribute(&num_sm, cudaDevAttrMultiProcessorCount, dev));
         BSLS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kWordsWarps * 32, 0));
@@ -499,7 +501,7 @@ int launch_pava_words_cfg(T *y, int32_t *w, const int32_t *starts, const int32_t
     }
     const int want = (npacks + kWordsWarps - 1) / kWordsWarps;
     int grid = want < full ? want : full;
-    if (cap_per_sm > 0 && grid > cap_per_sm * kNumSM) grid = cap_per_sm * kNumSM;
+    if (cap_per_sm > 0 && grid > cap_per_sm * num_sms()) grid = cap_per_sm * num_sms();
     k<<<grid, kWordsWarps * 32, 0, stream>>>(y, w, starts, ids, pack_first, npacks, first, nb, Kuni, make_fastdiv((uint32_t)(Kuni > 0 ? Kuni : 1)), update);
     BSLS_LAUNCH_CHECK();
     return BSLS_OK;

@@ -28,7 +28,7 @@ __global__ void layout_stats_kernel(const int32_t *__restrict__ starts, int nb, 
 static int grid_for(long long items, int threads) {
     long long want = (items + threads - 1) / threads;
     if (want < 1) want = 1;
-    return (int)(want < 8 * kNumSM ? want : 8 * kNumSM);
+    return (int)(want < 8 * num_sms() ? want : 8 * num_sms());
 }
 
 int plan_layout_stats(const int32_t *starts, int nb, int n, LayoutStats *d_out, cudaStream_t stream) {

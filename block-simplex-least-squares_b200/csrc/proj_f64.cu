@@ -11,10 +11,10 @@ int proj_uniform_f64(double *y, long long first, int nb, int K, int mode, int32_
 bool proj_step_fuses(int K) { return proj_uniform_fuses(K); }
 
 int proj_step_uniform_f64(const double *x, const double *g, double t, double *x_new, long long first, int nb, int K, int mode,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, const StepCtl *ctl) {
     double *xin = const_cast<double *>(x);
-    return mode == kBall ? launch_proj_uniform<double, kBall>(xin, first, nb, K, nullptr, stream, g, t, x_new)
-                         : launch_proj_uniform<double, kSimplex>(xin, first, nb, K, nullptr, stream, g, t, x_new);
+    return mode == kBall ? launch_proj_uniform<double, kBall>(xin, first, nb, K, nullptr, stream, g, t, x_new, ctl)
+                         : launch_proj_uniform<double, kSimplex>(xin, first, nb, K, nullptr, stream, g, t, x_new, ctl);
 }
 
 int proj_ragged_f64(double *y, const int32_t *starts, const int32_t *tile_first, int ntiles, const int32_t *mid_ids, int nmid,

@@ -475,11 +475,12 @@ int launch_proj_ragged(T *y, const int32_t *starts, const int32_t *tile_first, i
                        const int32_t *large_ids, int nlarge, int max_large, int32_t *slow, int nb, const RaggedStreams &rs,
                        void *huge_buf, int huge_cap, int *huge_lock, cudaStream_t stream) {
     const HugeScratch<T> huge = {reinterpret_cast<T *>(huge_buf), huge_cap, huge_lock};
-    int dev = 0, num_sm = kNumSM;
+    int dev = 0, num_sm = num_sms();
     BSLS_CUDA_TRY(cudaGetDevice(&dev));
     BSLS_CUDA_TRY(cudaDeviceGetAttribute(&num_sm, cudaDevAttrMultiProcessorCount, dev));
     auto large = proj_large_kernel<T, MODE>;
-    static thread_local bool attr_set = false;
+    static thread_local PerDevice<bool> attr_set_pd;
+    bool &attr_set = attr_set_pd.get(false);
     if (!attr_set) {
         BSLS_CUDA_TRY(cudaFuncSetAttribute(large, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kLargeMaxBlock * sizeof(T))));
         attr_set = true;
@@ -490,7 +491,8 @@ int launch_proj_ragged(T *y, const int32_t *starts, const int32_t *tile_first, i
     if (tiled && nmid > 0) {
         BSLS_CUDA_TRY(cudaStreamWaitEvent(rs.aux[0], rs.fork, 0));
         auto mid = proj_mid_kernel<T, MODE>;
-        static thread_local int mid_full = 0;
+        static thread_local PerDevice<int> mid_full_pd;
+        int &mid_full = mid_full_pd.get(0);
         if (!mid_full) {
             int per = 1;
             BSLS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, mid, kMidWarps * 32, 0));
@@ -515,7 +517,8 @@ int launch_proj_ragged(T *y, const int32_t *starts, const int32_t *tile_first, i
     }
     if (tiled) {
         auto kern = proj_tile_kernel<T, MODE>;
-        static thread_local int per_sm = 0;
+        static thread_local PerDevice<int> per_sm_pd;
+        int &per_sm = per_sm_pd.get(0);
         if (!per_sm) {
             BSLS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileThreads, 0));
             if (per_sm < 1) per_sm = 1;

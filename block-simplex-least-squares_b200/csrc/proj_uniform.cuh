@@ -102,7 +102,13 @@ __device__ __forceinline__ void load_block_regs(T (&v)[E], const T *blkp, int K,
 template <typename T, int E, int G, int THREADS, int MINB, int BPT, int STAGES, int KC, int MODE>
 __global__ void __launch_bounds__(THREADS, MINB)
 proj_uniform_kernel(T *__restrict__ y, long long first, int nb, int Krt, FastDiv kdiv, int aligned, const T *__restrict__ gsrc,
-                    T tstep, T *__restrict__ yout) {
+                    T tstep, T *__restrict__ yout, StepCtl ctl) {
+    // ctl.t != null (device-resident solver loop): the step is read from the device and nothing happens once the
+    // solver has stopped
+    if (ctl.t) {
+        if (*ctl.done) return;
+        tstep = (T)*ctl.t;
+    }
     // gsrc != null: FUSED projected-gradient step: the tile is formed as y + (-tstep) * gsrc on the
     // way in (np.add(x, -t*g, x_new), python/BATCH.py:91: product and sum rounded separately) and the
     // result goes to yout -- x, g are read once, x_new written once, no intermediate vector.
@@ -459,9 +465,12 @@ int launch_proj_select_cfg(T *y, long long first, int nb, int K, int32_t *slow, 
     auto kern = proj_select_kernel<T, THREADS, MINB, STAGES, KC, MODE>;
     const size_t smem = (size_t)STAGES * TB * K * sizeof(T) + (size_t)TB * sizeof(T) + (size_t)kSelMaxCand * THREADS * sizeof(T) +
                         sizeof(T) + 2 * sizeof(uint64_t);
-    static thread_local int cached_blocks_per_sm = -1;
-    static thread_local size_t cached_smem = 0;
-    static thread_local int num_sm = 0;
+    static thread_local PerDevice<int> cached_blocks_per_sm_pd;
+    int &cached_blocks_per_sm = cached_blocks_per_sm_pd.get(-1);
+    static thread_local PerDevice<size_t> cached_smem_pd;
+    size_t &cached_smem = cached_smem_pd.get(0);
+    static thread_local PerDevice<int> num_sm_pd;
+    int &num_sm = num_sm_pd.get(0);
     if (cached_blocks_per_sm < 0 || cached_smem != smem) {
         BSLS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int dev = 0;
@@ -493,13 +502,16 @@ int launch_proj_select_cfg(T *y, long long first, int nb, int K, int32_t *slow, 
 // ---- host side: pick a configuration for K and launch ------------------------------------------
 template <typename T, int E, int G, int THREADS, int MINB, int BPT, int STAGES, int KC, int MODE>
 int launch_proj_uniform_cfg(T *y, long long first, int nb, int K, cudaStream_t stream, const T *gsrc = nullptr, T tstep = T(0),
-                            T *yout = nullptr) {
+                            T *yout = nullptr, const StepCtl *ctl = nullptr) {
     constexpr int TB = THREADS / G * BPT;
     auto kern = proj_uniform_kernel<T, E, G, THREADS, MINB, BPT, STAGES, KC, MODE>;
     const size_t smem = (size_t)STAGES * TB * K * sizeof(T) + (size_t)(TB + (TB & 1)) * sizeof(T) + 2 * sizeof(uint64_t);
-    static thread_local int cached_blocks_per_sm = -1;
-    static thread_local size_t cached_smem = 0;
-    static thread_local int num_sm = 0;
+    static thread_local PerDevice<int> cached_blocks_per_sm_pd;
+    int &cached_blocks_per_sm = cached_blocks_per_sm_pd.get(-1);
+    static thread_local PerDevice<size_t> cached_smem_pd;
+    size_t &cached_smem = cached_smem_pd.get(0);
+    static thread_local PerDevice<int> num_sm_pd;
+    int &num_sm = num_sm_pd.get(0);
     if (cached_blocks_per_sm < 0 || cached_smem != smem) {
         BSLS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int dev = 0;
@@ -517,7 +529,7 @@ int launch_proj_uniform_cfg(T *y, long long first, int nb, int K, cudaStream_t s
     const int ntiles = (nb + TB - 1) / TB;
     const int grid = ntiles < num_sm * cached_blocks_per_sm ? ntiles : num_sm * cached_blocks_per_sm;
     const int aligned = ((reinterpret_cast<uintptr_t>((gsrc && yout ? yout : y) + first) % 16) == 0) ? 1 : 0;
-    kern<<<grid, THREADS, smem, stream>>>(y, first, nb, K, make_fastdiv((uint32_t)K), aligned, gsrc, tstep, yout);
+    kern<<<grid, THREADS, smem, stream>>>(y, first, nb, K, make_fastdiv((uint32_t)K), aligned, gsrc, tstep, yout, ctl ? *ctl : StepCtl{nullptr, nullptr});
     BSLS_LAUNCH_CHECK();
     return BSLS_OK;
 }
@@ -540,12 +552,12 @@ inline bool proj_uniform_fuses(int K) { return K < 32 || K > 128; }
 
 template <typename T, int MODE>
 int launch_proj_uniform(T *y, long long first, int nb, int K, int32_t *slow, cudaStream_t stream, const T *gsrc = nullptr, T tstep = T(0),
-                        T *yout = nullptr) {
+                        T *yout = nullptr, const StepCtl *ctl = nullptr) {
     if (nb <= 0) return BSLS_OK;
     const int tv = tune_variant();
     if (gsrc) slow = nullptr;  // fused mode: sorting kernels only
     // sizes the BASELINE configs name, with K known at compile time
-#define CFG(E, G, TH, MINB, BPT, ST, KC) return launch_proj_uniform_cfg<T, E, G, TH, MINB, BPT, ST, KC, MODE>(y, first, nb, K, stream, gsrc, tstep, yout)
+#define CFG(E, G, TH, MINB, BPT, ST, KC) return launch_proj_uniform_cfg<T, E, G, TH, MINB, BPT, ST, KC, MODE>(y, first, nb, K, stream, gsrc, tstep, yout, ctl)
 #define SEL(E, G, TH, MINB, ST, KC) return launch_proj_select_cfg<T, E, G, TH, MINB, ST, KC, MODE>(y, first, nb, K, slow, stream)
     // candidate selection instead of a full sort (BSLS_TUNE=100 keeps the sorting kernels everywhere)
     if (tv != 100 && slow != nullptr && K >= 32 && K <= 128) {

@@ -20,7 +20,7 @@ def z_space_parts(A, b, x0, N, block_sizes, device=None):
     proj = isotonic regression of every z-block, clipped to [0, 1]."""
     sizes = np.asarray(block_sizes, dtype=np.int64)
     if isinstance(A, LsqProblem):
-        problem = A
+        problem = A.with_b(torch.zeros(A.m, dtype=torch.float64, device=A.device))   # private handle: the caller's b stays
     else:
         problem = LsqProblem(A, np.zeros(A.shape[0]), device=device)
     dev = problem.device

@@ -66,7 +66,9 @@ def plan_for(blocks, n, device):
         return blocks
     if not torch.is_tensor(blocks):
         return BlockPlan(blocks, n, device)
-    key = (id(blocks), blocks._version, int(n), str(device))
+    # a plan's scratch serves one stream at a time (include/bsls_b200.h): one plan per (layout, stream)
+    stream = torch.cuda.current_stream(device).cuda_stream if torch.cuda.is_available() else 0
+    key = (id(blocks), blocks._version, int(n), str(device), stream)
     hit = _CACHE.get(key)
     if hit is not None and hit[0] is blocks:
         _CACHE.move_to_end(key)

@@ -230,8 +230,10 @@ class LsqProblem:
         else:
             import scipy.sparse as sps
             Ac = sps.csr_matrix(A)
+            if not Ac.has_sorted_indices:      # never reorder the caller's matrix in place
+                Ac = Ac.copy()
+                Ac.sort_indices()
             At = sps.csr_matrix(Ac.T)
-            Ac.sort_indices()
             At.sort_indices()
             self.m, self.n = Ac.shape
             a_ptr, a_idx, a_val = Ac.indptr, Ac.indices, Ac.data
@@ -275,6 +277,17 @@ class LsqProblem:
         self.b = _dev_tensor(b, _F64, self.device).reshape(-1)
         assert self.b.shape[0] == self.m
         _lib.check(_lib.lib().bsls_lsq_set_b(self._handle, self.b.data_ptr()))
+
+    def with_b(self, b):
+        """A second problem handle over the SAME matrix arrays (no copy) with its own right-hand side, residual and
+        workspace: lets a driver change ``b`` (the z-space target of main.py:48) without touching the caller's problem."""
+        other = LsqProblem((self.a_ptr, self.a_idx, self.a_val, self.t_ptr, self.t_idx, self.t_val, (self.m, self.n)), b,
+                           device=self.device, comm=self.comm)
+        if getattr(self, "panels", 1) > 1:
+            other.p_ptr, other.p_idx, other.p_val, other.panels = self.p_ptr, self.p_idx, self.p_val, self.panels
+            _lib.check(_lib.lib().bsls_lsq_set_panels(other._handle, self.panels, self.p_ptr.data_ptr(), self.p_idx.data_ptr(),
+                                                      None if self.p_val is None else self.p_val.data_ptr()), "lsq_set_panels")
+        return other
 
     def set_panels(self, panel_cols=None, l2_budget_bytes=48 << 20):
         """Build the column-panelled copy of A (``bsls_lsq_set_panels``) so that the slice of x a

@@ -43,6 +43,7 @@ extern "C" {
 #define BSLS_ERR_CUDA      2   /* CUDA runtime error; see bsls_last_error() */
 #define BSLS_ERR_NO_DEVICE 3   /* no sm_100 device: there is NO CPU fallback */
 #define BSLS_ERR_ALLOC     4
+#define BSLS_ERR_UNSUPPORTED 5 /* valid input this revision does not serve (fp32 projection of a block > 8192 entries) */
 
 BSLS_API const char *bsls_last_error(void);         /* text of the last failure on this thread */
 BSLS_API const char *bsls_version(void);
@@ -69,8 +70,10 @@ BSLS_API int bsls_isotonic_regression(double *y, int start, int end, int *weight
 /* replaces isotonic_regression_multi (isotonic_regression.h:85-92) */
 BSLS_API int bsls_isotonic_regression_multi(double *y, const int *blocks, int numblocks, int n, int *weight, int update);
 /* replace isotonic_regression_2 / _multi_2 (isotonic_regression.h:61-82,95-102) and
- * isotonic_regression_3 / _multi_3 (isotonic_regression.h:105-164): same regression, served
- * by the variant-1 kernel (values equal to ~1e-15 relative; weights are variant 1's). */
+ * isotonic_regression_3 / _multi_3 (isotonic_regression.h:105-164).  Both form their pool means in
+ * another order than variant 1, and variant 3 leaves another weight array (tail markers w[k-1],
+ * pools fused on ties): they run the reference's routine as written, one GPU thread per block, so
+ * values and weights are the reference's bits (csrc/pava_seq.cuh).  Not the hot path. */
 BSLS_API int bsls_isotonic_regression_2(double *y, int start, int end);
 BSLS_API int bsls_isotonic_regression_multi_2(double *y, const int *blocks, int numblocks, int n);
 BSLS_API int bsls_isotonic_regression_3(double *y, int start, int end, int *weight, int update);
@@ -88,9 +91,12 @@ BSLS_API int bsls_host_free(void *ptr);
 typedef struct bsls_plan bsls_plan;
 
 /* Analyse a block layout once: validates it (the reference's asserts), detects uniform
- * block size, bins ragged blocks into tiles / large blocks, allocates scratch.
- * `d_blocks` is a DEVICE array of numblocks int32 start offsets; it is copied.
- * Synchronises `stream` once (layout statistics come back to the host). */
+ * block size, bins ragged blocks into tiles / large blocks, allocates ALL scratch and auxiliary
+ * streams (the plan is immutable afterwards).  `d_blocks` is a DEVICE array of numblocks int32
+ * start offsets; it is copied.  Synchronises `stream` (layout statistics come back to the host).
+ * A plan belongs to the device that was current at creation.  Calls on one plan share its scratch
+ * (queue of dense blocks, fork/join streams): ONE STREAM AT A TIME PER PLAN -- give every stream
+ * its own plan (the Python layer keys its plan cache on the stream). */
 BSLS_API int bsls_plan_create(const int32_t *d_blocks, int numblocks, int n, bsls_stream_t stream, bsls_plan **out);
 BSLS_API int bsls_plan_destroy(bsls_plan *plan);
 /* layout facts: [0]=numblocks [1]=n [2]=first index [3]=uniform size or 0 [4]=min size
@@ -109,6 +115,9 @@ BSLS_API int bsls_dev_proj_multi_ball_f32(const bsls_plan *plan, float *y, bsls_
  * python/algorithm_utils.py:223-224). */
 BSLS_API int bsls_dev_isotonic_regression_multi_f64(const bsls_plan *plan, double *y, int32_t *weight, int update, int clip01, bsls_stream_t stream);
 BSLS_API int bsls_dev_isotonic_regression_multi_f32(const bsls_plan *plan, float *y, int32_t *weight, int update, int clip01, bsls_stream_t stream);
+/* variants 2 and 3 on device buffers (see the host entry points above); variant 3 needs a weight array (ones for a cold call) */
+BSLS_API int bsls_dev_isotonic_regression_multi_2_f64(const bsls_plan *plan, double *y, bsls_stream_t stream);
+BSLS_API int bsls_dev_isotonic_regression_multi_3_f64(const bsls_plan *plan, double *y, int32_t *weight, int update, bsls_stream_t stream);
 
 
 /* x <-> z change of variables (a7): z = running sums of every block without its last entry,

@@ -228,3 +228,138 @@ def test_full_size_properties(api, K, nb):
     ys = y.view(nb, K)[sample].reshape(-1).cpu().numpy().copy()
     port().pava_multi(ys, np.arange(0, ys.size, K))
     assert np.array_equal(X[sample].reshape(-1).cpu().numpy(), ys)
+
+
+# ---------------------------------------------------------------------------------------------
+# variants 2 and 3 (isotonic_regression.h:61-82,105-155): values AND weights are the reference's bits
+# ---------------------------------------------------------------------------------------------
+def test_variants_golden_bit_exact(api, golden_dir):
+    d = np.load(os.path.join(golden_dir, "pava.npz"))
+    for i in range(int(d["count"])):
+        y, starts = d["y%d" % i], d["starts%d" % i]
+        t = dev(y)
+        api.isotonic_regression_multi_c_2(t, dev(starts))
+        assert np.array_equal(t.cpu().numpy(), d["v2_y%d" % i]), i
+        h = y.copy()
+        api.isotonic_regression_multi_c_2(h, starts)                      # host ABI
+        assert np.array_equal(h, d["v2_y%d" % i]), i
+        for update in (1, 0):
+            t, w = dev(y), dev(np.ones(len(y), dtype=np.int32))
+            api.isotonic_regression_multi_c_3(t, dev(starts), w, update)
+            assert np.array_equal(t.cpu().numpy(), d["v3_u%d_y%d" % (update, i)]), (i, update)
+            assert np.array_equal(w.cpu().numpy(), d["v3_u%d_w%d" % (update, i)]), (i, update)   # tail markers w[k-1] included
+            h, hw = y.copy(), np.ones(len(y), dtype=np.int32)
+            api.isotonic_regression_multi_c_3(h, starts, hw, update)      # host ABI, weights in / out
+            assert np.array_equal(h, d["v3_u%d_y%d" % (update, i)]) and np.array_equal(hw, d["v3_u%d_w%d" % (update, i)])
+        t = dev(y)
+        api.isotonic_regression_multi_c_3(t, dev(starts))                 # weight=None: ones in, result dropped
+        assert np.array_equal(t.cpu().numpy(), d["v3_u1_y%d" % i])
+
+
+@pytest.mark.parametrize("kind", ["ref", "normal", "ints", "decreasing", "zspace"])
+def test_variants_against_oracle_and_reference(api, kind):
+    from oracle import cpu
+    rng = np.random.RandomState(SEED + 77)
+    sizes = np.concatenate((power_law_sizes(rng, 60000, 1, 700), [9000, 1, 2]))      # one block beyond the 8192 window
+    first = 3
+    starts = first + np.concatenate(([0], np.cumsum(sizes)[:-1]))
+    y = np.concatenate((rng.randn(first), make_input(rng, sizes, kind)))
+    checkers = [cpu.port()] + ([cpu.ref()] if cpu.ref() is not None else [])
+    for chk in checkers:
+        want2 = y.copy()
+        chk.pava_multi(want2, starts, variant=2)
+        t = dev(y)
+        api.isotonic_regression_multi_c_2(t, dev(starts))
+        assert np.array_equal(t.cpu().numpy(), want2), (kind, chk.kind)
+        for update in (1, 0):
+            want3 = y.copy()
+            w3 = chk.pava_multi(want3, starts, update=update, variant=3)
+            t, w = dev(y), dev(np.ones(len(y), dtype=np.int32))
+            api.isotonic_regression_multi_c_3(t, dev(starts), w, update)
+            assert np.array_equal(t.cpu().numpy(), want3), (kind, chk.kind, update)
+            assert np.array_equal(w.cpu().numpy(), w3), (kind, chk.kind, update)
+    # single-block entry points
+    s, e = int(starts[5]), int(starts[9])
+    for variant, fn in ((2, api.isotonic_regression_c_2), (3, api.isotonic_regression_c_3)):
+        want = y.copy()
+        cpu.port().pava(want, s, e, variant=variant)
+        t = dev(y)
+        fn(t, s, e)
+        assert np.array_equal(t.cpu().numpy(), want)
+
+
+# ---------------------------------------------------------------------------------------------
+# blocks beyond the 8192-entry shared-memory window: served by the sequential routine, any dtype
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("layout", ["uniform10000", "ragged", "single"])
+def test_long_blocks(api, layout):
+    rng = np.random.RandomState(SEED + 5)
+    if layout == "uniform10000":
+        sizes = np.full(7, 10000)
+    elif layout == "ragged":
+        sizes = np.concatenate((power_law_sizes(rng, 30000, 2, 3000), [20000], power_law_sizes(rng, 5000, 2, 40), [8193, 8192, 3]))
+    else:
+        sizes = np.array([150000])
+    starts = np.concatenate(([0], np.cumsum(sizes)[:-1]))
+    for kind in ("ref", "normal", "zspace"):
+        y = make_input(rng, sizes, kind)
+        want = y.copy()
+        ww = port().pava_multi(want, starts)
+        gy, gw = gpu_pava(api, y, starts)
+        assert np.array_equal(gw, ww) and np.array_equal(gy, want), (layout, kind)
+        gy, _ = gpu_pava(api, y, starts, with_weight=False, clip=True)
+        port().clip01(want)
+        assert np.array_equal(gy, want), (layout, kind)
+    # fp32 twin: no length limit either
+    y = make_input(rng, sizes, "normal").astype(np.float32)
+    want = y.astype(np.float64)
+    port().pava_multi(want, starts)
+    t = dev(y)
+    api.isotonic_regression_multi_c(t, dev(starts))
+    assert np.abs(t.cpu().numpy().astype(np.float64) - want).max() <= 1e-4 * max(1.0, np.abs(want).max())
+    # host ABI, single block (the reference's stress shape, test_stress_isotonic_regression.py:59)
+    h = make_input(rng, sizes, "ref")
+    want = h.copy()
+    port().pava_multi(want, starts)
+    api.isotonic_regression_multi_c(h, starts)
+    assert np.array_equal(h, want)
+
+
+def test_config3_full_size_with_weights(api):
+    """BASELINE config 3 at full size (power-law blocks 2..4096, 10^7 values): values and the weight array
+    bit-identical to the oracle (multi-threaded port), cold call and [0,1] clamp too."""
+    rng = np.random.RandomState(SEED + 2)
+    sizes = []
+    left = 10 ** 7
+    while left > 0:
+        k = np.floor(2 * rng.rand(65536) ** (-1.0 / 1.5)).clip(2, 4096).astype(np.int64)
+        c = np.cumsum(k)
+        cut = int(np.searchsorted(c, left, side="left"))
+        if cut >= len(k):
+            sizes.append(k)
+            left -= int(c[-1])
+            continue
+        take = k[:cut + 1].copy()
+        take[-1] -= int(c[cut] - left)
+        if take[-1] < 1:
+            take = take[:-1]
+        sizes.append(take)
+        left = 0
+    sizes = np.concatenate(sizes)
+    n = int(sizes.sum())
+    starts = np.concatenate(([0], np.cumsum(sizes)[:-1]))
+    pos = np.arange(n) - np.repeat(starts, sizes)
+    y = rng.randint(-50, 50, size=n) + 50.0 * np.log1p(pos)            # tests/fast/test_isotonic_regression.py:43 per block
+    want = y.copy()
+    ww = port().pava_multi(want, starts, threads=port().max_threads())
+    gy, gw = gpu_pava(api, y, starts)
+    assert np.array_equal(gw, ww)
+    assert np.array_equal(gy, want)
+    gy, _ = gpu_pava(api, y, starts, with_weight=False)
+    assert np.array_equal(gy, want)
+    z = rng.randn(n) * 0.3 + 0.5
+    want = z.copy()
+    port().pava_multi(want, starts, threads=port().max_threads())
+    port().clip01(want)
+    gy, _ = gpu_pava(api, z, starts, with_weight=False, clip=True)
+    assert np.array_equal(gy, want)

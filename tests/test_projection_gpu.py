@@ -158,6 +158,25 @@ def test_fp32_extension(api, K):
     assert np.abs(got.reshape(nb, K).sum(1) - 1).max() < 1e-5
 
 
+def test_fp32_block_length_limit_is_a_distinct_error(api):
+    """fp32 projection of a block longer than 8192 entries is not served (the candidate-selection margin is too wide in
+    fp32): NotImplementedError -- not the AssertionError the reference raises for invalid block arrays -- and the
+    buffer is left untouched; the fp64 entry point takes the same layout."""
+    rng = np.random.RandomState(SEED)
+    y = rng.randn(30000)
+    starts = np.array([0, 100, 9000], dtype=np.int64)            # last block: 21000 entries
+    t = dev(y.astype(np.float32))
+    before = t.clone()
+    with pytest.raises(NotImplementedError):
+        api.proj_multi_simplex_c(t, dev(starts))
+    assert torch.equal(t, before)
+    t64 = dev(y)
+    api.proj_multi_simplex_c(t64, dev(starts))
+    want = y.copy()
+    cpu_port().proj_multi_simplex(want, starts)
+    assert np.array_equal(t64.cpu().numpy(), want)
+
+
 @pytest.mark.parametrize("K", [3, 4, 16, 20, 24])
 def test_ball_sum_near_one(api, K):
     """l1-ball: the decision `clipped block sums to more than 1` (proj_simplex.h:54-62) on blocks whose sum is

@@ -445,6 +445,55 @@ def test_block_isotonic_regression_drop_in(B):
     assert np.array_equal(host(yd), want)
 
 
+def test_block_isotonic_regression_new_array_and_clip(B):
+    """block_isotonic_regression (block_isotonic_regression.py:8-16): a NEW vector, z-blocks of block_sizes - 1 entries
+    regressed and box-clipped to [0, 1]; blocks of one route have no z entries and are dropped.  Checked against the
+    reference's own formulation (scikit-learn per block, 1e-8 as in tests/fast/test_isotonic_regression.py) and,
+    bit for bit, against the oracle's PAVA + clip."""
+    from oracle import cpu
+    from sklearn.isotonic import IsotonicRegression
+    ir = IsotonicRegression()
+    rng = np.random.RandomState(11)
+    block_sizes = rng.randint(1, 25, size=300)                # includes single-route blocks (empty z-blocks)
+    zsizes = block_sizes - 1
+    blocks_start = np.concatenate(([0], np.cumsum(zsizes)[:-1]))
+    blocks_end = np.cumsum(zsizes)
+    x = 0.5 + 0.6 * rng.randn(int(zsizes.sum()))              # values on both sides of [0, 1]
+    box = lambda y: np.maximum(np.minimum(y, 1), 0)
+    ref = np.concatenate([ir.fit_transform(np.arange(k), x[s:e]) if k > 1 else box(x[s:e])
+                          for k, s, e in zip(zsizes, blocks_start, blocks_end) if k > 0])
+    ref = box(ref)
+    xd = dev(x)
+    out = B.block_isotonic_regression.block_isotonic_regression(xd, None, block_sizes, blocks_start, blocks_end)
+    assert out.data_ptr() != xd.data_ptr() and np.array_equal(host(xd), x)          # input untouched
+    assert np.abs(host(out) - ref).max() < 1e-8
+    want = x.copy()
+    cpu.port().pava_multi(want, blocks_start[zsizes > 0])
+    cpu.port().clip01(want)
+    assert np.array_equal(host(out), want)
+    # torch tensors for the layout arguments work too
+    out2 = B.block_isotonic_regression.block_isotonic_regression(xd, None, torch.as_tensor(block_sizes), torch.as_tensor(blocks_start),
+                                                                 torch.as_tensor(blocks_end))
+    assert torch.equal(out, out2)
+
+
+def test_f64_only_entry_points_reject_f32(B):
+    """x2z / z2x / N / N^T / block_scale have fp64 kernels only: an fp32 buffer must raise the reference's dtype error
+    instead of being read as 8-byte elements."""
+    starts = np.arange(0, 40, 4)
+    x64 = torch.rand(40, dtype=torch.float64, device="cuda")
+    z64 = torch.empty(30, dtype=torch.float64, device="cuda")
+    x32, z32 = x64.float(), z64.float()
+    cx = B.c_extensions
+    for call in (lambda: cx.x2z_c(x32, z64, starts), lambda: cx.x2z_c(x64, z32, starts), lambda: cx.z2x_c(x32, z64, starts),
+                 lambda: cx.z2x_c(x64, z32, starts), lambda: cx.n_dot(x32, z64, starts), lambda: cx.n_dot(x64, z32, starts),
+                 lambda: cx.nt_dot(z32, x64, starts), lambda: cx.nt_dot(z64, x32, starts),
+                 lambda: cx.block_scale(x32, starts, torch.ones(10, dtype=torch.float64, device="cuda"))):
+        with pytest.raises(ValueError, match="dtype mismatch"):
+            call()
+    cx.x2z_c(x64, z64, starts)   # the fp64 call still works
+
+
 # ---------------------------------------------------------------------------------------------
 # BASELINE configs as parity cases (SURVEY 8d): C1 at full size, C4 / C5 shapes reduced in size
 # ---------------------------------------------------------------------------------------------
