@@ -1,18 +1,21 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the block-simplex hot path (contract: see the task).
+"""bench.py -- headline benchmark of the block-simplex least-squares hot path (contract: see the task).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nproc-per-node N bench.py --gpus N ...       (one rank per GPU)
 
-Default workload = BASELINE.json configs[1]: the proj_simplex_c microbench, 10^6 uniform
-blocks of size 4, 16 and 64 in fp64.  One STEP = one pass of the segmented simplex
-projection over all three arrays (84e6 variables) on inputs that were never touched before
-(a fresh N(0,1) buffer set per step, far larger than L2 in aggregate).
+Headline workload = BASELINE.json configs[4]: the Barzilai-Borwein solve (BATCH.solve_BB semantics) on 10^7 OD blocks x
+16 routes, 10^6 links, 8 links per route (nnz = 1.28e9), OD blocks sharded over the GPUs, the partial link vector A x
+summed by one NCCL all-reduce per objective evaluation.  STRONG scaling: the same problem at every N (it fits one GPU).
+One STEP = one full solve from x = 1/K to the reference's stopping rule (|f_old - f| < 1e-12).
 
-Prints ONE JSON line.  `value` = projected variables / s over all GPUs with inputs resident
-in HBM; `e2e` = the same metric through the reference-facing host C ABI
-(bsls_proj_multi_simplex on pinned HOST buffers, copies inside the timed region);
-`roofline` = the dominant kernel (K=64 array) against the measured HBM peak;
-`cpu_baseline` = the reference's own C++ (oracle/_ref) timed on this box's host cores.
+Prints ONE JSON line.  `value` = BB iterations / s over the K timed solves (device time, max over ranks) with the
+problem resident in HBM; `e2e` = the same metric through the reference-facing Python API with HOST vectors (b and x_init
+uploaded from pinned memory, x downloaded, every step, on every rank); `roofline` = the dominant kernel of the solve
+(the SpMV pair) against the measured HBM peak; `cpu_baseline` = the reference's path (oracle restatement of
+BATCH.solve_BB + the reference's own compiled projection) on one host core, on a shard of the same problem; `parity` =
+final objective against the committed value of the single-GPU solve.  Sub-objects carry the other BASELINE configs:
+`c2` (projection microbench + its host-C-ABI e2e), `n1e8`, `c3`, `c3_1e8`, `c1`, `c4_*`.
 """
 import argparse
 import json
@@ -30,10 +33,17 @@ sys.path.insert(0, ROOT)
 SEED = 237423433
 SIZES = (4, 16, 64)
 NB = 10 ** 6
-METRIC = "projected_variables_per_sec"
-UNIT = "var/s"
-WORKLOAD = ("C2 proj_simplex_c microbench: 10^6 uniform blocks x K in {4,16,64}, fp64, N(0,1); "
-            "one step projects all three arrays (84e6 variables)")
+METRIC = "bb_iterations_per_sec"
+UNIT = "iter/s"
+C5 = dict(nb=10 ** 7, K=16, m=10 ** 6, L=8)
+C5_NNZ, C5_N, C5_M, C5_NB = 1280000000, 160000000, 1000000, 10000000
+MAX_ITER = 40
+WORKLOAD = ("C5: BATCH.solve_BB (max_iter 40, prog_tol 1e-12) on 10^7 OD blocks x 16 routes, 10^6 links, 8 links per route "
+            "(nnz 1.28e9), fp64, noise 0.1; OD blocks sharded over the GPUs, A x summed by one NCCL all-reduce per evaluation; "
+            "one step = one full solve from x = 1/K")
+CONFIG = {"workload": WORKLOAD,
+          "l2": "inputs larger than L2: every evaluation streams the 10.2 GB index arrays of A and A^T (126 MB L2)"}
+GOLDEN_C5 = os.path.join(ROOT, "tests", "golden", "c5_bb.json")
 
 
 def peaks():
@@ -123,25 +133,59 @@ def cpu_project_parallel(chk, y, K, threads):
         t.join()
 
 
-def cpu_baseline_sample(threads=1, reps=2):
-    """Reference CPU path on a bounded sample (the full 84e6-variable step, `reps` timed passes)."""
+def cpu_c5_scaled(scale, seed=SEED + 5):
+    """Config 5 scaled down by ``scale`` for the CPU legs (10^7 / scale OD blocks x 16 routes, 10^6 / scale links, 8 links
+    per route), generated on the host with the same rule as bsls_b200.generate (L distinct, ascending links per route;
+    x_true ~ Dirichlet(1) per block; b = A x_true + N(0, 0.1)).  Every term of an iteration's cost (non-zeros,
+    variables, links) shrinks by the same factor, so iterations/s of the full problem = measured / scale."""
+    import scipy.sparse as sps
+    nb, K, m, L = C5["nb"] // scale, C5["K"], C5["m"] // scale, C5["L"]
+    rng = np.random.RandomState(seed)
+    n = nb * K
+    links = np.sort(rng.randint(0, m - L + 1, size=(n, L), dtype=np.int32), axis=1) + np.arange(L, dtype=np.int32)
+    AT = sps.csr_matrix((np.ones(n * L), links.reshape(-1), np.arange(0, (n + 1) * L, L, dtype=np.int64)), shape=(n, m))
+    A = sps.csr_matrix(AT.T)
+    x_true = rng.dirichlet(np.ones(K), size=nb).reshape(-1)
+    b = A.dot(x_true) + 0.1 * rng.randn(m)
+    return A, b, np.arange(0, n, K), np.ones(n) / K
+
+
+def cpu_bb(scale, threads, steps, warmup):
+    """The reference's BATCH.solve_BB on a scaled-down C5, timed on the host: the oracle's statement-for-statement
+    restatement of the loop (oracle/solvers_np.py), CSR products as scipy's csr_matvec, projection by the reference's
+    own compiled C++ when oracle/_ref exists.  threads > 1 spreads the products and the projection over host threads
+    (the reference has no threading: this is the best-effort CPU number).  Returns per-step seconds and iterations."""
+    from oracle import solvers_np as S
     chk, kind = ref_checker()
-    rng = np.random.RandomState(SEED)
-    data = {K: rng.randn(NB * K) for K in SIZES}
-    best = float("inf")
-    for rep in range(reps + 1):
-        work = {K: data[K].copy() for K in SIZES}
+    A, b, starts, x0 = cpu_c5_scaled(scale)
+    K = C5["K"]
+    project = (lambda x: cpu_project_parallel(chk, x, K, threads))
+    parts = S.get_solver_parts(A, b, starts, 0.1, threads=threads, project=project)
+    times, its, f = [], [], None
+    for it in range(warmup + steps):
         t0 = time.perf_counter()
-        for K in SIZES:
-            cpu_project_parallel(chk, work[K], K, threads)
+        sol = S.solve_BB(parts[3], parts[1], parts[2], x0, max_iter=MAX_ITER)
         dt = time.perf_counter() - t0
-        if rep > 0:
-            best = min(best, dt)
-    nvar = NB * sum(SIZES)
-    return {"value": nvar / best, "unit": UNIT, "cores": threads, "kind": kind,
-            "sample": "one full step (10^6 blocks x K=4,16,64 = 84e6 variables), best of %d after 1 warm-up, "
-                      "%d host thread(s) over disjoint block ranges" % (reps, threads),
-            "seconds_per_step": best}
+        if it >= warmup:
+            times.append(dt)
+            its.append(sol["iterations"] - 1)
+        f = sol["f"]
+    return times, its, f, ("reference" if kind == "reference" else "port"), A.nnz
+
+
+def cpu_scale(threads):
+    """Scale factor of the CPU problem: ~10-30 s of CPU work per run (about 10 ns per non-zero and iteration on one core)."""
+    return 100 if threads <= 1 else 25
+
+
+def cpu_line_fields(times, its, nnz, threads, kind, scale):
+    value = float(np.sum(its)) / float(np.sum(times)) / scale
+    sample = ("BATCH.solve_BB on C5 scaled down by %d (%d OD blocks x 16 routes, %d links, nnz %.3g), %d iterations per solve, "
+              "%d host thread(s); iterations/s of the full problem = measured / %d (every cost term is linear in the size); "
+              "loop = oracle restatement of python/BATCH.py:55-106, projection = %s"
+              % (scale, C5["nb"] // scale, C5["m"] // scale, nnz, int(its[0]), threads, scale,
+                 "the reference's compiled C++ (oracle/_ref)" if kind == "reference" else "oracle port"))
+    return value, sample
 
 
 _REAL_STDOUT = None
@@ -161,38 +205,18 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    chk, kind = ref_checker()
-    rng = np.random.RandomState(SEED)
-    data = {K: rng.randn(NB * K) for K in SIZES}
-    # bounded sample: keep the whole run within a few minutes
-    probe = {K: data[K][: (NB // 16) * K].copy() for K in SIZES}
-    t0 = time.perf_counter()
-    for K in SIZES:
-        cpu_project_parallel(chk, probe[K], K, threads)
-    est_full = (time.perf_counter() - t0) * 16
-    frac = min(1.0, 120.0 / max(1e-9, est_full * (args.steps + args.warmup)))
-    nb_s = max(1000, int(NB * frac))
-    times = []
-    for it in range(args.warmup + args.steps):
-        work = {K: data[K][: nb_s * K].copy() for K in SIZES}
-        t0 = time.perf_counter()
-        for K in SIZES:
-            cpu_project_parallel(chk, work[K], K, threads)
-        dt = time.perf_counter() - t0
-        if it >= args.warmup:
-            times.append(dt)
+    scale = cpu_scale(threads)
+    times, its, f, kind, nnz = cpu_bb(scale, threads, args.steps, args.warmup)
+    value, sample = cpu_line_fields(times, its, nnz, threads, kind, scale)
     total = float(np.sum(times))
-    nvar = nb_s * sum(SIZES)
-    value = nvar * args.steps / total
-    sample = "%d of 10^6 blocks per K (%.0f%% of the workload) per step, %d host threads" % (nb_s, 100.0 * nb_s / NB, threads)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": CONFIG, "sample": sample,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                             "projection_kind": kind, "f_final_scaled_problem": f},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
-
 
 
 # --------------------------------------------------------------------------------------------
@@ -223,10 +247,10 @@ def power_law_sizes(total, lo=2, hi=4096, alpha=1.5, seed=SEED + 2):
     return np.concatenate(sizes)
 
 
-def bench_c3(bsls_b200, torch, dev, peak, steps=5):
-    """BASELINE config 3: power-law blocks 2..4096, 10^7 variables: projection and segmented PAVA
-    (values only, and with the pool-size array) on fresh inputs; CUDA events."""
-    sizes = power_law_sizes(10 ** 7)
+def bench_c3(bsls_b200, torch, dev, peak, steps=5, total=10 ** 7):
+    """BASELINE config 3: power-law blocks 2..4096, 10^7 variables (and the same layout scaled to 10^8):
+    projection and segmented PAVA (values only, and with the pool-size array) on fresh inputs; CUDA events."""
+    sizes = power_law_sizes(total)
     n, nb = int(sizes.sum()), len(sizes)
     starts = torch.as_tensor(np.concatenate(([0], np.cumsum(sizes)[:-1]))).to(dev)
     plan = bsls_b200.BlockPlan(starts, n)
@@ -407,66 +431,94 @@ def bench_c1_c4(bsls_b200, torch, dev, with_cpu):
     return out
 
 
-def cpu_bb_sample(seconds=12.0):
-    """The reference's BATCH.solve_BB (oracle restatement: scipy CSR products + the reference's C++
-    projection) on a reduced C5-shaped problem, one host thread."""
-    import scipy.sparse as sps
-    from oracle import solvers_np as S
-    nb, K, m, L = 100000, 16, 10000, 8
-    rng = np.random.RandomState(SEED + 5)
-    n = nb * K
-    base = np.sort(rng.randint(0, m - L + 1, size=(n, L)), axis=1) + np.arange(L)
-    A = sps.csr_matrix((np.ones(n * L), (base.reshape(-1), np.repeat(np.arange(n), L))), shape=(m, n))
-    x_true = rng.dirichlet(np.ones(K), size=nb).reshape(-1)
-    b = A.dot(x_true) + 0.1 * rng.randn(m)
-    starts = np.arange(0, n, K)
-    step_size, proj, line_search, obj = S.get_solver_parts(A, b, starts, 0.1)
+def bench_c2(bsls_b200, torch, dev, peak, steps=10, e2e_steps=3):
+    """BASELINE config 2 (round 1's headline): proj_simplex_c microbench, 10^6 uniform blocks of 4 / 16 / 64, fp64, on fresh
+    N(0,1) inputs; device-resident per-K launches timed by CUDA events, and the same call through the host C ABI
+    (bsls_proj_multi_simplex on pinned host buffers, copies inside the timed region)."""
+    from oracle import cpu
+    gen = torch.Generator(device=dev).manual_seed(SEED + 1)
+    starts = {K: torch.arange(0, NB * K, K, dtype=torch.int64, device=dev) for K in SIZES}
+    plans = {K: bsls_b200.BlockPlan(starts[K], NB * K) for K in SIZES}
+    out = {"workload": "C2 proj_simplex_c microbench: 10^6 uniform blocks x K in {4,16,64}, fp64, N(0,1), fresh input per launch"}
+    tot_ms = 0.0
+    for K in SIZES:
+        bufs = [torch.randn(NB * K, dtype=torch.float64, device=dev, generator=gen) for _ in range(steps + 3)]
+        keep = bufs[-1][: 1024 * K].clone()
+        for b in bufs[:3]:
+            bsls_b200.proj_multi_simplex_c(b, plans[K])
+        torch.cuda.synchronize()
+        evs = []
+        for b in bufs[3:]:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            bsls_b200.proj_multi_simplex_c(b, plans[K])
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+        want = keep.cpu().numpy().copy()
+        cpu.port().proj_multi_simplex(want, np.arange(0, want.size, K))
+        assert np.array_equal(bufs[-1][: 1024 * K].cpu().numpy(), want), "projection differs from the oracle (K=%d)" % K
+        bytes_ = 2 * 8 * NB * K + 4 * NB
+        out["K=%d" % K] = {"avg_ms": ms, "algorithmic_bytes": bytes_, "GBs": bytes_ / ms / 1e6, "frac": bytes_ / ms / 1e6 / peak,
+                           "var_per_s": NB * K / ms * 1e3}
+        tot_ms += ms
+        del bufs
+    out["var_per_s"] = NB * sum(SIZES) / tot_ms * 1e3
+    # host C ABI
+    rng = np.random.RandomState(SEED + 7)
+    host = {K: torch.empty(NB * K, dtype=torch.float64).pin_memory() for K in SIZES}
+    src = {K: rng.randn(NB * K) for K in SIZES}
+    hblocks = {K: np.arange(0, NB * K, K, dtype=np.int32) for K in SIZES}
+    times = []
+    for it in range(e2e_steps + 1):
+        for K in SIZES:
+            host[K].numpy()[:] = src[K]
+        t0 = time.perf_counter()
+        for K in SIZES:
+            bsls_b200.proj_multi_simplex_c(host[K].numpy(), hblocks[K])
+        dt = time.perf_counter() - t0
+        if it > 0:
+            times.append(dt)
+    for K in SIZES:
+        want = src[K][: 512 * K].copy()
+        cpu.port().proj_multi_simplex(want, np.arange(0, want.size, K))
+        assert np.array_equal(host[K].numpy()[: 512 * K], want)
+    t = float(np.mean(times))
+    out["e2e_host_abi"] = {"var_per_s": NB * sum(SIZES) / t, "ms_per_step": 1e3 * t, "h2d_bytes": sum(8 * NB * K + 4 * NB for K in SIZES),
+                           "d2h_bytes": sum(8 * NB * K for K in SIZES),
+                           "api": "bsls_proj_multi_simplex(double*, const int*, int, int) on pinned host buffers via ctypes"}
+    chk, kind = ref_checker()
+    data = {K: src[K].copy() for K in SIZES}
     t0 = time.perf_counter()
-    sol = S.solve_BB(obj, proj, line_search, np.ones(n) / K, max_iter=12)
+    for K in SIZES:
+        cpu_project_parallel(chk, data[K], K, 1)
     dt = time.perf_counter() - t0
-    its = sol["iterations"] - 1
-    return {"value": its / dt, "unit": "iter/s", "cores": 1, "kind": "port",
-            "sample": "BATCH.solve_BB, %d iterations on a 1/100-size C5 (nb=%d, K=%d, m=%d, L=%d: nnz=%.3g)" % (its, nb, K, m, L, n * L),
-            "seconds": dt, "nnz_iter_per_s": its * n * L / dt}
+    out["cpu_baseline"] = {"value": NB * sum(SIZES) / dt, "unit": "var/s", "cores": 1, "kind": kind,
+                           "sample": "one pass over the same three arrays (84e6 variables), one host thread"}
+    return out
 
 
-def bench_bb_c5(bsls_b200, torch, dist, dev, rank, world, peak, max_iter=40):
-    """BASELINE config 5: 10^7 OD blocks x 16 routes, 10^6 links, L = 8 links per route; OD blocks
-    sharded over ranks, A x summed by one NCCL all-reduce per objective evaluation; the whole BB
-    loop (BATCH.solve_BB semantics) runs inside the library.  Strong scaling."""
+def dist_parity_check(bsls_b200, torch, dist, dev, rank, world, comm):
+    """Driver-visible proof that the sharded path computes what one GPU computes: a config-5-shaped problem small enough to
+    be solved twice -- sharded over all ranks (NCCL all-reduce of A x, all-gather of the step scalars) and, by every rank
+    on its own, whole -- must reach the same objective (1e-6 relative, north_star's bar)."""
     from bsls_b200.generate import SyntheticProblem
-    comm = bsls_b200.Communicator() if world > 1 else None
-    sp = SyntheticProblem.config("C5", rank=rank, world=world, comm=comm, noise=0.1)
-    panels = sp.problem.set_panels() if sp.n * 8 > (64 << 20) else 1
-    step_size, proj, line_search, obj = sp.solver_parts()
-    bsls_b200.BATCH.solve_BB(obj, proj, line_search, sp.x_init, max_iter=4)          # warm-up
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.profiler.start()
-    sol = bsls_b200.BATCH.solve_BB(obj, proj, line_search, sp.x_init, max_iter=max_iter)
-    torch.cuda.profiler.stop()
-    ms = torch.tensor([sol["device_ms"]], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms.item())
-    its = sol["iterations"] - 1
-    nnz, n, m, nb = 1280000000, 160000000, 1000000, 10000000
-    b_bb = 24 * nnz + 72 * n + 32 * m + 4 * nb                     # SURVEY 8d, fp64 values + int32 indices
-    stored = 8 * nnz + 72 * n + 32 * m + 4 * nb + 16 * (n + m)     # what this build moves: index-only A, both sides
-    evals = sol["obj_evals"]
-    return {"workload": "C5: BB solve, 10^7 OD blocks x 16 routes, 10^6 links, nnz=1.28e9, sharded by OD block over %d GPU(s)" % world,
-            "iter_per_s": its / ms * 1e3, "iterations": its, "objective_evaluations": evals, "backtracks": sol["backtracks"],
-            "ms_per_iteration": ms / max(1, its), "ms_per_evaluation": ms / max(1, evals), "f_final": sol["f"],
-            "stop": sol["stop"], "scaling": "strong", "n_gpus": world, "panels_per_gpu": panels,
-            "kernel_launches": sol["kernel_launches"],
-            "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peak * world,
-                         "algorithmic_bytes_per_iteration": b_bb,
-                         "achieved": b_bb * evals / ms / 1e6, "frac": b_bb * evals / ms / 1e6 / (peak * world),
-                         "stored_bytes_per_iteration": stored, "achieved_stored": stored * evals / ms / 1e6,
-                         "note": "per objective evaluation (a back-track repeats the SpMV pair); A is held index-only "
-                                 "(values are implicit ones): `achieved` uses SURVEY 8d's fp64-value formula, "
-                                 "`achieved_stored` the bytes actually moved"}}
+    nb, K, m, L = 64000, 16, 5000, 8
+    whole = SyntheticProblem(nb, K, m, L, device=dev, noise=0.1)
+    parts = whole.solver_parts()
+    one = bsls_b200.BATCH.solve_BB(parts[3], parts[1], parts[2], whole.x_init, max_iter=300)
+    shard = SyntheticProblem(nb, K, m, L, device=dev, rank=rank, world=world, comm=comm, noise=0.1)
+    lo = shard.block_lo * K
+    assert torch.equal(shard.x_true, whole.x_true[lo:lo + shard.n]), "the shard is not a slice of the whole problem"
+    parts = shard.solver_parts()
+    many = bsls_b200.BATCH.solve_BB(parts[3], parts[1], parts[2], shard.x_init, max_iter=300)
+    rel = abs(many["f"] - one["f"]) / abs(one["f"])
+    assert rel <= 1e-6, "sharded BB objective %r differs from the single-GPU objective %r" % (many["f"], one["f"])
+    return {"problem": "%d OD blocks x %d routes, %d links, %d links per route" % (nb, K, m, L), "f_sharded": many["f"],
+            "f_single_gpu": one["f"], "rel_err": rel, "iterations_sharded": many["iterations"] - 1,
+            "iterations_single_gpu": one["iterations"] - 1, "n_gpus": world, "ok": True}
+
 
 # --------------------------------------------------------------------------------------------
 # our arm
@@ -483,161 +535,182 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.barrier()
     import bsls_b200
+    from bsls_b200.generate import SyntheticProblem
+    from bsls_b200 import _lib
 
     steps, warmup = args.steps, args.warmup
-    gen = torch.Generator(device=dev).manual_seed(SEED + 1 + rank)
-    starts = {K: torch.arange(0, NB * K, K, dtype=torch.int64, device=dev) for K in SIZES}
-    plans = {K: bsls_b200.BlockPlan(starts[K], NB * K) for K in SIZES}
-    # a fresh, never-touched input set for every step (672 MB each; aggregate >> 126 MB L2)
-    ksteps = min(steps, 10)   # extra, separately timed passes for the per-kernel numbers
-    bufs = [{K: torch.randn(NB * K, dtype=torch.float64, device=dev, generator=gen) for K in SIZES}
-            for _ in range(steps + warmup + ksteps)]
-    keep = {K: bufs[warmup + steps - 1][K][: 1024 * K].clone() for K in SIZES}  # for the post-run spot check
-    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    peak, peak_src = peaks()
 
-    def step(b, events=None):
-        for K in SIZES:
-            if events is not None:
-                e0 = torch.cuda.Event(enable_timing=True)
-                e0.record()
-            bsls_b200.proj_multi_simplex_c(b[K], plans[K])
-            if events is not None:
-                e1 = torch.cuda.Event(enable_timing=True)
-                e1.record()
-                events[K].append((e0, e1))
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
 
-    for i in range(warmup):
-        step(bufs[i])
-    flush.zero_()
-    torch.cuda.synchronize()
+    def max_over_ranks(v):
+        if world == 1:
+            return float(v)
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- the problem: config 5, this rank's OD blocks ------------------------------------------------
+    comm = bsls_b200.Communicator() if world > 1 else None
+    sp = SyntheticProblem.config("C5", rank=rank, world=world, comm=comm, noise=0.1)
+    panels = sp.problem.set_panels() if sp.n * 8 > (64 << 20) else 1
+    step_size, proj, line_search, obj = sp.solver_parts()
+    solve = lambda x0: bsls_b200.BATCH.solve_BB(obj, proj, line_search, x0, max_iter=MAX_ITER)
+
+    for _ in range(warmup):
+        solve(sp.x_init)
+    barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.25)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    events = {K: [] for K in SIZES}
+    barrier()
     t_wall0 = time.time()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.profiler.start()      # ncu --profile-from-start off: only the timed regions are listed
+    torch.cuda.profiler.start()      # ncu --profile-from-start off: only the timed region is listed
     ev0.record()
-    for i in range(steps):
-        step(bufs[warmup + i])
+    sols = [solve(sp.x_init) for _ in range(steps)]
     ev1.record()
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
-    # per-kernel durations: the same launches on further fresh inputs, each bracketed by its own events
-    # (kept out of the headline region: an event pair costs a few microseconds per launch)
-    for i in range(ksteps):
-        step(bufs[warmup + steps + i], events)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    barrier()
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1)
-    ms = ev0.elapsed_time(ev1)
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    its = sum(s_["iterations"] - 1 for s_ in sols)
+    evals = sum(s_["obj_evals"] for s_ in sols)
+    launches = sum(s_["kernel_launches"] for s_ in sols)
+    value = its / (ms * 1e-3)
+    sol = sols[-1]
+
+    # ---- parity: the objective the single-GPU solve reaches (committed), and sharded == single GPU at N > 1 -----
+    parity = {"f_final": sol["f"], "iterations": sol["iterations"] - 1, "stop": sol["stop"]}
+    if os.path.exists(GOLDEN_C5):
+        with open(GOLDEN_C5) as fh:
+            gold = json.load(fh)
+        parity["f_expected"] = gold["f_final"]
+        parity["expected_from"] = gold["from"]
+        parity["rel_err"] = abs(sol["f"] - gold["f_final"]) / abs(gold["f_final"])
+        parity["ok"] = bool(parity["rel_err"] <= 1e-6)
+        assert parity["ok"], "C5 objective %r differs from the committed single-GPU value %r" % (sol["f"], gold["f_final"])
     if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        parity["sharded_vs_single_gpu"] = dist_parity_check(bsls_b200, torch, dist, dev, rank, world, comm)
 
-    # spot check against the oracle (outside the timed region): bit-exact
-    from oracle import cpu
-    for K in SIZES:
-        want = keep[K].cpu().numpy().copy()
-        cpu.port().proj_multi_simplex(want, np.arange(0, want.size, K))
-        got = bufs[warmup + steps - 1][K][: 1024 * K].cpu().numpy()
-        assert np.array_equal(got, want), "bench output differs from the oracle (K=%d)" % K
-
-    nvar_step = NB * sum(SIZES)
-    value = world * nvar_step * steps / (ms * 1e-3)
-
-    # ---- BB solve on config 5 (all ranks take part; strong scaling) -------------------------------
-    peak, peak_src = peaks()
-    extras = {}
-    if not args.skip_extras:
-        for b in bufs:
-            b.clear()
-        del bufs
-        torch.cuda.empty_cache()
-        extras["bb_c5"] = bench_bb_c5(bsls_b200, torch, dist, dev, rank, world, peak)
-        torch.cuda.empty_cache()
-    if rank != 0:
-        return
+    # ---- per-kernel durations of the SpMV pair: the same launches, each bracketed by its own events -----
+    prob = sp.problem
+    L = _lib.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    xa, xb = sol["x"], sp.x_init
+    ga, gb = torch.empty_like(xa), torch.empty_like(xa)
+    tk = {"ax": [], "atr": []}
+    for rep in range(3 + 5):
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        _lib.check(L.bsls_dev_lsq_residual_f64(prob.handle, xa.data_ptr(), st))
+        e[1].record()
+        _lib.check(L.bsls_dev_lsq_gradient_bb_f64(prob.handle, ga.data_ptr(), gb.data_ptr(), xb.data_ptr(), xa.data_ptr(), st))
+        e[2].record()
+        torch.cuda.synchronize()
+        if rep >= 3:
+            tk["ax"].append(e[0].elapsed_time(e[1]))
+            tk["atr"].append(e[1].elapsed_time(e[2]))
+    del ga, gb
+    nnz_l, n_l, m_l = sp.nnz, sp.n, sp.m
     kern = {}
-    for K in SIZES:
-        d = np.array([a.elapsed_time(b) for a, b in events[K]])
-        bytes_ = 2 * 8 * NB * K + 4 * NB  # B_proj = 2*s*n + 4*nb
-        kern["K=%d" % K] = {"avg_ms": float(d.mean()), "algorithmic_bytes": bytes_, "GBs": bytes_ / d.mean() / 1e6,
-                            "frac": bytes_ / d.mean() / 1e6 / peak, "gvar_s": NB * K / d.mean() / 1e6}
-    dom = kern["K=64"]
-    roofline = {"bound": "hbm", "achieved": dom["GBs"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
-                "traffic": None, "kernel": "proj_select_kernel<double,THREADS=64,KC=64> on the K=64 array (76% of the step's bytes)",
-                "peak_source": peak_src, "per_kernel": kern}
+    for key, name, alg, stored, launches_per in (
+            ("ax", "r = A x - b: spmv_vector_kernel<EpiResidual> over %d column panels + panel_reduce_kernel" % panels,
+             12 * nnz_l + 8 * n_l + 24 * m_l, 4 * nnz_l + 8 * n_l + 8 * m_l * (panels + 2) + 8 * m_l * (panels if panels > 1 else 0), panels + 1),
+            ("atr", "g = A^T r + step dot products: spmv_ell_kernel<EpiGradBB, L=8>",
+             12 * nnz_l + 16 * n_l + 8 * m_l + 24 * n_l, 4 * nnz_l + 32 * n_l + 8 * m_l, 1)):
+        t = float(np.mean(tk[key]))
+        kern[key] = {"kernel": name, "avg_ms": t, "launches": launches_per, "algorithmic_bytes": alg, "stored_bytes": stored,
+                     "GBs": alg / t / 1e6, "frac": alg / t / 1e6 / peak, "GBs_stored": stored / t / 1e6,
+                     "frac_stored": stored / t / 1e6 / peak, "gathers_per_s": nnz_l / t * 1e3}
+    dom = max(kern.values(), key=lambda k: k["avg_ms"])
+    b_bb = 24 * C5_NNZ + 72 * C5_N + 32 * C5_M + 4 * C5_NB                       # SURVEY 8d, fp64 values + int32 indices
+    stored_it = 8 * C5_NNZ + 72 * C5_N + 32 * C5_M + 4 * C5_NB                   # index-only A, both sides
+    roofline = {"bound": "hbm", "achieved": dom["GBs"], "peak": peak, "unit": "GB/s", "frac": dom["frac"], "traffic": None,
+                "kernel": dom["kernel"], "peak_source": peak_src,
+                "achieved_stored": dom["GBs_stored"], "frac_stored": dom["frac_stored"],
+                "note": "A is held index-only (every stored entry is 1): `achieved` credits SURVEY 8d's 12 B per non-zero, "
+                        "`achieved_stored` the 4 B actually moved.  Both products are bound by the L1TEX wavefront rate of their "
+                        "scattered 8-byte gathers (one per non-zero), not by HBM: see gathers_per_s and DESIGN.md",
+                "per_kernel": kern,
+                "whole_solve": {"algorithmic_bytes_per_evaluation": b_bb, "stored_bytes_per_evaluation": stored_it,
+                                "GBs": b_bb * evals / ms / 1e6, "frac_of_n_gpus_peak": b_bb * evals / ms / 1e6 / (peak * world),
+                                "GBs_stored": stored_it * evals / ms / 1e6}}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         with open(prof) as fh:
-            roofline["traffic"] = json.load(fh).get("proj_uniform_K64_bytes_per_launch")
+            tr = json.load(fh)
+        roofline["traffic"] = tr.get("spmv_c5_bytes_per_launch")
+        roofline["traffic_source"] = tr.get("source")
 
-    # ---- e2e: host C ABI, pinned host buffers, copies inside the timed region -----------------
+    # ---- e2e: the reference-facing API with HOST vectors, on EVERY rank --------------------------------
     e2e_steps = max(1, min(steps, args.e2e_steps))
-    rng = np.random.RandomState(SEED + 7)
-    host = {K: torch.empty(NB * K, dtype=torch.float64).pin_memory() for K in SIZES}
-    src = {K: rng.randn(NB * K) for K in SIZES}
-    hblocks = {K: np.arange(0, NB * K, K, dtype=np.int32) for K in SIZES}
-    times = []
-    for it in range(e2e_steps + 1):
-        for K in SIZES:
-            host[K].numpy()[:] = src[K]
-        t0 = time.perf_counter()
-        for K in SIZES:
-            bsls_b200.proj_multi_simplex_c(host[K].numpy(), hblocks[K])
-        dt = time.perf_counter() - t0
-        if it > 0:
-            times.append(dt)
-    e2e_t = float(np.mean(times))
-    for K in SIZES:
-        want = src[K][: 512 * K].copy()
-        cpu.port().proj_multi_simplex(want, np.arange(0, want.size, K))
-        assert np.array_equal(host[K].numpy()[: 512 * K], want)
-    h2d = sum(8 * NB * K + 4 * NB for K in SIZES)
-    d2h = sum(8 * NB * K for K in SIZES)
-    e2e = {"value": world * nvar_step / e2e_t, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "ms_per_step": 1e3 * e2e_t, "steps": e2e_steps,
-           "api": "bsls_proj_multi_simplex(double*, const int*, int, int) on pinned host buffers via ctypes"}
+    xh = torch.full((sp.n,), 1.0 / sp.K, dtype=torch.float64).pin_memory()
+    bh = sp.b.cpu().pin_memory()
+    e2e_its, x_out = 0, None
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        prob.set_b(bh)                                      # measurements arrive from the host
+        res = bsls_b200.BATCH.solve_BB(obj, proj, line_search, xh, max_iter=MAX_ITER)   # x_init up, x back (pinned)
+        f_host = float(res["f"])
+        e2e_its += res["iterations"] - 1
+        x_out = res["x"]
+    torch.cuda.synchronize()
+    e2e_t = max_over_ranks(time.perf_counter() - t0)
+    assert not x_out.is_cuda and abs(f_host - sol["f"]) <= 1e-9 * abs(sol["f"])
+    e2e = {"value": e2e_its / e2e_t, "unit": UNIT, "h2d_bytes_per_step": 8 * (C5_N + world * C5_M), "d2h_bytes_per_step": 8 * C5_N + 8 * world,
+           "ms_per_step": 1e3 * e2e_t / e2e_steps, "steps": e2e_steps,
+           "api": "bsls_b200.BATCH.solve_BB(obj, proj, line_search, x_init) with x_init / b in pinned host memory and x returned to "
+                  "the host, on every rank (bytes are whole-job totals)"}
+    del xh, bh, x_out
 
-    cpu_base = cpu_baseline_sample(threads=1, reps=2) if world == 1 else None
-    extras["c3"] = bench_c3(bsls_b200, torch, dev, peak) if not args.skip_extras else None
-    extras["n1e8"] = bench_1e8(bsls_b200, torch, dev, peak) if not args.skip_extras else None
-    if not args.skip_extras:
-        extras.update(bench_c1_c4(bsls_b200, torch, dev, with_cpu=(world == 1)))
-    if cpu_base is not None and not args.skip_extras:
-        extras["bb_c5"]["cpu_baseline"] = cpu_bb_sample()
-
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
-            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": WORKLOAD, "l2": "fresh input buffers every step (inputs larger than L2); L2 flushed before timing",
-                       "per_gpu_variables_per_step": nvar_step},
-            "roofline": roofline, "e2e": e2e, "gpu_launches": 4 * steps, "clocks": clocks}
-    if cpu_base is not None:
-        line["cpu_baseline"] = cpu_base
-    for k, v in extras.items():
-        if v is not None:
-            line[k] = v
-    if "bb_c5" in line:
-        line["gpu_launches"] += line["bb_c5"]["kernel_launches"]
-    emit(line)
+    # ---- CPU baseline and the other BASELINE configs (rank 0, device-local work only) -----------------------
+    extras = {}
+    del sols, sol, sp, prob, obj, proj, line_search, step_size, solve, xa, xb
+    torch.cuda.empty_cache()
+    if rank == 0:
+        cpu_base = None
+        if world == 1:
+            scale = cpu_scale(1)
+            times, cits, cf, kind, cnnz = cpu_bb(scale, 1, 1, 1)
+            cval, csample = cpu_line_fields(times, cits, cnnz, 1, kind, scale)
+            cpu_base = {"value": cval, "unit": UNIT, "cores": 1, "kind": "port", "sample": csample, "projection_kind": kind}
+        if not args.skip_extras:
+            extras["c2"] = bench_c2(bsls_b200, torch, dev, peak)
+            extras["n1e8"] = bench_1e8(bsls_b200, torch, dev, peak)
+            extras["c3"] = bench_c3(bsls_b200, torch, dev, peak)
+            extras["c3_1e8"] = bench_c3(bsls_b200, torch, dev, peak, total=10 ** 8, steps=3)
+            extras.update(bench_c1_c4(bsls_b200, torch, dev, with_cpu=(world == 1)))
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+                "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": CONFIG,
+                "solve": {"iterations_per_solve": its // steps, "objective_evaluations_per_solve": evals // steps,
+                          "ms_per_iteration": ms / max(1, its), "ms_per_evaluation": ms / max(1, evals), "panels_per_gpu": panels,
+                          "note": "a back-tracked line search costs no extra product: the objective is quadratic along the step "
+                                  "(decide_kernel, lsq.cuh)"},
+                "parity": parity, "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+        if cpu_base is not None:
+            line["cpu_baseline"] = cpu_base
+        for k, v in extras.items():
+            if v is not None:
+                line[k] = v
+        emit(line)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--skip-extras", action="store_true", help="headline (C2 projection) only: no BB-on-C5 / C3 sub-objects")
+    ap.add_argument("--skip-extras", action="store_true", help="headline (BB solve on C5) only: no C1 / C2 / C3 / C4 / 10^8 sub-objects")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
 

@@ -15,6 +15,7 @@ import ctypes
 import time
 from collections import deque
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -24,6 +25,58 @@ from .sparse import axpby, copy_, default_workspace
 __all__ = ["solve", "solve_BB", "solve_LBFGS", "LBFGS_helper", "solve_MD"]
 
 _STOP = {0: 'continue', 1: 'max_iter'}
+
+
+def _stage_in(x_init, obj):
+    """The reference's solvers take and return NumPy vectors.  Host input (ndarray, or a CPU tensor -- pinned memory makes
+    the copy asynchronous) is copied to the device of the problem; the result then goes back the same way."""
+    if torch.is_tensor(x_init) and x_init.is_cuda:
+        return x_init, None
+    problem = getattr(obj, "problem", None)
+    device = problem.device if problem is not None else torch.device("cuda", torch.cuda.current_device())
+    host = x_init if torch.is_tensor(x_init) else torch.from_numpy(np.ascontiguousarray(x_init, dtype=np.float64))
+    assert host.dtype == torch.float64 and host.dim() == 1, "x_init: float64 vector expected"
+    return host.to(device, non_blocking=True), ("tensor" if torch.is_tensor(x_init) else "numpy")
+
+
+_PINNED_OUT = {}
+
+
+def _stage_out(sol, kind, like=None):
+    """Result back to the host.  NumPy in -> a new NumPy array out (as the reference).  A pinned CPU tensor in -> a pinned
+    CPU tensor out; pinning memory costs far more than the copy, so ONE pinned result buffer per vector length is kept
+    and reused by the next call of that length (copy it if two results must be alive at once)."""
+    if kind is None:
+        return sol
+    x = sol['x']
+    if kind == "numpy":
+        sol['x'] = x.cpu().numpy()
+    elif like is not None and like.is_pinned():
+        out = _PINNED_OUT.get(x.shape[0])
+        if out is None:
+            out = _PINNED_OUT[x.shape[0]] = torch.empty(x.shape, dtype=x.dtype).pin_memory()
+        out.copy_(x, non_blocking=False)
+        sol['x'] = out
+    else:
+        sol['x'] = x.cpu()
+    return sol
+
+
+def _host_api(fn):
+    """Wraps a solver so that host vectors are accepted for ``x_init`` (see _stage_in)."""
+    def wrapped(*args, **kw):
+        names = fn.__code__.co_varnames[:fn.__code__.co_argcount]
+        k = names.index("x_init")
+        x_init = args[k] if k < len(args) else kw["x_init"]
+        obj = args[0] if args else kw["obj"]
+        xd, kind = _stage_in(x_init, obj)
+        if k < len(args):
+            args = args[:k] + (xd,) + args[k + 1:]
+        else:
+            kw["x_init"] = xd
+        return _stage_out(fn(*args, **kw), kind, x_init if torch.is_tensor(x_init) else None)
+    wrapped.__name__, wrapped.__doc__ = fn.__name__, fn.__doc__
+    return wrapped
 
 
 def _native_parts(obj, proj, line_search=None, need_proj=True):
@@ -66,6 +119,7 @@ def _solve_native(problem, plan, method, proj_mode, x_init, use_line_search, f_m
             'device_ms': res.device_ms}
 
 
+@_host_api
 def solve(obj, proj, step_size, x_init, line_search=None, f_min=None, opt_tol=1e-6,
           max_iter=2000, prog_tol=1e-12):
     """Projected batch gradient descent with line search (BATCH.py:7-52)
@@ -105,6 +159,7 @@ def solve(obj, proj, step_size, x_init, line_search=None, f_min=None, opt_tol=1e
     return {'f': f, 'x': x, 'stop': stop, 'iterations': i, 'progress': progress}
 
 
+@_host_api
 def solve_BB(obj, proj, line_search, x_init, f_min=None, opt_tol=1e-6,
              max_iter=2000, prog_tol=1e-12):
     """Projected batch gradient descent with Barzilai-Borwein step (BATCH.py:55-106)"""
@@ -147,6 +202,7 @@ def solve_BB(obj, proj, line_search, x_init, f_min=None, opt_tol=1e-6,
     return {'f': f, 'x': x, 'stop': stop, 'iterations': i, 'progress': progress}
 
 
+@_host_api
 def solve_LBFGS(obj, proj, line_search, x_init, f_min=None, opt_tol=1e-6,
                 max_iter=1000, prog_tol=1e-12, corrections=50):
     """Projected L-BFGS (BATCH.py:110-193).  As in the reference, the history deques hold
@@ -240,6 +296,7 @@ def LBFGS_helper(q_delta_g, q_delta_x, q_rho, g, d, alpha, ws=None, bb=None):
     ws.axpy_dot(d, -1.0, None, None, None, None, None)  # d *= -1.0
 
 
+@_host_api
 def solve_MD(obj, block_starts, step_size, x_init, line_search=None, f_min=None, opt_tol=1e-6,
              max_iter=1000, prog_tol=0.0):
     """mirror descent algorithm (BATCH.py:217-250)"""

@@ -91,6 +91,7 @@ def lib():
         L.bsls_lsq_obj_f64.argtypes = [c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_dbl), c_void_p]
         L.bsls_dev_lsq_residual_f64.argtypes = [c_void_p, c_void_p, c_void_p]
         L.bsls_dev_lsq_gradient_f64.argtypes = [c_void_p, c_void_p, c_void_p]
+        L.bsls_dev_lsq_gradient_bb_f64.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
         L.bsls_dev_lsq_matvec_f64.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
         L.bsls_dev_lsq_rmatvec_f64.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
         L.bsls_lsq_scalars.argtypes = [c_void_p, ctypes.POINTER(c_dbl * 16), c_void_p]

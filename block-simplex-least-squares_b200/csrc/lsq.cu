@@ -10,6 +10,7 @@
 
 #include "kernels.h"
 #include "lsq.cuh"
+#include "solver_tiny.cuh"
 
 using namespace bsls;
 
@@ -107,7 +108,6 @@ struct bsls_lsq {
     double *r = nullptr;                          // m
     double *r2 = nullptr;                         // m: residual of the trial point (solver loop; allocated with the workspace)
     int t_ell = 0, a_ell = 0;                     // common row length of A^T / A when every row has the same (1..16 supported), else 0
-    cudaTextureObject_t tex_r[2] = {0, 0};        // texture views of r / r2 (experiment: BSLS_ELL_TEX)
     double *wg = nullptr, *wxn = nullptr, *wgn = nullptr;  // n each, solver workspace
     bsls_ws *ws = nullptr;                        // owned
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -175,20 +175,19 @@ int launch_vector(bsls_ws *w, int64_t rows, const int64_t *ptr, const int32_t *i
 
 // rows of exactly L entries: no pointers, no staging (spmv_ell_kernel)
 template <class Epi, int L>
-int launch_ell(bsls_ws *w, int64_t rows, const int32_t *idx, const double *val, const double *v, cudaTextureObject_t tex, const Epi &epi,
-               cudaStream_t st, const int *skip) {
+int launch_ell(bsls_ws *w, int64_t rows, const int32_t *idx, const double *val, const double *v, const Epi &epi, cudaStream_t st,
+               const int *skip) {
     constexpr int T = 256;
-#define ELL_GO(HV, TX)                                                                                             \
+#define ELL_GO(HV)                                                                                                 \
     {                                                                                                              \
         static thread_local PerDevice<int> full_pd;                                                                \
         int &full = full_pd.get(0);                                                                                \
-        if (!full) full = resident_grid(spmv_ell_kernel<Epi, T, L, HV, TX>, T);                                    \
+        if (!full) full = resident_grid(spmv_ell_kernel<Epi, T, L, HV>, T);                                        \
         const int64_t want = (rows + T - 1) / T;                                                                   \
-        spmv_ell_kernel<Epi, T, L, HV, TX><<<(int)(want < full ? want : full), T, 0, st>>>(rows, idx, val, v, tex, epi, w->red, skip); \
+        spmv_ell_kernel<Epi, T, L, HV><<<(int)(want < full ? want : full), T, 0, st>>>(rows, idx, val, v, epi, w->red, skip); \
     }
-    if (val) ELL_GO(true, 0)
-    else if (tex) ELL_GO(false, 1)
-    else ELL_GO(false, 0)
+    if (val) ELL_GO(true)
+    else ELL_GO(false)
 #undef ELL_GO
     return 0;
 }
@@ -198,17 +197,17 @@ inline bool ell_supported(int L) { return L == 4 || L == 6 || L == 8 || L == 10 
 // mode: 1 = stream, 2 = ELL (ell = common row length), 4/8/16/32 = lanes per row
 template <class Epi>
 int launch_spmv(bsls_ws *w, int mode, int64_t rows, const int64_t *ptr, const int32_t *idx, const double *val, const double *v,
-                const Epi &epi, cudaStream_t st, const int *skip = nullptr, int ell = 0, cudaTextureObject_t tex = 0) {
+                const Epi &epi, cudaStream_t st, const int *skip = nullptr, int ell = 0) {
     constexpr int T = 256;
     if (rows <= 0) return BSLS_OK;
     if (mode == 2 && ell_supported(ell)) {
         switch (ell) {
-            case 4: launch_ell<Epi, 4>(w, rows, idx, val, v, tex, epi, st, skip); break;
-            case 6: launch_ell<Epi, 6>(w, rows, idx, val, v, tex, epi, st, skip); break;
-            case 8: launch_ell<Epi, 8>(w, rows, idx, val, v, tex, epi, st, skip); break;
-            case 10: launch_ell<Epi, 10>(w, rows, idx, val, v, tex, epi, st, skip); break;
-            case 12: launch_ell<Epi, 12>(w, rows, idx, val, v, tex, epi, st, skip); break;
-            default: launch_ell<Epi, 16>(w, rows, idx, val, v, tex, epi, st, skip); break;
+            case 4: launch_ell<Epi, 4>(w, rows, idx, val, v, epi, st, skip); break;
+            case 6: launch_ell<Epi, 6>(w, rows, idx, val, v, epi, st, skip); break;
+            case 8: launch_ell<Epi, 8>(w, rows, idx, val, v, epi, st, skip); break;
+            case 10: launch_ell<Epi, 10>(w, rows, idx, val, v, epi, st, skip); break;
+            case 12: launch_ell<Epi, 12>(w, rows, idx, val, v, epi, st, skip); break;
+            default: launch_ell<Epi, 16>(w, rows, idx, val, v, epi, st, skip); break;
         }
     } else if (mode == 1 || mode == 2) {
         static thread_local PerDevice<int> full_pd;
@@ -238,10 +237,7 @@ int allreduce(bsls_ws *w, double *buf, int64_t count, int op, cudaStream_t st) {
 
 // A^T w with an epilogue, on whichever kernel the side was given
 template <class Epi> int launch_at(bsls_lsq *q, const double *w, const Epi &epi, cudaStream_t st, const int *skip = nullptr) {
-    cudaTextureObject_t tex = 0;
-    if (w == q->r) tex = q->tex_r[0];
-    if (w == q->r2) tex = q->tex_r[1];
-    return launch_spmv(q->ws, q->t_mode, q->n, q->t_ptr, q->t_idx, q->t_val, w, epi, st, skip, q->t_ell, tex);
+    return launch_spmv(q->ws, q->t_mode, q->n, q->t_ptr, q->t_idx, q->t_val, w, epi, st, skip, q->t_ell);
 }
 
 // r = A x - b (summed over ranks), scalar F = 0.5 <r, r>; with r_old also <r_old, r - r_old> and |r - r_old|^2
@@ -275,28 +271,9 @@ int residual(bsls_lsq *q, const double *x, double *r, const double *b, cudaStrea
     return BSLS_OK;
 }
 
-// texture view of an m-vector of doubles (as int2 texels), for the BSLS_ELL_TEX experiment
-int make_tex(const double *p, int64_t m, cudaTextureObject_t *out) {
-    static const bool on = [] {
-        const char *e = getenv("BSLS_ELL_TEX");
-        return e && atoi(e) != 0;
-    }();
-    if (!on || *out) return BSLS_OK;
-    cudaResourceDesc rd{};
-    rd.resType = cudaResourceTypeLinear;
-    rd.res.linear.devPtr = const_cast<double *>(p);
-    rd.res.linear.desc = cudaCreateChannelDesc<int2>();
-    rd.res.linear.sizeInBytes = (size_t)m * sizeof(double);
-    cudaTextureDesc td{};
-    td.readMode = cudaReadModeElementType;
-    BSLS_CUDA_TRY(cudaCreateTextureObject(out, &rd, &td, nullptr));
-    return BSLS_OK;
-}
-
 int ensure_workspace(bsls_lsq *q) {
     if (q->wg) return BSLS_OK;
     BSLS_CUDA_TRY(cudaMalloc(&q->r2, sizeof(double) * (size_t)q->m));
-    if (int rc = make_tex(q->r2, q->m, &q->tex_r[1])) return rc;
     BSLS_CUDA_TRY(cudaMalloc(&q->wg, sizeof(double) * (size_t)q->n));
     BSLS_CUDA_TRY(cudaMalloc(&q->wxn, sizeof(double) * (size_t)q->n));
     BSLS_CUDA_TRY(cudaMalloc(&q->wgn, sizeof(double) * (size_t)q->n));
@@ -533,7 +510,6 @@ int bsls_lsq_create(int64_t m, int64_t n, int64_t nnz, const int64_t *a_ptr, con
         }                                                                                    \
     } while (0)
     TRY_OR_FAIL(cudaMalloc(&q->r, sizeof(double) * (size_t)m));
-    if (int rc = make_tex(q->r, m, &q->tex_r[0])) return fail(rc);
     TRY_OR_FAIL(cudaEventCreate(&q->ev0));
     TRY_OR_FAIL(cudaEventCreate(&q->ev1));
 #undef TRY_OR_FAIL
@@ -546,8 +522,6 @@ int bsls_lsq_destroy(bsls_lsq *q) {
     if (!q) return BSLS_OK;
     if (q->r) cudaFree(q->r);
     if (q->r2) cudaFree(q->r2);
-    for (int k = 0; k < 2; ++k)
-        if (q->tex_r[k]) cudaDestroyTextureObject(q->tex_r[k]);
     if (q->partial) cudaFree(q->partial);
     if (q->wg) cudaFree(q->wg);
     if (q->wxn) cudaFree(q->wxn);
@@ -619,6 +593,12 @@ int bsls_dev_lsq_residual_f64(bsls_lsq *q, const double *x, bsls_stream_t s) {
 int bsls_dev_lsq_gradient_f64(bsls_lsq *q, double *g, bsls_stream_t s) {
     if (!q || !g) return BSLS_ERR_ARG;
     EpiPlain epi{g};
+    return launch_at(q, q->r, epi, (cudaStream_t)s);
+}
+
+int bsls_dev_lsq_gradient_bb_f64(bsls_lsq *q, double *g_new, const double *g, const double *x, const double *x_new, bsls_stream_t s) {
+    if (!q || !g_new || !g || !x || !x_new) return BSLS_ERR_ARG;
+    EpiGradBB epi{g_new, g, x, x_new};
     return launch_at(q, q->r, epi, (cudaStream_t)s);
 }
 
@@ -955,6 +935,94 @@ int ensure_loop_scratch(bsls_ws *w, int prog_cap) {
     return BSLS_OK;
 }
 
+DevOpts make_dev_opts(const bsls_batch_opts *o, const bsls_ws *w, int cap) {
+    DevOpts d{};
+    d.method = o->method;
+    d.search = (o->method == 1) || (o->method == 0 && o->use_line_search);
+    d.has_f_min = o->has_f_min;
+    d.max_iter = o->max_iter;
+    d.f_min = o->f_min;
+    d.opt_tol = o->opt_tol;
+    d.prog_tol = o->prog_tol;
+    d.min_eig = o->min_eig;
+    d.nranks = (w->comm && w->comm->nranks > 1) ? w->comm->nranks : 1;
+    d.progress_cap = cap;
+    return d;
+}
+
+void finish_result(bsls_batch_result *res, const DevState &fin, int launches, float ms, double *progress_t, int cap) {
+    if (cap > 0 && progress_t) {  // device time stamps (ns) -> seconds since the first objective value
+        const int np = fin.i < cap ? fin.i : cap;
+        const double t0 = progress_t[0];
+        for (int j = 0; j < np; ++j) progress_t[j] = (progress_t[j] - t0) * 1e-9;
+    }
+    res->f = fin.f;
+    res->iterations = fin.i;
+    res->stop_code = fin.done;
+    res->stop_value = fin.stop_value;
+    res->obj_evals = fin.evals;
+    res->backtracks = fin.backtracks;
+    res->kernel_launches = launches;
+    res->device_ms = ms;
+}
+
+// Problems whose vectors fit one SM's shared memory: the whole loop in one launch of one CTA (solver_tiny.cuh).
+// Returns 0 when the problem does not qualify (the caller goes on), -1 when it was solved here, > 0 on error.
+int solve_tiny(bsls_lsq *q, const bsls_plan *plan, double *x, const bsls_batch_opts *o, bsls_batch_result *res, double *progress_f,
+               double *progress_t, int cap, cudaStream_t st) {
+    const char *e = getenv("BSLS_NO_TINY");  // read per call: the tests run the same problems through both loops
+    const bool off = e && atoi(e) != 0;
+    bsls_ws *w = q->ws;
+    const size_t smem = tiny_smem_bytes((int)q->n, (int)q->m);
+    if (off || (w->comm && w->comm->nranks > 1) || o->method > 1 || o->proj_mode > 1 || plan->max_size > kTinyMaxBlock || plan->first != 0 ||
+        smem > 220 * 1024 || q->n > (1 << 20))
+        return 0;
+    static thread_local PerDevice<bool> attr_pd;
+    bool &attr = attr_pd.get(false);
+    if (!attr) {
+        BSLS_CUDA_TRY(cudaFuncSetAttribute(solver_tiny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr = true;
+    }
+    TinyArgs a{};
+    a.n = (int)q->n;
+    a.m = (int)q->m;
+    a.nb = plan->nb;
+    a.starts = plan->d_starts;
+    a.a_ptr = q->a_ptr;
+    a.t_ptr = q->t_ptr;
+    a.a_idx = q->a_idx;
+    a.t_idx = q->t_idx;
+    a.a_val = q->a_val;
+    a.t_val = q->t_val;
+    a.b = q->b;
+    a.x = x;
+    a.st = w->d_state;
+    a.progress_f = cap > 0 ? w->d_prog : nullptr;
+    a.progress_t = cap > 0 ? w->d_prog + w->prog_cap : nullptr;
+    a.proj_mode = o->proj_mode;
+    const DevOpts d = make_dev_opts(o, w, cap);
+    BSLS_CUDA_TRY(cudaEventRecord(q->ev0, st));
+    solver_tiny_kernel<<<1, kTinyThreads, smem, st>>>(a, d);
+    BSLS_LAUNCH_CHECK();
+    BSLS_CUDA_TRY(cudaEventRecord(q->ev1, st));
+    BSLS_CUDA_TRY(cudaMemcpyAsync(&w->h_state[0], w->d_state, sizeof(DevState), cudaMemcpyDeviceToHost, st));
+    BSLS_CUDA_TRY(cudaStreamSynchronize(st));
+    const DevState fin = w->h_state[0];
+    if (!fin.done) {
+        set_error("batch_solve (single-CTA loop): ended without a stop code (i=%d)", fin.i);
+        return BSLS_ERR_CUDA;
+    }
+    if (cap > 0) {
+        const int np = fin.i < cap ? fin.i : cap;
+        BSLS_CUDA_TRY(cudaMemcpy(progress_f, w->d_prog, sizeof(double) * (size_t)np, cudaMemcpyDeviceToHost));
+        if (progress_t) BSLS_CUDA_TRY(cudaMemcpy(progress_t, w->d_prog + w->prog_cap, sizeof(double) * (size_t)np, cudaMemcpyDeviceToHost));
+    }
+    float ms = 0.f;
+    BSLS_CUDA_TRY(cudaEventElapsedTime(&ms, q->ev0, q->ev1));
+    finish_result(res, fin, 1, ms, progress_t, cap);
+    return -1;
+}
+
 // one iteration of BATCH.solve / solve_BB / solve_MD on the device: trial point, objective + gradient there, decision
 int enqueue_iteration(bsls_lsq *q, const bsls_plan *plan, const LoopBuffers &B, int cur, const DevOpts &d, int proj_mode, cudaStream_t st,
                       int *extra_launches) {
@@ -1033,17 +1101,8 @@ int bsls_batch_solve_f64(bsls_lsq *q, const bsls_plan *plan, double *x, const bs
     bsls_ws *w = q->ws;
     const int cap = (progress_f && progress_cap > 0) ? progress_cap : 0;
     if (int rc = ensure_loop_scratch(w, cap)) return rc;
-    DevOpts d{};
-    d.method = o->method;
-    d.search = (o->method == 1) || (o->method == 0 && o->use_line_search);
-    d.has_f_min = o->has_f_min;
-    d.max_iter = o->max_iter;
-    d.f_min = o->f_min;
-    d.opt_tol = o->opt_tol;
-    d.prog_tol = o->prog_tol;
-    d.min_eig = o->min_eig;
-    d.nranks = (w->comm && w->comm->nranks > 1) ? w->comm->nranks : 1;
-    d.progress_cap = cap;
+    if (int rc = solve_tiny(q, plan, x, o, res, progress_f, progress_t, cap, st)) return rc < 0 ? BSLS_OK : rc;
+    const DevOpts d = make_dev_opts(o, w, cap);
     LoopBuffers B{{x, q->wxn}, {q->wg, q->wgn}, {q->r, q->r2}};
     const int launches0 = w->launches;
     int extra = 0;
@@ -1088,21 +1147,9 @@ int bsls_batch_solve_f64(bsls_lsq *q, const bsls_plan *plan, double *x, const bs
     }
     BSLS_CUDA_TRY(cudaEventRecord(q->ev1, st));
     BSLS_CUDA_TRY(cudaStreamSynchronize(st));
-    if (cap > 0 && progress_t) {  // device time stamps (ns) -> seconds since the first objective value
-        const int np = fin.i < cap ? fin.i : cap;
-        const double t0 = progress_t[0];
-        for (int j = 0; j < np; ++j) progress_t[j] = (progress_t[j] - t0) * 1e-9;
-    }
     float ms = 0.f;
     BSLS_CUDA_TRY(cudaEventElapsedTime(&ms, q->ev0, q->ev1));
-    res->f = fin.f;
-    res->iterations = fin.i;
-    res->stop_code = fin.done;
-    res->stop_value = fin.stop_value;
-    res->obj_evals = fin.evals;
-    res->backtracks = fin.backtracks;
-    res->kernel_launches = (w->launches - launches0) + extra;
-    res->device_ms = ms;
+    finish_result(res, fin, (w->launches - launches0) + extra, ms, progress_t, cap);
     return BSLS_OK;
 }
 

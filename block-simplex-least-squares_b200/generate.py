@@ -52,27 +52,46 @@ def transpose_pattern(rows_of_nnz, n_rows_out, n_cols_in_per, chunk=None):
     return ptr, idx
 
 
+def chunk_count(nb):
+    """The blocks of a problem are generated in this many equal chunks, each from its own seed, so that the GLOBAL problem
+    does not depend on how many ranks share it (a rank generates the chunks it owns)."""
+    for g in (64, 8):
+        if nb % g == 0:
+            return g
+    return 1
+
+
 class SyntheticProblem:
     """One rank's slice of a synthetic problem: ``problem`` (LsqProblem over the local columns),
-    ``plan`` / ``starts`` (local block layout), ``x_true``, ``x_init`` (local), ``b`` (global)."""
+    ``plan`` / ``starts`` (local block layout), ``x_true``, ``x_init`` (local), ``b`` (global).
+    The global problem is the same for every world size that divides ``chunk_count(nb)``."""
 
     def __init__(self, nb, K, m, L, device=None, seed=SEED, rank=0, world=1, comm=None, implicit_ones=True, noise=0.0):
         device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.nb_global, self.K, self.m, self.L = nb, K, m, L
+        G = chunk_count(nb)
+        assert G % world == 0 or world == 1, "world size %d must divide the %d generation chunks" % (world, G)
+        if G % world:
+            G = 1
         lo, hi = block_range(nb, rank, world)
         self.block_lo, self.block_hi = lo, hi
         nbl = hi - lo
         n = nbl * K
         self.nb, self.n = nbl, n
-        gen = torch.Generator(device=device).manual_seed(seed + 7919 * rank)
-        links = route_links(n, m, L, gen, device)                  # CSR of A^T: row = route, L links each
-        t_idx = links.reshape(-1).contiguous()
+        per = nb // G                                               # blocks per chunk
+        t_idx = torch.empty(n * L, dtype=torch.int32, device=device)   # CSR of A^T: row = route, L links each
+        self.x_true = torch.empty(n, dtype=torch.float64, device=device)
+        for c in range(lo // per, (hi + per - 1) // per):
+            gen = torch.Generator(device=device).manual_seed(seed + 7919 * c)
+            r0 = (c * per - lo) * K                                     # first local route of the chunk
+            links = route_links(per * K, m, L, gen, device)
+            t_idx[r0 * L:(r0 + per * K) * L] = links.reshape(-1)
+            del links
+            e = -torch.log(torch.rand(per, K, generator=gen, device=device, dtype=torch.float64))
+            self.x_true[r0:r0 + per * K] = (e / e.sum(1, keepdim=True)).reshape(-1)
+            del e
         t_ptr = torch.arange(0, (n + 1) * L, L, dtype=torch.int64, device=device)
         a_ptr, a_idx = transpose_pattern(t_idx, m, L)              # CSR of A: row = link
-        del links
-        e = -torch.log(torch.rand(nbl, K, generator=gen, device=device, dtype=torch.float64))
-        self.x_true = (e / e.sum(1, keepdim=True)).reshape(-1).contiguous()
-        del e
         self.starts = torch.arange(0, n, K, dtype=torch.int64, device=device)
         self.plan = BlockPlan(self.starts, n, device)
         self.x_init = torch.full((n,), 1.0 / K, dtype=torch.float64, device=device)

@@ -190,6 +190,11 @@ BSLS_API int bsls_lsq_obj_f64(bsls_lsq *lsq, const double *x, double *g, double 
 /* the same in two asynchronous halves; the residual stays inside the handle */
 BSLS_API int bsls_dev_lsq_residual_f64(bsls_lsq *lsq, const double *x, bsls_stream_t stream);
 BSLS_API int bsls_dev_lsq_gradient_f64(bsls_lsq *lsq, double *g, bsls_stream_t stream);
+/* the gradient half fused with the step scalars of BATCH.solve_BB / line_search_np (python/BATCH.py:89,99-100,
+ * python/algorithm_utils.py:120,126): g_new = A^T r, and scalar slots [1] <x_new - x, g_new - g>, [2] |g_new - g|^2,
+ * [3] <g, x_new - x>, [4] |g_new|^2, [5] max |x_new - x| (this rank's share when sharded) */
+BSLS_API int bsls_dev_lsq_gradient_bb_f64(bsls_lsq *lsq, double *g_new, const double *g, const double *x, const double *x_new,
+                                          bsls_stream_t stream);
 /* plain products: out = A v (m entries, summed over ranks) and out = A^T w (n entries) -- the
  * `linop` / `linop_T` of DORE.solve (python/DORE.py:6, python/gradient_descent.py:62-63) */
 BSLS_API int bsls_dev_lsq_matvec_f64(bsls_lsq *lsq, const double *v, double *out, bsls_stream_t stream);

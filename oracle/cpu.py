@@ -142,6 +142,29 @@ class Port:
         self.lib.orc_csr_matvec(rows, _lp(ptr), _ip(idx), _dp(val), _dp(v), _dp(out))
         return out
 
+    def csr_matvec_mt(self, ptr, idx, val, v, out, threads):
+        """out = M v with the rows cut into ``threads`` contiguous ranges, one host thread each (the C routine runs
+        without the GIL); every row is still summed left to right, so the result equals csr_matvec's bit for bit."""
+        import threading
+        rows = len(ptr) - 1
+        if threads <= 1:
+            self.lib.orc_csr_matvec(rows, _lp(ptr), _ip(idx), _dp(val), _dp(v), _dp(out))
+            return out
+        nnz_cuts = np.linspace(0, int(ptr[-1]), threads + 1)
+        cuts = np.searchsorted(ptr, nnz_cuts, side="left").astype(np.int64)
+        cuts[0], cuts[-1] = 0, rows
+
+        def work(k):
+            lo, hi = int(cuts[k]), int(cuts[k + 1])
+            if hi > lo:
+                self.lib.orc_csr_matvec(hi - lo, _lp(ptr[lo:hi + 1]), _ip(idx), _dp(val), _dp(v), _dp(out[lo:hi]))
+        ths = [threading.Thread(target=work, args=(k,)) for k in range(threads)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        return out
+
     def lsq_obj(self, A_csr, AT_csr, x, b, g):
         """f = 0.5 |Ax-b|^2 and g <- A^T(Ax-b); A_csr/AT_csr are (ptr int64, idx int32, val f64)."""
         m = len(A_csr[0]) - 1

@@ -79,13 +79,28 @@ def normalization(x, block_starts, block_ends):
         np.copyto(x[start:end], x[start:end] / np.sum(x[start:end]))
 
 
-def get_solver_parts(A, b, block_starts, min_eig, lasso=False, in_z=False):
+def get_solver_parts(A, b, block_starts, min_eig, lasso=False, in_z=False, threads=0, project=None):
+    """``threads`` > 1 (bench.py's reference arm only): the two CSR products run on that many host threads over row
+    ranges (same arithmetic per row as scipy's csr_matvec) and ``project`` replaces the projection (the compiled
+    reference over block ranges).  The reference itself has no threading; see bench.py."""
     A_sparse = sps.csr_matrix(A)
     A_sparse_T = sps.csr_matrix(A.T)
     block_starts = np.asarray(block_starts)
 
-    def obj(x, g=None):
-        return sparse_least_squares_obj(x, A_sparse_T, A_sparse, b, g)
+    if threads and threads > 1:
+        port = cpu.port()
+        Ap, Ai, Av = A_sparse.indptr.astype(np.int64), A_sparse.indices.astype(np.int32), A_sparse.data
+        Tp, Ti, Tv = A_sparse_T.indptr.astype(np.int64), A_sparse_T.indices.astype(np.int32), A_sparse_T.data
+        tmp_m = np.empty(A_sparse.shape[0])
+
+        def obj(x, g=None):
+            port.csr_matvec_mt(Ap, Ai, Av, x, tmp_m, threads)
+            np.subtract(tmp_m, b, tmp_m)
+            port.csr_matvec_mt(Tp, Ti, Tv, tmp_m, g, threads)
+            return .5 * tmp_m.dot(tmp_m)
+    else:
+        def obj(x, g=None):
+            return sparse_least_squares_obj(x, A_sparse_T, A_sparse, b, g)
 
     def step_size(i):
         return 1.0 / (min_eig * i + 1.0)
@@ -104,6 +119,8 @@ def get_solver_parts(A, b, block_starts, min_eig, lasso=False, in_z=False):
     else:
         def proj(x):
             chk.proj_multi_simplex(x, block_starts)
+    if project is not None:
+        proj = project
 
     def line_search(x, f, g, x_new, f_new, g_new, i):
         return line_search_np(x, f, g, x_new, f_new, g_new, obj)

@@ -275,10 +275,24 @@ def run_batch(B, name, parts, starts, x0, native):
     return B.BATCH.solve_LBFGS(obj_, proj_, ls_, x0, max_iter=150)
 
 
+@pytest.fixture(params=["tiny", "loop"])
+def native_loop(request, monkeypatch):
+    """The native BATCH solvers have two device-resident loops: one CTA with everything in shared memory for problems
+    that fit (solver_tiny.cuh) and the multi-kernel loop (lsq.cu).  The small test problems qualify for the first;
+    BSLS_NO_TINY=1 sends them through the second."""
+    if request.param == "loop":
+        monkeypatch.setenv("BSLS_NO_TINY", "1")
+    else:
+        monkeypatch.delenv("BSLS_NO_TINY", raising=False)
+    return request.param
+
+
 @pytest.mark.parametrize("tag", TAGS)
 @pytest.mark.parametrize("name", ["bb", "pg", "md", "lbfgs"])
 @pytest.mark.parametrize("native", [True, False])
-def test_batch_solvers_match_reference(B, gold, tag, name, native):
+def test_batch_solvers_match_reference(B, gold, tag, name, native, native_loop):
+    if native_loop == "loop" and (not native or name == "lbfgs"):
+        pytest.skip("the generic / L-BFGS loops do not depend on the native loop kind")
     A, b, starts, x0 = problem(gold, tag)
     parts = B.algorithm_utils.get_solver_parts((A, b), starts, 0.1, is_sparse=True)
     parts[3].problem.set_modes(1, 1)
