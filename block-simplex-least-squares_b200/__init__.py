@@ -9,6 +9,7 @@ mirrors the reference's operator API for the hot path:
     bsls_b200.algorithm_utils get_solver_parts, sparse_least_squares_obj, line_search_np, stopping, normalization
     bsls_b200.BATCH           solve, solve_BB, solve_LBFGS, solve_MD
     bsls_b200.BB / LBFGS / DORE / mirror_descent / solvers / gradient_descent / bsls_utils / main.solve_in_z
+    bsls_b200.bsls_matrices   BSLSMatrices (problem construction on the device); main.LS_postprocess, main.main
 
 All compute runs in libbsls_b200.so (hand-written CUDA behind a C ABI, include/bsls_b200.h).
 """
@@ -20,7 +21,7 @@ from .c_extensions import (proj_simplex_c, proj_multi_simplex_c, proj_multi_ball
 from .c_extensions import x2z_c, z2x_c
 from .plan import BlockPlan, plan_for
 from .sparse import LsqProblem, Communicator, Workspace
-from . import algorithm_utils, BATCH, BB, LBFGS, DORE, mirror_descent, solvers, gradient_descent, bsls_utils, main
+from . import algorithm_utils, BATCH, BB, LBFGS, DORE, mirror_descent, solvers, gradient_descent, bsls_utils, main, bsls_matrices
 from .isotonic_regression import block_isotonic_regression
 
 __version__ = "0.1.0"

@@ -102,6 +102,7 @@ def lib():
         L.bsls_dev_axpby_f64.argtypes = [c_void_p, c_dbl, c_void_p, c_dbl, c_void_p, c_i64, c_void_p]
         L.bsls_ws_dots_f64.argtypes = [c_void_p, c_int, ctypes.POINTER(c_void_p * 4), ctypes.POINTER(c_void_p * 4), c_i64, c_int,
                                        ctypes.POINTER(c_dbl * 5), c_void_p]
+        L.bsls_ws_flow_metrics_f64.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_dbl, ctypes.POINTER(c_dbl * 5), c_void_p]
         L.bsls_dev_axpy_dot_f64.argtypes = [c_void_p, c_void_p, c_dbl, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64,
                                             c_void_p]
         L.bsls_dev_md_update_f64.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_dbl, c_int, c_void_p]

@@ -136,6 +136,26 @@ int uniform_row_length(const int64_t *d_ptr, int64_t rows, int64_t nnz) {
     return h_bad ? 0 : (int)L;
 }
 
+// every stored value exactly 1.0?  (route-link incidence, python/bsls_utils.py:494-507): the products then skip the value
+// arrays altogether -- 1.0 * w is exact, so the results keep their bits and two thirds of the matrix traffic go away
+__global__ void all_ones_kernel(const double *__restrict__ val, int64_t nnz, int *bad) {
+    int b = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x)
+        if (val[i] != 1.0) b = 1;
+    if (__any_sync(0xffffffffu, b) && (threadIdx.x & 31) == 0) atomicOr(bad, 1);
+}
+bool all_ones(const double *d_val, int64_t nnz) {
+    if (!d_val || nnz <= 0) return false;
+    int *d_bad = nullptr, h_bad = 1;
+    if (cudaMalloc(&d_bad, sizeof(int)) != cudaSuccess) return false;
+    cudaMemset(d_bad, 0, sizeof(int));
+    int64_t want = (nnz + 255) / 256;
+    all_ones_kernel<<<(int)(want < 1184 ? want : 1184), 256>>>(d_val, nnz, d_bad);
+    if (cudaMemcpy(&h_bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) h_bad = 1;
+    cudaFree(d_bad);
+    return !h_bad;
+}
+
 int pick_mode(int64_t nnz, int64_t rows) {
     const double avg = rows > 0 ? (double)nnz / (double)rows : 0.0;
     if (avg <= 32.0) return 1;
@@ -487,6 +507,7 @@ int bsls_lsq_create(int64_t m, int64_t n, int64_t nnz, const int64_t *a_ptr, con
     q->t_ptr = at_ptr;
     q->t_idx = at_idx;
     q->t_val = at_val;
+    if (a_val && at_val && all_ones(a_val, nnz) && all_ones(at_val, nnz)) q->a_val = q->t_val = nullptr;  // 0/1 incidence
     q->b = b;
     q->a_mode = pick_mode(nnz, m);
     q->t_mode = pick_mode(nnz, n);
@@ -573,7 +594,7 @@ int bsls_lsq_set_panels(bsls_lsq *q, int panels, const int64_t *ptr, const int32
     q->panels = panels;
     q->p_ptr = ptr;
     q->p_idx = idx;
-    q->p_val = val;
+    q->p_val = (q->a_val == nullptr) ? nullptr : val;  // unit values were detected at creation: the copy needs none either
     q->p_mode = pick_mode(q->nnz, q->m * panels);
     if (const char *e = getenv("BSLS_SPMV_P")) q->p_mode = atoi(e);
     return BSLS_OK;
@@ -655,6 +676,20 @@ int bsls_ws_dots_f64(bsls_ws *q, int count, const double *const *x, const double
     if (int rc = allreduce(q, q->d_scal + kScalDot0, 4, kNcclSum, st)) return rc;
     if (want_max)
         if (int rc = allreduce(q, q->d_scal + kScalMax0, 1, kNcclMax, st)) return rc;
+    if (int rc = fetch_scalars(q, st)) return rc;
+    for (int k = 0; k < 5; ++k) out[k] = q->h_scal[kScalDot0 + k];
+    return BSLS_OK;
+}
+
+int bsls_ws_flow_metrics_f64(bsls_ws *q, const double *scaling, const double *x_true, const double *x_hat, int64_t n, double thresh,
+                             double out[5], bsls_stream_t s) {
+    if (!q || !x_true || !x_hat || !out || n <= 0) return BSLS_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)s;
+    RedCtx red = q->red;
+    red.out = q->d_scal + kScalDot0;  // slots 6..10
+    flow_metrics_kernel<<<grid_elems(n), 256, 0, st>>>(scaling, x_true, x_hat, thresh, n, red);
+    BSLS_LAUNCH_CHECK();
+    q->launches++;
     if (int rc = fetch_scalars(q, st)) return rc;
     for (int k = 0; k < 5; ++k) out[k] = q->h_scal[kScalDot0 + k];
     return BSLS_OK;

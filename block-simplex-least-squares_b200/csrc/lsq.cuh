@@ -451,6 +451,24 @@ __global__ void __launch_bounds__(256) dots_kernel(DotArgs a, int64_t n, RedCtx 
     grid_reduce<4, 1, 256, FinDots>(acc, red);
 }
 
+// route-flow error metrics of LS_postprocess (python/main.py:112-134) for one iterate, in one pass:
+//   out[0] = sum |s (xt - xh)|, out[1] = sum s xt, out[2] = #{xt - xh > thresh}, out[3] = sum (xt - xh)^2, out[4] = max s (xt - xh)
+__global__ void __launch_bounds__(256) flow_metrics_kernel(const double *__restrict__ s, const double *__restrict__ xt,
+                                                            const double *__restrict__ xh, double thresh, int64_t n, RedCtx red) {
+    double acc[5] = {0, 0, 0, 0, 0};
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const double sc = s ? s[i] : 1.0, t = xt[i];
+        const double d = t - xh[i];
+        const double sd = sc * d;
+        acc[0] += fabs(sd);
+        acc[1] += sc * t;
+        acc[2] += (d > thresh) ? 1.0 : 0.0;
+        acc[3] += d * d;
+        acc[4] = fmax(acc[4], sd);
+    }
+    grid_reduce<4, 1, 256, FinDots>(acc, red);
+}
+
 // d <- d + c * v  (c from device scalars) and, in the same pass, <w, d_new> -> out[0]  scaled by *scale
 // The L-BFGS two-loop recursion chains these without the host (LBFGS.py:60-71, BATCH.py:196-214).
 struct FinScaled {

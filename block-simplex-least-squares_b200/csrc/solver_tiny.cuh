@@ -15,7 +15,7 @@
 namespace bsls {
 
 constexpr int kTinyThreads = 1024;
-constexpr int kTinyMaxBlock = 64;  // longest OD block the per-thread projection takes
+constexpr int kTinyMaxBlock = 64;  // longest OD block the per-thread projection takes (insertion sort: short blocks only)
 
 struct TinyArgs {
     int n, m, nb;
@@ -58,9 +58,9 @@ template <int NS, int NM> __device__ __forceinline__ void tiny_reduce(double (&a
     __syncthreads();
 }
 
-// proj_simplex (proj_simplex.h:17-34) of w[0..K) into out[0..K): the reference's own order of operations
-__device__ __forceinline__ void tiny_proj_simplex(const double *w, double *out, int K) {
-    double u[kTinyMaxBlock];
+// proj_simplex (proj_simplex.h:17-34) in place on w[0..K) (shared memory), u[0..K) = scratch for the sorted copy:
+// the reference's own order of operations
+__device__ __forceinline__ void tiny_proj_simplex(double *w, double *u, int K) {
     for (int i = 0; i < K; ++i) {  // insertion sort, descending (the sorted values do not depend on the algorithm)
         const double v = w[i];
         int j = i;
@@ -79,8 +79,30 @@ __device__ __forceinline__ void tiny_proj_simplex(const double *w, double *out, 
     }
     for (int i = 0; i < K; ++i) {
         const double t = lambda + w[i];
-        out[i] = t > 0. ? t : 0.;
+        w[i] = t > 0. ? t : 0.;
     }
+}
+
+// One row of a CSR product, entries added left to right (scipy's csr_matvec), the index / value loads issued eight at
+// a time so that their L2 latency overlaps (the adds stay in order).
+__device__ __forceinline__ double tiny_row_dot(const int32_t *__restrict__ idx, const double *__restrict__ val, int64_t p0, int64_t p1,
+                                               const double *v) {
+    double sum = 0.0;
+    int64_t p = p0;
+    for (; p + 8 <= p1; p += 8) {
+        int32_t j[8];
+        double a[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) j[k] = idx[p + k];
+        if (val) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] = val[p + k];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sum += (val ? a[k] : 1.0) * v[j[k]];
+    }
+    for (; p < p1; ++p) sum += (val ? val[p] : 1.0) * v[idx[p]];
+    return sum;
 }
 
 __global__ void __launch_bounds__(kTinyThreads, 1) solver_tiny_kernel(TinyArgs a, DevOpts o) {
@@ -108,9 +130,7 @@ __global__ void __launch_bounds__(kTinyThreads, 1) solver_tiny_kernel(TinyArgs a
     auto residual = [&](const double *x, double *r, const double *r_old) {
         double acc[3] = {0, 0, 0};
         for (int row = tid; row < m; row += kTinyThreads) {
-            double sum = 0.0;
-            const int64_t p1 = a.a_ptr[row + 1];
-            for (int64_t p = a.a_ptr[row]; p < p1; ++p) sum += (a.a_val ? a.a_val[p] : 1.0) * x[a.a_idx[p]];
+            const double sum = tiny_row_dot(a.a_idx, a.a_val, a.a_ptr[row], a.a_ptr[row + 1], x);
             const double v = sum - bs[row];
             r[row] = v;
             residual_sums(v, r_old ? r_old[row] : 0.0, r_old != nullptr, acc);
@@ -126,9 +146,7 @@ __global__ void __launch_bounds__(kTinyThreads, 1) solver_tiny_kernel(TinyArgs a
     auto gradient = [&](const double *r, double *g_new, const double *g, const double *x, const double *x_new) {
         double acc[5] = {0, 0, 0, 0, 0};
         for (int row = tid; row < n; row += kTinyThreads) {
-            double dot = 0.0;
-            const int64_t p1 = a.t_ptr[row + 1];
-            for (int64_t p = a.t_ptr[row]; p < p1; ++p) dot += (a.t_val ? a.t_val[p] : 1.0) * r[a.t_idx[p]];
+            const double dot = tiny_row_dot(a.t_idx, a.t_val, a.t_ptr[row], a.t_ptr[row + 1], r);
             g_new[row] = dot;
             acc[3] += dot * dot;
             if (g) {
@@ -162,7 +180,7 @@ __global__ void __launch_bounds__(kTinyThreads, 1) solver_tiny_kernel(TinyArgs a
         // ---- x_new = proj(x - t g): one thread per OD block ---------------------------------------
         for (int blk = tid; blk < a.nb; blk += kTinyThreads) {
             const int s = a.starts[blk], K = a.starts[blk + 1] - s;
-            double w[kTinyMaxBlock];
+            double *w = xs[nxt] + s;   // the trial point is formed in place; the trial gradient's slot is the sort scratch
             double sum = 0.0;
             for (int i = 0; i < K; ++i) {
                 const double u = nt * gs[cur][s + i];  // np.add(x, -t*g, x_new): product and sum rounded separately
@@ -175,11 +193,7 @@ __global__ void __launch_bounds__(kTinyThreads, 1) solver_tiny_kernel(TinyArgs a
                 }
                 w[i] = v;
             }
-            if (a.proj_mode == 1 && !(sum > 1.0)) {
-                for (int i = 0; i < K; ++i) xs[nxt][s + i] = w[i];
-            } else {
-                tiny_proj_simplex(w, xs[nxt] + s, K);
-            }
+            if (a.proj_mode == 0 || sum > 1.0) tiny_proj_simplex(w, gs[nxt] + s, K);
         }
         __syncthreads();
         // ---- objective and gradient at the trial point, decision, pull-back ------------------------------

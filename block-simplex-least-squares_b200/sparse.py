@@ -149,6 +149,21 @@ class Workspace:
     def max_abs_diff(self, x, y):
         return self.dots([(x, y)], want_max=True)[1]
 
+    def flow_metrics(self, scaling, x_true, x_hat, thresh=1e-3):
+        """[sum |s (xt - xh)|, sum s xt, #{xt - xh > thresh}, |xt - xh|^2, max s (xt - xh)] in one pass
+        (the per-iterate reductions of LS_postprocess, python/main.py:112-134)."""
+        n = x_true.shape[0]
+        _check_vec(x_true, n, "x_true")
+        _check_vec(x_hat, n, "x_hat")
+        if scaling is not None:
+            _check_vec(scaling, n, "scaling")
+        out = (ctypes.c_double * 5)()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().bsls_ws_flow_metrics_f64(self._handle, None if scaling is None else scaling.data_ptr(), x_true.data_ptr(),
+                                                           x_hat.data_ptr(), n, float(thresh), ctypes.byref(out), _stream(self.device)),
+                       "flow_metrics")
+        return [float(v) for v in out]
+
     def axpy_dot(self, d, scale, c0, c1, v, w, out=None):
         """d <- d + c v with c = scale * ((*c0 or 1) - (*c1 or 0)), c0/c1 DEVICE scalar addresses
         or None; v None: d <- c d.  If ``w`` is given, the DEVICE double at address ``out``

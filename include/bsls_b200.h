@@ -210,6 +210,11 @@ BSLS_API int bsls_dev_axpby_f64(double *out, double a, const double *x, double b
  * want_max; blocking, results in out[0..3] and out[4] */
 BSLS_API int bsls_ws_dots_f64(bsls_ws *ws, int count, const double *const *x, const double *const *y, int64_t n,
                                int want_max, double out[5], bsls_stream_t stream);
+/* route-flow error metrics of LS_postprocess (python/main.py:112-134) for one iterate x_hat against x_true, one pass:
+ * out[0] = sum |s (xt - xh)|, [1] = sum s xt, [2] = #{xt - xh > thresh}, [3] = |xt - xh|^2, [4] = max s (xt - xh)
+ * (scaling NULL: ones).  Blocking, single GPU. */
+BSLS_API int bsls_ws_flow_metrics_f64(bsls_ws *ws, const double *scaling, const double *x_true, const double *x_hat, int64_t n,
+                                      double thresh, double out[5], bsls_stream_t stream);
 /* d <- d + c v with c = scale * ((c0 ? *c0 : 1) - (c1 ? *c1 : 0)) read from DEVICE scalars (v NULL:
  * d <- c d), and *out (a DEVICE double, summed over ranks) <- <w, d> in the same pass (w NULL: no
  * dot).  Chains the L-BFGS two-loop recursion without the host (python/LBFGS.py:60-71,

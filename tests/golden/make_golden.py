@@ -359,6 +359,97 @@ def golden_solvers():
     return len(cases)
 
 
+def golden_pipeline():
+    """The steps either side of the hot loop: BSLSMatrices.degree_reduced_form / get_LS /
+    reconstruct (python/bsls_matrices.py:56-160), main.solve_in_z + LS_postprocess (python/main.py:41-136) on
+    bsls_utils.generate_data problems (the reference's own end-to-end test input, tests/fast/test_main.py), and
+    line_search_exact_quad_obj (python/algorithm_utils.py:140-155)."""
+    import contextlib
+    import io
+    import types
+    # the CLI module imports plotting and a site config that do not exist here: empty stand-ins, nothing numeric
+    for name in ("matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    cfg = types.ModuleType("config")
+    cfg.ACCEPTED_LOG_LEVELS = ['CRITICAL', 'ERROR', 'WARNING', 'INFO', 'DEBUG', 'WARN']
+    sys.modules["config"] = cfg
+    import algorithm_utils as au
+    import bsls_utils as bu
+    import main as ref_main
+    from bsls_matrices import BSLSMatrices
+
+    cases = {}
+    quiet = io.StringIO()
+    config = {'full': True, 'L': True, 'OD': True, 'CP': True, 'LP': True, 'eq': 'CP', 'init': False}
+    variants = {
+        "default": dict(),
+        "sparse_x": dict(alpha=0.5),
+        "sparse_A": dict(A_sparse=0.05),
+        "permuted": dict(permute=True),
+        "larger": dict(n=400, m1=30, m2=40),
+        "zeroed": dict(),          # tests/fast/test_bsls_matrices.py:64-90: a zero row of A and a zero block
+    }
+    for tag, kw in variants.items():
+        np.random.seed(SEED)
+        data = bu.generate_data(**kw)
+        if tag == "zeroed":
+            n = data['x_true'].size
+            data['A'][0, :] = np.zeros(n)
+            data['f'][0] = 0
+            data['x_true'] = (data['U'].T.dot(data['f']) > 0) * data['x_true']
+            data['b'] = data['A'].dot(data['x_true'])
+        for k in ("A", "b", "x_true", "U", "f", "block_sizes"):
+            cases["%s_in_%s" % (tag, k)] = np.asarray(data[k], dtype=np.float64)
+        bm = BSLSMatrices(data=data, **config)
+        bm.degree_reduced_form()
+        AA, bb, N, block_sizes, x_split, nz, scaling, rsort_index, x0 = bm.get_LS()
+        cases[tag + "_AA"] = np.asarray(AA.todense())
+        cases[tag + "_bb"] = np.asarray(bb, dtype=np.float64)
+        cases[tag + "_block_sizes"] = np.asarray(block_sizes, dtype=np.int64)
+        cases[tag + "_x_split"] = np.asarray(x_split, dtype=np.float64)
+        cases[tag + "_nz"] = np.asarray(nz, dtype=np.int64)
+        cases[tag + "_scaling"] = np.asarray(scaling, dtype=np.float64)
+        cases[tag + "_rsort_index"] = np.asarray(rsort_index, dtype=np.int64)
+        cases[tag + "_x0"] = np.asarray(x0, dtype=np.float64).reshape(-1)
+        cases[tag + "_x_true_rec"] = BSLSMatrices.reconstruct(x_split, rsort_index=rsort_index, scaling=scaling, nz=nz,
+                                                              n=data['x_true'].size)
+        with contextlib.redirect_stdout(quiet):
+            iters, times, states = ref_main.solve_in_z(AA, bb, x0, N, block_sizes, 'BB')
+        x_last, error, output = ref_main.LS_postprocess(states, x0, AA, bb, x_split, scaling=scaling, block_sizes=block_sizes,
+                                                        N=N, output={})
+        cases[tag + "_iters"] = np.asarray(iters, dtype=np.int64)
+        cases[tag + "_z_last"] = np.asarray(states[-1], dtype=np.float64)
+        cases[tag + "_x_last"] = np.asarray(x_last, dtype=np.float64)
+        cases[tag + "_error"] = np.asarray(error, dtype=np.float64)
+        cases[tag + "_start_error"] = np.array(output['0.5norm(Ax_init-b)^2'])
+        cases[tag + "_opt_error"] = np.array(output['0.5norm(Ax*-b)^2'])
+        cases[tag + "_max_f_diff"] = np.asarray(output['max|f * (x-x_true)|'], dtype=np.float64)
+        cases[tag + "_wrong"] = np.asarray(output['incorrect x entries'], dtype=np.int64)
+        cases[tag + "_per_flow"] = np.asarray(output['percent flow allocated incorrectly'], dtype=np.float64)
+        cases[tag + "_start_dist"] = np.array(output['max|f * (x_init-x_true)|'])
+    # line_search_exact_quad_obj on seeded dense QPs
+    rng = np.random.RandomState(SEED + 11)
+    for k in range(4):
+        n = (3, 8, 20, 50)[k]
+        M = rng.randn(n, n)
+        Q = M.T.dot(M) + 0.1 * np.eye(n)
+        c = rng.randn(n)
+        x = rng.rand(n)
+        x_new = x + (rng.randn(n) if k < 3 else 1e-10 * rng.randn(n))       # last case: step below progTol
+        g = Q.dot(x) + c
+        f = .5 * x.dot(Q.dot(x)) + c.dot(x)
+        g_new = np.zeros(n)
+        xn = x_new.copy()
+        f_new = au.line_search_exact_quad_obj(x, f, g, xn, 0.0, g_new, Q, c)
+        for name, v in (("Q", Q), ("c", c), ("x", x), ("x_new_in", x_new), ("g", g), ("f", np.array(f)), ("x_new_out", xn),
+                        ("g_new_out", g_new), ("f_new", np.array(f_new))):
+            cases["ls%d_%s" % (k, name)] = v
+    cases["ls_count"] = np.array(4)
+    cases["tags"] = np.array(sorted(variants))
+    np.savez_compressed(os.path.join(HERE, "pipeline.npz"), **cases)
+    return len(cases)
+
+
 def run_reference_tests():
     """Replays the reference's own unit tests for the path against the scratch build, so
     the fixtures are known to come from a reference that passes its own suite."""
@@ -393,6 +484,7 @@ def main():
     print("pava cases:", golden_pava(cx))
     print("x2z cases:", golden_x2z(cx))
     print("solver arrays:", golden_solvers())
+    print("pipeline arrays:", golden_pipeline())
 
 
 if __name__ == "__main__":
