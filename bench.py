@@ -402,13 +402,16 @@ def bench_c1_c4(bsls_b200, torch, dev, with_cpu):
     parts = sp.solver_parts()
     bsls_b200.BATCH.solve_LBFGS(parts[3], parts[1], parts[2], sp.x_init, max_iter=8)
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
     sol = bsls_b200.BATCH.solve_LBFGS(parts[3], parts[1], parts[2], sp.x_init, max_iter=60)
     torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
     its = sol["iterations"] - 1
-    out["c4_lbfgs"] = {"workload": "C4: BATCH.solve_LBFGS (corrections=50), same problem; wall clock around the call (host-driven loop)",
-                       "iter_per_s": its / dt, "iterations": its, "ms_per_iteration": 1e3 * dt / max(1, its), "f_final": sol["f"]}
+    out["c4_lbfgs"] = {"workload": "C4: BATCH.solve_LBFGS (corrections=50), same problem; device-resident loop, CUDA-event time of the solve",
+                       "iter_per_s": its / sol["device_ms"] * 1e3, "iterations": its, "ms_per_iteration": sol["device_ms"] / max(1, its),
+                       "f_final": sol["f"], "stop": sol["stop"], "objective_evaluations": sol["obj_evals"]}
+    sol = bsls_b200.BATCH.solve_BB(parts[3], parts[1], parts[2], sp.x_init, max_iter=60)
+    its = sol["iterations"] - 1
+    out["c4_bb"] = {"workload": "C4: BATCH.solve_BB, same problem", "iter_per_s": its / sol["device_ms"] * 1e3, "iterations": its,
+                    "ms_per_iteration": sol["device_ms"] / max(1, its), "f_final": sol["f"], "stop": sol["stop"]}
     if with_cpu:
         from oracle import solvers_np as S
         rng = np.random.RandomState(SEED + 4)
@@ -653,6 +656,8 @@ def run_ours(args, rank, world, local_rank):
     xh = torch.full((sp.n,), 1.0 / sp.K, dtype=torch.float64).pin_memory()
     bh = sp.b.cpu().pin_memory()
     e2e_its, x_out = 0, None
+    prob.set_b(bh)
+    bsls_b200.BATCH.solve_BB(obj, proj, line_search, xh, max_iter=3)     # untimed: pins the result buffer once
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):

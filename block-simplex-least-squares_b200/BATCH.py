@@ -36,7 +36,9 @@ def _stage_in(x_init, obj):
     device = problem.device if problem is not None else torch.device("cuda", torch.cuda.current_device())
     host = x_init if torch.is_tensor(x_init) else torch.from_numpy(np.ascontiguousarray(x_init, dtype=np.float64))
     assert host.dtype == torch.float64 and host.dim() == 1, "x_init: float64 vector expected"
-    return host.to(device, non_blocking=True), ("tensor" if torch.is_tensor(x_init) else "numpy")
+    staged = host.to(device, non_blocking=True)
+    staged._bsls_private = True        # a fresh device copy: the native loop may work in it instead of cloning again
+    return staged, ("tensor" if torch.is_tensor(x_init) else "numpy")
 
 
 _PINNED_OUT = {}
@@ -92,12 +94,14 @@ def _native_parts(obj, proj, line_search=None, need_proj=True):
     return problem
 
 
-def _solve_native(problem, plan, method, proj_mode, x_init, use_line_search, f_min, opt_tol, max_iter, prog_tol, min_eig=0.0):
+def _solve_native(problem, plan, method, proj_mode, x_init, use_line_search, f_min, opt_tol, max_iter, prog_tol, min_eig=0.0,
+                  corrections=0):
     L = _lib.lib()
-    x = x_init.clone()
+    x = x_init if getattr(x_init, "_bsls_private", False) else x_init.clone()
     opts = _lib.BatchOpts(method=method, proj_mode=proj_mode, use_line_search=int(bool(use_line_search)),
                           has_f_min=int(f_min is not None), f_min=0.0 if f_min is None else float(f_min),
-                          opt_tol=float(opt_tol), prog_tol=float(prog_tol), min_eig=float(min_eig), max_iter=int(max_iter))
+                          opt_tol=float(opt_tol), prog_tol=float(prog_tol), min_eig=float(min_eig), max_iter=int(max_iter),
+                          corrections=int(corrections))
     res = _lib.BatchResult()
     cap = max(2, int(max_iter) + 1)
     pf = (ctypes.c_double * cap)()
@@ -209,7 +213,15 @@ def solve_LBFGS(obj, proj, line_search, x_init, f_min=None, opt_tol=1e-6,
     REFERENCES to the two difference buffers, which the loop overwrites in place every
     iteration -- so every stored pair aliases the latest (delta_x, delta_g) while the stored
     curvatures ``rho`` stay distinct.  That is what the reference computes, and what its
-    results (and tests) are pinned to, so it is kept."""
+    results (and tests) are pinned to, so it is kept.
+
+    NATIVE path (closures of get_solver_parts, at most 64 corrections): the loop runs inside the library.  Because all
+    pairs are the same two vectors, the two-loop recursion reduces to scalar recurrences on <s,g>, <y,g>, <s,y>, <y,y>
+    (taken on the device) and d = cg g + cy delta_g + cs delta_x: one vector pass instead of 2 x corrections."""
+    problem = _native_parts(obj, proj, line_search)
+    if problem is not None and corrections <= 64:
+        return _solve_native(problem, proj.plan, 5, proj.mode, x_init, True, f_min, opt_tol, max_iter, prog_tol,
+                             corrections=corrections)
     ws = default_workspace(x_init.device)
     q_delta_g = deque()
     q_delta_x = deque()

@@ -17,7 +17,8 @@ _lib = None
 class BatchOpts(ctypes.Structure):  # bsls_batch_opts (include/bsls_b200.h)
     _fields_ = [("method", ctypes.c_int), ("proj_mode", ctypes.c_int), ("use_line_search", ctypes.c_int),
                 ("has_f_min", ctypes.c_int), ("f_min", ctypes.c_double), ("opt_tol", ctypes.c_double),
-                ("prog_tol", ctypes.c_double), ("min_eig", ctypes.c_double), ("max_iter", ctypes.c_int)]
+                ("prog_tol", ctypes.c_double), ("min_eig", ctypes.c_double), ("max_iter", ctypes.c_int),
+                ("corrections", ctypes.c_int)]
 
 
 class BatchResult(ctypes.Structure):  # bsls_batch_result
@@ -108,6 +109,7 @@ def lib():
         L.bsls_dev_md_update_f64.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_dbl, c_int, c_void_p]
         L.bsls_batch_solve_f64.argtypes = [c_void_p, c_void_p, c_void_p, ctypes.POINTER(BatchOpts), ctypes.POINTER(BatchResult),
                                            c_void_p, c_void_p, c_int, c_void_p]
+        L.bsls_md_least_squares_f64.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_dbl, c_dbl, ctypes.POINTER(BatchResult), c_void_p]
         _lib = L
     return _lib
 

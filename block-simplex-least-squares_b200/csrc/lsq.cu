@@ -84,7 +84,7 @@ struct bsls_ws {
     // device-resident solver loop
     DevState *d_state = nullptr, *h_state = nullptr;  // h_state: 2 pinned copies (one per iteration in flight)
     cudaEvent_t ev_state[2] = {nullptr, nullptr};
-    double *d_gather = nullptr;                        // nranks * 5 doubles (all-gather of the per-rank step scalars)
+    double *d_gather = nullptr;                        // nranks * kStepScalars doubles (all-gather of the per-rank step scalars)
     int gather_cap = 0;
     double *d_prog = nullptr;                          // 2 * prog_cap doubles: objective and device time stamp per iteration
     int prog_cap = 0;
@@ -958,7 +958,7 @@ int ensure_loop_scratch(bsls_ws *w, int prog_cap) {
     if (nr > w->gather_cap) {
         if (w->d_gather) cudaFree(w->d_gather);
         w->d_gather = nullptr;
-        BSLS_CUDA_TRY(cudaMalloc(&w->d_gather, sizeof(double) * 5 * (size_t)nr));
+        BSLS_CUDA_TRY(cudaMalloc(&w->d_gather, sizeof(double) * kStepScalars * (size_t)nr));
         w->gather_cap = nr;
     }
     if (prog_cap > w->prog_cap) {
@@ -973,7 +973,8 @@ int ensure_loop_scratch(bsls_ws *w, int prog_cap) {
 DevOpts make_dev_opts(const bsls_batch_opts *o, const bsls_ws *w, int cap) {
     DevOpts d{};
     d.method = o->method;
-    d.search = (o->method == 1) || (o->method == 0 && o->use_line_search);
+    d.corrections = o->corrections > 0 ? (o->corrections < 64 ? o->corrections : 64) : 50;
+    d.search = (o->method == 1) || (o->method == 5) || (o->method == 0 && o->use_line_search);
     d.has_f_min = o->has_f_min;
     d.max_iter = o->max_iter;
     d.f_min = o->f_min;
@@ -1070,6 +1071,16 @@ int enqueue_iteration(bsls_lsq *q, const bsls_plan *plan, const LoopBuffers &B, 
     // ---- trial point --------------------------------------------------------------------------
     if (d.method == 2) {
         if (int rc = md_update(w, plan, B.x[nxt], B.x[cur], B.g[cur], 0.0, 0, st, S)) return rc;
+    } else if (d.method == 5) {  // x_new = proj(x + d), d from the scalar two-loop recursion; the trial set still holds (x_prev, g_prev)
+        lbfgs_step_kernel<<<grid_elems(n), 256, 0, st>>>(B.x[nxt], B.x[cur], B.x[nxt], B.g[cur], B.g[nxt], S, n);
+        BSLS_LAUNCH_CHECK();
+        ++*extra_launches;
+        if (proj_mode == 2) {
+            if (int rc = pava_clip_f64(plan, B.x[nxt], nullptr, 1, 1, st)) return rc;
+        } else {
+            if (int rc = project_f64(plan, B.x[nxt], proj_mode, st)) return rc;
+        }
+        ++*extra_launches;
     } else {
         bool fused = false;
         const StepCtl ctl{&S->t, done};
@@ -1089,12 +1100,12 @@ int enqueue_iteration(bsls_lsq *q, const bsls_plan *plan, const LoopBuffers &B, 
     }
     // ---- objective and gradient at the trial point ------------------------------------------------
     if (int rc = residual(q, B.x[nxt], B.r[nxt], q->b, st, B.r[cur], done)) return rc;
-    const bool need_dots = d.method == 1 || d.search;
+    const bool need_dots = d.method == 1 || d.method == 5 || d.search;
     if (need_dots) {
         EpiGradBB epi{B.g[nxt], B.g[cur], B.x[cur], B.x[nxt]};
         if (int rc = launch_at(q, B.r[nxt], epi, st, done)) return rc;
         if (dist)  // every rank needs every rank's share of the step scalars: one small all-gather (slots 1..5)
-            BSLS_NCCL_TRY(g_nccl.AllGather(w->d_scal + kScalSxy, w->d_gather, 5, kNcclFloat64, w->comm->comm, st));
+            BSLS_NCCL_TRY(g_nccl.AllGather(w->d_scal + kScalSxy, w->d_gather, kStepScalars, kNcclFloat64, w->comm->comm, st));
     } else {
         EpiPlain epi{B.g[nxt]};
         if (int rc = launch_at(q, B.r[nxt], epi, st, done)) return rc;
@@ -1124,13 +1135,13 @@ int bsls_batch_solve_f64(bsls_lsq *q, const bsls_plan *plan, double *x, const bs
         set_error("batch_solve: plan covers %d variables, A has %lld columns", plan->n, (long long)q->n);
         return BSLS_ERR_ARG;
     }
-    if (o->method < 0 || o->method > 2) return BSLS_ERR_ARG;
+    if (!(o->method == 0 || o->method == 1 || o->method == 2 || o->method == 5)) return BSLS_ERR_ARG;
     if (int rc = ensure_workspace(q)) return rc;
     static const bool legacy = [] {
         const char *e = getenv("BSLS_BATCH_LEGACY");
         return e && atoi(e) != 0;
     }();
-    if (legacy) return batch_solve_legacy(q, plan, x, o, res, progress_f, progress_t, progress_cap, s);
+    if (legacy && o->method <= 2) return batch_solve_legacy(q, plan, x, o, res, progress_f, progress_t, progress_cap, s);
 
     cudaStream_t st = (cudaStream_t)s;
     bsls_ws *w = q->ws;
@@ -1185,6 +1196,70 @@ int bsls_batch_solve_f64(bsls_lsq *q, const bsls_plan *plan, double *x, const bs
     float ms = 0.f;
     BSLS_CUDA_TRY(cudaEventElapsedTime(&ms, q->ev0, q->ev1));
     finish_result(res, fin, (w->launches - launches0) + extra, ms, progress_t, cap);
+    return BSLS_OK;
+}
+
+// mirror_descent.least_squares (python/mirror_descent.py:7-53) as a device-resident loop: per iteration the SpMV pair,
+// one fused exponentiate / normalise / max-change kernel whose step sqrt(2 ln K) / (sqrt(k) Lf) is formed on the device
+// from the iteration counter, [one scalar max all-reduce when sharded,] and the stop test max |x - x_prev| < tolerance
+// taken by decide_kernel.  x: in = starting point (1 / K_block), out = result.
+int bsls_md_least_squares_f64(bsls_lsq *q, const bsls_plan *plan, double *x, int iters, double tolerance, double Lf, bsls_batch_result *res,
+                              bsls_stream_t s) {
+    if (!q || !plan || !x || !res || !q->b || plan->n != q->n || !(Lf > 0)) {
+        set_error("md_least_squares: bad argument");
+        return BSLS_ERR_ARG;
+    }
+    if (int rc = ensure_workspace(q)) return rc;
+    cudaStream_t st = (cudaStream_t)s;
+    bsls_ws *w = q->ws;
+    DevOpts d{};
+    d.method = 4;
+    d.max_iter = iters;
+    d.tolerance = tolerance;
+    d.Lf = Lf;
+    d.nranks = (w->comm && w->comm->nranks > 1) ? w->comm->nranks : 1;
+    double *X[2] = {x, q->wxn};
+    double *g = q->wg;
+    const int launches0 = w->launches;
+    int extra = 0;
+    BSLS_CUDA_TRY(cudaEventRecord(q->ev0, st));
+    BSLS_CUDA_TRY(cudaMemsetAsync(w->d_state, 0, sizeof(DevState), st));
+    decide_kernel<<<1, 32, 0, st>>>(w->d_state, w->d_scal, nullptr, d, nullptr, nullptr, 1);
+    BSLS_LAUNCH_CHECK();
+    BSLS_CUDA_TRY(cudaMemcpyAsync(&w->h_state[1], w->d_state, sizeof(DevState), cudaMemcpyDeviceToHost, st));
+    BSLS_CUDA_TRY(cudaEventRecord(w->ev_state[1], st));
+    const int *done = &w->d_state->done;
+    for (int k = 0; k < iters; ++k) {
+        const int cur = k & 1, nxt = cur ^ 1;
+        if (int rc = residual(q, X[cur], q->r, q->b, st, nullptr, done)) return rc;
+        EpiPlain epi{g};
+        if (int rc = launch_at(q, q->r, epi, st, done)) return rc;
+        if (int rc = md_update(w, plan, X[nxt], X[cur], g, Lf, 1, st, w->d_state)) return rc;
+        if (int rc = allreduce(w, w->d_scal + kScalMax0, 1, kNcclMax, st)) return rc;
+        decide_kernel<<<1, 32, 0, st>>>(w->d_state, w->d_scal, nullptr, d, nullptr, nullptr, 0);
+        BSLS_LAUNCH_CHECK();
+        ++extra;
+        BSLS_CUDA_TRY(cudaMemcpyAsync(&w->h_state[k & 1], w->d_state, sizeof(DevState), cudaMemcpyDeviceToHost, st));
+        BSLS_CUDA_TRY(cudaEventRecord(w->ev_state[k & 1], st));
+        BSLS_CUDA_TRY(cudaEventSynchronize(w->ev_state[(k + 1) & 1]));  // the state one iteration back: the GPU keeps a full iteration queued
+        if (w->h_state[(k + 1) & 1].done) break;
+    }
+    BSLS_CUDA_TRY(cudaStreamSynchronize(st));
+    DevState fin;
+    BSLS_CUDA_TRY(cudaMemcpy(&fin, w->d_state, sizeof(DevState), cudaMemcpyDeviceToHost));
+    if (fin.parity != 0) BSLS_CUDA_TRY(cudaMemcpyAsync(x, X[1], sizeof(double) * (size_t)q->n, cudaMemcpyDeviceToDevice, st));
+    BSLS_CUDA_TRY(cudaEventRecord(q->ev1, st));
+    BSLS_CUDA_TRY(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    BSLS_CUDA_TRY(cudaEventElapsedTime(&ms, q->ev0, q->ev1));
+    res->f = 0.0;
+    res->iterations = fin.i - 1;  // update steps taken
+    res->stop_code = fin.done;
+    res->stop_value = fin.change;
+    res->obj_evals = fin.evals;
+    res->backtracks = 0;
+    res->kernel_launches = (w->launches - launches0) + extra + 1;
+    res->device_ms = ms;
     return BSLS_OK;
 }
 

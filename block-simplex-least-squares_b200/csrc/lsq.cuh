@@ -112,6 +112,7 @@ enum Scal {
     kScalGd = 3,    // <g, x_new - x>
     kScalGnn = 4,   // <g_new, g_new>
     kScalStep = 5,  // max |x_new - x|
+    kScalYgo = 6,   // <g_new - g, g>  (L-BFGS; shares the first generic slot, which no solver loop uses)
     kScalDot0 = 6,  // generic dot products: 6..9
     kScalMax0 = 10, // generic maximum
     kScalRR = 11,   // <r, r> (not halved)
@@ -136,10 +137,14 @@ struct DevState {
     int done;              // 0 = running, else the stop code (1 max_iter, 2 f - f_min < opt_tol, 3 |f_old - f| < prog_tol, ...)
     int evals, backtracks;
     int parity;            // which buffer set holds the current iterate
-    int pad;
+    int hist;              // L-BFGS: stored curvature pairs
+    double cg, cy, cs;     // L-BFGS: next trial point = proj(x + cg g + cy (g - g_prev) + cs (x - x_prev))
+    double rho[64];        // L-BFGS: 1 / <dx, dg> of the stored pairs, oldest first
 };
+constexpr int kStepScalars = 6;  // slots 1..6 of every rank travel in the all-gather of a sharded solve
 struct DevOpts {
-    int method;            // 0 projected gradient, 1 Barzilai-Borwein, 2 mirror descent (BATCH); 3 BB.solve, 4 mirror_descent.least_squares
+    int method;            // BATCH: 0 projected gradient, 1 Barzilai-Borwein, 2 mirror descent, 5 L-BFGS; 4 mirror_descent.least_squares
+    int corrections;       // method 5: history length (at most 64)
     int search;            // run line_search_np
     int has_f_min, max_iter;
     double f_min, opt_tol, prog_tol, min_eig;
@@ -192,11 +197,11 @@ struct EpiPlain {  // out = M v
     }
     static __device__ __forceinline__ void store(double *o, int k, double v) { o[kScalGnn] = v; }
 };
-struct EpiGradBB {  // g_new = A^T r and the Barzilai-Borwein / line-search dot products (BATCH.py:89,99-100; algorithm_utils.py:120)
-    static constexpr int NSUM = 4, NMAX = 1;
+struct EpiGradBB {  // g_new = A^T r and the Barzilai-Borwein / line-search / L-BFGS dot products (BATCH.py:89,99-100,160-167; algorithm_utils.py:120)
+    static constexpr int NSUM = 5, NMAX = 1;
     double *g_new;
     const double *g, *x, *x_new;
-    __device__ __forceinline__ void apply(int64_t i, double dot, double (&acc)[5]) const {
+    __device__ __forceinline__ void apply(int64_t i, double dot, double (&acc)[6]) const {
         const double go = g[i];
         const double dx = x_new[i] - x[i];
         const double dg = dot - go;
@@ -205,10 +210,11 @@ struct EpiGradBB {  // g_new = A^T r and the Barzilai-Borwein / line-search dot 
         acc[1] += dg * dg;
         acc[2] += go * dx;
         acc[3] += dot * dot;
-        acc[4] = fmax(acc[4], fabs(dx));
+        acc[4] += dg * go;
+        acc[5] = fmax(acc[5], fabs(dx));
     }
     static __device__ __forceinline__ void store(double *o, int k, double v) {
-        constexpr int slot[5] = {kScalSxy, kScalSyy, kScalGd, kScalGnn, kScalStep};
+        constexpr int slot[6] = {kScalSxy, kScalSyy, kScalGd, kScalGnn, kScalYgo, kScalStep};
         o[slot[k]] = v;
     }
 };
@@ -534,6 +540,28 @@ __global__ void __launch_bounds__(256) step_axpy_kernel(double *__restrict__ out
     }
 }
 
+// L-BFGS trial point before projection: out = x + d with d = cg g + cy (g - g_prev) + cs (x - x_prev).  In the reference's
+// solve_LBFGS every stored pair is a reference to the SAME two difference buffers (python/BATCH.py:153-155: the deques
+// hold delta_x / delta_g themselves, which the loop overwrites in place), so the two-loop recursion (:196-214) only ever
+// combines g, the latest delta_g and the latest delta_x: its inner products obey scalar recurrences (decide_step) and d
+// is this one combination.  `out` may be the buffer of x_prev (element i is read before it is written).
+__global__ void __launch_bounds__(256) lbfgs_step_kernel(double *out, const double *__restrict__ x, const double *xp,
+                                                          const double *__restrict__ g, const double *__restrict__ gp, const DevState *st,
+                                                          int64_t n) {
+    if (st->done) return;
+    const double cg = st->cg, cy = st->cy, cs = st->cs;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const double gi = g[i], xi = x[i];
+        double d = cg * gi;
+        if (cy != 0.0 || cs != 0.0) {
+            const double u = cy * (gi - gp[i]);
+            const double v = cs * (xi - xp[i]);
+            d = (d + u) + v;
+        }
+        out[i] = xi + d;
+    }
+}
+
 // After a back-tracked line search (tau < 1) the trial point, its gradient and its residual are pulled back along the
 // segment: v_new <- (1 - tau) v + tau v_new for x (the reference's own update, algorithm_utils.py:133), and -- the
 // objective being quadratic -- for g and r, which the reference recomputes with two more products (:134).  tau == 0 is
@@ -581,7 +609,28 @@ __device__ __forceinline__ void decide_step(DevState *st, const double *scal, co
     }
     unsigned long long now;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+    if (o.method == 4) {  // mirror_descent.least_squares (mirror_descent.py:37-52): no objective, stop on max |x - x_prev|
+        if (first) {
+            st->i = 1;
+            st->parity = 0;
+            st->done = o.max_iter < 1 ? 1 : 0;
+            return;
+        }
+        st->change = scal[kScalMax0];
+        st->parity ^= 1;
+        st->i += 1;
+        st->evals += 1;
+        if (st->change < o.tolerance)
+            st->done = 4;
+        else if (st->i > o.max_iter)
+            st->done = 1;
+        return;
+    }
+    double gd_acc = 0.0, ygo_acc = 0.0, sxy_raw = 0.0, syy_raw = 0.0, tau_acc = 1.0;
     if (first) {  // f = obj(x, g) of the starting point (BATCH.py:29,77,228)
+        st->hist = 0;
+        st->cg = -1.0;  // first step: x - g (BATCH.py:149)
+        st->cy = st->cs = 0.0;
         st->f = scal[kScalF];
         st->f_old = __longlong_as_double(0x7ff0000000000000LL);
         st->i = 1;
@@ -597,16 +646,18 @@ __device__ __forceinline__ void decide_step(DevState *st, const double *scal, co
             progress_t[0] = (double)now;
         }
     } else {
-        double sxy = scal[kScalSxy], syy = scal[kScalSyy], gd = scal[kScalGd], step = scal[kScalStep];
+        double sxy = scal[kScalSxy], syy = scal[kScalSyy], gd = scal[kScalGd], step = scal[kScalStep], ygo = scal[kScalYgo];
         if (gathered) {
-            sxy = syy = gd = step = 0.0;
+            sxy = syy = gd = step = ygo = 0.0;
             for (int r = 0; r < o.nranks; ++r) {  // rank order: every rank forms the same sums
-                sxy += gathered[r * 5 + 0];
-                syy += gathered[r * 5 + 1];
-                gd += gathered[r * 5 + 2];
-                step = fmax(step, gathered[r * 5 + 4]);
+                sxy += gathered[r * kStepScalars + 0];
+                syy += gathered[r * kStepScalars + 1];
+                gd += gathered[r * kStepScalars + 2];
+                step = fmax(step, gathered[r * kStepScalars + 4]);
+                ygo += gathered[r * kStepScalars + 5];
             }
         }
+        gd_acc = gd, ygo_acc = ygo, sxy_raw = sxy, syy_raw = syy;
         const double f = st->f;
         double f_new = scal[kScalF];
         double tau = 1.0;
@@ -629,6 +680,7 @@ __device__ __forceinline__ void decide_step(DevState *st, const double *scal, co
                 ++bt;
             }
         }
+        tau_acc = tau;
         st->tau = tau;
         st->backtracks += bt;
         st->evals += 1;
@@ -650,6 +702,44 @@ __device__ __forceinline__ void decide_step(DevState *st, const double *scal, co
         st->t = (i == 1) ? 1.0 : st->sxy / st->syy;  // BATCH.py:87-91
     else
         st->t = 1.0 / (o.min_eig * i + 1.0);         // decreasing_step_size(i, 1.0, min_eig), BATCH.py:38,238
+    if (o.method == 5 && !first) {
+        // solve_LBFGS (BATCH.py:150-167) for iteration i: append the pair of the step just taken, keep the last
+        // `corrections`, then BB direction while i <= 5, else the two-loop recursion -- on scalars, see lbfgs_step_kernel.
+        // s = dx, y = dg (tau-scaled), g = gradient at the new iterate = g_old + tau dg:
+        const double c = st->sxy, yy = st->syy;                             // <s,y>, <y,y>
+        const double sg = tau_acc * gd_acc + (tau_acc * tau_acc) * sxy_raw;  // <s,g>
+        const double yg = tau_acc * ygo_acc + (tau_acc * tau_acc) * syy_raw; // <y,g>
+        int m = st->hist;
+        if (m == o.corrections) {  // popleft (the append below brings the count back to `corrections`)
+            for (int j = 1; j < m; ++j) st->rho[j - 1] = st->rho[j];
+            --m;
+        }
+        st->rho[m++] = 1.0 / c;
+        st->hist = m;
+        const double t = c / yy;
+        if (i <= 5) {
+            st->cg = -t;
+            st->cy = st->cs = 0.0;
+        } else {
+            double al[64];
+            double sd = sg, A = 0.0;
+            for (int j = m - 1; j >= 0; --j) {  // alpha_j = rho_j <s,d>; d -= alpha_j y
+                al[j] = st->rho[j] * sd;
+                sd -= al[j] * c;
+                A += al[j];
+            }
+            double yd = t * (yg - A * yy), Bc = 0.0;  // d *= t; <y,d>
+            for (int j = 0; j < m; ++j) {              // beta_j = rho_j <y,d>; d += s (alpha_j - beta_j)
+                const double beta = st->rho[j] * yd;
+                const double coef = al[j] - beta;
+                yd += coef * c;
+                Bc += coef;
+            }
+            st->cg = -t;       // d = -(t g - t A y + Bc s)
+            st->cy = t * A;
+            st->cs = -Bc;
+        }
+    }
     // algorithm_utils.stopping (:158-172): later tests overwrite the reason of earlier ones
     int code = 0;
     if (i == o.max_iter) code = 1;

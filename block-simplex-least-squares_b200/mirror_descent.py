@@ -26,19 +26,15 @@ def least_squares(A, b, blocks, iters=1000, tolerance=1e-9, Lf=None, device=None
     if Lf is None:
         from .bsls_utils import largest_singular_value
         Lf = largest_singular_value(problem)
-    g = torch.empty_like(x)
-    x_new = torch.empty_like(x)
+    # the whole loop runs inside the library (bsls_md_least_squares_f64): SpMV pair + ONE fused exponentiate / normalise /
+    # max-change kernel per iteration, step t_k = sqrt(2 ln K_block) / (sqrt(k) Lf) and the stop test on the device
     from . import _lib
-    L = _lib.lib()
-    for _iter in range(1, iters + 1):
-        with torch.cuda.device(problem.device):
-            st = torch.cuda.current_stream(problem.device).cuda_stream
-            _lib.check(L.bsls_dev_lsq_residual_f64(problem.handle, x.data_ptr(), st))
-            _lib.check(L.bsls_dev_lsq_gradient_f64(problem.handle, g.data_ptr(), st))
-        # t_k = sqrt(2 ln K_block) / (sqrt(k) Lf);  x <- normalise(x exp(-t_k g))
-        problem.ws.md_update(plan, x_new, x, g, np.sqrt(_iter) * Lf, per_block_log=True)
-        change = problem.ws.scalars()[10]
-        x, x_new = x_new, x
-        if change < tolerance:
-            break
+    import ctypes
+    res = _lib.BatchResult()
+    with torch.cuda.device(problem.device):
+        st = torch.cuda.current_stream(problem.device).cuda_stream
+        _lib.check(_lib.lib().bsls_md_least_squares_f64(problem.handle, plan.handle, x.data_ptr(), int(iters), float(tolerance), float(Lf),
+                                                        ctypes.byref(res), st), "md_least_squares")
+    least_squares.last = {"iterations": res.iterations, "device_ms": res.device_ms, "change": res.stop_value,
+                          "kernel_launches": res.kernel_launches}
     return x

@@ -232,12 +232,13 @@ BSLS_API int bsls_dev_md_update_f64(bsls_ws *ws, const bsls_plan *plan, double *
  * (python/BATCH.py:7-106,217-250) with get_solver_parts' sparse objective, proj_multi_simplex_c
  * (proj_mode 0) or proj_multi_ball_c (1) and line_search_np (python/algorithm_utils.py:113-137). */
 typedef struct {
-    int method;          /* 0 projected gradient, 1 Barzilai-Borwein, 2 mirror descent */
+    int method;          /* 0 projected gradient, 1 Barzilai-Borwein, 2 mirror descent, 5 L-BFGS (solve_LBFGS, python/BATCH.py:110-214) */
     int proj_mode;       /* 0 simplex, 1 l1-ball, 2 isotonic regression + clip to [0,1] (problem posed in z) */
     int use_line_search; /* BB always searches; solve() only when given one */
     int has_f_min;
     double f_min, opt_tol, prog_tol, min_eig;
     int max_iter;
+    int corrections;     /* method 5 (L-BFGS): pairs kept, at most 64 (0: the reference's default 50) */
 } bsls_batch_opts;
 typedef struct {
     double f;
@@ -250,6 +251,13 @@ typedef struct {
 BSLS_API int bsls_batch_solve_f64(bsls_lsq *lsq, const bsls_plan *plan, double *x, const bsls_batch_opts *opts,
                                   bsls_batch_result *res, double *progress_f, double *progress_t, int progress_cap,
                                   bsls_stream_t stream);
+
+/* replaces mirror_descent.least_squares (python/mirror_descent.py:7-53): exponentiated gradient on the block simplices with
+ * step sqrt(2 ln K_block) / (sqrt(k) Lf), at most `iters` updates, stops when max |x - x_prev| < tolerance.  x: in = the
+ * starting point (1 / K_block), out = the result.  res->iterations = updates taken, stop_code 4 = tolerance reached,
+ * stop_value = the last max |x - x_prev|.  The loop is device-resident (no host decision inside). */
+BSLS_API int bsls_md_least_squares_f64(bsls_lsq *lsq, const bsls_plan *plan, double *x, int iters, double tolerance, double Lf,
+                                       bsls_batch_result *res, bsls_stream_t stream);
 
 #ifdef __cplusplus
 }

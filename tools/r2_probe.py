@@ -111,6 +111,7 @@ def main():
         parts = sp.solver_parts()
         for name, fn in (("bb", lambda mi: bsls_b200.BATCH.solve_BB(parts[3], parts[1], parts[2], sp.x_init, max_iter=mi)),
                          ("md", lambda mi: bsls_b200.BATCH.solve_MD(parts[3], sp.starts, parts[0], sp.x_init, max_iter=mi)),
+                         ("lbfgs", lambda mi: bsls_b200.BATCH.solve_LBFGS(parts[3], parts[1], parts[2], sp.x_init, max_iter=mi)),
                          ("pg", lambda mi: bsls_b200.BATCH.solve(parts[3], parts[1], parts[0], sp.x_init, line_search=parts[2], max_iter=mi))):
             fn(5)
             t0 = time.perf_counter()
