@@ -109,6 +109,10 @@ struct bsls_lsq {
     double *r2 = nullptr;                         // m: residual of the trial point (solver loop; allocated with the workspace)
     int t_ell = 0, a_ell = 0;                     // common row length of A^T / A when every row has the same (1..16 supported), else 0
     double *wg = nullptr, *wxn = nullptr, *wgn = nullptr;  // n each, solver workspace
+    // sliced-ELL copies of A and A^T for the single-CTA solver (built on first use; owned)
+    int32_t *sell_idx[2] = {nullptr, nullptr}, *sell_goff[2] = {nullptr, nullptr};
+    double *sell_val[2] = {nullptr, nullptr};
+    bool sell_ready = false;
     bsls_ws *ws = nullptr;                        // owned
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
@@ -544,6 +548,11 @@ int bsls_lsq_destroy(bsls_lsq *q) {
     if (q->r) cudaFree(q->r);
     if (q->r2) cudaFree(q->r2);
     if (q->partial) cudaFree(q->partial);
+    for (int k = 0; k < 2; ++k) {
+        if (q->sell_idx[k]) cudaFree(q->sell_idx[k]);
+        if (q->sell_goff[k]) cudaFree(q->sell_goff[k]);
+        if (q->sell_val[k]) cudaFree(q->sell_val[k]);
+    }
     if (q->wg) cudaFree(q->wg);
     if (q->wxn) cudaFree(q->wxn);
     if (q->wgn) cudaFree(q->wgn);
@@ -1002,6 +1011,24 @@ void finish_result(bsls_batch_result *res, const DevState &fin, int launches, fl
     res->device_ms = ms;
 }
 
+// sliced-ELL copy of one CSR side (solver_tiny.cuh)
+int build_sell(const int64_t *ptr, const int32_t *idx, const double *val, int rows, int32_t **goff_out, int32_t **sidx_out, double **sval_out,
+               cudaStream_t st) {
+    const int groups = (rows + 31) / 32;
+    BSLS_CUDA_TRY(cudaMalloc(goff_out, sizeof(int32_t) * ((size_t)groups + 1)));
+    sell_widths_kernel<<<(groups + 127) / 128, 128, 0, st>>>(ptr, rows, groups, *goff_out);
+    sell_scan_kernel<<<1, 32, 0, st>>>(*goff_out, groups);
+    BSLS_LAUNCH_CHECK();
+    int32_t total = 0;
+    BSLS_CUDA_TRY(cudaMemcpyAsync(&total, *goff_out + groups, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    BSLS_CUDA_TRY(cudaStreamSynchronize(st));
+    BSLS_CUDA_TRY(cudaMalloc(sidx_out, sizeof(int32_t) * (size_t)(total > 0 ? total : 1)));
+    if (val) BSLS_CUDA_TRY(cudaMalloc(sval_out, sizeof(double) * (size_t)(total > 0 ? total : 1)));
+    sell_fill_kernel<<<(32 * groups + 255) / 256, 256, 0, st>>>(ptr, idx, val, rows, groups, *goff_out, *sidx_out, val ? *sval_out : nullptr);
+    BSLS_LAUNCH_CHECK();
+    return BSLS_OK;
+}
+
 // Problems whose vectors fit one SM's shared memory: the whole loop in one launch of one CTA (solver_tiny.cuh).
 // Returns 0 when the problem does not qualify (the caller goes on), -1 when it was solved here, > 0 on error.
 int solve_tiny(bsls_lsq *q, const bsls_plan *plan, double *x, const bsls_batch_opts *o, bsls_batch_result *res, double *progress_f,
@@ -1011,7 +1038,7 @@ int solve_tiny(bsls_lsq *q, const bsls_plan *plan, double *x, const bsls_batch_o
     bsls_ws *w = q->ws;
     const size_t smem = tiny_smem_bytes((int)q->n, (int)q->m);
     if (off || (w->comm && w->comm->nranks > 1) || o->method > 1 || o->proj_mode > 1 || plan->max_size > kTinyMaxBlock || plan->first != 0 ||
-        smem > 220 * 1024 || q->n > (1 << 20))
+        smem > 220 * 1024 || q->n > (1 << 20) || q->nnz > (1 << 26))
         return 0;
     static thread_local PerDevice<bool> attr_pd;
     bool &attr = attr_pd.get(false);
@@ -1019,17 +1046,18 @@ int solve_tiny(bsls_lsq *q, const bsls_plan *plan, double *x, const bsls_batch_o
         BSLS_CUDA_TRY(cudaFuncSetAttribute(solver_tiny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr = true;
     }
+    if (!q->sell_ready) {
+        if (int rc = build_sell(q->a_ptr, q->a_idx, q->a_val, (int)q->m, &q->sell_goff[0], &q->sell_idx[0], &q->sell_val[0], st)) return rc;
+        if (int rc = build_sell(q->t_ptr, q->t_idx, q->t_val, (int)q->n, &q->sell_goff[1], &q->sell_idx[1], &q->sell_val[1], st)) return rc;
+        q->sell_ready = true;
+    }
     TinyArgs a{};
     a.n = (int)q->n;
     a.m = (int)q->m;
     a.nb = plan->nb;
     a.starts = plan->d_starts;
-    a.a_ptr = q->a_ptr;
-    a.t_ptr = q->t_ptr;
-    a.a_idx = q->a_idx;
-    a.t_idx = q->t_idx;
-    a.a_val = q->a_val;
-    a.t_val = q->t_val;
+    a.A = SellMatrix{q->sell_idx[0], q->sell_val[0], q->sell_goff[0]};
+    a.AT = SellMatrix{q->sell_idx[1], q->sell_val[1], q->sell_goff[1]};
     a.b = q->b;
     a.x = x;
     a.st = w->d_state;
