@@ -110,6 +110,8 @@ def lib():
         L.bsls_batch_solve_f64.argtypes = [c_void_p, c_void_p, c_void_p, ctypes.POINTER(BatchOpts), ctypes.POINTER(BatchResult),
                                            c_void_p, c_void_p, c_int, c_void_p]
         L.bsls_md_least_squares_f64.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_dbl, c_dbl, ctypes.POINTER(BatchResult), c_void_p]
+        L.bsls_zbb_run_f64.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_dbl,
+                                       ctypes.POINTER(BatchResult), c_void_p]
         _lib = L
     return _lib
 

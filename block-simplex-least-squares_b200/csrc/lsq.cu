@@ -113,6 +113,7 @@ struct bsls_lsq {
     int32_t *sell_idx[2] = {nullptr, nullptr}, *sell_goff[2] = {nullptr, nullptr};
     double *sell_val[2] = {nullptr, nullptr};
     bool sell_ready = false;
+    double *wz = nullptr;                         // n: one more vector for the z-space BB loop (allocated on first use)
     bsls_ws *ws = nullptr;                        // owned
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
@@ -553,6 +554,7 @@ int bsls_lsq_destroy(bsls_lsq *q) {
         if (q->sell_goff[k]) cudaFree(q->sell_goff[k]);
         if (q->sell_val[k]) cudaFree(q->sell_val[k]);
     }
+    if (q->wz) cudaFree(q->wz);
     if (q->wg) cudaFree(q->wg);
     if (q->wxn) cudaFree(q->wxn);
     if (q->wgn) cudaFree(q->wgn);
@@ -1287,6 +1289,110 @@ int bsls_md_least_squares_f64(bsls_lsq *q, const bsls_plan *plan, double *x, int
     res->obj_evals = fin.evals;
     res->backtracks = 0;
     res->kernel_launches = (w->launches - launches0) + extra + 1;
+    res->device_ms = ms;
+    return BSLS_OK;
+}
+
+// BB.solve (python/BB.py:7-45) for the z-space problem of main.solve_in_z (python/main.py:47-65) as a device-resident loop:
+//   f(z) = 0.5 |A (N z) - b'|^2 with b' = -target held by the handle, grad = N^T A^T r, proj = isotonic regression + clip.
+// Per iteration: A^T r, N^T, one pass for the four sums, z - t g, the projection, N z, A x -- and the decision
+// (BB step, the "no change in gradient" exit, solvers.stopping) by decide_kernel.  The reference evaluates A N z three
+// times per iteration (gradient, objective, next gradient); here the residual at the new point serves the stopping test
+// and the next gradient: two products.  Runs iterations i_start + 1 .. i_end (segments let the caller record states every
+// `record_every` iterations as the reference's log callback does); z, z_prev, g_prev are updated in place.
+int bsls_zbb_run_f64(bsls_lsq *q, const bsls_plan *xplan, const bsls_plan *zplan, double *z, double *z_prev, double *g_prev, int i_start,
+                     int i_end, int max_iter, double opt_tol, bsls_batch_result *res, bsls_stream_t s) {
+    if (!q || !xplan || !zplan || !z || !z_prev || !g_prev || !res || !q->b || xplan->n != q->n || i_end < i_start) {
+        set_error("zbb_run: bad argument");
+        return BSLS_ERR_ARG;
+    }
+    const int64_t n = q->n, nz = zplan->n;
+    if (nz != n - xplan->nb) {
+        set_error("zbb_run: z has %lld entries, expected n - numblocks = %lld", (long long)nz, (long long)(n - xplan->nb));
+        return BSLS_ERR_ARG;
+    }
+    if (int rc = ensure_workspace(q)) return rc;
+    if (!q->wz) BSLS_CUDA_TRY(cudaMalloc(&q->wz, sizeof(double) * (size_t)q->n));
+    cudaStream_t st = (cudaStream_t)s;
+    bsls_ws *w = q->ws;
+    DevOpts d{};
+    d.method = 3;
+    d.max_iter = max_iter;
+    d.opt_tol = opt_tol;
+    d.nranks = (w->comm && w->comm->nranks > 1) ? w->comm->nranks : 1;
+    double *Z[3] = {z, z_prev, q->wgn}, *G[2] = {g_prev, q->wz};
+    double *xbuf = q->wxn, *gx = q->wg;
+    const int lanes = lanes_for(xplan);
+    const int ngrid = grid_groups(xplan->nb, lanes);
+    auto n_dot = [&](double *x_out, const double *zz) -> int {  // x = N z
+        DISPATCH_LANES(lanes, nz_kernel, ngrid, st, x_out, zz, 0, layout_of(xplan));
+        BSLS_LAUNCH_CHECK();
+        return BSLS_OK;
+    };
+    const int launches0 = w->launches;
+    int extra = 0;
+    BSLS_CUDA_TRY(cudaEventRecord(q->ev0, st));
+    DevState init{};
+    init.i = i_start;
+    BSLS_CUDA_TRY(cudaMemcpyAsync(w->d_state, &init, sizeof(DevState), cudaMemcpyHostToDevice, st));
+    const int *done = &w->d_state->done;
+    // r = A N z - b' at the starting point of the segment
+    if (int rc = n_dot(xbuf, Z[0])) return rc;
+    if (int rc = residual(q, xbuf, q->r, q->b, st)) return rc;
+    BSLS_CUDA_TRY(cudaMemcpyAsync(&w->h_state[1], w->d_state, sizeof(DevState), cudaMemcpyDeviceToHost, st));
+    BSLS_CUDA_TRY(cudaEventRecord(w->ev_state[1], st));
+    const int todo = i_end - i_start;
+    for (int k = 0; k < todo; ++k) {
+        const int cur = (2 * k) % 3, prev = (2 * k + 1) % 3, nxt = (2 * k + 2) % 3;  // cur_k = -k, prev_k = 1 - k, nxt_k = 2 - k (mod 3)
+        const int gc = (k + 1) & 1, gp = k & 1;
+        // g = N^T A^T r
+        EpiPlain epi{gx};
+        if (int rc = launch_at(q, q->r, epi, st, done)) return rc;
+        DISPATCH_LANES(lanes, ntv_kernel, ngrid, st, G[gc], gx, layout_of(xplan));
+        BSLS_LAUNCH_CHECK();
+        zbb_dots_kernel<<<grid_elems(nz), 256, 0, st>>>(Z[cur], Z[prev], G[gc], G[gp], nz, w->red, done);
+        BSLS_LAUNCH_CHECK();
+        if (int rc = allreduce(w, w->d_scal + kScalSxy, 4, kNcclSum, st)) return rc;
+        // z_new = proj(z - t g)
+        zbb_step_kernel<<<grid_elems(nz), 256, 0, st>>>(Z[nxt], Z[cur], G[gc], w->d_scal, done, nz);
+        BSLS_LAUNCH_CHECK();
+        if (int rc = pava_clip_f64(zplan, Z[nxt], nullptr, 1, 1, st)) return rc;
+        // f(z_new) -- and the residual the next gradient starts from
+        if (int rc = n_dot(xbuf, Z[nxt])) return rc;
+        if (int rc = residual(q, xbuf, q->r, q->b, st, nullptr, done)) return rc;
+        decide_kernel<<<1, 32, 0, st>>>(w->d_state, w->d_scal, nullptr, d, nullptr, nullptr, 0);
+        BSLS_LAUNCH_CHECK();
+        extra += 6;
+        BSLS_CUDA_TRY(cudaMemcpyAsync(&w->h_state[k & 1], w->d_state, sizeof(DevState), cudaMemcpyDeviceToHost, st));
+        BSLS_CUDA_TRY(cudaEventRecord(w->ev_state[k & 1], st));
+        BSLS_CUDA_TRY(cudaEventSynchronize(w->ev_state[(k + 1) & 1]));  // the state one iteration back
+        if (w->h_state[(k + 1) & 1].done) break;
+    }
+    BSLS_CUDA_TRY(cudaStreamSynchronize(st));
+    DevState fin;
+    BSLS_CUDA_TRY(cudaMemcpy(&fin, w->d_state, sizeof(DevState), cudaMemcpyDeviceToHost));
+    // hand the three vectors back in the caller's buffers: K completed iterations rotated the roles K times
+    const int K = fin.i - i_start;
+    const size_t zb = sizeof(double) * (size_t)nz;
+    if (K % 3 == 1) {         // cur = Z[2], prev = Z[0]
+        BSLS_CUDA_TRY(cudaMemcpyAsync(Z[1], Z[0], zb, cudaMemcpyDeviceToDevice, st));
+        BSLS_CUDA_TRY(cudaMemcpyAsync(Z[0], Z[2], zb, cudaMemcpyDeviceToDevice, st));
+    } else if (K % 3 == 2) {  // cur = Z[1], prev = Z[2]
+        BSLS_CUDA_TRY(cudaMemcpyAsync(Z[0], Z[1], zb, cudaMemcpyDeviceToDevice, st));
+        BSLS_CUDA_TRY(cudaMemcpyAsync(Z[1], Z[2], zb, cudaMemcpyDeviceToDevice, st));
+    }
+    if (K & 1) BSLS_CUDA_TRY(cudaMemcpyAsync(G[0], G[1], zb, cudaMemcpyDeviceToDevice, st));
+    BSLS_CUDA_TRY(cudaEventRecord(q->ev1, st));
+    BSLS_CUDA_TRY(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    BSLS_CUDA_TRY(cudaEventElapsedTime(&ms, q->ev0, q->ev1));
+    res->f = fin.f;
+    res->iterations = fin.i;
+    res->stop_code = fin.done;
+    res->stop_value = fin.t;
+    res->obj_evals = fin.evals;
+    res->backtracks = 0;
+    res->kernel_launches = (w->launches - launches0) + extra;
     res->device_ms = ms;
     return BSLS_OK;
 }

@@ -143,7 +143,7 @@ struct DevState {
 };
 constexpr int kStepScalars = 6;  // slots 1..6 of every rank travel in the all-gather of a sharded solve
 struct DevOpts {
-    int method;            // BATCH: 0 projected gradient, 1 Barzilai-Borwein, 2 mirror descent, 5 L-BFGS; 4 mirror_descent.least_squares
+    int method;            // BATCH: 0 projected gradient, 1 Barzilai-Borwein, 2 mirror descent, 5 L-BFGS; 3 BB.solve in z; 4 mirror_descent.least_squares
     int corrections;       // method 5: history length (at most 64)
     int search;            // run line_search_np
     int has_f_min, max_iter;
@@ -540,6 +540,37 @@ __global__ void __launch_bounds__(256) step_axpy_kernel(double *__restrict__ out
     }
 }
 
+// BB.solve in z (python/BB.py:17-37): the four sums of an iteration in one pass over the z-vectors --
+// <z - z_prev, g - g_prev>, |g - g_prev|^2, sum(g - g_prev) (the reference's "no change in gradient" test, :22) and |g|^2
+// (solvers.stopping, python/solvers.py:47) -- into scalar slots 1..4.
+struct FinZbb {
+    static __device__ __forceinline__ void store(double *o, int k, double v) { o[kScalSxy + k] = v; }
+};
+__global__ void __launch_bounds__(256) zbb_dots_kernel(const double *__restrict__ z, const double *__restrict__ zp, const double *__restrict__ g,
+                                                        const double *__restrict__ gp, int64_t n, RedCtx red, const int *__restrict__ skip) {
+    if (skip && *skip) return;
+    double acc[4] = {0, 0, 0, 0};
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const double gi = g[i];
+        const double dg = gi - gp[i], dz = z[i] - zp[i];
+        acc[0] += dz * dg;
+        acc[1] += dg * dg;
+        acc[2] += dg;
+        acc[3] += gi * gi;
+    }
+    grid_reduce<4, 0, 256, FinZbb>(acc, red);
+}
+// x_next = x - t g with t = <dx,dg> / <dg,dg> read from the scalar block (BB.py:26,29)
+__global__ void __launch_bounds__(256) zbb_step_kernel(double *__restrict__ out, const double *__restrict__ z, const double *__restrict__ g,
+                                                        const double *__restrict__ scal, const int *__restrict__ skip, int64_t n) {
+    if (skip && *skip) return;
+    const double t = scal[kScalSxy] / scal[kScalSyy];
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const double u = t * g[i];
+        out[i] = z[i] - u;
+    }
+}
+
 // L-BFGS trial point before projection: out = x + d with d = cg g + cy (g - g_prev) + cs (x - x_prev).  In the reference's
 // solve_LBFGS every stored pair is a reference to the SAME two difference buffers (python/BATCH.py:153-155: the deques
 // hold delta_x / delta_g themselves, which the loop overwrites in place), so the two-loop recursion (:196-214) only ever
@@ -609,6 +640,30 @@ __device__ __forceinline__ void decide_step(DevState *st, const double *scal, co
     }
     unsigned long long now;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+    if (o.method == 3) {  // BB.solve (python/BB.py:17-37) with solvers.stopping (python/solvers.py:40-63)
+        if (first) {      // st->i was set by the host to the number of iterations already done (segmented runs)
+            st->parity = 0;
+            st->done = 0;
+            return;
+        }
+        if (scal[kScalGd] == 0.0) {  // sum(delta_g) == 0: 'Exiting... no change in gradient', x stays where it is (BB.py:22-24)
+            st->done = 5;
+            return;
+        }
+        const double fx = scal[kScalF];
+        st->t = scal[kScalSxy] / scal[kScalSyy];
+        st->f = fx;
+        st->i += 1;
+        st->parity += 1;
+        st->evals += 1;
+        if (st->i >= o.max_iter)
+            st->done = 1;
+        else if (scal[kScalGnn] <= o.opt_tol * (1.0 + fabs(fx)))
+            st->done = 6;   // 'Exiting... norm(grad) too small'
+        else if (sqrt(scal[kScalSyy]) == 0.0)
+            st->done = 5;
+        return;
+    }
     if (o.method == 4) {  // mirror_descent.least_squares (mirror_descent.py:37-52): no objective, stop on max |x - x_prev|
         if (first) {
             st->i = 1;

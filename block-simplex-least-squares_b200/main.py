@@ -56,6 +56,9 @@ def z_space_parts(A, b, x0, N, block_sizes, device=None):
         cx.isotonic_regression_multi_c(z, zplan, None, 1, clip01=True)
         return z
 
+    # the handles behind the closures: lets BB.solve run the whole loop inside the library (bsls_zbb_run_f64)
+    zspace = {"problem": problem, "N": N, "zplan": zplan}
+    f.zspace = nabla_f.zspace = proj.zspace = zspace
     return z0, target, f, nabla_f, proj, problem, N
 
 

@@ -259,6 +259,16 @@ BSLS_API int bsls_batch_solve_f64(bsls_lsq *lsq, const bsls_plan *plan, double *
 BSLS_API int bsls_md_least_squares_f64(bsls_lsq *lsq, const bsls_plan *plan, double *x, int iters, double tolerance, double Lf,
                                        bsls_batch_result *res, bsls_stream_t stream);
 
+/* replaces BB.solve (python/BB.py:7-45) for the z-space problem main.solve_in_z builds (python/main.py:47-65):
+ * f(z) = 0.5 |A N z + target|^2 (the handle's b must hold -target), projection = isotonic regression of every z-block
+ * clipped to [0, 1], stopping = solvers.stopping (python/solvers.py:40-63).  Runs iterations i_start + 1 .. i_end as a
+ * device-resident loop (segments: the caller records a state every `record_every` iterations like the reference's log
+ * callback).  xplan = blocks of x (defines N), zplan = blocks of z.  z, z_prev, g_prev (n - numblocks entries each) are
+ * updated in place.  res->iterations = the reference's `i` at exit; stop_code 0 = segment finished, 1 = max_iter,
+ * 5 = no change in gradient, 6 = norm(grad) too small; res->f = f at the returned z; stop_value = the last BB step. */
+BSLS_API int bsls_zbb_run_f64(bsls_lsq *lsq, const bsls_plan *xplan, const bsls_plan *zplan, double *z, double *z_prev, double *g_prev,
+                              int i_start, int i_end, int max_iter, double opt_tol, bsls_batch_result *res, bsls_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

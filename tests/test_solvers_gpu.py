@@ -406,8 +406,23 @@ def test_z_space_drivers_match_reference(B, gold, tag):
     np.testing.assert_allclose(host(z_init), gold[tag + "_z0"], rtol=0, atol=0)
     log = lambda it, state, dur: 0.0
     opts = {"max_iter": 200, "opt_tol": 1e-30, "verbose": 0}
+    # BB in z: the library's device-resident loop (bsls_zbb_run_f64) and the generic closure-driven loop
     zbb = B.BB.solve(z_init.clone(), f, nabla_f, B.solvers.stopping, proj=proj, log=log, options=opts)
+    assert B.BB.solve.last["kernel_launches"] > 0 and B.BB.solve.last["iterations"] <= 200
     assert f(zbb) == pytest.approx(float(gold[tag + "_zbb_f"]), rel=1e-6, abs=1e-10)
+    zbb_g = B.BB.solve(z_init.clone(), f, nabla_f, B.solvers.stopping, proj=proj, log=log, options=dict(opts, generic_loop=True))
+    assert f(zbb_g) == pytest.approx(float(gold[tag + "_zbb_f"]), rel=1e-6, abs=1e-10)
+    # states are recorded every `record_every` iterations plus the first and the last, as the reference's log does
+    seen = []
+    B.BB.solve(z_init.clone(), f, nabla_f, B.solvers.stopping, proj=proj, log=lambda it, state, dur: seen.append((it, state.clone())) or 0.0,
+               options={"max_iter": 35, "opt_tol": 1e-30, "verbose": 0}, record_every=10)
+    assert [it for it, _ in seen] == [0, 10, 20, 30, 35]
+    seen_g = []
+    B.BB.solve(z_init.clone(), f, nabla_f, B.solvers.stopping, proj=proj, log=lambda it, state, dur: seen_g.append((it, state.clone())) or 0.0,
+               options={"max_iter": 35, "opt_tol": 1e-30, "verbose": 0, "generic_loop": True}, record_every=10)
+    assert [it for it, _ in seen_g] == [0, 10, 20, 30, 35]
+    for (_, a), (_, b_) in zip(seen[:3], seen_g[:3]):      # the first iterations follow the same trajectory
+        np.testing.assert_allclose(host(a), host(b_), rtol=1e-9, atol=1e-12)
     ones = torch.ones_like(z_init)
     zl = B.LBFGS.solve(z_init + ones, f, nabla_f, B.solvers.stopping, proj=proj, log=log,
                        options={"max_iter": 40, "opt_tol": 1e-30, "verbose": 0})
