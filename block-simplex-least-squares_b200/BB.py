@@ -40,10 +40,11 @@ def _solve_native(x0, f, nabla_f, zs, record_every, log, options):
         i = res.iterations
         if res.stop_code == 5:
             print('Exiting... no change in gradient')
+            break
+        if i % record_every == 0 and i > 0:      # BB.py:39-40 runs before the loop condition is looked at again
+            start = log(i, z.clone(), time.time() - start)
         if res.stop_code != 0 or i >= max_iter:
             break
-        if i % record_every == 0:
-            start = log(i, z.clone(), time.time() - start)
     solve.last.update(iterations=i, stop_code=res.stop_code, f=res.f)
     log(i, z, time.time() - start)
     return z

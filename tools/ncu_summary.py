@@ -11,7 +11,10 @@ WANT = ['Kernel Name', 'launch__grid_size', 'launch__block_size', 'launch__regis
         'sm__inst_executed_pipe_fp64.sum', 'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_alu.sum', 'sm__inst_executed_pipe_lsu.sum',
         'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
-        'lts__t_sector_hit_rate.pct',
+        'lts__t_sector_hit_rate.pct', 'lts__t_sectors.sum', 'lts__t_sectors_op_read.sum', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum',
+        'l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum', 'l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_ld.sum',
+        'l1tex__t_sector_hit_rate.pct', 'sm__cycles_elapsed.avg',
         'smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct', 'smsp__warp_issue_stalled_barrier_per_warp_active.pct',
         'smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct',
         'smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct', 'smsp__warp_issue_stalled_wait_per_warp_active.pct',
