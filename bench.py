@@ -560,6 +560,11 @@ def run_ours(args, rank, world, local_rank):
     comm = bsls_b200.Communicator() if world > 1 else None
     sp = SyntheticProblem.config("C5", rank=rank, world=world, comm=comm, noise=0.1)
     panels = sp.problem.set_panels() if sp.n * 8 > (64 << 20) else 1
+    exchange = "none (one GPU)"
+    if world > 1:
+        p2p = bool(_lib.lib().bsls_comm_p2p_ready(comm.handle))
+        exchange = ("NVLink peer memory: reduce-scatter + all-gather of A x fused with - b and the norms in one kernel (csrc/p2p.cuh)"
+                    if p2p else "NCCL: ncclAllReduce of A x + ncclAllGather of the step scalars")
     step_size, proj, line_search, obj = sp.solver_parts()
     solve = lambda x0: bsls_b200.BATCH.solve_BB(obj, proj, line_search, x0, max_iter=MAX_ITER)
 
@@ -697,6 +702,7 @@ def run_ours(args, rank, world, local_rank):
                 "data": "synthetic", "config": CONFIG,
                 "solve": {"iterations_per_solve": its // steps, "objective_evaluations_per_solve": evals // steps,
                           "ms_per_iteration": ms / max(1, its), "ms_per_evaluation": ms / max(1, evals), "panels_per_gpu": panels,
+                          "exchange": exchange,
                           "note": "a back-tracked line search costs no extra product: the objective is quadratic along the step "
                                   "(decide_kernel, lsq.cuh)"},
                 "parity": parity, "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}

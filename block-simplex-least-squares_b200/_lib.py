@@ -74,6 +74,10 @@ def lib():
         L.bsls_comm_create.argtypes = [c_char_p, c_int, c_int, c_void_p, PP]
         L.bsls_comm_destroy.argtypes = [c_void_p]
         L.bsls_comm_allreduce_sum_f64.argtypes = [c_void_p, c_void_p, c_i64, c_void_p]
+        L.bsls_comm_p2p_alloc.argtypes = [c_void_p, c_i64, c_void_p]
+        L.bsls_comm_p2p_open.argtypes = [c_void_p, c_void_p]
+        L.bsls_comm_p2p_ready.argtypes = [c_void_p]
+        L.bsls_comm_p2p_disable.argtypes = [c_void_p]
         L.bsls_ws_create.argtypes = [PP]
         L.bsls_ws_destroy.argtypes = [c_void_p]
         L.bsls_ws_set_comm.argtypes = [c_void_p, c_void_p]

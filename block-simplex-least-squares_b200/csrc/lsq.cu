@@ -10,6 +10,7 @@
 
 #include "kernels.h"
 #include "lsq.cuh"
+#include "p2p.cuh"
 #include "solver_tiny.cuh"
 
 using namespace bsls;
@@ -73,7 +74,35 @@ int nccl_load(const char *path) {
 struct bsls_comm {
     void *comm = nullptr;
     int nranks = 1, rank = 0;
+    // peer-memory exchange (p2p.cuh): this rank's region, the mapped regions of the others, the epoch of the last evaluation
+    void *region = nullptr;
+    void *peer_base[kP2pMaxRanks] = {};
+    int64_t p2p_m = 0;
+    bool p2p_ready = false;
+    P2pView view{};
+    unsigned long long epoch = 0;
+    unsigned *ticket = nullptr;
+    double *cta_partials = nullptr;
+    int reduce_grid = 0;
 };
+
+// layout of an exchange region, in 8-byte words: partial[m] | rfull0[m] | rfull1[m] | slots[P*8] | gath[P*8] | flags[3*P]
+static void p2p_fill_view(bsls_comm *c) {
+    const int P = c->nranks;
+    const int64_t m = (c->p2p_m + 1) & ~int64_t(1);
+    for (int q = 0; q < P; ++q) {
+        double *base = reinterpret_cast<double *>(q == c->rank ? c->region : c->peer_base[q]);
+        c->view.partial[q] = base;
+        c->view.rfull[q][0] = base + m;
+        c->view.rfull[q][1] = base + 2 * m;
+        c->view.slots[q] = base + 3 * m;
+        c->view.gath[q] = base + 3 * m + P * 8;
+        c->view.flags[q] = reinterpret_cast<unsigned long long *>(base + 3 * m + 2 * P * 8);
+    }
+    c->view.nranks = P;
+    c->view.rank = c->rank;
+}
+static size_t p2p_region_bytes(int P, int64_t m) { return sizeof(double) * (size_t)(3 * ((m + 1) & ~int64_t(1)) + 2 * P * 8 + 3 * P + 8); }
 
 // reduction scratch + device/host scalar block + communicator: everything a reducing kernel needs
 struct bsls_ws {
@@ -265,11 +294,21 @@ template <class Epi> int launch_at(bsls_lsq *q, const double *w, const Epi &epi,
     return launch_spmv(q->ws, q->t_mode, q->n, q->t_ptr, q->t_idx, q->t_val, w, epi, st, skip, q->t_ell);
 }
 
-// r = A x - b (summed over ranks), scalar F = 0.5 <r, r>; with r_old also <r_old, r - r_old> and |r - r_old|^2
+// the sharded solver loop exchanges over peer memory when the communicator has its regions mapped for this m
+bool use_p2p(const bsls_lsq *q) {
+    const bsls_comm *c = q->ws->comm;
+    return c && c->nranks > 1 && c->p2p_ready && c->p2p_m == q->m;
+}
+
+// r = A x - b (summed over ranks), scalar F = 0.5 <r, r>; with r_old also <r_old, r - r_old> and |r - r_old|^2.
+// p2p_nxt >= 0 (solver loop, peer-memory build): r is residual buffer `p2p_nxt` of the exchange region, r_old the other
+// one; the sum over ranks, - b, the three sums and the distribution to all ranks are ONE kernel over NVLink (p2p.cuh).
 int residual(bsls_lsq *q, const double *x, double *r, const double *b, cudaStream_t st, const double *r_old = nullptr,
-             const int *skip = nullptr) {
+             const int *skip = nullptr, int p2p_nxt = -1) {
     bsls_ws *w = q->ws;
     const bool dist = w->comm && w->comm->nranks > 1;
+    const bool p2p = dist && p2p_nxt >= 0 && b && use_p2p(q);
+    double *local = p2p ? w->comm->view.partial[w->comm->rank] : r;
     if (q->panels > 1) {
         // one launch per panel: the kernel boundary keeps all CTAs inside the same slice of x, which
         // therefore stays L2-resident (a single launch lets CTAs drift several panels apart)
@@ -277,15 +316,23 @@ int residual(bsls_lsq *q, const double *x, double *r, const double *b, cudaStrea
             EpiResidual epi{q->partial + (size_t)p * q->m, nullptr, nullptr};
             if (int rc = launch_spmv(w, q->p_mode, q->m, q->p_ptr + (size_t)p * q->m, q->p_idx, q->p_val, x, epi, st, skip)) return rc;
         }
-        panel_reduce_kernel<<<grid_elems(q->m), 256, 0, st>>>(r, q->partial, dist ? nullptr : b, r_old, q->m, q->panels, w->red, skip);
+        panel_reduce_kernel<<<grid_elems(q->m), 256, 0, st>>>(local, q->partial, dist ? nullptr : b, r_old, q->m, q->panels, w->red, skip);
         BSLS_LAUNCH_CHECK();
         w->launches++;
     } else {
         const bool fin = !dist && b;
-        EpiResidual epi{r, fin ? b : nullptr, fin ? r_old : nullptr};
+        EpiResidual epi{local, fin ? b : nullptr, fin ? r_old : nullptr};
         if (int rc = launch_spmv(w, q->a_mode, q->m, q->a_ptr, q->a_idx, q->a_val, x, epi, st, skip, q->a_ell)) return rc;
     }
-    if (dist) {
+    if (p2p) {
+        bsls_comm *c = w->comm;
+        ++c->epoch;
+        p2p_reduce_kernel<<<c->reduce_grid, kP2pThreads, 0, st>>>(c->view, b, q->m, p2p_nxt, c->epoch, c->ticket, c->cta_partials, skip);
+        BSLS_LAUNCH_CHECK();
+        p2p_wait_kernel<<<1, 32, 0, st>>>(c->view, c->epoch, w->d_scal, skip);
+        BSLS_LAUNCH_CHECK();
+        w->launches += 2;
+    } else if (dist) {
         if (int rc = allreduce(w, r, q->m, kNcclSum, st)) return rc;
         if (b) {
             residual_finish_kernel<<<grid_elems(q->m), 256, 0, st>>>(r, b, r_old, q->m, w->red, skip);
@@ -405,8 +452,58 @@ int bsls_comm_create(const char *nccl_path, int nranks, int rank, const char id[
     return BSLS_OK;
 }
 
+// Peer-memory exchange: allocate this rank's region for link vectors of m entries and return its IPC handle (64 bytes) ...
+int bsls_comm_p2p_alloc(bsls_comm *c, int64_t m, char handle[64]) {
+    if (!c || !handle || m <= 0 || c->nranks < 2 || c->nranks > kP2pMaxRanks) {
+        set_error("comm_p2p_alloc: needs 2..%d ranks of one node", kP2pMaxRanks);
+        return BSLS_ERR_ARG;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (c->region) return BSLS_ERR_ARG;
+    c->p2p_m = m;
+    const size_t bytes = p2p_region_bytes(c->nranks, m);
+    BSLS_CUDA_TRY(cudaMalloc(&c->region, bytes));
+    BSLS_CUDA_TRY(cudaMemset(c->region, 0, bytes));
+    BSLS_CUDA_TRY(cudaMalloc(&c->ticket, sizeof(unsigned)));
+    BSLS_CUDA_TRY(cudaMemset(c->ticket, 0, sizeof(unsigned)));
+    const int64_t rows = (m + c->nranks - 1) / c->nranks;
+    int64_t want = (rows + kP2pThreads - 1) / kP2pThreads;
+    c->reduce_grid = (int)(want < 2 * num_sms() ? (want < 1 ? 1 : want) : 2 * num_sms());
+    BSLS_CUDA_TRY(cudaMalloc(&c->cta_partials, sizeof(double) * 3 * (size_t)c->reduce_grid));
+    cudaIpcMemHandle_t h;
+    BSLS_CUDA_TRY(cudaIpcGetMemHandle(&h, c->region));
+    memcpy(handle, &h, 64);
+    BSLS_CUDA_TRY(cudaDeviceSynchronize());
+    return BSLS_OK;
+}
+
+// ... and map the regions of the other ranks from their handles (nranks x 64 bytes, in rank order).
+int bsls_comm_p2p_open(bsls_comm *c, const char *handles) {
+    if (!c || !handles || !c->region) return BSLS_ERR_ARG;
+    for (int q = 0; q < c->nranks; ++q) {
+        if (q == c->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + 64 * q, 64);
+        BSLS_CUDA_TRY(cudaIpcOpenMemHandle(&c->peer_base[q], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    p2p_fill_view(c);
+    c->p2p_ready = true;
+    return BSLS_OK;
+}
+
+int bsls_comm_p2p_ready(const bsls_comm *c) { return c && c->p2p_ready ? 1 : 0; }
+int bsls_comm_p2p_disable(bsls_comm *c) {  // a rank failed to map its peers: every rank goes back to NCCL
+    if (c) c->p2p_ready = false;
+    return BSLS_OK;
+}
+
 int bsls_comm_destroy(bsls_comm *c) {
     if (!c) return BSLS_OK;
+    for (int q = 0; q < kP2pMaxRanks; ++q)
+        if (c->peer_base[q]) cudaIpcCloseMemHandle(c->peer_base[q]);
+    if (c->region) cudaFree(c->region);
+    if (c->ticket) cudaFree(c->ticket);
+    if (c->cta_partials) cudaFree(c->cta_partials);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     delete c;
     return BSLS_OK;
@@ -1129,20 +1226,32 @@ int enqueue_iteration(bsls_lsq *q, const bsls_plan *plan, const LoopBuffers &B, 
         ++*extra_launches;
     }
     // ---- objective and gradient at the trial point ------------------------------------------------
-    if (int rc = residual(q, B.x[nxt], B.r[nxt], q->b, st, B.r[cur], done)) return rc;
+    const bool p2p = dist && use_p2p(q);
+    if (int rc = residual(q, B.x[nxt], B.r[nxt], q->b, st, B.r[cur], done, p2p ? nxt : -1)) return rc;
     const bool need_dots = d.method == 1 || d.method == 5 || d.search;
     if (need_dots) {
         EpiGradBB epi{B.g[nxt], B.g[cur], B.x[cur], B.x[nxt]};
         if (int rc = launch_at(q, B.r[nxt], epi, st, done)) return rc;
-        if (dist)  // every rank needs every rank's share of the step scalars: one small all-gather (slots 1..5)
+        if (p2p) {  // every rank needs every rank's share of the step scalars: pushed over NVLink, flag C (p2p.cuh) ...
+            p2p_post_kernel<<<1, 32, 0, st>>>(w->comm->view, w->comm->epoch, w->d_scal, done);
+            BSLS_LAUNCH_CHECK();
+            ++*extra_launches;
+        } else if (dist) {  // ... or one small NCCL all-gather (slots 1..6)
             BSLS_NCCL_TRY(g_nccl.AllGather(w->d_scal + kScalSxy, w->d_gather, kStepScalars, kNcclFloat64, w->comm->comm, st));
+        }
     } else {
         EpiPlain epi{B.g[nxt]};
         if (int rc = launch_at(q, B.r[nxt], epi, st, done)) return rc;
     }
     // ---- decision, and the pull-back of a back-tracked trial point ----------------------------------
-    decide_kernel<<<1, 32, 0, st>>>(S, w->d_scal, (need_dots && dist) ? w->d_gather : nullptr, d, w->d_prog,
-                                    w->d_prog ? w->d_prog + w->prog_cap : nullptr, 0);
+    if (need_dots && p2p) {
+        const bsls_comm *c = w->comm;
+        decide_kernel<<<1, 32, 0, st>>>(S, w->d_scal, c->view.gath[c->rank], d, w->d_prog, w->d_prog ? w->d_prog + w->prog_cap : nullptr, 0,
+                                        c->view.flags[c->rank] + 2 * c->nranks, c->epoch);
+    } else {
+        decide_kernel<<<1, 32, 0, st>>>(S, w->d_scal, (need_dots && dist) ? w->d_gather : nullptr, d, w->d_prog,
+                                        w->d_prog ? w->d_prog + w->prog_cap : nullptr, 0);
+    }
     BSLS_LAUNCH_CHECK();
     ++*extra_launches;
     if (d.search) {
@@ -1180,13 +1289,17 @@ int bsls_batch_solve_f64(bsls_lsq *q, const bsls_plan *plan, double *x, const bs
     if (int rc = solve_tiny(q, plan, x, o, res, progress_f, progress_t, cap, st)) return rc < 0 ? BSLS_OK : rc;
     const DevOpts d = make_dev_opts(o, w, cap);
     LoopBuffers B{{x, q->wxn}, {q->wg, q->wgn}, {q->r, q->r2}};
+    if (use_p2p(q)) {  // the residual lives in the exchange region: the owners of the rows write it there
+        B.r[0] = w->comm->view.rfull[w->comm->rank][0];
+        B.r[1] = w->comm->view.rfull[w->comm->rank][1];
+    }
     const int launches0 = w->launches;
     int extra = 0;
 
     BSLS_CUDA_TRY(cudaEventRecord(q->ev0, st));
     BSLS_CUDA_TRY(cudaMemsetAsync(w->d_state, 0, sizeof(DevState), st));
     // f = obj(x, g) at the starting point
-    if (int rc = residual(q, B.x[0], B.r[0], q->b, st)) return rc;
+    if (int rc = residual(q, B.x[0], B.r[0], q->b, st, nullptr, nullptr, use_p2p(q) ? 0 : -1)) return rc;
     {
         EpiPlain epi{B.g[0]};
         if (int rc = launch_at(q, B.r[0], epi, st)) return rc;

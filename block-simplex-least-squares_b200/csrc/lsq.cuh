@@ -809,9 +809,20 @@ __device__ __forceinline__ void decide_step(DevState *st, const double *scal, co
     st->done = code;
 }
 
-__global__ void decide_kernel(DevState *st, const double *__restrict__ scal, const double *__restrict__ gathered, DevOpts o,
-                              double *__restrict__ progress_f, double *__restrict__ progress_t, int first) {
-    if (threadIdx.x || blockIdx.x) return;
+// wait_flags != null (peer-memory build, p2p.cuh): the step scalars of the other ranks arrive by NVLink stores; lane q waits
+// until rank q has raised its flag for this evaluation before lane 0 reads them
+__global__ void decide_kernel(DevState *st, const double *__restrict__ scal, const double *gathered, DevOpts o,
+                              double *__restrict__ progress_f, double *__restrict__ progress_t, int first,
+                              const unsigned long long *wait_flags = nullptr, unsigned long long epoch = 0) {
+    if (blockIdx.x) return;
+    if (wait_flags && !st->done && (int)threadIdx.x < o.nranks) {
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(wait_flags + threadIdx.x) : "memory");
+        } while (v < epoch);
+    }
+    __syncwarp();
+    if (threadIdx.x) return;
     decide_step(st, scal, gathered, o, progress_f, progress_t, first);
 }
 

@@ -74,6 +74,36 @@ class Communicator:
     def handle(self):
         return self._handle
 
+    def enable_p2p(self, m):
+        """Peer-memory exchange for link vectors of ``m`` entries (bsls_comm_p2p_alloc / _open): every rank allocates its
+        region, torch.distributed carries the 64-byte CUDA IPC handles, every rank maps the regions of the others.  The
+        sharded solver loop then reduces A x over NVLink loads / stores (csrc/p2p.cuh) instead of ncclAllReduce.
+        Collective: every rank of the group must call it.  Returns True when the exchange is in place; on any failure
+        (no peer access, more than 8 ranks, BSLS_P2P=0) the NCCL path stays and False is returned."""
+        import torch.distributed as dist
+        L = _lib.lib()
+        if getattr(self, "_p2p_m", None) is not None:
+            return self._p2p_m == int(m) and bool(L.bsls_comm_p2p_ready(self._handle))
+        self._p2p_m = int(m)
+        ok = os.environ.get("BSLS_P2P", "1") != "0" and 2 <= self.world <= 8
+        handle = ctypes.create_string_buffer(64)
+        if ok:
+            with torch.cuda.device(self.device):
+                ok = L.bsls_comm_p2p_alloc(self._handle, int(m), handle) == _lib.OK
+        box = [None] * self.world
+        dist.all_gather_object(box, bytes(handle.raw) if ok else None)
+        if any(h is None for h in box):
+            L.bsls_comm_p2p_disable(self._handle)
+            return False
+        blob = ctypes.create_string_buffer(b"".join(box), 64 * self.world)
+        with torch.cuda.device(self.device):
+            opened = L.bsls_comm_p2p_open(self._handle, blob) == _lib.OK
+        flags = [None] * self.world
+        dist.all_gather_object(flags, bool(opened))
+        if not all(flags):
+            L.bsls_comm_p2p_disable(self._handle)
+        return all(flags) and bool(L.bsls_comm_p2p_ready(self._handle))
+
     def allreduce_sum_(self, t):
         _check_vec(t, t.shape[0], "buffer")
         with torch.cuda.device(t.device):
@@ -287,6 +317,8 @@ class LsqProblem:
         """OD blocks sharded over ranks: A x is summed over the ranks of ``comm``."""
         self.comm = comm
         _lib.check(_lib.lib().bsls_lsq_set_comm(self._handle, None if comm is None else comm.handle))
+        if comm is not None and comm.world > 1:
+            comm.enable_p2p(self.m)      # collective; falls back to NCCL when peer memory cannot be mapped
 
     def set_b(self, b):
         self.b = _dev_tensor(b, _F64, self.device).reshape(-1)

@@ -146,6 +146,16 @@ BSLS_API int bsls_comm_unique_id(const char *nccl_path, char id[128]);
 BSLS_API int bsls_comm_create(const char *nccl_path, int nranks, int rank, const char id[128], bsls_comm **out);
 BSLS_API int bsls_comm_destroy(bsls_comm *comm);
 BSLS_API int bsls_comm_allreduce_sum_f64(bsls_comm *comm, double *d_buf, int64_t count, bsls_stream_t stream);
+/* Optional peer-memory exchange for the sharded solver loop (2..8 ranks of one NVSwitch domain): every rank allocates an
+ * exchange region for link vectors of m entries (bsls_comm_p2p_alloc returns its 64-byte CUDA IPC handle), the caller
+ * gathers the handles of all ranks (in rank order) and every rank maps them (bsls_comm_p2p_open).  The solver loop then
+ * sums the link vector, subtracts b, forms the norms and distributes the result with ONE kernel over NVLink loads /
+ * stores instead of ncclAllReduce + kernel, and exchanges the step scalars by NVLink stores instead of ncclAllGather.
+ * Results are bit-identical on all ranks (sums in rank order).  Everything else keeps using NCCL. */
+BSLS_API int bsls_comm_p2p_alloc(bsls_comm *comm, int64_t m, char handle[64]);
+BSLS_API int bsls_comm_p2p_open(bsls_comm *comm, const char *handles);
+BSLS_API int bsls_comm_p2p_ready(const bsls_comm *comm);
+BSLS_API int bsls_comm_p2p_disable(bsls_comm *comm);   /* all ranks together, when one of them could not map its peers */
 
 /* The problem 0.5 |A x - b|^2.  A is given as CSR with m rows and A^T as CSR with n rows -- the
  * two matrices the reference keeps (python/algorithm_utils.py:199-200).  All arrays are DEVICE

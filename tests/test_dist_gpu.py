@@ -42,23 +42,30 @@ assert abs(f0 - .5 * r.dot(r)) <= 1e-12 * abs(f0), (f0, .5 * r.dot(r))
 np.testing.assert_allclose(g.cpu().numpy(), A.T.dot(r)[lo:hi], rtol=1e-11, atol=1e-12)
 sol = bsls_b200.BATCH.solve_BB(parts[3], parts[1], parts[2], xl, max_iter=300)
 md = bsls_b200.BATCH.solve_MD(parts[3], ls, parts[0], xl, max_iter=40)
+lb = bsls_b200.BATCH.solve_LBFGS(parts[3], parts[1], parts[2], xl, max_iter=60)
+p2p = bool(bsls_b200._lib.lib().bsls_comm_p2p_ready(comm.handle))
 xs = [None] * world
 dist.all_gather_object(xs, sol["x"].cpu().numpy())
 if rank == 0:
     x = np.concatenate(xs)
     rr = A.dot(x) - b
-    print("RESULT " + json.dumps({"f": sol["f"], "f_check": float(.5 * rr.dot(rr)), "iters": sol["iterations"], "md_f": md["f"]}))
+    print("RESULT " + json.dumps({"f": sol["f"], "f_check": float(.5 * rr.dot(rr)), "iters": sol["iterations"], "md_f": md["f"],
+                                  "lbfgs_f": lb["f"], "p2p": p2p}))
 dist.barrier()
 dist.destroy_process_group()
 '''
 
 
-def test_sharded_bb_matches_single_gpu(tmp_path):
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+def test_sharded_bb_matches_single_gpu(tmp_path, exchange):
+    """exchange = p2p: the link vector is reduced by the library's own kernel over NVLink peer memory (csrc/p2p.cuh);
+    nccl: ncclAllReduce + ncclAllGather (BSLS_P2P=0)."""
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     script = tmp_path / "worker.py"
     script.write_text(WORKER % ROOT)
     env = dict(os.environ)
+    env["BSLS_P2P"] = "1" if exchange == "p2p" else "0"
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                           "--master-addr", "127.0.0.1", "--master-port", "29617", str(script)],
                          capture_output=True, text=True, timeout=600, env=env)
@@ -66,6 +73,7 @@ def test_sharded_bb_matches_single_gpu(tmp_path):
     line = [l for l in out.stdout.splitlines() if l.startswith("RESULT ")][-1]
     res = json.loads(line[len("RESULT "):])
     assert res["f"] == pytest.approx(res["f_check"], rel=1e-10)
+    assert res["p2p"] == (exchange == "p2p")
     # single GPU, same problem
     import numpy as np
     import scipy.sparse as sps
@@ -84,3 +92,5 @@ def test_sharded_bb_matches_single_gpu(tmp_path):
     assert res["f"] == pytest.approx(sol["f"], rel=1e-6)
     md = bsls_b200.BATCH.solve_MD(parts[3], starts, parts[0], x0, max_iter=40)
     assert res["md_f"] == pytest.approx(md["f"], rel=1e-9)
+    lb = bsls_b200.BATCH.solve_LBFGS(parts[3], parts[1], parts[2], x0, max_iter=60)
+    assert res["lbfgs_f"] == pytest.approx(lb["f"], rel=1e-6)
