@@ -343,7 +343,11 @@ class LsqProblem:
         matrix with torch's sort on the device; the per-iteration products use only library kernels."""
         L = _lib.lib()
         if panel_cols is None:
-            panel_cols = max(1, l2_budget_bytes // 8)
+            # as few panels as fit the budget, all of the same width (a short last panel has short row pieces, which cost
+            # more per entry): 160 MB of x -> 4 x 40 MB rather than 3 x 48 + 16
+            budget_cols = max(1, l2_budget_bytes // 8)
+            P = (self.n + budget_cols - 1) // budget_cols
+            panel_cols = (self.n + P - 1) // P if P > 0 else self.n
         P = (self.n + panel_cols - 1) // panel_cols
         if P <= 1:
             _lib.check(L.bsls_lsq_set_panels(self._handle, 0, None, None, None))
