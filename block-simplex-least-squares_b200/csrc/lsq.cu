@@ -214,14 +214,28 @@ template <class K> int resident_grid(K kern, int threads) {
     return g < kRedMaxGrid ? g : kRedMaxGrid;
 }
 
+// BSLS_SPMV_V8=0 keeps the round-1 inner loop (4 gathers per lane and pass + remainder loop) for A/B measurements
+inline bool vector8_on() {
+    const char *e = getenv("BSLS_SPMV_V8");
+    return !(e && atoi(e) == 0);
+}
+
 template <class Epi, int LANES>
 int launch_vector(bsls_ws *w, int64_t rows, const int64_t *ptr, const int32_t *idx, const double *val, const double *v,
                   const Epi &epi, cudaStream_t st, const int *skip) {
     constexpr int T = 256;
+    int64_t want = (rows * LANES + T - 1) / T;
+    if (vector8_on()) {
+        static thread_local PerDevice<int> full8_pd;
+        int &full8 = full8_pd.get(0);
+        if (!full8) full8 = resident_grid(spmv_vector8_kernel<Epi, T, LANES>, T);
+        const int grid = (int)(want < full8 ? (want < 1 ? 1 : want) : full8);
+        spmv_vector8_kernel<Epi, T, LANES><<<grid, T, 0, st>>>(rows, ptr, idx, val, v, epi, w->red, skip);
+        return 0;
+    }
     static thread_local PerDevice<int> full_pd;
     int &full = full_pd.get(0);
     if (!full) full = resident_grid(spmv_vector_kernel<Epi, T, LANES>, T);
-    int64_t want = (rows * LANES + T - 1) / T;
     const int grid = (int)(want < full ? (want < 1 ? 1 : want) : full);
     spmv_vector_kernel<Epi, T, LANES><<<grid, T, 0, st>>>(rows, ptr, idx, val, v, epi, w->red, skip);
     return 0;

@@ -395,6 +395,57 @@ spmv_vector_kernel(int64_t rows, const int64_t *__restrict__ ptr, const int32_t 
     grid_reduce<Epi::NSUM, Epi::NMAX, THREADS, Epi>(acc, red);
 }
 
+// ---- VECTOR SpMV for short rows: every lane takes up to 8 entries of its row in ONE pass ----------------------------
+// The column panels of A cut a link row into pieces of ~40-50 entries.  The kernel above walks such a piece in steps of
+// 4 * LANES plus a remainder loop: two dependent rounds of gathers.  Here a lane fetches its (up to) eight indices at
+// once, predicated on the row end, and has all its gathers in flight together; longer rows take further passes.
+template <class Epi, int THREADS, int LANES>
+__global__ void __launch_bounds__(THREADS)
+spmv_vector8_kernel(int64_t rows, const int64_t *__restrict__ ptr, const int32_t *__restrict__ idx,
+                    const double *__restrict__ val, const double *__restrict__ v, Epi epi, RedCtx red, const int *__restrict__ skip) {
+    if (skip && *skip) return;
+    constexpr int NA = Epi::NSUM + Epi::NMAX;
+    double acc[NA];
+#pragma unroll
+    for (int k = 0; k < NA; ++k) acc[k] = 0.0;
+    const int sub = threadIdx.x & (LANES - 1);
+    const int64_t group = ((int64_t)blockIdx.x * THREADS + threadIdx.x) / LANES;
+    const int64_t ngroups = (int64_t)gridDim.x * THREADS / LANES;
+    const int64_t rounds = (rows + ngroups - 1) / ngroups;  // uniform trip count: shuffles stay converged
+    for (int64_t it = 0; it < rounds; ++it) {
+        const int64_t row = it * ngroups + group;
+        const bool valid = row < rows;
+        const int64_t p0 = valid ? ptr[row] : 0, p1 = valid ? ptr[row + 1] : 0;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        for (int64_t p = p0 + sub; p < p1; p += 8 * LANES) {
+            int32_t j[8];
+            double w[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) j[u] = (p + u * LANES < p1) ? __ldcs(idx + p + u * LANES) : -1;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) w[u] = (j[u] >= 0) ? gather(v, j[u]) : 0.0;
+            if (val) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (j[u] >= 0) w[u] *= __ldcs(val + p + u * LANES);
+            }
+            s0 += w[0];
+            s1 += w[1];
+            s2 += w[2];
+            s3 += w[3];
+            s0 += w[4];
+            s1 += w[5];
+            s2 += w[6];
+            s3 += w[7];
+        }
+        double sum = (s0 + s1) + (s2 + s3);
+#pragma unroll
+        for (int o = LANES / 2; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (valid && sub == 0) epi.apply(row, sum, acc);
+    }
+    grid_reduce<Epi::NSUM, Epi::NMAX, THREADS, Epi>(acc, red);
+}
+
 // ---- vector kernels -------------------------------------------------------------------------------
 // out = a x + b y, each product rounded on its own (np.add(x, -t*g, x_new); (1-t)*x + t*x_new)
 // `out` may alias x or y (element i is read before it is written).
