@@ -190,10 +190,16 @@ bool all_ones(const double *d_val, int64_t nnz) {
     return !h_bad;
 }
 
+// BSLS_SPMV_V8=0 keeps the round-1 inner loop (4 gathers per lane and pass + remainder loop) for A/B measurements
+inline bool vector8_on() {
+    const char *e = getenv("BSLS_SPMV_V8");
+    return !(e && atoi(e) == 0);
+}
+
 int pick_mode(int64_t nnz, int64_t rows) {
     const double avg = rows > 0 ? (double)nnz / (double)rows : 0.0;
     if (avg <= 32.0) return 1;
-    if (avg < 64.0) return 8;
+    if (avg < 64.0) return vector8_on() ? 4 : 8;  // spmv_vector8_kernel: 4 lanes x 8 entries cover a ~40-50-entry row piece in two passes (measured: 0.726 against 0.754 ms for 1.6e8 entries)
     if (avg < 128.0) return 16;
     return 32;
 }
@@ -212,12 +218,6 @@ template <class K> int resident_grid(K kern, int threads) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, threads, 0) != cudaSuccess || per < 1) per = 1;
     const int g = sms * per;
     return g < kRedMaxGrid ? g : kRedMaxGrid;
-}
-
-// BSLS_SPMV_V8=0 keeps the round-1 inner loop (4 gathers per lane and pass + remainder loop) for A/B measurements
-inline bool vector8_on() {
-    const char *e = getenv("BSLS_SPMV_V8");
-    return !(e && atoi(e) == 0);
 }
 
 template <class Epi, int LANES>
@@ -1125,8 +1125,8 @@ void finish_result(bsls_batch_result *res, const DevState &fin, int launches, fl
 }
 
 // sliced-ELL copy of one CSR side (solver_tiny.cuh)
-int build_sell(const int64_t *ptr, const int32_t *idx, const double *val, int rows, int32_t **goff_out, int32_t **sidx_out, double **sval_out,
-               cudaStream_t st) {
+int build_sell(const int64_t *ptr, const int32_t *idx, const double *val, int rows, int pad, int32_t **goff_out, int32_t **sidx_out,
+               double **sval_out, cudaStream_t st) {
     const int groups = (rows + 31) / 32;
     BSLS_CUDA_TRY(cudaMalloc(goff_out, sizeof(int32_t) * ((size_t)groups + 1)));
     sell_widths_kernel<<<(groups + 127) / 128, 128, 0, st>>>(ptr, rows, groups, *goff_out);
@@ -1137,7 +1137,7 @@ int build_sell(const int64_t *ptr, const int32_t *idx, const double *val, int ro
     BSLS_CUDA_TRY(cudaStreamSynchronize(st));
     BSLS_CUDA_TRY(cudaMalloc(sidx_out, sizeof(int32_t) * (size_t)(total > 0 ? total : 1)));
     if (val) BSLS_CUDA_TRY(cudaMalloc(sval_out, sizeof(double) * (size_t)(total > 0 ? total : 1)));
-    sell_fill_kernel<<<(32 * groups + 255) / 256, 256, 0, st>>>(ptr, idx, val, rows, groups, *goff_out, *sidx_out, val ? *sval_out : nullptr);
+    sell_fill_kernel<<<(32 * groups + 255) / 256, 256, 0, st>>>(ptr, idx, val, rows, groups, *goff_out, *sidx_out, val ? *sval_out : nullptr, pad);
     BSLS_LAUNCH_CHECK();
     return BSLS_OK;
 }
@@ -1160,8 +1160,8 @@ int solve_tiny(bsls_lsq *q, const bsls_plan *plan, double *x, const bsls_batch_o
         attr = true;
     }
     if (!q->sell_ready) {
-        if (int rc = build_sell(q->a_ptr, q->a_idx, q->a_val, (int)q->m, &q->sell_goff[0], &q->sell_idx[0], &q->sell_val[0], st)) return rc;
-        if (int rc = build_sell(q->t_ptr, q->t_idx, q->t_val, (int)q->n, &q->sell_goff[1], &q->sell_idx[1], &q->sell_val[1], st)) return rc;
+        if (int rc = build_sell(q->a_ptr, q->a_idx, q->a_val, (int)q->m, (int)q->n, &q->sell_goff[0], &q->sell_idx[0], &q->sell_val[0], st)) return rc;
+        if (int rc = build_sell(q->t_ptr, q->t_idx, q->t_val, (int)q->n, (int)q->m, &q->sell_goff[1], &q->sell_idx[1], &q->sell_val[1], st)) return rc;
         q->sell_ready = true;
     }
     TinyArgs a{};

@@ -39,7 +39,7 @@ struct TinyArgs {
     int proj_mode;           // 0 simplex, 1 l1-ball
 };
 
-inline size_t tiny_smem_bytes(int n, int m) { return sizeof(double) * (4 * (size_t)n + 3 * (size_t)m + 64); }
+inline size_t tiny_smem_bytes(int n, int m) { return sizeof(double) * (4 * (size_t)(n + 1) + 3 * (size_t)(m + 1) + 64); }
 
 // deterministic CTA reduction of NS sums and NM maxima (fixed tree); result valid in thread 0
 template <int NS, int NM> __device__ __forceinline__ void tiny_reduce(double (&acc)[NS + NM], double *s_red /* 32 * (NS+NM) */, double *out) {
@@ -92,26 +92,32 @@ __device__ __forceinline__ void tiny_proj_simplex(double *w, double *u, int K) {
     }
 }
 
-// One row of a product, entries added left to right (scipy's csr_matvec order), the index loads issued eight at a time so
-// that their L2 latency overlaps (the adds stay in order).  All lanes of a warp belong to one group: the trip count is
-// warp-uniform.
-__device__ __forceinline__ double tiny_row_dot(const SellMatrix &M, int row, const double *v) {
+// One row of a product, entries added left to right (scipy's csr_matvec order).  Padding entries point at a slot that holds
+// 0.0 (sum + 0.0 keeps the bits of sum), group widths are multiples of 4: the loop is unconditional, four index loads in
+// flight per pass.  `vec` is an offset into the shared-memory arena: the compiler emits LDS, not generic loads.
+__device__ __forceinline__ double tiny_row_dot(const SellMatrix &M, int row, const double *sm, int vec) {
     const int g = row >> 5, lane = row & 31;
-    const int base = M.goff[g] + lane;
+    const int32_t *ip = M.idx + M.goff[g] + lane;
     const int width = (M.goff[g + 1] - M.goff[g]) >> 5;
     double sum = 0.0;
-    for (int k0 = 0; k0 < width; k0 += 8) {
-        int32_t j[8];
-        double a[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) j[u] = (k0 + u < width) ? M.idx[base + 32 * (k0 + u)] : -1;
-        if (M.val) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) a[u] = (k0 + u < width) ? M.val[base + 32 * (k0 + u)] : 0.0;
+    if (M.val) {
+        const double *vp = M.val + M.goff[g] + lane;
+        for (int k = 0; k < width; k += 4) {
+            const int j0 = ip[32 * k], j1 = ip[32 * k + 32], j2 = ip[32 * k + 64], j3 = ip[32 * k + 96];
+            const double a0 = vp[32 * k], a1 = vp[32 * k + 32], a2 = vp[32 * k + 64], a3 = vp[32 * k + 96];
+            sum += a0 * sm[vec + j0];
+            sum += a1 * sm[vec + j1];
+            sum += a2 * sm[vec + j2];
+            sum += a3 * sm[vec + j3];
         }
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-            if (j[u] >= 0) sum += (M.val ? a[u] : 1.0) * v[j[u]];
+    } else {
+        for (int k = 0; k < width; k += 4) {
+            const int j0 = ip[32 * k], j1 = ip[32 * k + 32], j2 = ip[32 * k + 64], j3 = ip[32 * k + 96];
+            sum += sm[vec + j0];
+            sum += sm[vec + j1];
+            sum += sm[vec + j2];
+            sum += sm[vec + j3];
+        }
     }
     return sum;
 }
@@ -121,7 +127,7 @@ __global__ void sell_widths_kernel(const int64_t *__restrict__ ptr, int rows, in
     for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x) {
         int w = 0;
         for (int r = 32 * g; r < 32 * g + 32 && r < rows; ++r) w = max(w, (int)(ptr[r + 1] - ptr[r]));
-        goff[g + 1] = 32 * w;
+        goff[g + 1] = 32 * ((w + 3) & ~3);  // widths are multiples of 4 (tiny_row_dot)
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) goff[0] = 0;
 }
@@ -133,14 +139,15 @@ __global__ void sell_scan_kernel(int32_t *goff, int groups) {  // a few hundred 
         goff[g] = run;
     }
 }
+// pad = the column id padding entries carry (the slot after the last entry of the gathered vector, which holds 0.0)
 __global__ void sell_fill_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ idx, const double *__restrict__ val, int rows,
-                                 int groups, const int32_t *__restrict__ goff, int32_t *__restrict__ sidx, double *__restrict__ sval) {
+                                 int groups, const int32_t *__restrict__ goff, int32_t *__restrict__ sidx, double *__restrict__ sval, int pad) {
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < 32 * groups; r += gridDim.x * blockDim.x) {
         const int g = r >> 5, lane = r & 31;
         const int base = goff[g] + lane, width = (goff[g + 1] - goff[g]) >> 5;
         const int64_t p0 = r < rows ? ptr[r] : 0, len = r < rows ? ptr[r + 1] - p0 : 0;
         for (int k = 0; k < width; ++k) {
-            sidx[base + 32 * k] = k < len ? idx[p0 + k] : -1;
+            sidx[base + 32 * k] = k < len ? idx[p0 + k] : pad;
             if (sval) sval[base + 32 * k] = k < len ? val[p0 + k] : 0.0;
         }
     }
@@ -149,32 +156,31 @@ __global__ void sell_fill_kernel(const int64_t *__restrict__ ptr, const int32_t 
 __global__ void __launch_bounds__(kTinyThreads, 1) solver_tiny_kernel(TinyArgs a, DevOpts o) {
     extern __shared__ __align__(16) double tiny_sm[];
     const int n = a.n, m = a.m, tid = threadIdx.x;
-    double *xs[2] = {tiny_sm, tiny_sm + n};
-    double *gs[2] = {tiny_sm + 2 * n, tiny_sm + 3 * n};
-    double *rs[2] = {tiny_sm + 4 * n, tiny_sm + 4 * n + m};
-    double *bs = tiny_sm + 4 * n + 2 * m;
-    double *scal = bs + m;  // kScalCount scalars + reduction scratch
+    // arena offsets (vectors carry one extra slot that holds 0.0: the target of padding entries)
+    const int n1 = n + 1, m1 = m + 1;
+    const int XS = 0, GS = 2 * n1, RS = 4 * n1, BS = 4 * n1 + 2 * m1, SC = BS + m1;  // x[2], g[2], r[2], b, scalars
+    double *scal = tiny_sm + SC;
     __shared__ double s_red[32 * 5];
     __shared__ double s_out[5];
     __shared__ DevState s_state;  // the solver state lives on chip for the whole solve; copied out at the end
     DevState *st = &s_state;
-    if (tid == 0) {
-        s_state = DevState{};
+    if (tid == 0) s_state = DevState{};
+    for (int i = tid; i < n; i += kTinyThreads) tiny_sm[XS + i] = a.x[i];
+    for (int i = tid; i < m; i += kTinyThreads) tiny_sm[BS + i] = a.b[i];
+    if (tid < 2) {
+        tiny_sm[XS + tid * n1 + n] = 0.0;
+        tiny_sm[RS + tid * m1 + m] = 0.0;
     }
-
-    for (int i = tid; i < n; i += kTinyThreads) xs[0][i] = a.x[i];
-    for (int i = tid; i < m; i += kTinyThreads) bs[i] = a.b[i];
     if (tid < kScalCount) scal[tid] = 0.0;
     __syncthreads();
 
-    // r = A x - b and the sums of EpiResidual; g = A^T r and the sums of EpiGradBB (or only <g,g>)
-    auto residual = [&](const double *x, double *r, const double *r_old) {
+    // r = A x - b and the sums of EpiResidual (x, r, r_old: arena offsets; r_old < 0: none)
+    auto residual = [&](int x, int r, int r_old) {
         double acc[3] = {0, 0, 0};
         for (int row = tid; row < m; row += kTinyThreads) {
-            const double sum = tiny_row_dot(a.A, row, x);
-            const double v = sum - bs[row];
-            r[row] = v;
-            residual_sums(v, r_old ? r_old[row] : 0.0, r_old != nullptr, acc);
+            const double v = tiny_row_dot(a.A, row, tiny_sm, x) - tiny_sm[BS + row];
+            tiny_sm[r + row] = v;
+            residual_sums(v, r_old >= 0 ? tiny_sm[r_old + row] : 0.0, r_old >= 0, acc);
         }
         tiny_reduce<3, 0>(acc, s_red, s_out);
         if (tid == 0) {
@@ -184,14 +190,15 @@ __global__ void __launch_bounds__(kTinyThreads, 1) solver_tiny_kernel(TinyArgs a
             scal[kScalDrdr] = s_out[2];
         }
     };
-    auto gradient = [&](const double *r, double *g_new, const double *g, const double *x, const double *x_new) {
+    // g_new = A^T r and the sums of EpiGradBB (g < 0: only <g_new, g_new>)
+    auto gradient = [&](int r, int g_new, int g, int x, int x_new) {
         double acc[5] = {0, 0, 0, 0, 0};
         for (int row = tid; row < n; row += kTinyThreads) {
-            const double dot = tiny_row_dot(a.AT, row, r);
-            g_new[row] = dot;
+            const double dot = tiny_row_dot(a.AT, row, tiny_sm, r);
+            tiny_sm[g_new + row] = dot;
             acc[3] += dot * dot;
-            if (g) {
-                const double go = g[row], dx = x_new[row] - x[row], dg = dot - go;
+            if (g >= 0) {
+                const double go = tiny_sm[g + row], dx = tiny_sm[x_new + row] - tiny_sm[x + row], dg = dot - go;
                 acc[0] += dx * dg;
                 acc[1] += dg * dg;
                 acc[2] += go * dx;
@@ -209,24 +216,25 @@ __global__ void __launch_bounds__(kTinyThreads, 1) solver_tiny_kernel(TinyArgs a
     };
 
     // f = obj(x, g) at the starting point
-    residual(xs[0], rs[0], nullptr);
-    gradient(rs[0], gs[0], nullptr, nullptr, nullptr);
+    residual(XS, RS, -1);
+    gradient(RS, GS, -1, -1, -1);
     if (tid == 0) decide_step(st, scal, nullptr, o, a.progress_f, a.progress_t, 1);
     __syncthreads();
 
     int cur = 0;
     while (!st->done) {
         const int nxt = cur ^ 1;
+        const int xc = XS + cur * n1, xn = XS + nxt * n1, gc = GS + cur * n1, gn = GS + nxt * n1, rc = RS + cur * m1, rn = RS + nxt * m1;
         const double nt = -st->t;
         // ---- x_new = proj(x - t g): one thread per OD block ---------------------------------------
         for (int blk = tid; blk < a.nb; blk += kTinyThreads) {
             const int s = a.starts[blk], K = a.starts[blk + 1] - s;
-            double *w = xs[nxt] + s;   // the trial point is formed in place; the trial gradient's slot is the sort scratch
+            double *w = tiny_sm + xn + s;   // the trial point is formed in place; the trial gradient's slot is the sort scratch
             double sum = 0.0;
             for (int i = 0; i < K; ++i) {
-                const double u = nt * gs[cur][s + i];  // np.add(x, -t*g, x_new): product and sum rounded separately
-                double v = xs[cur][s + i] + u;
-                if (a.proj_mode == 1) {                // proj_multi_ball (proj_simplex.h:54-62)
+                const double u = nt * tiny_sm[gc + s + i];  // np.add(x, -t*g, x_new): product and sum rounded separately
+                double v = tiny_sm[xc + s + i] + u;
+                if (a.proj_mode == 1) {                     // proj_multi_ball (proj_simplex.h:54-62)
                     if (v < 0.0)
                         v = 0.0;
                     else
@@ -234,12 +242,12 @@ __global__ void __launch_bounds__(kTinyThreads, 1) solver_tiny_kernel(TinyArgs a
                 }
                 w[i] = v;
             }
-            if (a.proj_mode == 0 || sum > 1.0) tiny_proj_simplex(w, gs[nxt] + s, K);
+            if (a.proj_mode == 0 || sum > 1.0) tiny_proj_simplex(w, tiny_sm + gn + s, K);
         }
         __syncthreads();
         // ---- objective and gradient at the trial point, decision, pull-back ------------------------------
-        residual(xs[nxt], rs[nxt], rs[cur]);
-        gradient(rs[nxt], gs[nxt], gs[cur], xs[cur], xs[nxt]);
+        residual(xn, rn, rc);
+        gradient(rn, gn, gc, xc, xn);
         if (tid == 0) decide_step(st, scal, nullptr, o, a.progress_f, a.progress_t, 0);
         __syncthreads();
         const double tau = st->tau;
@@ -247,28 +255,28 @@ __global__ void __launch_bounds__(kTinyThreads, 1) solver_tiny_kernel(TinyArgs a
             const double c = 1.0 - tau;
             for (int i = tid; i < n; i += kTinyThreads) {
                 if (tau == 0.0) {
-                    xs[nxt][i] = xs[cur][i];
-                    gs[nxt][i] = gs[cur][i];
+                    tiny_sm[xn + i] = tiny_sm[xc + i];
+                    tiny_sm[gn + i] = tiny_sm[gc + i];
                 } else {
-                    const double u = c * xs[cur][i];
-                    xs[nxt][i] = u + tau * xs[nxt][i];
-                    const double v = c * gs[cur][i];
-                    gs[nxt][i] = v + tau * gs[nxt][i];
+                    const double u = c * tiny_sm[xc + i];
+                    tiny_sm[xn + i] = u + tau * tiny_sm[xn + i];
+                    const double v = c * tiny_sm[gc + i];
+                    tiny_sm[gn + i] = v + tau * tiny_sm[gn + i];
                 }
             }
             for (int i = tid; i < m; i += kTinyThreads) {
                 if (tau == 0.0) {
-                    rs[nxt][i] = rs[cur][i];
+                    tiny_sm[rn + i] = tiny_sm[rc + i];
                 } else {
-                    const double u = c * rs[cur][i];
-                    rs[nxt][i] = u + tau * rs[nxt][i];
+                    const double u = c * tiny_sm[rc + i];
+                    tiny_sm[rn + i] = u + tau * tiny_sm[rn + i];
                 }
             }
             __syncthreads();
         }
         cur = nxt;
     }
-    for (int i = tid; i < n; i += kTinyThreads) a.x[i] = xs[cur][i];
+    for (int i = tid; i < n; i += kTinyThreads) a.x[i] = tiny_sm[XS + cur * n1 + i];
     if (tid == 0) *a.st = s_state;
 }
 
