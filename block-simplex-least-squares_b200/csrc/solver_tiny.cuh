@@ -11,6 +11,7 @@
 // A^T stream from L2, from sliced-ELL copies made once per problem (SellMatrix).  No host round trip, no kernel boundary, no global synchronisation inside the solve.
 #pragma once
 #include "lsq.cuh"
+#include "simplex_core.cuh"
 
 namespace bsls {
 
@@ -99,27 +100,48 @@ __device__ __forceinline__ double tiny_row_dot(const SellMatrix &M, int row, con
     const int g = row >> 5, lane = row & 31;
     const int32_t *ip = M.idx + M.goff[g] + lane;
     const int width = (M.goff[g + 1] - M.goff[g]) >> 5;
+    const char *base = reinterpret_cast<const char *>(sm + vec);  // the stored ids are BYTE offsets (8 * column): LDS [id + base]
+    auto at = [&](int off) { return *reinterpret_cast<const double *>(base + off); };
     double sum = 0.0;
     if (M.val) {
         const double *vp = M.val + M.goff[g] + lane;
         for (int k = 0; k < width; k += 4) {
             const int j0 = ip[32 * k], j1 = ip[32 * k + 32], j2 = ip[32 * k + 64], j3 = ip[32 * k + 96];
             const double a0 = vp[32 * k], a1 = vp[32 * k + 32], a2 = vp[32 * k + 64], a3 = vp[32 * k + 96];
-            sum += a0 * sm[vec + j0];
-            sum += a1 * sm[vec + j1];
-            sum += a2 * sm[vec + j2];
-            sum += a3 * sm[vec + j3];
+            sum += a0 * at(j0);
+            sum += a1 * at(j1);
+            sum += a2 * at(j2);
+            sum += a3 * at(j3);
         }
     } else {
         for (int k = 0; k < width; k += 4) {
             const int j0 = ip[32 * k], j1 = ip[32 * k + 32], j2 = ip[32 * k + 64], j3 = ip[32 * k + 96];
-            sum += sm[vec + j0];
-            sum += sm[vec + j1];
-            sum += sm[vec + j2];
-            sum += sm[vec + j3];
+            sum += at(j0);
+            sum += at(j1);
+            sum += at(j2);
+            sum += at(j3);
         }
     }
     return sum;
+}
+
+// x_new block = proj(w) for one OD block in shared memory: blocks of at most 8 values go through the library's register
+// sorting network and its restatement of the reference's scan (simplex_core.cuh: bit-identical to proj_simplex.h:17-34),
+// longer ones through the insertion sort above.
+__device__ __forceinline__ void tiny_project_block(double *w, double *scratch, int K) {
+    if (K <= 8) {
+        double v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = e < K ? w[e] : Num<double>::neg_inf();
+        sort_desc_regs<double, 8>(v);
+        const double shift = simplex_shift_sorted<double, 8, 1>(v, K, 0);
+        for (int e = 0; e < K; ++e) {
+            const double t = shift + w[e];
+            w[e] = (t < 0.0) ? 0.0 : t;
+        }
+    } else {
+        tiny_proj_simplex(w, scratch, K);
+    }
 }
 
 // ---- building the sliced-ELL copies (once per problem handle) ------------------------------------------------
@@ -147,7 +169,7 @@ __global__ void sell_fill_kernel(const int64_t *__restrict__ ptr, const int32_t 
         const int base = goff[g] + lane, width = (goff[g + 1] - goff[g]) >> 5;
         const int64_t p0 = r < rows ? ptr[r] : 0, len = r < rows ? ptr[r + 1] - p0 : 0;
         for (int k = 0; k < width; ++k) {
-            sidx[base + 32 * k] = k < len ? idx[p0 + k] : pad;
+            sidx[base + 32 * k] = 8 * (k < len ? idx[p0 + k] : pad);  // byte offset into the gathered vector
             if (sval) sval[base + 32 * k] = k < len ? val[p0 + k] : 0.0;
         }
     }
@@ -242,7 +264,7 @@ __global__ void __launch_bounds__(kTinyThreads, 1) solver_tiny_kernel(TinyArgs a
                 }
                 w[i] = v;
             }
-            if (a.proj_mode == 0 || sum > 1.0) tiny_proj_simplex(w, tiny_sm + gn + s, K);
+            if (a.proj_mode == 0 || sum > 1.0) tiny_project_block(w, tiny_sm + gn + s, K);
         }
         __syncthreads();
         // ---- objective and gradient at the trial point, decision, pull-back ------------------------------
