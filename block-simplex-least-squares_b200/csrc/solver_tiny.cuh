@@ -96,33 +96,67 @@ __device__ __forceinline__ void tiny_proj_simplex(double *w, double *u, int K) {
 // One row of a product, entries added left to right (scipy's csr_matvec order).  Padding entries point at a slot that holds
 // 0.0 (sum + 0.0 keeps the bits of sum), group widths are multiples of 4: the loop is unconditional, four index loads in
 // flight per pass.  `vec` is an offset into the shared-memory arena: the compiler emits LDS, not generic loads.
-__device__ __forceinline__ double tiny_row_dot(const SellMatrix &M, int row, const double *sm, int vec) {
-    const int g = row >> 5, lane = row & 31;
-    const int32_t *ip = M.idx + M.goff[g] + lane;
-    const int width = (M.goff[g + 1] - M.goff[g]) >> 5;
+// R rows of one thread (row0, row0 + kTinyThreads, ...) at once: their index loads are in flight together, so a pass costs
+// ONE round trip to L2 whatever R is (a thread owns 2 rows of A and 5 of A^T on config 1; one row at a time made the
+// solve latency-bound: 33 dependent round trips per iteration).  Rows beyond `total` give 0.
+template <int R, bool HV>
+__device__ __forceinline__ void tiny_rows_dot_impl(const SellMatrix &M, int row0, int total, const double *sm, int vec, double (&sum)[R]) {
     const char *base = reinterpret_cast<const char *>(sm + vec);  // the stored ids are BYTE offsets (8 * column): LDS [id + base]
     auto at = [&](int off) { return *reinterpret_cast<const double *>(base + off); };
-    double sum = 0.0;
-    if (M.val) {
-        const double *vp = M.val + M.goff[g] + lane;
-        for (int k = 0; k < width; k += 4) {
-            const int j0 = ip[32 * k], j1 = ip[32 * k + 32], j2 = ip[32 * k + 64], j3 = ip[32 * k + 96];
-            const double a0 = vp[32 * k], a1 = vp[32 * k + 32], a2 = vp[32 * k + 64], a3 = vp[32 * k + 96];
-            sum += a0 * at(j0);
-            sum += a1 * at(j1);
-            sum += a2 * at(j2);
-            sum += a3 * at(j3);
+    const int lane = row0 & 31;
+    const int32_t *ip[R];
+    const double *vp[R];
+    int width[R], wmax = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int row = row0 + r * kTinyThreads;
+        sum[r] = 0.0;
+        width[r] = 0;
+        ip[r] = M.idx;
+        vp[r] = M.val;
+        if (row < total) {  // uniform over the warp (total is a multiple of 32 for the padded groups or the whole warp is out)
+            const int g = row >> 5;
+            const int o = M.goff[g];
+            ip[r] = M.idx + o + lane;
+            vp[r] = HV ? M.val + o + lane : nullptr;
+            width[r] = (M.goff[g + 1] - o) >> 5;
         }
+        wmax = max(wmax, width[r]);
+    }
+    for (int k = 0; k < wmax; k += 4) {
+        int j[R][4];
+        double a[HV ? R : 1][4];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (k < width[r]) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) j[r][u] = ip[r][32 * (k + u)];
+                if (HV) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) a[r][u] = vp[r][32 * (k + u)];
+                }
+            }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (k < width[r]) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) sum[r] += HV ? a[r][u] * at(j[r][u]) : at(j[r][u]);
+            }
+    }
+}
+// index-only matrices (0/1 incidence) take R rows at once; with a value array the registers allow one row at a time
+template <int R>
+__device__ __forceinline__ void tiny_rows_dot(const SellMatrix &M, int row0, int total, const double *sm, int vec, double (&sum)[R]) {
+    if (!M.val) {
+        tiny_rows_dot_impl<R, false>(M, row0, total, sm, vec, sum);
     } else {
-        for (int k = 0; k < width; k += 4) {
-            const int j0 = ip[32 * k], j1 = ip[32 * k + 32], j2 = ip[32 * k + 64], j3 = ip[32 * k + 96];
-            sum += at(j0);
-            sum += at(j1);
-            sum += at(j2);
-            sum += at(j3);
+#pragma unroll 1
+        for (int r = 0; r < R; ++r) {
+            double one[1];
+            tiny_rows_dot_impl<1, true>(M, row0 + r * kTinyThreads, total, sm, vec, one);
+            sum[r] = one[0];
         }
     }
-    return sum;
 }
 
 // x_new block = proj(w) for one OD block in shared memory: blocks of at most 8 values go through the library's register
@@ -199,10 +233,19 @@ __global__ void __launch_bounds__(kTinyThreads, 1) solver_tiny_kernel(TinyArgs a
     // r = A x - b and the sums of EpiResidual (x, r, r_old: arena offsets; r_old < 0: none)
     auto residual = [&](int x, int r, int r_old) {
         double acc[3] = {0, 0, 0};
-        for (int row = tid; row < m; row += kTinyThreads) {
-            const double v = tiny_row_dot(a.A, row, tiny_sm, x) - tiny_sm[BS + row];
-            tiny_sm[r + row] = v;
-            residual_sums(v, r_old >= 0 ? tiny_sm[r_old + row] : 0.0, r_old >= 0, acc);
+        constexpr int R = 2;
+        for (int row0 = tid; row0 < m; row0 += R * kTinyThreads) {
+            double dot[R];
+            tiny_rows_dot<R>(a.A, row0, m, tiny_sm, x, dot);
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const int row = row0 + q * kTinyThreads;
+                if (row < m) {
+                    const double v = dot[q] - tiny_sm[BS + row];
+                    tiny_sm[r + row] = v;
+                    residual_sums(v, r_old >= 0 ? tiny_sm[r_old + row] : 0.0, r_old >= 0, acc);
+                }
+            }
         }
         tiny_reduce<3, 0>(acc, s_red, s_out);
         if (tid == 0) {
@@ -215,16 +258,25 @@ __global__ void __launch_bounds__(kTinyThreads, 1) solver_tiny_kernel(TinyArgs a
     // g_new = A^T r and the sums of EpiGradBB (g < 0: only <g_new, g_new>)
     auto gradient = [&](int r, int g_new, int g, int x, int x_new) {
         double acc[5] = {0, 0, 0, 0, 0};
-        for (int row = tid; row < n; row += kTinyThreads) {
-            const double dot = tiny_row_dot(a.AT, row, tiny_sm, r);
-            tiny_sm[g_new + row] = dot;
-            acc[3] += dot * dot;
-            if (g >= 0) {
-                const double go = tiny_sm[g + row], dx = tiny_sm[x_new + row] - tiny_sm[x + row], dg = dot - go;
-                acc[0] += dx * dg;
-                acc[1] += dg * dg;
-                acc[2] += go * dx;
-                acc[4] = fmax(acc[4], fabs(dx));
+        constexpr int R = 3;
+        for (int row0 = tid; row0 < n; row0 += R * kTinyThreads) {
+            double dots[R];
+            tiny_rows_dot<R>(a.AT, row0, n, tiny_sm, r, dots);
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const int row = row0 + q * kTinyThreads;
+                if (row < n) {
+                    const double dot = dots[q];
+                    tiny_sm[g_new + row] = dot;
+                    acc[3] += dot * dot;
+                    if (g >= 0) {
+                        const double go = tiny_sm[g + row], dx = tiny_sm[x_new + row] - tiny_sm[x + row], dg = dot - go;
+                        acc[0] += dx * dg;
+                        acc[1] += dg * dg;
+                        acc[2] += go * dx;
+                        acc[4] = fmax(acc[4], fabs(dx));
+                    }
+                }
             }
         }
         tiny_reduce<4, 1>(acc, s_red, s_out);

@@ -320,6 +320,26 @@ def test_batch_solvers_match_reference(B, gold, tag, name, native, native_loop):
     assert xs.min() >= 0.0
 
 
+def test_batch_solvers_accept_host_vectors(B, gold):
+    """The reference's solvers take and return NumPy vectors: host input (ndarray, pinned or pageable CPU tensor) is staged
+    to the device, the result comes back the same way and equals the device-vector call."""
+    A, b, starts, x0 = problem(gold, "noisy")
+    parts = B.algorithm_utils.get_solver_parts((A, b), starts, 0.1, is_sparse=True)
+    ref = B.BATCH.solve_BB(parts[3], parts[1], parts[2], dev(x0), max_iter=300)
+    for make in (lambda: x0.copy(), lambda: torch.from_numpy(x0.copy()), lambda: torch.from_numpy(x0.copy()).pin_memory()):
+        xin = make()
+        keep = xin.copy() if isinstance(xin, np.ndarray) else xin.clone()
+        sol = B.BATCH.solve_BB(parts[3], parts[1], parts[2], xin, max_iter=300)
+        out = sol["x"]
+        assert isinstance(out, np.ndarray) if isinstance(xin, np.ndarray) else (torch.is_tensor(out) and not out.is_cuda)
+        assert np.array_equal(np.asarray(out), host(ref["x"])) and sol["f"] == ref["f"]
+        assert np.array_equal(np.asarray(xin), np.asarray(keep))            # the caller's start vector is not touched
+    for name in ("pg", "md", "lbfgs"):
+        a = run_batch(B, name, parts, starts, dev(x0), True)
+        h = run_batch(B, name, parts, starts, x0.copy(), True)
+        assert isinstance(h["x"], np.ndarray) and np.array_equal(h["x"], host(a["x"]))
+
+
 def test_small_qp_known_answer(B, gold):
     """tests/fast/test_BATCH.py of the reference: 2-variable QP, solution [.25, .75], f_min 1.875."""
     Q, c, x_true, f_min, min_eig = B.bsls_utils.generate_small_qp()
