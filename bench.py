@@ -650,7 +650,11 @@ def run_ours(args, rank, world, local_rank):
     if os.path.exists(prof):
         with open(prof) as fh:
             tr = json.load(fh)
-        roofline["traffic"] = tr.get("spmv_c5_bytes_per_launch")
+        dom_key = "ax" if dom is kern["ax"] else "atr"
+        per = tr.get("spmv_c5_bytes_per_launch", {})
+        # measured on the full problem of one GPU; a rank of a sharded run moves 1 / world of it
+        roofline["traffic"] = per.get(dom_key) / world if per.get(dom_key) else None
+        roofline["traffic_note"] = per.get(dom_key + "_note")
         roofline["traffic_source"] = tr.get("source")
 
     # ---- e2e: the reference-facing API with HOST vectors, on EVERY rank --------------------------------

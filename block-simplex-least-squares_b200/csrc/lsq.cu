@@ -1325,7 +1325,8 @@ int bsls_batch_solve_f64(bsls_lsq *q, const bsls_plan *plan, double *x, const bs
     BSLS_CUDA_TRY(cudaEventRecord(w->ev_state[1], st));
 
     // iteration k may run only if the state after iteration k - 1 is not `done`; the host learns that one iteration late
-    const int max_body = o->max_iter > 1 ? o->max_iter - 1 : 0;  // the reference stops at i == max_iter, i starting at 1
+    // the reference stops at i == max_iter, i starting at 1; max_iter <= 0 never matches: no iteration limit there either
+    const int max_body = o->max_iter > 1 ? o->max_iter - 1 : (o->max_iter == 1 ? 0 : 0x7fffffff);
     int k = 0;
     for (; k < max_body; ++k) {
         if (int rc = enqueue_iteration(q, plan, B, k & 1, d, o->proj_mode, st, &extra)) return rc;
