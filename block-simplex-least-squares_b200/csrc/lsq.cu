@@ -1179,7 +1179,21 @@ int solve_tiny(bsls_lsq *q, const bsls_plan *plan, double *x, const bsls_batch_o
     a.proj_mode = o->proj_mode;
     const DevOpts d = make_dev_opts(o, w, cap);
     BSLS_CUDA_TRY(cudaEventRecord(q->ev0, st));
-    solver_tiny_kernel<<<1, kTinyThreads, smem, st>>>(a, d);
+    // eight CTAs pay off once a CTA's share is a few rows per warp; BSLS_TINY_CLUSTER=0 / 1 forces one kernel or the other
+    // (both are tested on every small problem)
+    const char *ce = getenv("BSLS_TINY_CLUSTER");
+    const bool clustered = ce ? atoi(ce) != 0 : (plan->nb >= 4 * kTinyCluster && q->m >= 32 * kTinyCluster);
+    if (clustered) {
+        static thread_local PerDevice<bool> cattr_pd;
+        bool &cattr = cattr_pd.get(false);
+        if (!cattr) {
+            BSLS_CUDA_TRY(cudaFuncSetAttribute(solver_tiny_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+            cattr = true;
+        }
+        solver_tiny_cluster_kernel<<<kTinyCluster, kTinyThreads, smem, st>>>(a, d);
+    } else {
+        solver_tiny_kernel<<<1, kTinyThreads, smem, st>>>(a, d);
+    }
     BSLS_LAUNCH_CHECK();
     BSLS_CUDA_TRY(cudaEventRecord(q->ev1, st));
     BSLS_CUDA_TRY(cudaMemcpyAsync(&w->h_state[0], w->d_state, sizeof(DevState), cudaMemcpyDeviceToHost, st));

@@ -275,15 +275,18 @@ def run_batch(B, name, parts, starts, x0, native):
     return B.BATCH.solve_LBFGS(obj_, proj_, ls_, x0, max_iter=150)
 
 
-@pytest.fixture(params=["tiny", "loop"])
+@pytest.fixture(params=["tiny", "cluster", "loop"])
 def native_loop(request, monkeypatch):
-    """The native BATCH solvers have two device-resident loops: one CTA with everything in shared memory for problems
-    that fit (solver_tiny.cuh) and the multi-kernel loop (lsq.cu).  The small test problems qualify for the first;
-    BSLS_NO_TINY=1 sends them through the second."""
+    """The native BATCH solvers have three device-resident loops: one CTA with everything in shared memory for problems
+    that fit, the same on a cluster of 8 CTAs that exchange their slices through distributed shared memory
+    (solver_tiny.cuh), and the multi-kernel loop (lsq.cu).  The small test problems qualify for the first two
+    (BSLS_TINY_CLUSTER picks); BSLS_NO_TINY=1 sends them through the third."""
+    monkeypatch.delenv("BSLS_NO_TINY", raising=False)
+    monkeypatch.delenv("BSLS_TINY_CLUSTER", raising=False)
     if request.param == "loop":
         monkeypatch.setenv("BSLS_NO_TINY", "1")
     else:
-        monkeypatch.delenv("BSLS_NO_TINY", raising=False)
+        monkeypatch.setenv("BSLS_TINY_CLUSTER", "1" if request.param == "cluster" else "0")
     return request.param
 
 
@@ -291,7 +294,7 @@ def native_loop(request, monkeypatch):
 @pytest.mark.parametrize("name", ["bb", "pg", "md", "lbfgs"])
 @pytest.mark.parametrize("native", [True, False])
 def test_batch_solvers_match_reference(B, gold, tag, name, native, native_loop):
-    if native_loop == "loop" and (not native or name == "lbfgs"):
+    if native_loop != "tiny" and (not native or name == "lbfgs"):
         pytest.skip("the generic / L-BFGS loops do not depend on the native loop kind")
     A, b, starts, x0 = problem(gold, tag)
     parts = B.algorithm_utils.get_solver_parts((A, b), starts, 0.1, is_sparse=True)

@@ -99,13 +99,15 @@ def main():
         sp = SyntheticProblem.config("C1", noise=0.1, implicit_ones=False)
         parts = sp.solver_parts()
         bsls_b200.BATCH.solve_BB(parts[3], parts[1], parts[2], sp.x_init, max_iter=50)
-        for rep in range(2):
+        for rep in range(4):
+            os.environ["BSLS_TINY_CLUSTER"] = str(rep // 2)
             t0 = time.perf_counter()
             sol = bsls_b200.BATCH.solve_BB(parts[3], parts[1], parts[2], sp.x_init, max_iter=2000)
             wall = time.perf_counter() - t0
             its = sol["iterations"] - 1
             out(what="bb_c1", iterations=its, evals=sol["obj_evals"], backtracks=sol["backtracks"], device_ms=sol["device_ms"],
                 wall_ms=1e3 * wall, iter_per_s=its / sol["device_ms"] * 1e3, f=sol["f"], stop=sol["stop"])
+        os.environ.pop("BSLS_TINY_CLUSTER", None)
     if "c4" in what:
         sp = SyntheticProblem.config("C4", noise=0.1)
         parts = sp.solver_parts()
