@@ -5,12 +5,16 @@
 
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
+#include <algorithm>
 
 #include "kernels.h"
 #include "lsq.cuh"
 #include "p2p.cuh"
+#include "solver_cluster.cuh"
 #include "solver_tiny.cuh"
 
 using namespace bsls;
@@ -142,6 +146,7 @@ struct bsls_lsq {
     int32_t *sell_idx[2] = {nullptr, nullptr}, *sell_goff[2] = {nullptr, nullptr};
     double *sell_val[2] = {nullptr, nullptr};
     bool sell_ready = false;
+    std::vector<int32_t> sell_hgoff[2];  // host copies of the group offsets (the cluster solver sizes its shares from them)
     double *wz = nullptr;                         // n: one more vector for the z-space BB loop (allocated on first use)
     bsls_ws *ws = nullptr;                        // owned
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -430,6 +435,63 @@ int md_update(bsls_ws *q, const bsls_plan *plan, double *x_new, const double *x,
     BSLS_LAUNCH_CHECK();
     q->launches++;
     return BSLS_OK;
+}
+
+// shared-memory layout of the cluster solver: sized for the largest share (group offsets known on the host)
+bool cluster_layout(const bsls_lsq *q, int max_k, ClusterLayout *L, size_t *smem) {
+    const int n = (int)q->n, m = (int)q->m;
+    const std::vector<int32_t> &ga = q->sell_hgoff[0], &gt = q->sell_hgoff[1];
+    L->groups_a = (m + 31) / 32;
+    L->groups_t = (n + 31) / 32;
+    L->max_k = max_k;
+    if ((int)ga.size() != L->groups_a + 1 || (int)gt.size() != L->groups_t + 1) return false;
+    int na = 0, nt = 0, wa = 0, wt = 0;
+    for (int c = 0; c < kClusterCtas; ++c) {
+        const int a0 = cluster_share(L->groups_a, c), a1 = cluster_share(L->groups_a, c + 1);
+        const int t0 = cluster_share(L->groups_t, c), t1 = cluster_share_end(L->groups_t, c, max_k);
+        na = std::max(na, ga[a1] - ga[a0]);
+        nt = std::max(nt, gt[t1] - gt[t0]);
+        wa = std::max(wa, a1 - a0);
+        wt = std::max(wt, t1 - t0);
+    }
+    int d = 0;  // doubles
+    L->x_off = d, d += 2 * (n + 1);
+    L->r_off = d, d += 2 * (m + 1);
+    L->g_cap = 32 * wt;
+    L->g_off = d, d += 2 * L->g_cap;
+    L->b_off = d, d += 32 * wa;
+    L->sc_off = d, d += 64;
+    L->part_off = d, d += 2 * kClusterCtas * 8;
+    int w = 2 * d;  // 32-bit words
+    L->ia_off = w, w += na;
+    L->it_off = w, w += nt;
+    L->ga_off = w, w += wa + 1;
+    L->gt_off = w, w += wt + 1;
+    L->st_off = w, w += 32 * wt + 2;  // at most one block per column of the share
+    *smem = sizeof(int32_t) * (size_t)w + 16;
+    return *smem <= 220 * 1024;
+}
+
+template <bool HV, int E, int G>
+int launch_cluster_one(const TinyArgs &a, const DevOpts &d, const ClusterLayout &lay, size_t smem, cudaStream_t st) {
+    static thread_local PerDevice<bool> attr_pd;
+    bool &attr = attr_pd.get(false);
+    if (!attr) {
+        BSLS_CUDA_TRY(cudaFuncSetAttribute(solver_cluster_kernel<HV, E, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr = true;
+    }
+    solver_cluster_kernel<HV, E, G><<<kClusterCtas, kTinyThreads, smem, st>>>(a, d, lay);
+    return BSLS_OK;
+}
+template <bool HV>
+int launch_cluster_hv(const TinyArgs &a, const DevOpts &d, const ClusterLayout &lay, size_t smem, int max_k, cudaStream_t st) {
+    if (max_k <= 8) return launch_cluster_one<HV, 2, 4>(a, d, lay, smem, st);
+    if (max_k <= 16) return launch_cluster_one<HV, 2, 8>(a, d, lay, smem, st);
+    if (max_k <= 32) return launch_cluster_one<HV, 4, 8>(a, d, lay, smem, st);
+    return launch_cluster_one<HV, 8, 8>(a, d, lay, smem, st);
+}
+int launch_cluster(const TinyArgs &a, const DevOpts &d, const ClusterLayout &lay, size_t smem, bool has_values, int max_k, cudaStream_t st) {
+    return has_values ? launch_cluster_hv<true>(a, d, lay, smem, max_k, st) : launch_cluster_hv<false>(a, d, lay, smem, max_k, st);
 }
 
 }  // namespace
@@ -1126,15 +1188,16 @@ void finish_result(bsls_batch_result *res, const DevState &fin, int launches, fl
 
 // sliced-ELL copy of one CSR side (solver_tiny.cuh)
 int build_sell(const int64_t *ptr, const int32_t *idx, const double *val, int rows, int pad, int32_t **goff_out, int32_t **sidx_out,
-               double **sval_out, cudaStream_t st) {
+               double **sval_out, std::vector<int32_t> *hgoff, cudaStream_t st) {
     const int groups = (rows + 31) / 32;
     BSLS_CUDA_TRY(cudaMalloc(goff_out, sizeof(int32_t) * ((size_t)groups + 1)));
     sell_widths_kernel<<<(groups + 127) / 128, 128, 0, st>>>(ptr, rows, groups, *goff_out);
     sell_scan_kernel<<<1, 32, 0, st>>>(*goff_out, groups);
     BSLS_LAUNCH_CHECK();
-    int32_t total = 0;
-    BSLS_CUDA_TRY(cudaMemcpyAsync(&total, *goff_out + groups, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    hgoff->resize((size_t)groups + 1);
+    BSLS_CUDA_TRY(cudaMemcpyAsync(hgoff->data(), *goff_out, sizeof(int32_t) * ((size_t)groups + 1), cudaMemcpyDeviceToHost, st));
     BSLS_CUDA_TRY(cudaStreamSynchronize(st));
+    const int32_t total = hgoff->back();
     BSLS_CUDA_TRY(cudaMalloc(sidx_out, sizeof(int32_t) * (size_t)(total > 0 ? total : 1)));
     if (val) BSLS_CUDA_TRY(cudaMalloc(sval_out, sizeof(double) * (size_t)(total > 0 ? total : 1)));
     sell_fill_kernel<<<(32 * groups + 255) / 256, 256, 0, st>>>(ptr, idx, val, rows, groups, *goff_out, *sidx_out, val ? *sval_out : nullptr, pad);
@@ -1150,8 +1213,10 @@ int solve_tiny(bsls_lsq *q, const bsls_plan *plan, double *x, const bsls_batch_o
     const bool off = e && atoi(e) != 0;
     bsls_ws *w = q->ws;
     const size_t smem = tiny_smem_bytes((int)q->n, (int)q->m);
+    const bool single_fits = smem <= 220 * 1024;
+    const bool cluster_may_fit = 16 * (size_t)(q->n + q->m + 2) <= 200 * 1024;  // x and r twice; the exact need follows below
     if (off || (w->comm && w->comm->nranks > 1) || o->method > 1 || o->proj_mode > 1 || plan->max_size > kTinyMaxBlock || plan->first != 0 ||
-        smem > 220 * 1024 || q->n > (1 << 20) || q->nnz > (1 << 26))
+        (!single_fits && !cluster_may_fit) || q->n > (1 << 20) || q->nnz > (1 << 26))
         return 0;
     static thread_local PerDevice<bool> attr_pd;
     bool &attr = attr_pd.get(false);
@@ -1160,8 +1225,8 @@ int solve_tiny(bsls_lsq *q, const bsls_plan *plan, double *x, const bsls_batch_o
         attr = true;
     }
     if (!q->sell_ready) {
-        if (int rc = build_sell(q->a_ptr, q->a_idx, q->a_val, (int)q->m, (int)q->n, &q->sell_goff[0], &q->sell_idx[0], &q->sell_val[0], st)) return rc;
-        if (int rc = build_sell(q->t_ptr, q->t_idx, q->t_val, (int)q->n, (int)q->m, &q->sell_goff[1], &q->sell_idx[1], &q->sell_val[1], st)) return rc;
+        if (int rc = build_sell(q->a_ptr, q->a_idx, q->a_val, (int)q->m, (int)q->n, &q->sell_goff[0], &q->sell_idx[0], &q->sell_val[0], &q->sell_hgoff[0], st)) return rc;
+        if (int rc = build_sell(q->t_ptr, q->t_idx, q->t_val, (int)q->n, (int)q->m, &q->sell_goff[1], &q->sell_idx[1], &q->sell_val[1], &q->sell_hgoff[1], st)) return rc;
         q->sell_ready = true;
     }
     TinyArgs a{};
@@ -1177,20 +1242,26 @@ int solve_tiny(bsls_lsq *q, const bsls_plan *plan, double *x, const bsls_batch_o
     a.progress_f = cap > 0 ? w->d_prog : nullptr;
     a.progress_t = cap > 0 ? w->d_prog + w->prog_cap : nullptr;
     a.proj_mode = o->proj_mode;
-    const DevOpts d = make_dev_opts(o, w, cap);
-    BSLS_CUDA_TRY(cudaEventRecord(q->ev0, st));
-    // eight CTAs pay off once a CTA's share is a few rows per warp; BSLS_TINY_CLUSTER=0 / 1 forces one kernel or the other
-    // (both are tested on every small problem)
+    // A cluster of 8 CTAs (solver_cluster.cuh) when the shares fit and are worth it; BSLS_TINY_CLUSTER=0 / 1 forces one
+    // kernel or the other where both fit (both are tested on every small problem).
     const char *ce = getenv("BSLS_TINY_CLUSTER");
-    const bool clustered = ce ? atoi(ce) != 0 : (plan->nb >= 4 * kTinyCluster && q->m >= 32 * kTinyCluster);
+    ClusterLayout lay{};
+    size_t csmem = 0;
+    const bool cluster_fits = cluster_layout(q, plan->max_size, &lay, &csmem);
+    if (!single_fits && !cluster_fits) return 0;
+    const bool clustered =
+        cluster_fits && (!single_fits || (ce ? atoi(ce) != 0 : (plan->nb >= 4 * kClusterCtas && q->m >= 32 * kClusterCtas)));
+    const DevOpts d = make_dev_opts(o, w, cap);
+    const char *pe = getenv("BSLS_TINY_PROF");  // development: phase cycle counts of the cluster kernel on stderr
+    long long *d_prof = nullptr;
+    if (pe && atoi(pe)) {
+        BSLS_CUDA_TRY(cudaMalloc(&d_prof, 16 * sizeof(long long)));
+        BSLS_CUDA_TRY(cudaMemsetAsync(d_prof, 0, 16 * sizeof(long long), st));
+        a.prof = d_prof;
+    }
+    BSLS_CUDA_TRY(cudaEventRecord(q->ev0, st));
     if (clustered) {
-        static thread_local PerDevice<bool> cattr_pd;
-        bool &cattr = cattr_pd.get(false);
-        if (!cattr) {
-            BSLS_CUDA_TRY(cudaFuncSetAttribute(solver_tiny_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-            cattr = true;
-        }
-        solver_tiny_cluster_kernel<<<kTinyCluster, kTinyThreads, smem, st>>>(a, d);
+        if (int rc = launch_cluster(a, d, lay, csmem, q->sell_val[0] != nullptr, plan->max_size, st)) return rc;
     } else {
         solver_tiny_kernel<<<1, kTinyThreads, smem, st>>>(a, d);
     }
@@ -1199,6 +1270,16 @@ int solve_tiny(bsls_lsq *q, const bsls_plan *plan, double *x, const bsls_batch_o
     BSLS_CUDA_TRY(cudaMemcpyAsync(&w->h_state[0], w->d_state, sizeof(DevState), cudaMemcpyDeviceToHost, st));
     BSLS_CUDA_TRY(cudaStreamSynchronize(st));
     const DevState fin = w->h_state[0];
+    if (d_prof) {
+        long long h[16];
+        BSLS_CUDA_TRY(cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost));
+        cudaFree(d_prof);
+        static const char *names[12] = {"project", "sync_x", "rows_Ax", "publish_r", "rows_Atr", "publish_g", "decide", "sync_decide",
+                                        "pullback", "-", "-", "-"};
+        fprintf(stderr, "[tiny prof] iterations %d, cycles per iteration:", fin.i);
+        for (int k = 0; k < 9; ++k) fprintf(stderr, " %s=%.0f", names[k], (double)h[k] / (fin.i > 1 ? fin.i - 1 : 1));
+        fprintf(stderr, "\n");
+    }
     if (!fin.done) {
         set_error("batch_solve (single-CTA loop): ended without a stop code (i=%d)", fin.i);
         return BSLS_ERR_CUDA;

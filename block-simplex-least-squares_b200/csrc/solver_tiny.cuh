@@ -10,8 +10,6 @@
 // decide_step (lsq.cuh) in thread 0 and pulls a back-tracked trial point back.  Only the index / value arrays of A and
 // A^T stream from L2, from sliced-ELL copies made once per problem (SellMatrix).  No host round trip, no kernel boundary, no global synchronisation inside the solve.
 #pragma once
-#include <cooperative_groups.h>
-
 #include "lsq.cuh"
 #include "simplex_core.cuh"
 
@@ -40,6 +38,7 @@ struct TinyArgs {
     DevState *st;
     double *progress_f, *progress_t;
     int proj_mode;           // 0 simplex, 1 l1-ball
+    long long *prof;         // development: 16 phase cycle counters of CTA 0 / thread 0 (BSLS_TINY_PROF=1), else null
 };
 
 inline size_t tiny_smem_bytes(int n, int m) { return sizeof(double) * (4 * (size_t)(n + 1) + 3 * (size_t)(m + 1) + 64); }
@@ -235,7 +234,7 @@ __global__ void __launch_bounds__(kTinyThreads, 1) solver_tiny_kernel(TinyArgs a
     // r = A x - b and the sums of EpiResidual (x, r, r_old: arena offsets; r_old < 0: none)
     auto residual = [&](int x, int r, int r_old) {
         double acc[3] = {0, 0, 0};
-        constexpr int R = 2;
+        constexpr int R = 1;  // measured: 2 rows in flight per thread are slower (32 warps already hide the latency)
         for (int row0 = tid; row0 < m; row0 += R * kTinyThreads) {
             double dot[R];
             tiny_rows_dot<R>(a.A, row0, m, tiny_sm, x, dot);
@@ -260,7 +259,7 @@ __global__ void __launch_bounds__(kTinyThreads, 1) solver_tiny_kernel(TinyArgs a
     // g_new = A^T r and the sums of EpiGradBB (g < 0: only <g_new, g_new>)
     auto gradient = [&](int r, int g_new, int g, int x, int x_new) {
         double acc[5] = {0, 0, 0, 0, 0};
-        constexpr int R = 3;
+        constexpr int R = 1;
         for (int row0 = tid; row0 < n; row0 += R * kTinyThreads) {
             double dots[R];
             tiny_rows_dot<R>(a.AT, row0, n, tiny_sm, r, dots);
@@ -354,189 +353,6 @@ __global__ void __launch_bounds__(kTinyThreads, 1) solver_tiny_kernel(TinyArgs a
     }
     for (int i = tid; i < n; i += kTinyThreads) a.x[i] = tiny_sm[XS + cur * n1 + i];
     if (tid == 0) *a.st = s_state;
-}
-
-// ---- the same loop on a thread-block CLUSTER ------------------------------------------------------------------
-// One CTA is bound by the latency of its own index stream (every thread walks 2 rows of A and 5 of A^T per iteration).
-// A cluster of kTinyCluster CTAs (8 SMs, the portable maximum) cuts that chain eight-fold: every CTA keeps the FULL
-// vectors in its shared memory, computes the OD blocks / link rows / route rows of its share and writes what the others
-// need -- its slice of x_new after the projection, its slice of r_new after the product A x -- into the shared memory of
-// all CTAs of the cluster (distributed shared memory stores), with a cluster barrier after each of the two phases.  The
-// partial sums of a reduction are exchanged the same way and added in rank order, so every CTA holds the same scalars and
-// takes the same decision on its own copy of the solver state: no further communication.  The gradient and the BB sums
-// only involve a CTA's own routes.
-constexpr int kTinyCluster = 8;
-
-__global__ void __cluster_dims__(kTinyCluster, 1, 1) __launch_bounds__(kTinyThreads, 1) solver_tiny_cluster_kernel(TinyArgs a, DevOpts o) {
-    namespace cg = cooperative_groups;
-    cg::cluster_group cluster = cg::this_cluster();
-    const int C = kTinyCluster, me = (int)cluster.block_rank();
-    extern __shared__ __align__(16) double tiny_sm[];
-    const int n = a.n, m = a.m, tid = threadIdx.x;
-    const int n1 = n + 1, m1 = m + 1;
-    const int XS = 0, GS = 2 * n1, RS = 4 * n1, BS = 4 * n1 + 2 * m1, SC = BS + m1;
-    double *scal = tiny_sm + SC;
-    __shared__ double s_red[32 * 5];
-    __shared__ double s_out[5];
-    // partial sums of every CTA of the cluster, written by their owners; the residual's and the gradient's totals use
-    // separate slots, so a CTA that runs ahead into the gradient cannot overwrite residual sums a peer has yet to read
-    __shared__ double s_part[2][kTinyCluster][8];
-    __shared__ DevState s_state;
-    DevState *st = &s_state;
-    // my share: OD blocks [b_lo, b_hi) = routes [c_lo, c_hi), link rows [r_lo, r_hi)
-    const int b_lo = (int)((long long)a.nb * me / C), b_hi = (int)((long long)a.nb * (me + 1) / C);
-    const int c_lo = a.starts[b_lo], c_hi = a.starts[b_hi];
-    const int r_lo = (int)((long long)((m + 31) / 32) * me / C) * 32, r_hi = min(m, (int)((long long)((m + 31) / 32) * (me + 1) / C) * 32);
-    double *peer[kTinyCluster];
-    double *peer_part[kTinyCluster];
-#pragma unroll
-    for (int q = 0; q < kTinyCluster; ++q) {
-        peer[q] = cluster.map_shared_rank(tiny_sm, q);
-        peer_part[q] = cluster.map_shared_rank(&s_part[0][0][0], q);
-    }
-    if (tid == 0) s_state = DevState{};
-    for (int i = tid; i < n; i += kTinyThreads) tiny_sm[XS + i] = a.x[i];
-    for (int i = tid; i < m; i += kTinyThreads) tiny_sm[BS + i] = a.b[i];
-    if (tid < 2) {
-        tiny_sm[XS + tid * n1 + n] = 0.0;
-        tiny_sm[RS + tid * m1 + m] = 0.0;
-    }
-    if (tid < kScalCount) scal[tid] = 0.0;
-    cluster.sync();
-
-    // sums over the cluster: every CTA publishes its NS + NM partial results in every CTA, barrier, rank-order total
-    auto cluster_total = [&](int slot, int count, int nsum, double *dst) {
-        if (tid < count)
-            for (int q = 0; q < C; ++q) peer_part[q][(slot * C + me) * 8 + tid] = s_out[tid];
-        cluster.sync();
-        if (tid < count) {
-            double v = s_part[slot][0][tid];
-            for (int q = 1; q < C; ++q) v = tid < nsum ? v + s_part[slot][q][tid] : fmax(v, s_part[slot][q][tid]);
-            dst[tid] = v;
-        }
-        __syncthreads();
-    };
-    __shared__ double s_tot[5];
-
-    auto residual = [&](int x, int r, int r_old) {
-        double acc[3] = {0, 0, 0};
-        constexpr int R = 1;
-        for (int row0 = r_lo + tid; row0 < r_hi; row0 += R * kTinyThreads) {
-            double dot[R];
-            tiny_rows_dot<R>(a.A, row0, r_hi, tiny_sm, x, dot);
-            const double v = dot[0] - tiny_sm[BS + row0];
-            for (int q = 0; q < C; ++q) peer[q][r + row0] = v;  // every CTA needs the whole residual for A^T r
-            residual_sums(v, r_old >= 0 ? tiny_sm[r_old + row0] : 0.0, r_old >= 0, acc);
-        }
-        tiny_reduce<3, 0>(acc, s_red, s_out);
-        cluster_total(0, 3, 3, s_tot);  // its barrier also publishes the residual slices
-        if (tid == 0) {
-            scal[kScalF] = 0.5 * s_tot[0];
-            scal[kScalRR] = s_tot[0];
-            scal[kScalRdr] = s_tot[1];
-            scal[kScalDrdr] = s_tot[2];
-        }
-    };
-    auto gradient = [&](int r, int g_new, int g, int x, int x_new) {
-        double acc[5] = {0, 0, 0, 0, 0};
-        constexpr int R = 1;
-        for (int row0 = c_lo + tid; row0 < c_hi; row0 += R * kTinyThreads) {
-            double dots[R];
-            tiny_rows_dot<R>(a.AT, row0, c_hi, tiny_sm, r, dots);
-            const double dot = dots[0];
-            tiny_sm[g_new + row0] = dot;  // the gradient of my routes stays here: only my blocks step along it
-            acc[3] += dot * dot;
-            if (g >= 0) {
-                const double go = tiny_sm[g + row0], dx = tiny_sm[x_new + row0] - tiny_sm[x + row0], dg = dot - go;
-                acc[0] += dx * dg;
-                acc[1] += dg * dg;
-                acc[2] += go * dx;
-                acc[4] = fmax(acc[4], fabs(dx));
-            }
-        }
-        tiny_reduce<4, 1>(acc, s_red, s_out);
-        cluster_total(1, 5, 4, s_tot);
-        if (tid == 0) {
-            scal[kScalSxy] = s_tot[0];
-            scal[kScalSyy] = s_tot[1];
-            scal[kScalGd] = s_tot[2];
-            scal[kScalGnn] = s_tot[3];
-            scal[kScalStep] = s_tot[4];
-        }
-    };
-
-    residual(XS, RS, -1);
-    gradient(RS, GS, -1, -1, -1);
-    if (tid == 0) decide_step(st, scal, nullptr, o, me == 0 ? a.progress_f : nullptr, me == 0 ? a.progress_t : nullptr, 1);
-    __syncthreads();
-
-    int cur = 0;
-    while (!st->done) {
-        const int nxt = cur ^ 1;
-        const int xc = XS + cur * n1, xn = XS + nxt * n1, gc = GS + cur * n1, gn = GS + nxt * n1, rc = RS + cur * m1, rn = RS + nxt * m1;
-        const double nt = -st->t;
-        // ---- x_new = proj(x - t g) for my OD blocks, written to every CTA ---------------------------------
-        for (int blk = b_lo + tid; blk < b_hi; blk += kTinyThreads) {
-            const int s = a.starts[blk], K = a.starts[blk + 1] - s;
-            double *w = tiny_sm + xn + s;
-            double sum = 0.0;
-            for (int i = 0; i < K; ++i) {
-                const double u = nt * tiny_sm[gc + s + i];
-                double v = tiny_sm[xc + s + i] + u;
-                if (a.proj_mode == 1) {
-                    if (v < 0.0)
-                        v = 0.0;
-                    else
-                        sum += v;
-                }
-                w[i] = v;
-            }
-            if (a.proj_mode == 0 || sum > 1.0) tiny_project_block(w, tiny_sm + gn + s, K);
-            for (int q = 0; q < C; ++q)
-                if (q != me)
-                    for (int i = 0; i < K; ++i) peer[q][xn + s + i] = w[i];
-        }
-        cluster.sync();
-        residual(xn, rn, rc);
-        gradient(rn, gn, gc, xc, xn);
-        if (tid == 0) decide_step(st, scal, nullptr, o, me == 0 ? a.progress_f : nullptr, me == 0 ? a.progress_t : nullptr, 0);
-        __syncthreads();
-        const double tau = st->tau;
-        if (tau != 1.0) {  // every CTA pulls back its own full copies of x_new and r_new, and the gradient of its routes
-            const double c = 1.0 - tau;
-            for (int i = tid; i < n; i += kTinyThreads) {
-                if (tau == 0.0) {
-                    tiny_sm[xn + i] = tiny_sm[xc + i];
-                } else {
-                    const double u = c * tiny_sm[xc + i];
-                    tiny_sm[xn + i] = u + tau * tiny_sm[xn + i];
-                }
-            }
-            for (int i = c_lo + tid; i < c_hi; i += kTinyThreads) {
-                if (tau == 0.0) {
-                    tiny_sm[gn + i] = tiny_sm[gc + i];
-                } else {
-                    const double v = c * tiny_sm[gc + i];
-                    tiny_sm[gn + i] = v + tau * tiny_sm[gn + i];
-                }
-            }
-            for (int i = tid; i < m; i += kTinyThreads) {
-                if (tau == 0.0) {
-                    tiny_sm[rn + i] = tiny_sm[rc + i];
-                } else {
-                    const double u = c * tiny_sm[rc + i];
-                    tiny_sm[rn + i] = u + tau * tiny_sm[rn + i];
-                }
-            }
-            // the pull-back read x (buffer `cur`), which the peers overwrite with their slices of the next trial point:
-            // they must not start before every CTA is through (tau is the same everywhere: the branch is cluster-uniform)
-            cluster.sync();
-        }
-        cur = nxt;
-    }
-    cluster.sync();  // nobody leaves while a peer may still write into its shared memory
-    for (int i = c_lo + tid; i < c_hi; i += kTinyThreads) a.x[i] = tiny_sm[XS + cur * n1 + i];
-    if (tid == 0 && me == 0) *a.st = s_state;
 }
 
 }  // namespace bsls
