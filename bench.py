@@ -523,6 +523,28 @@ def dist_parity_check(bsls_b200, torch, dist, dev, rank, world, comm):
 # --------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------
+def bind_near_gpu(torch, index):
+    """Run this rank's host threads on the cores NVML lists as local to its GPU, so that the pinned staging buffers of the
+    e2e leg (first touched by this process) sit on the GPU's NUMA node: with 8 ranks copying at once, buffers on the
+    far socket halve the PCIe rate.  Deployment placement (what `numactl` per rank does), not part of the library."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = "GPU-" + str(torch.cuda.get_device_properties(index).uuid)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1} & os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return "%d cores local to the GPU (NVML cpu affinity)" % len(cpus)
+    except Exception as e:   # no NVML, no affinity support: leave the placement to the OS
+        return None
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -530,6 +552,7 @@ def run_ours(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    bound = None if args.no_bind else bind_near_gpu(torch, local_rank)
     if rank == 0:
         g.build()
     if world > 1:
@@ -676,7 +699,7 @@ def run_ours(args, rank, world, local_rank):
     e2e_t = max_over_ranks(time.perf_counter() - t0)
     assert not x_out.is_cuda and abs(f_host - sol["f"]) <= 1e-9 * abs(sol["f"])
     e2e = {"value": e2e_its / e2e_t, "unit": UNIT, "h2d_bytes_per_step": 8 * (C5_N + world * C5_M), "d2h_bytes_per_step": 8 * C5_N + 8 * world,
-           "ms_per_step": 1e3 * e2e_t / e2e_steps, "steps": e2e_steps,
+           "ms_per_step": 1e3 * e2e_t / e2e_steps, "steps": e2e_steps, "host_placement": bound or "left to the OS",
            "api": "bsls_b200.BATCH.solve_BB(obj, proj, line_search, x_init) with x_init / b in pinned host memory and x returned to "
                   "the host, on every rank (bytes are whole-job totals)"}
     del xh, bh, x_out
@@ -722,6 +745,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-bind", action="store_true", help="do not bind the rank's host threads to the cores local to its GPU")
     ap.add_argument("--skip-extras", action="store_true", help="headline (BB solve on C5) only: no C1 / C2 / C3 / C4 / 10^8 sub-objects")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup

@@ -29,16 +29,30 @@ _STOP = {0: 'continue', 1: 'max_iter'}
 
 def _stage_in(x_init, obj):
     """The reference's solvers take and return NumPy vectors.  Host input (ndarray, or a CPU tensor -- pinned memory makes
-    the copy asynchronous) is copied to the device of the problem; the result then goes back the same way."""
+    the copy asynchronous) is copied to the device of the problem; the result then goes back the same way.
+
+    float32 input (host or device) is accepted as well: the path is bound by 8-byte gathers that cost one 32-byte sector
+    each whatever the element size, so single precision would buy no time; it is widened on the way in, the loop runs in
+    float64 and ``x`` comes back as float32 (north_star's fp32 bar, 1e-4, is met with room: tests/test_solvers_gpu.py)."""
     if torch.is_tensor(x_init) and x_init.is_cuda:
+        if x_init.dtype == torch.float32:
+            staged = x_init.to(torch.float64)
+            staged._bsls_private = True
+            return staged, ("cuda", True)
         return x_init, None
     problem = getattr(obj, "problem", None)
     device = problem.device if problem is not None else torch.device("cuda", torch.cuda.current_device())
-    host = x_init if torch.is_tensor(x_init) else torch.from_numpy(np.ascontiguousarray(x_init, dtype=np.float64))
-    assert host.dtype == torch.float64 and host.dim() == 1, "x_init: float64 vector expected"
-    staged = host.to(device, non_blocking=True)
+    f32 = (x_init.dtype == torch.float32) if torch.is_tensor(x_init) else (np.asarray(x_init).dtype == np.float32)
+    if f32:
+        host = x_init if torch.is_tensor(x_init) else torch.from_numpy(np.ascontiguousarray(x_init))
+        assert host.dim() == 1, "x_init: vector expected"
+        staged = host.to(device, non_blocking=True).to(torch.float64)
+    else:
+        host = x_init if torch.is_tensor(x_init) else torch.from_numpy(np.ascontiguousarray(x_init, dtype=np.float64))
+        assert host.dtype == torch.float64 and host.dim() == 1, "x_init: float64 (or float32) vector expected"
+        staged = host.to(device, non_blocking=True)
     staged._bsls_private = True        # a fresh device copy: the native loop may work in it instead of cloning again
-    return staged, ("tensor" if torch.is_tensor(x_init) else "numpy")
+    return staged, ("tensor" if torch.is_tensor(x_init) else "numpy", f32)
 
 
 _PINNED_OUT = {}
@@ -50,13 +64,17 @@ def _stage_out(sol, kind, like=None):
     and reused by the next call of that length (copy it if two results must be alive at once)."""
     if kind is None:
         return sol
-    x = sol['x']
-    if kind == "numpy":
+    where, f32 = kind
+    x = sol['x'].to(torch.float32) if f32 else sol['x']
+    if where == "cuda":
+        sol['x'] = x
+    elif where == "numpy":
         sol['x'] = x.cpu().numpy()
     elif like is not None and like.is_pinned():
-        out = _PINNED_OUT.get(x.shape[0])
+        key = (x.shape[0], x.dtype)
+        out = _PINNED_OUT.get(key)
         if out is None:
-            out = _PINNED_OUT[x.shape[0]] = torch.empty(x.shape, dtype=x.dtype).pin_memory()
+            out = _PINNED_OUT[key] = torch.empty(x.shape, dtype=x.dtype).pin_memory()
         out.copy_(x, non_blocking=False)
         sol['x'] = out
     else:

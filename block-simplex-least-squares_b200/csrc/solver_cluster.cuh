@@ -10,12 +10,21 @@
 //     columns of A^T and ITS OD blocks only -- the sliced-ELL index arrays, b, the block starts and the two gradient
 //     buffers.  After the prologue the loop loads nothing from global memory (value arrays of a general A excepted).
 //   * projection: G lanes per OD block (register sorting network across lanes, simplex_core.cuh) for the CTA's blocks;
-//     the new entries of x go straight into the x buffer of all 8 CTAs (st.shared::cluster), barrier.
-//   * r = A x - b for the CTA's link rows, written into the r buffer of all 8 CTAs together with the CTA's partial sums,
-//     barrier.
-//   * g = A^T r for the CTA's routes (kept local: only its own blocks step along it) with the BB sums, partial sums to
-//     all CTAs, barrier; thread 0 of EVERY CTA adds the partials in rank order and takes the decision on its own copy of
+//     the CTA's slice of the new x then goes to the x buffer of the 7 other CTAs.
+//   * r = A x - b for the CTA's link rows; the slice and the CTA's partial sums go to the 7 other CTAs.
+//   * g = A^T r for the CTA's routes (kept local: only its own blocks step along it) with the BB sums; partial sums to
+//     the other CTAs; thread 0 of EVERY CTA adds the partials in rank order and takes the decision on its own copy of
 //     the solver state -- identical inputs, identical code, identical result: no further exchange.
+//
+// The exchange: a slice is ONE bulk copy per peer, shared memory to the peer's shared memory (cp.async.bulk
+// shared::cluster <- shared::cta, issued by 7 threads), that completes on an mbarrier of the RECEIVER: a CTA waits until
+// the bytes it expects for a phase have landed, nobody waits for a cluster-wide barrier (whose release is a
+// MEMBAR.ALL.GPU: a third of the first version's time, profiles/r02_c1_cluster_solver_stalls.txt) and no thread issues
+// remote stores one value at a time (the other third).  Odd ends of a slice (16-byte alignment) travel as single
+// st.async values on the same mbarrier.  No receiver-to-sender handshake is needed: a CTA can only send its slice of
+// phase p+1 after it has received every slice of phase p, and a peer sends that only after it has finished reading what
+// phase p+1 overwrites (x and r are double-buffered; the one exception, the pull-back of a back-tracked point, ends in
+// a full cluster barrier).
 //
 // Column shares are aligned to OD blocks, link shares to groups of 32 rows.  A column share starts at the first block at or
 // after column 32 * (groups * q / 8), so the host can bound the shared-memory need of a share from the group offsets
@@ -53,9 +62,32 @@ __device__ __forceinline__ uint32_t cluster_map(uint32_t shared_addr, int rank) 
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(shared_addr), "r"(rank));
     return r;
 }
-__device__ __forceinline__ void cluster_store(uint32_t addr, double v) {
-    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+// one value into a peer's shared memory, counted on the peer's mbarrier when it lands
+__device__ __forceinline__ void cluster_store_tx(uint32_t addr, double v, uint32_t mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(addr), "l"(__double_as_longlong(v)), "r"(mbar)
+                 : "memory");
 }
+// `bytes` (a multiple of 16, both addresses 16-byte aligned) from my shared memory into a peer's, by the bulk-copy
+// engine; counted on the peer's mbarrier when they have landed
+__device__ __forceinline__ void cluster_copy_tx(uint32_t dst, uint32_t src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "r"(src), "r"(bytes),
+                 "r"(mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nW: mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n@p bra D;\nbra W;\nD:\n}\n" ::"r"(mbar),
+        "r"(parity)
+        : "memory");
+}
+// my generic-proxy writes to shared memory, made visible to the bulk-copy engine that reads them next
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // HV: A carries values (read from global memory; the index arrays are on chip either way).  E x G: registers per lane x
 // lanes per OD block of the projection (E * G >= max_k).
@@ -70,7 +102,8 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kTinyThre
     const int n = a.n, m = a.m, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n1 = n + 1, m1 = m + 1;
     double *scal = tiny_sm + L.sc_off;
-    __shared__ double s_red[32 * 5];
+    __shared__ double s_red2[2][32 * 5];  // per slot: warps of a CTA that is through with the residual's sums may already write the gradient's
+    __shared__ __align__(8) uint64_t s_mbar[3];  // bytes landed in my shared memory: x slices / r slices + sums / gradient sums
     __shared__ int s_blk[2];
     __shared__ DevState s_state;
     __shared__ long long prof_acc[12];
@@ -94,6 +127,13 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kTinyThre
     }
     if (tid == 0) s_state = DevState{};
     if (tid < 12) prof_acc[tid] = 0;
+    const uint32_t mb_x = (uint32_t)__cvta_generic_to_shared(&s_mbar[0]), mb_r = mb_x + 8, mb_g = mb_x + 16;
+    if (tid == 0) {
+        mbar_init(mb_x, 1);
+        mbar_init(mb_r, 1);
+        mbar_init(mb_g, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
     const int b_lo = s_blk[0], nbl = s_blk[1] - s_blk[0];
     const int c_lo = a.starts[b_lo], c_hi = a.starts[b_lo + nbl];
@@ -113,15 +153,28 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kTinyThre
         }
         if (tid < kScalCount) scal[tid] = 0.0;
     }
-    uint32_t peer[C];  // the arena of every CTA of the cluster in the shared::cluster window
-    {
-        const uint32_t base = (uint32_t)__cvta_generic_to_shared(tiny_sm);
-#pragma unroll
-        for (int q = 0; q < C; ++q) peer[q] = cluster_map(base, q);
+    const uint32_t arena = (uint32_t)__cvta_generic_to_shared(tiny_sm);
+    // bytes a phase delivers into my shared memory (the other CTAs' slices; their 3 or 5 partial sums)
+    const int my_rows = max(0, min(m, 32 * ga1) - row0);
+    const uint32_t x_bytes = 8u * (uint32_t)(n - (c_hi - c_lo)), r_bytes = 8u * (uint32_t)(m - my_rows) + 24u * (C - 1), g_bytes = 40u * (C - 1);
+    uint32_t ph_x = 0, ph_r = 0, ph_g = 0;
+    if (tid == 0) {  // the expectation of a phase is posted as soon as the previous one is through
+        mbar_expect(mb_x, x_bytes);
+        mbar_expect(mb_r, r_bytes);
+        mbar_expect(mb_g, g_bytes);
     }
-    auto to_all = [&](int off /* doubles */, double v) {
-#pragma unroll
-        for (int q = 0; q < C; ++q) cluster_store(peer[q] + 8u * (uint32_t)off, v);
+    // my entries [lo, hi) of the vector at arena offset `vec` (doubles) to the same place in CTA q, counted on its
+    // mbarrier `mb`: the 16-byte aligned middle as one bulk copy, an odd first / last entry as single values
+    auto send_slice = [&](int q, int vec, int lo, int hi, uint32_t mb) {
+        const uint32_t peer = cluster_map(arena, q), pmb = cluster_map(mb, q);
+        const int a0 = lo + ((vec + lo) & 1), a1 = hi - ((vec + hi) & 1);  // the aligned middle [a0, a1)
+        if (a1 > a0) {
+            cluster_copy_tx(peer + 8u * (uint32_t)(vec + a0), arena + 8u * (uint32_t)(vec + a0), 8u * (uint32_t)(a1 - a0), pmb);
+            if (a0 > lo) cluster_store_tx(peer + 8u * (uint32_t)(vec + lo), tiny_sm[vec + lo], pmb);
+            if (a1 < hi) cluster_store_tx(peer + 8u * (uint32_t)(vec + hi - 1), tiny_sm[vec + hi - 1], pmb);
+        } else {  // at most two entries
+            for (int i = lo; i < hi; ++i) cluster_store_tx(peer + 8u * (uint32_t)(vec + i), tiny_sm[vec + i], pmb);
+        }
     };
     // phase clock of thread 0 of CTA 0 (development aid; a.prof is null in production)
     const bool prof = a.prof != nullptr && me == 0 && tid == 0;
@@ -135,10 +188,18 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kTinyThre
     };
     cluster.sync();
 
-    // CTA sums (fixed tree: lanes, then warps) -> slot `slot` of the partial-sum table of every CTA; cluster barrier
-    auto publish = [&](auto &acc, auto ns_tag, int slot) {
+    // one value to the same place in every other CTA, counted on their mbarrier `mb`
+    auto to_peers = [&](int off /* doubles */, double v, uint32_t mb) {
+#pragma unroll
+        for (int q = 0; q < C; ++q)
+            if (q != me) cluster_store_tx(cluster_map(arena, q) + 8u * (uint32_t)off, v, cluster_map(mb, q));
+    };
+    // CTA sums (fixed tree: lanes, then warps) -> row (slot, me) of the partial-sum table of every CTA; then wait until
+    // everything the other CTAs send in this phase (their sums, and their rows of r in the residual's phase) is here
+    auto publish = [&](auto &acc, auto ns_tag, int slot, uint32_t mb, uint32_t &phase, uint32_t bytes) {
         constexpr int NS = decltype(ns_tag)::value;
         constexpr int N = sizeof(acc) / sizeof(double);
+        double *s_red = s_red2[slot];
 #pragma unroll
         for (int k = 0; k < N; ++k) {
             double v = acc[k];
@@ -151,6 +212,7 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kTinyThre
         }
         __syncthreads();
         if (wid == 0) {
+            const int row = L.part_off + (slot * C + me) * 8;
 #pragma unroll
             for (int k = 0; k < N; ++k) {
                 double v = s_red[lane * N + k];  // T / 32 == 32 warps
@@ -159,10 +221,14 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kTinyThre
                     const double u = __shfl_xor_sync(0xffffffffu, v, d);
                     v = (k < NS) ? v + u : fmax(v, u);
                 }
-                if (lane == 0) to_all(L.part_off + (slot * C + me) * 8 + k, v);
+                if (lane == 0) tiny_sm[row + k] = v;
+                if (lane < C && lane != me)  // the butterfly left the total in every lane: lane q sends to CTA q
+                    cluster_store_tx(cluster_map(arena, lane) + 8u * (uint32_t)(row + k), v, cluster_map(mb, lane));
             }
         }
-        cluster.sync();
+        mbar_wait(mb, phase);
+        phase ^= 1u;
+        if (tid == 0) mbar_expect(mb, bytes);  // the next use of this barrier
     };
     // thread 0: the cluster's totals in rank order (the same bits in every CTA)
     auto total = [&](int slot, int k, bool is_max) {
@@ -200,12 +266,13 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kTinyThre
                     }
                 }
                 const double v = sum - tiny_sm[L.b_off + lr];
-                to_all(r + row, v);
+                tiny_sm[r + row] = v;
+                to_peers(r + row, v, mb_r);
                 residual_sums(v, r_old >= 0 ? tiny_sm[r_old + row] : 0.0, r_old >= 0, acc);
             }
         }
         stamp(2);
-        publish(acc, std::integral_constant<int, 3>{}, 0);
+        publish(acc, std::integral_constant<int, 3>{}, 0, mb_r, ph_r, r_bytes);
         stamp(3);
     };
     // g_new = A^T r for my routes (local) and the sums of EpiGradBB (g < 0: only <g_new, g_new>)
@@ -246,7 +313,7 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kTinyThre
             }
         }
         stamp(4);
-        publish(acc, std::integral_constant<int, 4>{}, 1);
+        publish(acc, std::integral_constant<int, 4>{}, 1, mb_g, ph_g, g_bytes);
         stamp(5);
     };
     auto decide = [&](int first) {
@@ -331,12 +398,17 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kTinyThre
                         w = shift + w;
                         w = (w < 0.0) ? 0.0 : w;
                     }
-                    to_all(xn + s + pos, w);
+                    tiny_sm[xn + s + pos] = w;
                 }
             }
         }
         stamp(0);
-        cluster.sync();
+        fence_async_smem();
+        __syncthreads();
+        if (tid < C && tid != me && c_hi > c_lo) send_slice(tid, xn, c_lo, c_hi, mb_x);
+        mbar_wait(mb_x, ph_x);
+        ph_x ^= 1u;
+        if (tid == 0) mbar_expect(mb_x, x_bytes);
         stamp(1);
         residual(xn, rn, rc);
         gradient(rn, gn, gc, xc, xn);
@@ -370,6 +442,7 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kTinyThre
             }
             // the pull-back read buffer `cur` of x and r, which the peers overwrite with their slices of the next trial
             // point: they must not start before every CTA is through (tau is the same everywhere: a cluster-uniform branch)
+            fence_async_smem();
             cluster.sync();
             stamp(8);
         }

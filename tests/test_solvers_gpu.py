@@ -343,6 +343,39 @@ def test_batch_solvers_accept_host_vectors(B, gold):
         assert isinstance(h["x"], np.ndarray) and np.array_equal(h["x"], host(a["x"]))
 
 
+def test_batch_solvers_float32_inputs(B, gold):
+    """north_star's fp32 bar: projected vectors and objectives within 1e-4 relative.  The solvers take float32 problems
+    and start vectors (NumPy, CPU tensor, CUDA tensor), widen them on the way in -- the loop is bound by 8-byte gathers
+    that cost a 32-byte sector each whatever the element size -- and return x as float32.  Checked against the float64
+    ORACLE run on the float32-rounded data, and against the float64 run on the original data at 1e-4."""
+    from oracle import solvers_np as S
+    A, b, starts, x0 = problem(gold, "noisy")
+    A32, b32, x32 = A.astype(np.float32), b.astype(np.float32), x0.astype(np.float32)
+    parts64 = B.algorithm_utils.get_solver_parts((A, b), starts, 0.1, is_sparse=True)
+    ref64 = B.BATCH.solve_BB(parts64[3], parts64[1], parts64[2], dev(x0), max_iter=300)
+    parts = B.algorithm_utils.get_solver_parts((A32, b32), starts, 0.1, is_sparse=True)
+    op = S.get_solver_parts(A32.astype(np.float64), b32.astype(np.float64), starts, 0.1)
+    want = S.solve_BB(op[3], op[1], op[2], x32.astype(np.float64), max_iter=300)
+    for make in (lambda: x32.copy(), lambda: torch.from_numpy(x32.copy()), lambda: torch.from_numpy(x32.copy()).cuda()):
+        xin = make()
+        sol = B.BATCH.solve_BB(parts[3], parts[1], parts[2], xin, max_iter=300)
+        out = sol["x"]
+        if isinstance(xin, np.ndarray):
+            assert isinstance(out, np.ndarray) and out.dtype == np.float32
+        else:
+            assert torch.is_tensor(out) and out.dtype == torch.float32 and out.is_cuda == xin.is_cuda
+        got = host(out) if torch.is_tensor(out) else out
+        assert sol["f"] == pytest.approx(want["f"], rel=1e-6, abs=1e-10)
+        np.testing.assert_allclose(got, want["x"], rtol=1e-4, atol=1e-6)
+        assert sol["f"] == pytest.approx(ref64["f"], rel=1e-4, abs=1e-8)
+        np.testing.assert_allclose(got, host(ref64["x"]), rtol=1e-4, atol=1e-4)
+    for name in ("pg", "md"):
+        h = run_batch(B, name, parts, starts, x32.copy(), True)
+        a = run_batch(B, name, parts64, starts, dev(x0), True)
+        assert h["x"].dtype == np.float32
+        np.testing.assert_allclose(h["x"], host(a["x"]), rtol=1e-4, atol=1e-4)
+
+
 def test_small_qp_known_answer(B, gold):
     """tests/fast/test_BATCH.py of the reference: 2-variable QP, solution [.25, .75], f_min 1.875."""
     Q, c, x_true, f_min, min_eig = B.bsls_utils.generate_small_qp()
