@@ -80,9 +80,11 @@ __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect(uint32_t mbar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
 }
+// (the default .acquire.cta form: what lands in SHARED memory needs no L1 invalidation; the .acquire.cluster form emits a
+// CCTL.IVALL per waiting warp, which was a quarter of the kernel's stall samples)
 __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
     asm volatile(
-        "{\n.reg .pred p;\nW: mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n@p bra D;\nbra W;\nD:\n}\n" ::"r"(mbar),
+        "{\n.reg .pred p;\nW: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra D;\nbra W;\nD:\n}\n" ::"r"(mbar),
         "r"(parity)
         : "memory");
 }
