@@ -609,6 +609,44 @@ def test_config1_bb_full_size(B):
         np.testing.assert_allclose(xs.reshape(-1, 5).sum(1), 1.0, atol=1e-9)
 
 
+@pytest.mark.parametrize("nb,K,m,L,ragged", [(1000, 6, 2500, 6, False), (700, 9, 1500, 5, True), (40, 33, 300, 4, True)])
+def test_cluster_solver_shapes(B, monkeypatch, nb, K, m, L, ragged):
+    """The cluster loop (solver_cluster.cuh) on shapes around its limits: a problem whose vectors do not fit ONE CTA's
+    shared memory but fit a cluster's shares (the environment switch is not consulted there), ragged blocks whose
+    column shares start in the middle of a 32-column group, and blocks longer than a group (halo of a share).  Checked
+    against the oracle's solve and, to 1e-9 on the objective trace, against the multi-kernel loop."""
+    from oracle import solvers_np as S
+    rng = np.random.RandomState(nb + K)
+    if ragged:
+        sizes = rng.randint(max(2, K - 7), K + 1, size=nb)
+        sizes[rng.randint(nb)] = min(64, K + 20)
+    else:
+        sizes = np.full(nb, K)
+    n = int(sizes.sum())
+    starts = np.concatenate(([0], np.cumsum(sizes)[:-1])).astype(np.int64)
+    base = np.sort(rng.randint(0, m - L + 1, size=(n, L)), axis=1) + np.arange(L)
+    A = sps.csr_matrix((np.ones(n * L), (base.reshape(-1), np.repeat(np.arange(n), L))), shape=(m, n))
+    x_true = np.concatenate([rng.dirichlet(np.ones(k)) for k in sizes])
+    b = A.dot(x_true) + 0.1 * rng.randn(m)
+    x0 = np.concatenate([np.full(k, 1.0 / k) for k in sizes])
+    ref_parts = S.get_solver_parts(A, b, starts, 0.1)
+    ref = S.solve_BB(ref_parts[3], ref_parts[1], ref_parts[2], x0, max_iter=400)
+    parts = B.algorithm_utils.get_solver_parts((A, b), starts, 0.1, is_sparse=True)
+    monkeypatch.delenv("BSLS_NO_TINY", raising=False)
+    monkeypatch.setenv("BSLS_TINY_CLUSTER", "1")
+    sol = B.BATCH.solve_BB(parts[3], parts[1], parts[2], dev(x0), max_iter=400)
+    monkeypatch.setenv("BSLS_NO_TINY", "1")
+    loop = B.BATCH.solve_BB(parts[3], parts[1], parts[2], dev(x0), max_iter=400)
+    assert sol["f"] == pytest.approx(ref["f"], rel=1e-6, abs=1e-10)
+    assert loop["f"] == pytest.approx(ref["f"], rel=1e-6, abs=1e-10)
+    k = min(8, len(sol["progress"]), len(ref["progress"]), len(loop["progress"]))
+    np.testing.assert_allclose([p[1] for p in sol["progress"][:k]], [p[1] for p in ref["progress"][:k]], rtol=1e-9)
+    np.testing.assert_allclose([p[1] for p in sol["progress"][:k]], [p[1] for p in loop["progress"][:k]], rtol=1e-9)
+    xs = host(sol["x"])
+    assert xs.min() >= 0.0
+    np.testing.assert_allclose(np.add.reduceat(xs, starts), 1.0, atol=1e-9)
+
+
 def test_config4_shape_md_and_lbfgs(B):
     """BASELINE config 4 shape (K = 20, L = 10; 1/10 of the blocks and links): mirror descent and L-BFGS."""
     from oracle import solvers_np as S
