@@ -637,6 +637,7 @@ def test_cluster_solver_shapes(B, monkeypatch, nb, K, m, L, ragged):
     sol = B.BATCH.solve_BB(parts[3], parts[1], parts[2], dev(x0), max_iter=400)
     monkeypatch.setenv("BSLS_NO_TINY", "1")
     loop = B.BATCH.solve_BB(parts[3], parts[1], parts[2], dev(x0), max_iter=400)
+    assert sol["kernel_launches"] == 1 and loop["kernel_launches"] > 1      # one launch of the cluster; the multi-kernel loop
     assert sol["f"] == pytest.approx(ref["f"], rel=1e-6, abs=1e-10)
     assert loop["f"] == pytest.approx(ref["f"], rel=1e-6, abs=1e-10)
     k = min(8, len(sol["progress"]), len(ref["progress"]), len(loop["progress"]))
