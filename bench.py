@@ -703,6 +703,9 @@ def run_ours(args, rank, world, local_rank):
            "api": "bsls_b200.BATCH.solve_BB(obj, proj, line_search, x_init) with x_init / b in pinned host memory and x returned to "
                   "the host, on every rank (bytes are whole-job totals)"}
     del xh, bh, x_out
+    if comm is not None and os.environ.get("BSLS_P2P_PROF"):   # development: the exchange kernels' wait / transfer times on stderr
+        barrier()
+        comm.close()
 
     # ---- CPU baseline and the other BASELINE configs (rank 0, device-local work only) -----------------------
     extras = {}

@@ -80,6 +80,7 @@ struct bsls_comm {
     int nranks = 1, rank = 0;
     // peer-memory exchange (p2p.cuh): this rank's region, the mapped regions of the others, the epoch of the last evaluation
     void *region = nullptr;
+    unsigned long long *d_prof = nullptr;  // BSLS_P2P_PROF=1: wait / transfer times of the exchange kernels (development)
     void *peer_base[kP2pMaxRanks] = {};
     int64_t p2p_m = 0;
     bool p2p_ready = false;
@@ -105,6 +106,7 @@ static void p2p_fill_view(bsls_comm *c) {
     }
     c->view.nranks = P;
     c->view.rank = c->rank;
+    c->view.prof = c->d_prof;
 }
 static size_t p2p_region_bytes(int P, int64_t m) { return sizeof(double) * (size_t)(3 * ((m + 1) & ~int64_t(1)) + 2 * P * 8 + 3 * P + 8); }
 
@@ -546,6 +548,11 @@ int bsls_comm_p2p_alloc(bsls_comm *c, int64_t m, char handle[64]) {
     int64_t want = (rows + kP2pThreads - 1) / kP2pThreads;
     c->reduce_grid = (int)(want < 2 * num_sms() ? (want < 1 ? 1 : want) : 2 * num_sms());
     BSLS_CUDA_TRY(cudaMalloc(&c->cta_partials, sizeof(double) * 3 * (size_t)c->reduce_grid));
+    if (const char *e = getenv("BSLS_P2P_PROF"))
+        if (atoi(e)) {
+            BSLS_CUDA_TRY(cudaMalloc(&c->d_prof, 8 * sizeof(unsigned long long)));
+            BSLS_CUDA_TRY(cudaMemset(c->d_prof, 0, 8 * sizeof(unsigned long long)));
+        }
     cudaIpcMemHandle_t h;
     BSLS_CUDA_TRY(cudaIpcGetMemHandle(&h, c->region));
     memcpy(handle, &h, 64);
@@ -577,6 +584,14 @@ int bsls_comm_destroy(bsls_comm *c) {
     if (!c) return BSLS_OK;
     for (int q = 0; q < kP2pMaxRanks; ++q)
         if (c->peer_base[q]) cudaIpcCloseMemHandle(c->peer_base[q]);
+    if (c->d_prof) {
+        unsigned long long h[8] = {0};
+        cudaMemcpy(h, c->d_prof, sizeof(h), cudaMemcpyDeviceToHost);
+        const double k = h[3] ? 1e-3 / (double)h[3] : 0.0;
+        fprintf(stderr, "[p2p prof] rank %d: %llu exchanges; per exchange: wait for every rank's partial vector %.1f us, reduce + push %.1f us, "
+                        "wait for every rank's rows %.1f us\n", c->rank, h[3], k * h[0], k * h[1], k * h[2]);
+        cudaFree(c->d_prof);
+    }
     if (c->region) cudaFree(c->region);
     if (c->ticket) cudaFree(c->ticket);
     if (c->cta_partials) cudaFree(c->cta_partials);

@@ -40,7 +40,14 @@ struct P2pView {
     double *slots[kP2pMaxRanks];               // nranks x 8: residual sums of every source rank
     double *gath[kP2pMaxRanks];                // nranks x kStepScalars: step scalars of every source rank
     unsigned long long *flags[kP2pMaxRanks];   // 3 x nranks: flag A / B / C of every source rank
+    unsigned long long *prof;                  // development (BSLS_P2P_PROF=1): ns waited for flags A / spent reducing / waited for flags B, calls; else null
 };
+
+__device__ __forceinline__ unsigned long long p2p_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -72,19 +79,46 @@ p2p_reduce_kernel(P2pView v, const double *__restrict__ b, int64_t m, int nxt, u
         __threadfence_system();
         st_release_sys(v.flags[tid] + 0 * P + me, epoch);
     }
+    const unsigned long long t0 = (v.prof && blockIdx.x == 0 && tid == 0) ? p2p_now() : 0ull;
     p2p_wait_flags(v.flags[me] + 0 * P, P, epoch);
+    if (v.prof && blockIdx.x == 0 && tid == 0) {
+        const unsigned long long t1 = p2p_now();
+        v.prof[0] += t1 - t0;
+        v.prof[6] = t1;
+    }
     const int64_t lo = m * me / P, hi = m * (me + 1) / P;
     const double *r_old = v.rfull[me][nxt ^ 1];
     double acc[3] = {0, 0, 0};
-    for (int64_t i = lo + (int64_t)blockIdx.x * kP2pThreads + tid; i < hi; i += (int64_t)gridDim.x * kP2pThreads) {
-        double s = __ldcv(v.partial[0] + i);
-        for (int q = 1; q < P; ++q) s += __ldcv(v.partial[q] + i);  // rank order: the same bits on every rank
-        const double r = s - b[i];
-        residual_sums(r, r_old[i], true, acc);
-        for (int q = 0; q < P; ++q) v.rfull[q][nxt][i] = r;
+    // two rows per thread and trip: 2 x P loads over NVLink in flight before the first sum
+    const int64_t stride = (int64_t)gridDim.x * kP2pThreads;
+    for (int64_t i = lo + (int64_t)blockIdx.x * kP2pThreads + tid; i < hi; i += 2 * stride) {
+        const int64_t j = i + stride;
+        const bool two = j < hi;
+        double s0 = __ldcv(v.partial[0] + i), s1 = two ? __ldcv(v.partial[0] + j) : 0.0;
+        double t0v[kP2pMaxRanks], t1v[kP2pMaxRanks];
+#pragma unroll
+        for (int q = 1; q < kP2pMaxRanks; ++q) {
+            t0v[q] = q < P ? __ldcv(v.partial[q] + i) : 0.0;
+            t1v[q] = (q < P && two) ? __ldcv(v.partial[q] + j) : 0.0;
+        }
+#pragma unroll
+        for (int q = 1; q < kP2pMaxRanks; ++q)
+            if (q < P) {  // rank order: the same bits on every rank
+                s0 += t0v[q];
+                s1 += t1v[q];
+            }
+        const double r0 = s0 - b[i];
+        residual_sums(r0, r_old[i], true, acc);
+        for (int q = 0; q < P; ++q) v.rfull[q][nxt][i] = r0;
+        if (two) {
+            const double r1 = s1 - b[j];
+            residual_sums(r1, r_old[j], true, acc);
+            for (int q = 0; q < P; ++q) v.rfull[q][nxt][j] = r1;
+        }
     }
-    // deterministic sum over the CTA, then over the grid by the last CTA (fixed order); system-scope fences because the
-    // stores above went to peer memory and flag B must not overtake them
+    // deterministic sum over the CTA, then over the grid by the last CTA (fixed order).  One system-scope fence per CTA,
+    // by the thread that takes the ticket after the CTA barrier (fences are cumulative: the barrier orders the other
+    // threads' peer stores before it); flag B must not overtake them
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         double x = acc[k];
@@ -92,9 +126,9 @@ p2p_reduce_kernel(P2pView v, const double *__restrict__ b, int64_t m, int nxt, u
         for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
         if ((tid & 31) == 0) s_w[tid >> 5][k] = x;
     }
-    __threadfence_system();
     __syncthreads();
     if (tid == 0) {
+        __threadfence_system();
         for (int k = 0; k < 3; ++k) {
             double x = s_w[0][k];
             for (int w = 1; w < kP2pThreads / 32; ++w) x += s_w[w][k];
@@ -106,22 +140,42 @@ p2p_reduce_kernel(P2pView v, const double *__restrict__ b, int64_t m, int nxt, u
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    if (tid < 3) {
-        double x = 0.0;
-        for (unsigned c = 0; c < gridDim.x; ++c) x += __ldcg(cta_partials + c * 3 + tid);
-        for (int q = 0; q < P; ++q) v.slots[q][me * 8 + tid] = x;
+    {   // the grid's sums: every thread adds a strided share of the CTA partials, then the fixed tree over the CTA
+        double g[3] = {0, 0, 0};
+        for (unsigned c = tid; c < gridDim.x; c += kP2pThreads)
+            for (int k = 0; k < 3; ++k) g[k] += __ldcg(cta_partials + c * 3 + k);
+        __syncthreads();  // s_w is reused
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            double x = g[k];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if ((tid & 31) == 0) s_w[tid >> 5][k] = x;
+        }
+        __syncthreads();
+        if (tid < 3) {
+            double x = s_w[0][tid];
+            for (int w = 1; w < kP2pThreads / 32; ++w) x += s_w[w][tid];
+            for (int q = 0; q < P; ++q) v.slots[q][me * 8 + tid] = x;
+            __threadfence_system();
+        }
     }
-    __threadfence_system();
     __syncthreads();
     if (tid < P) st_release_sys(v.flags[tid] + 1 * P + me, epoch);  // flag B: my rows and my sums are everywhere
     if (tid == 0) *ticket = 0u;
+    if (v.prof && tid == 0) v.prof[1] += p2p_now() - v.prof[6];
 }
 
 // The residual is complete on this rank once every rank has raised flag B; the scalar block gets the sums in rank order.
 __global__ void p2p_wait_kernel(P2pView v, unsigned long long epoch, double *scal, const int *__restrict__ skip) {
     if (skip && *skip) return;
     const int P = v.nranks, me = v.rank;
+    const unsigned long long t0 = (v.prof && threadIdx.x == 0) ? p2p_now() : 0ull;
     p2p_wait_flags(v.flags[me] + 1 * P, P, epoch);
+    if (v.prof && threadIdx.x == 0) {
+        v.prof[2] += p2p_now() - t0;
+        v.prof[3] += 1;
+    }
     if (threadIdx.x == 0) {
         double s[3] = {0, 0, 0};
         for (int q = 0; q < P; ++q)
