@@ -40,3 +40,18 @@ def test_small_integer_division_is_correctly_rounded(tmp_path):
     assert res.returncode == 0, res.stderr[-2000:]
     run = subprocess.run([exe, "20000000"], capture_output=True, text=True, timeout=120)
     assert run.returncode == 0 and "bad(two-step)=0" in run.stdout, run.stdout + run.stderr
+
+
+@pytest.mark.skipif(not os.path.exists(NVCC), reason="nvcc not found")
+def test_cluster_solver_share_arithmetic_on_host(tmp_path):
+    """The share arithmetic of the cluster solver (csrc/solver_cluster.cuh: cluster_share / cluster_share_end, and the
+    block search of the kernel) on 20,000 random layouts: the columns a CTA owns stay inside the groups its shared memory
+    is sized for, shares tile all blocks and all rows (tools/cluster_share_check.cu)."""
+    exe = str(tmp_path / "cluster_share_check")
+    cmd = [NVCC, "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-I",
+           os.path.join(ROOT, "block-simplex-least-squares_b200", "csrc"), "-o", exe, os.path.join(ROOT, "tools", "cluster_share_check.cu")]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-2000:]
+    run = subprocess.run([exe, "20000"], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stdout[-500:] + run.stderr[-2000:]
+    assert run.stdout.startswith("ok ")
